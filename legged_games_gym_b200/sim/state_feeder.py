@@ -1,0 +1,162 @@
+"""Synthetic sim backend: stands where Isaac Gym / PhysX stands in the reference.
+
+The reference env talks to PhysX through the tensor API on ``self.gym``
+(legged_robot.py:92-96, 111-112, 410, 434, 444, 515-520).  PhysX is out of scope here ("fed by
+state tensors"), so the env is constructed over a ``SimBackend`` exposing the same method names.
+``StateFeeder`` owns the three state tensors (root_states, dof_state, net_contact_forces) on the
+device and fills them with the seeded synthetic distributions of SURVEY.md section 8(d);
+``HostStateFeeder`` keeps the sim state in pinned HOST memory and copies across PCIe at the same API
+points where a CPU-pipeline PhysX would (the e2e leg of bench.py).
+"""
+import numpy as np
+import torch
+
+
+def synth_state(num_envs, num_bodies, num_dof=12, seed=0, p_contact=0.3, actors_per_env=1):
+    """numpy dict of seeded synthetic inputs (PCG64: stable across torch versions)."""
+    g = np.random.default_rng(seed)
+    N = num_envs
+    na = N * actors_per_env
+    root = np.zeros((na, 13), dtype=np.float32)
+    root[:, 0] = g.uniform(-2., 83., na)
+    root[:, 1] = g.uniform(-2., 163., na)
+    root[:, 2] = g.normal(0.5, 0.1, na)
+    q = g.normal(0., 1., (na, 4))
+    q[:, :2] *= 0.3
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    root[:, 3:7] = q
+    root[:, 7:13] = g.normal(0., 1., (na, 6))
+    dof = g.normal(0., 1., (N * num_dof, 2)).astype(np.float32)
+    contact = (g.normal(0., 2., (N * num_bodies, 3)) *
+               (g.uniform(0., 1., (N * num_bodies, 1)) < p_contact)).astype(np.float32)
+    actions = g.normal(0., 1., (N, num_dof)).astype(np.float32)
+    ep_len = g.integers(0, 1000, N).astype(np.int64)
+    return dict(root_states=root, dof_state=dof, contact_forces=contact, actions=actions,
+                episode_length_buf=ep_len)
+
+
+def synth_height_field(rows=1300, cols=2100, seed=0):
+    g = np.random.default_rng(seed + 7919)
+    return g.integers(-300, 300, (rows, cols)).astype(np.int16)
+
+
+def synth_terrain_origins(cfg_terrain):
+    """Deterministic stand-in for Terrain.env_origins (reference utils/terrain.py:147-164): centre of
+    sub-terrain (level i, type j) with a patterned platform height."""
+    rows, cols = cfg_terrain.num_rows, cfg_terrain.num_cols
+    o = np.zeros((rows, cols, 3))
+    for i in range(rows):
+        for j in range(cols):
+            o[i, j, 0] = (i + 0.5) * cfg_terrain.terrain_length
+            o[i, j, 1] = (j + 0.5) * cfg_terrain.terrain_width
+            o[i, j, 2] = 0.05 * ((3 * i + 7 * j) % 11)
+    return o
+
+
+class SimBackend:
+    """Method names = the Isaac Gym calls the hot path makes.  All are stream-ordered and non-blocking."""
+
+    def acquire_actor_root_state_tensor(self):
+        raise NotImplementedError
+
+    def acquire_dof_state_tensor(self):
+        raise NotImplementedError
+
+    def acquire_net_contact_force_tensor(self):
+        raise NotImplementedError
+
+    def refresh_dof_state_tensor(self):
+        pass
+
+    def refresh_actor_root_state_tensor(self):
+        pass
+
+    def refresh_net_contact_force_tensor(self):
+        pass
+
+    def set_dof_actuation_force_tensor(self, torques):
+        pass
+
+    def simulate(self):
+        pass
+
+    def fetch_results(self):
+        pass
+
+    def set_dof_state_tensor_indexed(self, dof_state, env_ids_int32, count):
+        pass
+
+    def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count):
+        pass
+
+    def set_actor_root_state_tensor(self, root_states):
+        pass
+
+
+class StateFeeder(SimBackend):
+    """Device-resident synthetic state (inputs already in HBM when a step starts)."""
+
+    def __init__(self, num_envs, num_bodies, num_dof=12, device="cuda", seed=0, p_contact=0.3,
+                 actors_per_env=1):
+        s = synth_state(num_envs, num_bodies, num_dof, seed, p_contact, actors_per_env)
+        self.device = torch.device(device)
+        self.root_states = torch.from_numpy(s["root_states"]).to(self.device)
+        self.dof_state = torch.from_numpy(s["dof_state"]).to(self.device)
+        self.contact_forces = torch.from_numpy(s["contact_forces"]).to(self.device)
+        self.synthetic_actions = torch.from_numpy(s["actions"]).to(self.device)
+        self.synthetic_episode_length = torch.from_numpy(s["episode_length_buf"]).to(self.device)
+
+    def acquire_actor_root_state_tensor(self):
+        return self.root_states
+
+    def acquire_dof_state_tensor(self):
+        return self.dof_state
+
+    def acquire_net_contact_force_tensor(self):
+        return self.contact_forces
+
+
+class HostStateFeeder(StateFeeder):
+    """Sim state lives in pinned host memory (the reference's ``sim_device=cpu`` pipeline: PhysX
+    results are host tensors).  refresh_* = H2D copy; set_* = D2H copy.  Byte counters feed bench.py's
+    ``e2e.h2d_bytes_per_step`` / ``d2h_bytes_per_step``."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.h_root = self.root_states.cpu().pin_memory()
+        self.h_dof = self.dof_state.cpu().pin_memory()
+        self.h_contact = self.contact_forces.cpu().pin_memory()
+        self.h_torques = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _h2d(self, dst, src):
+        dst.copy_(src, non_blocking=True)
+        self.h2d_bytes += src.numel() * src.element_size()
+
+    def _d2h(self, dst, src):
+        dst.copy_(src, non_blocking=True)
+        self.d2h_bytes += src.numel() * src.element_size()
+
+    def refresh_dof_state_tensor(self):
+        self._h2d(self.dof_state, self.h_dof)
+
+    def refresh_actor_root_state_tensor(self):
+        self._h2d(self.root_states, self.h_root)
+
+    def refresh_net_contact_force_tensor(self):
+        self._h2d(self.contact_forces, self.h_contact)
+
+    def set_dof_actuation_force_tensor(self, torques):
+        if self.h_torques is None:
+            self.h_torques = torch.empty(torques.shape, dtype=torques.dtype).pin_memory()
+        self._d2h(self.h_torques, torques)
+
+    def set_dof_state_tensor_indexed(self, dof_state, env_ids_int32, count):
+        self._d2h(self.h_dof, dof_state)
+
+    def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count):
+        self._d2h(self.h_root, root_states)
+
+    def set_actor_root_state_tensor(self, root_states):
+        self._d2h(self.h_root, root_states)

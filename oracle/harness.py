@@ -1,0 +1,114 @@
+"""TEST INFRASTRUCTURE ONLY -- shared scaffolding for parity tests, golden fixtures and the CPU baseline.
+
+``TASKS`` maps each registered task name (reference legged_gym/envs/__init__.py:49-56) to the oracle
+``kind`` and the product-side cfg class; ``build_case`` creates seeded synthetic inputs
+(SURVEY.md section 8(d)); ``step_tables`` makes the per-step uniform tables from oracle/philox.py.
+"""
+import copy
+import os
+
+import numpy as np
+import torch
+
+from . import philox
+from .legged_oracle import OracleEnv
+
+_PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "legged_games_gym_b200")
+LSTM_NPZ = os.path.join(_PKG, "resources", "actuator_nets", "anydrive_v3_lstm.npz")
+
+TASKS = {
+    "anymal_c_rough": ("anymal", "envs.anymal_c.mixed_terrains.anymal_c_rough_config", "AnymalCRoughCfg"),
+    "anymal_c_flat": ("anymal", "envs.anymal_c.flat.anymal_c_flat_config", "AnymalCFlatCfg"),
+    "anymal_b": ("anymal", "envs.anymal_b.anymal_b_config", "AnymalBRoughCfg"),
+    "a1": ("legged", "envs.a1.a1_config", "A1RoughCfg"),
+    "cassie": ("cassie", "envs.cassie.cassie_config", "CassieRoughCfg"),
+}
+
+
+def lstm_weights():
+    return dict(np.load(LSTM_NPZ))
+
+
+def product_cfg(task, num_envs, overrides=None):
+    import importlib
+    kind, mod, cls = TASKS[task]
+    cfg = getattr(importlib.import_module("legged_games_gym_b200." + mod), cls)()
+    cfg.env.num_envs = num_envs
+    apply_overrides(cfg, overrides)
+    return cfg
+
+
+def apply_overrides(cfg, overrides):
+    for path, val in (overrides or {}).items():
+        obj = cfg
+        parts = path.split(".")
+        for p in parts[:-1]:
+            obj = getattr(obj, p)
+        setattr(obj, parts[-1], val)
+
+
+def build_case(task, num_envs, seed=0, overrides=None, hf_shape=None):
+    """Returns dict(cfg, consts, state(np), height_samples(np int16|None), terrain_origins, init_levels)."""
+    from legged_games_gym_b200.sim.asset_model import model_for_asset
+    from legged_games_gym_b200.sim.state_feeder import synth_state, synth_height_field, synth_terrain_origins
+    cfg = product_cfg(task, num_envs, overrides)
+    model = model_for_asset(cfg.asset)
+    consts = model.consts(cfg.asset)
+    st = synth_state(num_envs, model.num_bodies, model.num_dof, seed)
+    rough = cfg.terrain.mesh_type in ("heightfield", "trimesh")
+    hs = None
+    origins = None
+    levels = None
+    if rough:
+        t = cfg.terrain
+        rows = int(t.num_rows * t.terrain_length / t.horizontal_scale) + 2 * int(t.border_size / t.horizontal_scale)
+        cols = int(t.num_cols * t.terrain_width / t.horizontal_scale) + 2 * int(t.border_size / t.horizontal_scale)
+        if hf_shape is not None:
+            rows, cols = hf_shape
+        hs = synth_height_field(rows, cols, seed)
+        origins = synth_terrain_origins(t)
+        g = np.random.default_rng(seed + 104729)
+        max_init = t.max_init_terrain_level if t.curriculum else t.num_rows - 1
+        levels = g.integers(0, max_init + 1, num_envs).astype(np.int64)
+    return dict(task=task, kind=TASKS[task][0], cfg=cfg, consts=consts, state=st, height_samples=hs,
+                terrain_origins=origins, init_levels=levels, seed=seed)
+
+
+def torch_state(case):
+    return {k: torch.from_numpy(case["state"][k].copy()) for k in ("root_states", "dof_state", "contact_forces")}
+
+
+def make_oracle(case, state=None):
+    state = state if state is not None else torch_state(case)
+    hs = None if case["height_samples"] is None else torch.from_numpy(case["height_samples"].copy())
+    w = lstm_weights() if case["kind"] == "anymal" else None
+    env = OracleEnv(copy.deepcopy(case["cfg"]), case["consts"], state, kind=case["kind"], height_samples=hs,
+                    terrain_origins=case["terrain_origins"], init_levels=case["init_levels"], lstm_weights=w)
+    env.episode_length_buf[:] = torch.from_numpy(case["state"]["episode_length_buf"])
+    return env
+
+
+def step_tables(seed, step, num_envs, num_obs, num_dof=12, env_offset=0):
+    ids = np.arange(env_offset, env_offset + num_envs)
+    return {
+        philox.STREAM_CMD: philox.uniforms(seed, step, ids, philox.STREAM_CMD, 3),
+        philox.STREAM_PUSH: philox.uniforms(seed, step, ids, philox.STREAM_PUSH, 2),
+        philox.STREAM_RESET_DOF: philox.uniforms(seed, step, ids, philox.STREAM_RESET_DOF, num_dof),
+        philox.STREAM_RESET_ROOT: philox.uniforms(seed, step, ids, philox.STREAM_RESET_ROOT, 8),
+        philox.STREAM_RESET_CMD: philox.uniforms(seed, step, ids, philox.STREAM_RESET_CMD, 3),
+        philox.STREAM_TERRAIN: philox.raw_u32(seed, step, ids, philox.STREAM_TERRAIN, 1),
+        philox.STREAM_OBS: philox.uniforms(seed, step, ids, philox.STREAM_OBS, num_obs),
+    }
+
+
+def perturb_state(state, step, seed):
+    """Cheap deterministic stand-in for a physics step between env steps: new dof/contact/root
+    velocities so consecutive steps are not identical.  Applied identically to every implementation."""
+    g = np.random.default_rng(seed * 1000003 + step)
+    for k in ("dof_state", "contact_forces"):
+        t = state[k]
+        noise = g.normal(0., 0.05, tuple(t.shape)).astype(np.float32)
+        t += torch.from_numpy(noise).to(t.device) * (t != 0)
+    r = state["root_states"]
+    r[:, 7:13] += torch.from_numpy(g.normal(0., 0.05, (r.shape[0], 6)).astype(np.float32)).to(r.device)
+    r[:, 0:2] += torch.from_numpy(g.normal(0., 0.02, (r.shape[0], 2)).astype(np.float32)).to(r.device)

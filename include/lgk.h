@@ -1,0 +1,272 @@
+/* lgk.h -- C ABI of liblgk.so: the B200 (sm_100a) kernels behind legged_gym's per-environment step.
+ *
+ * Every entry point takes plain device pointers, sizes and a cudaStream_t (as void*), returns
+ * 0 on success or a non-zero code (LGK_ERR_* or 1000+cudaError_t), never throws, never allocates
+ * and never synchronises: all work is stream-ordered and CUDA-graph capturable.
+ * Citations are to /root/reference/legged_gym/... : LR = envs/base/legged_robot.py,
+ * ANY = envs/anymal_c/anymal.py, MATH = utils/math.py, CAS = envs/cassie/cassie.py.
+ * rsl_rl (not vendored in the reference; call sites utils/task_registry.py:37-38,154) is cited by
+ * function name.
+ *
+ * Tensor layouts are the reference's own: env-major row-major fp32 unless noted.
+ */
+#ifndef LGK_H
+#define LGK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGK_ABI_VERSION 1
+#define LGK_NUM_DOF 12          /* every registered task has 12 DOF = 12 actions */
+#define LGK_MAX_FEET 4
+#define LGK_MAX_PEN 16
+#define LGK_MAX_TERM 8
+#define LGK_MAX_BODIES 32
+
+enum {
+  LGK_OK = 0,
+  LGK_ERR_ARG = 1,          /* bad size / null pointer / unsupported configuration */
+  LGK_ERR_ALIGN = 2,        /* a pointer violates the 16-byte alignment the kernels assume */
+  LGK_ERR_CUDA_BASE = 1000  /* 1000 + cudaError_t */
+};
+
+/* reward terms, in the ALPHABETICAL order the reference sums them (helpers.py:41-56 walks dir();
+ * LR:583-607).  "termination" is applied after the positive clip (LR:204-210). */
+enum {
+  LGK_R_ACTION_RATE = 0, LGK_R_ANG_VEL_XY, LGK_R_BASE_HEIGHT, LGK_R_COLLISION, LGK_R_DOF_ACC,
+  LGK_R_DOF_POS_LIMITS, LGK_R_DOF_VEL, LGK_R_DOF_VEL_LIMITS, LGK_R_FEET_AIR_TIME,
+  LGK_R_FEET_CONTACT_FORCES, LGK_R_LIN_VEL_Z, LGK_R_NO_FLY, LGK_R_ORIENTATION, LGK_R_STAND_STILL,
+  LGK_R_STUMBLE, LGK_R_TERMINATION, LGK_R_TORQUE_LIMITS, LGK_R_TORQUES, LGK_R_TRACKING_ANG_VEL,
+  LGK_R_TRACKING_LIN_VEL, LGK_R_COUNT
+};
+
+/* random streams of the counter-based generator (Philox4x32-10, key = seed,
+ * counter = (global env id, word_index/4, stream, step)); uniform = (word >> 8) * 2^-24. */
+enum {
+  LGK_STREAM_CMD = 0, LGK_STREAM_PUSH = 1, LGK_STREAM_RESET_DOF = 2, LGK_STREAM_RESET_ROOT = 3,
+  LGK_STREAM_RESET_CMD = 4, LGK_STREAM_TERRAIN = 5, LGK_STREAM_OBS = 6, LGK_STREAM_ACT = 7
+};
+
+enum { LGK_CTRL_P = 0, LGK_CTRL_V = 1, LGK_CTRL_T = 2 };
+
+/* phases of lgk_post_physics (bit mask).  PRE = LR:114-127 up to the per-term reward sum;
+ * POST = positive clip + termination term (LR:204-210), reset_idx (LR:147-191), observations
+ * (LR:212-230) and the history copies (LR:132-134).  PRE|POST runs fused in one launch; the host
+ * splits them only when Python code must run in between (user reward terms, command curriculum). */
+enum { LGK_PHASE_PRE = 1, LGK_PHASE_POST = 2 };
+
+/* ------------------------------------------------------------------ torques (LR:371-395, ANY:71-81) */
+typedef struct LgkTorqueParams {
+  int32_t num_envs;
+  int32_t control_type;               /* LGK_CTRL_*; ignored when lstm != 0 */
+  int32_t use_lstm;                   /* ANY:73 cfg.control.use_actuator_network */
+  float action_scale;                 /* cfg.control.action_scale */
+  float clip_actions;                 /* LR:86-87: actions are clipped to +-clip on load */
+  float inv_sim_dt_unused;            /* reserved */
+  float sim_dt;                       /* LR:390 divides by sim_params.dt ("V" control) */
+  float p_gains[LGK_NUM_DOF];         /* LR:566-580 */
+  float d_gains[LGK_NUM_DOF];
+  float torque_limits[LGK_NUM_DOF];   /* LR:395 clip (PD path only; ANY:77-78 does not clip) */
+  float default_dof_pos[LGK_NUM_DOF]; /* LR:565-581 */
+  const float* actions_in;            /* [N,12] raw policy output */
+  float* actions_clipped;             /* [N,12] or NULL: self.actions (LR:87) */
+  const float* dof_state;             /* [N*12,2] (pos,vel) interleaved, LR:524-526 */
+  const float* last_dof_vel;          /* [N,12] ("V" control only) */
+  float* torques;                     /* [N,12] out */
+  float* sea_hidden_state;            /* [2,N*12,8] r/w (ANY:65-69) */
+  float* sea_cell_state;              /* [2,N*12,8] r/w */
+} LgkTorqueParams;
+
+/* LSTM actuator weights (resources/actuator_nets/anydrive_v3_lstm.pt: LSTM(2,8,layers=2) + Linear(8,1),
+ * buffers in_scale[2], out_scale[1]); torch gate order i,f,g,o.  Uploaded once into __constant__. */
+typedef struct LgkLstmWeights {
+  float w_ih0[32 * 2], w_hh0[32 * 8], b_ih0[32], b_hh0[32];
+  float w_ih1[32 * 8], w_hh1[32 * 8], b_ih1[32], b_hh1[32];
+  float lin_w[8], lin_b[1];
+  float in_scale[2], out_scale[1];
+} LgkLstmWeights;
+
+int lgk_set_lstm_weights(const LgkLstmWeights* host_weights, void* stream);
+int lgk_compute_torques(const LgkTorqueParams* p, void* stream);
+
+/* ------------------------------------------------------------------ post-physics step (LR:106-230, 329-508, 831-969) */
+typedef struct LgkStepParams {
+  /* sizes */
+  int32_t num_envs;
+  int32_t num_bodies;                 /* NB: contact_forces is [N, NB, 3] (LR:529) */
+  int32_t num_obs;                    /* O = 48 + P when measure_heights else 48 */
+  int32_t num_height_points;          /* P (0 when !measure_heights) */
+  int32_t actors_per_env;             /* root_states rows per env (1; 2 in low_level_game, LLG:532) */
+  int32_t root_actor_offset;          /* row of the robot inside the env's actor group (prey index) */
+  int32_t phase_mask;                 /* LGK_PHASE_* */
+  int32_t step;                       /* common_step_counter AFTER the += 1 of LR:115 (RNG counter) */
+  uint64_t seed;
+  int64_t env_id_offset;              /* global id of env 0 (multi-GPU sharding keeps streams disjoint) */
+
+  /* flags */
+  int32_t heading_command;            /* cfg.commands.heading_command (LR:337, 359) */
+  int32_t measure_heights;            /* cfg.terrain.measure_heights (LR:342) */
+  int32_t terrain_is_plane;           /* mesh_type == 'plane' -> zeros (LR:844-845) */
+  int32_t do_push;                    /* push_robots && counter % push_interval == 0 (LR:344) */
+  int32_t add_noise;                  /* LR:229 */
+  int32_t only_positive_rewards;      /* LR:204 */
+  int32_t terrain_curriculum;         /* LR:160 (cfg.terrain.curriculum after _parse_cfg LR:786-787) */
+  int32_t custom_origins;             /* LR:422 */
+  int32_t send_timeouts;              /* LR:190 */
+  int32_t zero_lstm_on_reset;         /* ANY:56-60 */
+
+  /* scalars */
+  float dt;                           /* decimation * sim.dt (LR:782) */
+  int32_t resample_period;            /* int(resampling_time / dt) (LR:334) */
+  float max_episode_length;           /* np.ceil(episode_length_s / dt) (LR:789); compared with > (LR:144) */
+  float max_episode_length_s;
+  float max_push_vel;                 /* LR:441 */
+  float cmd_lo[4], cmd_range[4];      /* x, y, yaw, heading: lo and (float)(hi - lo) (LR:353-366) */
+  float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_dof_pos, obs_scale_dof_vel, obs_scale_height;
+  float clip_obs;                     /* LR:100-101 */
+  float tracking_sigma, base_height_target, max_contact_force;
+  float soft_dof_vel_limit, soft_torque_limit;
+  float border_size, horizontal_scale, vertical_scale;   /* LR:856-857, 869 */
+  int32_t hf_rows, hf_cols;           /* height_samples.shape */
+  float half_env_length;              /* terrain.env_length / 2 (LR:458) */
+  int32_t max_terrain_level;          /* LR:766 */
+  int32_t terrain_num_cols;           /* terrain_origins is [rows, cols, 3] */
+
+  /* per-robot constants */
+  float default_dof_pos[LGK_NUM_DOF];
+  float dof_pos_lo[LGK_NUM_DOF], dof_pos_hi[LGK_NUM_DOF];  /* soft limits LR:310-313 */
+  float dof_vel_limits[LGK_NUM_DOF], torque_limits[LGK_NUM_DOF];
+  float base_init_state[13];          /* LR:704-705 */
+  int32_t num_feet, num_pen, num_term;
+  int32_t feet_idx[LGK_MAX_FEET], pen_idx[LGK_MAX_PEN], term_idx[LGK_MAX_TERM];
+  float reward_scale[LGK_R_COUNT];    /* already multiplied by dt (LR:593); 0 = term inactive */
+  int32_t reward_active[LGK_R_COUNT]; /* non-zero scale in cfg (LR:588-593) */
+  int32_t reward_slot[LGK_R_COUNT];   /* row of episode_sums for the term, -1 if inactive */
+  int32_t num_reward_slots;
+
+  /* sim-owned state (LR:523-530) */
+  float* root_states;                 /* [N*actors_per_env, 13] pos3 quat4(xyzw) linvel3 angvel3 */
+  float* dof_state;                   /* [N*12, 2] */
+  const float* contact_forces;        /* [N*NB, 3] */
+  /* env-owned state */
+  const float* actions;               /* [N,12] clipped (LR:87) */
+  const float* torques;               /* [N,12] last sub-step's torques (LR:91) */
+  float* commands;                    /* [N,4] */
+  int64_t* episode_length_buf;        /* [N] */
+  float* last_actions;                /* [N,12] */
+  float* last_dof_vel;                /* [N,12] */
+  float* last_root_vel;               /* [N,6] */
+  float* feet_air_time;               /* [N,F] */
+  uint8_t* last_contacts;             /* [N,F] bool */
+  float* episode_sums;                /* [num_reward_slots, N] one row per active term */
+  int64_t* terrain_levels;            /* [N] (curriculum only) */
+  const int64_t* terrain_types;       /* [N] */
+  const float* terrain_origins;       /* [rows, cols, 3] */
+  float* env_origins;                 /* [N,3] */
+  float* sea_hidden_state;            /* [2,N*12,8] or NULL */
+  float* sea_cell_state;
+  /* outputs */
+  float* base_lin_vel;                /* [N,3] */
+  float* base_ang_vel;                /* [N,3] */
+  float* projected_gravity;           /* [N,3] */
+  float* measured_heights;            /* [N,P] */
+  float* obs_buf;                     /* [N,O], already clipped to +-clip_obs */
+  float* rew_buf;                     /* [N] */
+  uint8_t* reset_buf;                 /* [N] bool */
+  uint8_t* time_out_buf;              /* [N] bool */
+  /* constants in device memory */
+  const int16_t* height_min3;         /* [hf_rows, hf_cols] from lgk_height_min3 (see below) */
+  const float* height_points_xy;      /* [P,2] base-frame grid (LR:815-829), x outer / y inner */
+  const float* noise_scale_vec;       /* [O] (LR:485-508) */
+  /* cross-env accumulators, two slots ping-ponged on (step & 1): [2][num_reward_slots + 2] floats:
+   * per-term sum of episode_sums over the envs reset this step, then reset count, then
+   * sum(terrain_levels) over all envs (LR:181-186) */
+  float* reset_stats;
+} LgkStepParams;
+
+int lgk_post_physics(const LgkStepParams* p, void* stream);
+
+/* reset_idx(env_ids) on an explicit id list (LR:147-191), e.g. BaseTask.reset() (base_task.py:114-118).
+ * Accumulates into the same reset_stats slot as a step with p->step. */
+int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int32_t num_ids, void* stream);
+
+/* After lgk_post_physics / lgk_reset_idx: single-CTA pass that (a) compacts reset_buf into an ascending
+ * int32 id list + count (what set_*_tensor_indexed needs, LR:409-412, 433-436), (b) if count > 0 writes the
+ * extras the reference refreshes only when something was reset (LR:157-158, 179-191):
+ * episode_means[slot] = sum/count/max_episode_length_s, episode_means[nslots] = mean terrain level, and a copy
+ * of time_out_buf into time_outs_extras; (c) clears the other ping-pong slot of reset_stats. */
+int lgk_finalize_step(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset_count,
+                      float* episode_means, uint8_t* time_outs_extras, void* stream);
+
+/* ------------------------------------------------------------------ height field (LR:831-869) */
+/* min3[r,c] = min(hs[r,c], hs[r+1,c], hs[r,c+1]) for r<=rows-2, c<=cols-2 (the three samples LR:863-867
+ * takes after clipping px<=rows-2, py<=cols-2); border row/col copy hs.  Built once per terrain. */
+int lgk_height_min3(const int16_t* height_samples, int16_t* min3, int32_t rows, int32_t cols, void* stream);
+
+/* Stand-alone _get_heights (LR:831-869 + MATH:38-42): measured_heights[N,P] and optionally the clipped
+ * integer sample indices px,py [N,P] int32 (parity tests assert those bit-exactly). */
+int lgk_height_scan(const float* root_states, int32_t actors_per_env, int32_t root_actor_offset,
+                    int32_t num_envs, const float* height_points_xy, int32_t num_points,
+                    const int16_t* height_min3, int32_t rows, int32_t cols, float border_size,
+                    float horizontal_scale, float vertical_scale, float* measured_heights,
+                    int32_t* px_out, int32_t* py_out, void* stream);
+
+/* ------------------------------------------------------------------ RNG tap */
+/* Dump the uniforms / raw words a step consumes: out[n,count] for global env ids
+ * env_id_offset..+n.  kind 0 = float32 uniforms, 1 = raw uint32 words, 2 = Box-Muller normals (ACT). */
+int lgk_rng_dump(uint64_t seed, int32_t step, int64_t env_id_offset, int32_t num_envs, int32_t stream_id,
+                 int32_t count, int32_t kind, void* out, void* stream);
+
+/* ------------------------------------------------------------------ rsl_rl: ActorCritic.act / evaluate */
+/* Fused actor + critic MLP forward (ELU), Normal(mean, std).sample(), log_prob.sum(-1)
+ * (rsl_rl ActorCritic.act / evaluate / get_actions_log_prob; PPO.act).  Weights are nn.Linear layout
+ * [out,in] fp32.  Hidden layers run on tcgen05 tensor cores in TF32 with FP32 accumulation in TMEM. */
+typedef struct LgkPolicyParams {
+  int32_t num_envs, num_obs, num_critic_obs, num_actions;
+  int32_t hidden[3];                  /* actor and critic hidden sizes (must match pairwise) */
+  const float* obs;                   /* [N, num_obs] */
+  const float* critic_obs;            /* [N, num_critic_obs] (== obs when no privileged obs) */
+  const float* actor_w[4];            /* [h0,O] [h1,h0] [h2,h1] [A,h2] */
+  const float* actor_b[4];
+  const float* critic_w[4];           /* [h0,Oc] [h1,h0] [h2,h1] [1,h2] */
+  const float* critic_b[4];
+  const float* std;                   /* [A] */
+  uint64_t seed; int32_t step; int64_t env_id_offset;
+  int32_t sample;                     /* 1: actions = mu + std*eps (act); 0: actions = mu (act_inference) */
+  float* actions;                     /* [N,A] */
+  float* action_mean;                 /* [N,A] */
+  float* action_sigma;                /* [N,A] */
+  float* values;                      /* [N,1] */
+  float* actions_log_prob;            /* [N] */
+  void* workspace; int64_t workspace_bytes;   /* see lgk_policy_workspace_bytes */
+} LgkPolicyParams;
+
+int64_t lgk_policy_workspace_bytes(const LgkPolicyParams* p);
+int lgk_policy_act(const LgkPolicyParams* p, void* stream);
+
+/* ------------------------------------------------------------------ rsl_rl: RolloutStorage.compute_returns */
+/* Reverse GAE scan over [T,N] + global advantage normalisation (unbiased std, +1e-8).
+ * rewards/values/returns/advantages: [T,N] fp32 (the [T,N,1] storage tensors); dones: [T,N] uint8;
+ * last_values: [N].  scratch: >= 4 doubles, zeroed by the call. */
+int lgk_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+            int32_t T, int32_t N, float gamma, float lam, float* returns, float* advantages,
+            double* scratch, void* stream);
+
+/* ------------------------------------------------------------------ misc */
+const char* lgk_last_error_string(void);
+int lgk_abi_version(void);
+/* Write `bytes` of a scratch buffer (L2 flush between timed iterations; bench only). */
+int lgk_l2_flush(void* scratch, int64_t bytes, void* stream);
+/* number of kernel launches issued through this library since load (bench's gpu_launches). */
+int64_t lgk_launch_count(void);
+/* sizeof() of the parameter structs as compiled (0 Torque, 1 LstmWeights, 2 Step, 3 Policy): lets a foreign-language
+ * binding (ctypes / cgo / JNI) verify its mirror of the layout before the first call. */
+int lgk_struct_size(int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGK_H */

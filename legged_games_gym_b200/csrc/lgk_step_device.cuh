@@ -1,0 +1,260 @@
+// lgk_step_device.cuh -- per-environment pieces of post_physics_step shared by the fused tile kernel,
+// the explicit reset_idx kernel and tests/hostcheck (host build; NOT a product path).
+// "tile-local" pointers address one env's row inside a staged tile (shared memory on the device).
+#pragma once
+#include "lgk_math.cuh"
+
+namespace lgk {
+
+// OBS-stream word mapping: column j of the observation row uses word (j/32)%4 of Philox block
+// 32*(j/128) + j%32, so that lane l of a warp computes ONE block per 128 columns and stores four
+// coalesced 128-byte segments (oracle/philox.py obs_uniforms restates the same mapping).
+LGK_HD uint32_t obs_block_of(int j) { return (uint32_t)(32 * (j >> 7) + (j & 31)); }
+LGK_HD int obs_word_of(int j) { return (j >> 5) & 3; }
+
+struct EnvScalars {
+  V3 blv, bav, pg;       // base_lin_vel, base_ang_vel, projected_gravity (LR:119-121)
+  long long ep_len;      // episode_length_buf after += 1 (LR:114)
+  bool reset, time_out;  // LR:139-145
+  float rew;             // rew_buf (LR:193-210)
+};
+
+// ---- LR:114-127 for one env: rotate velocities, resample/heading commands, push, termination and the
+// reward sum.  root/dof/contact/... are the env's rows inside the staged tile (read+write).
+// `sums` points at episode_sums[0*N + env]; row stride = num_envs.
+// `mean_height_err` = mean_p(z - h_p) when the base_height term is active, else unused.
+LGK_HD void env_pre(const LgkStepParams& p, const RngKey& key, uint32_t genv, float* root, const float* dof,
+                    const float* contact, const float* act, const float* tq, const float* lact,
+                    const float* ldv, float* cmd, float* fat, uint8_t* lc, float* sums, int sums_stride,
+                    long long ep_in, float mean_height_err, EnvScalars& o) {
+  o.ep_len = ep_in + 1;
+  const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+  o.blv = quat_rotate_inverse(qx, qy, qz, qw, V3{root[7], root[8], root[9]});
+  o.bav = quat_rotate_inverse(qx, qy, qz, qw, V3{root[10], root[11], root[12]});
+  o.pg = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
+  // _post_physics_step_callback LR:329-345
+  if (o.ep_len % (long long)p.resample_period == 0)
+    resample_commands(p, cmd, rng_block(key, genv, LGK_STREAM_CMD, 0));
+  if (p.heading_command) {
+    const float h = heading_of(qx, qy, qz, qw);
+    cmd[2] = clampf(0.5f * wrap_to_pi(cmd[3] - h), -1.f, 1.f);
+  }
+  if (p.do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
+    const U4 r = rng_block(key, genv, LGK_STREAM_PUSH, 0);
+    const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
+    root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));
+    root[8] = scale_uniform(range, lo, u32_to_uniform(r.y));
+  }
+  // check_termination LR:139-145
+  bool term = false;
+  for (int t = 0; t < p.num_term; ++t) {
+    const float* f = contact + 3 * p.term_idx[t];
+    term = term || (norm3(f[0], f[1], f[2]) > 1.0f);
+  }
+  o.time_out = (float)o.ep_len > p.max_episode_length;
+  o.reset = term || o.time_out;
+
+  // compute_reward LR:193-210, terms in alphabetical order
+  float rew = 0.f;
+  const float cmd_norm = norm2(cmd[0], cmd[1]);
+#define LGK_TERM(ID, EXPR)                                            \
+  if (p.reward_active[ID]) {                                          \
+    const float r_ = (EXPR) * p.reward_scale[ID];                     \
+    rew += r_;                                                        \
+    sums[(size_t)p.reward_slot[ID] * sums_stride] += r_;              \
+  }
+  if (p.reward_active[LGK_R_ACTION_RATE]) {                           // LR:901-903
+    float s = 0.f;
+    for (int d = 0; d < kDof; ++d) { const float e = lact[d] - act[d]; s += e * e; }
+    LGK_TERM(LGK_R_ACTION_RATE, s)
+  }
+  LGK_TERM(LGK_R_ANG_VEL_XY, o.bav.x * o.bav.x + o.bav.y * o.bav.y)   // LR:876-878
+  if (p.reward_active[LGK_R_BASE_HEIGHT]) {                           // LR:884-887
+    const float e = mean_height_err - p.base_height_target;
+    LGK_TERM(LGK_R_BASE_HEIGHT, e * e)
+  }
+  if (p.reward_active[LGK_R_COLLISION]) {                             // LR:905-908
+    float s = 0.f;
+    for (int b = 0; b < p.num_pen; ++b) {
+      const float* f = contact + 3 * p.pen_idx[b];
+      s += norm3(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f;
+    }
+    LGK_TERM(LGK_R_COLLISION, s)
+  }
+  if (p.reward_active[LGK_R_DOF_ACC]) {                               // LR:897-899
+    float s = 0.f;
+    for (int d = 0; d < kDof; ++d) { const float a = (ldv[d] - dof[2 * d + 1]) / p.dt; s += a * a; }
+    LGK_TERM(LGK_R_DOF_ACC, s)
+  }
+  if (p.reward_active[LGK_R_DOF_POS_LIMITS]) {                        // LR:914-918
+    float s = 0.f;
+    for (int d = 0; d < kDof; ++d) {
+      const float q = dof[2 * d];
+      s += -fminf(q - p.dof_pos_lo[d], 0.f) + fmaxf(q - p.dof_pos_hi[d], 0.f);
+    }
+    LGK_TERM(LGK_R_DOF_POS_LIMITS, s)
+  }
+  if (p.reward_active[LGK_R_DOF_VEL]) {                               // LR:893-895
+    float s = 0.f;
+    for (int d = 0; d < kDof; ++d) { const float v = dof[2 * d + 1]; s += v * v; }
+    LGK_TERM(LGK_R_DOF_VEL, s)
+  }
+  if (p.reward_active[LGK_R_DOF_VEL_LIMITS]) {                        // LR:920-925
+    float s = 0.f;
+    for (int d = 0; d < kDof; ++d)
+      s += clampf(fabsf(dof[2 * d + 1]) - p.dof_vel_limits[d] * p.soft_dof_vel_limit, 0.f, 1.f);
+    LGK_TERM(LGK_R_DOF_VEL_LIMITS, s)
+  }
+  if (p.reward_active[LGK_R_FEET_AIR_TIME]) {                         // LR:942-954 (stateful)
+    float s = 0.f;
+    for (int f = 0; f < p.num_feet; ++f) {
+      const bool c = contact[3 * p.feet_idx[f] + 2] > 1.0f;
+      const bool filt = c || (lc[f] != 0);
+      lc[f] = c ? 1 : 0;
+      const bool first = (fat[f] > 0.f) && filt;
+      const float air = fat[f] + p.dt;
+      s += (air - 0.5f) * (first ? 1.f : 0.f);
+      fat[f] = filt ? 0.f * air : air;     // air *= ~filt
+    }
+    s *= cmd_norm > 0.1f ? 1.f : 0.f;
+    LGK_TERM(LGK_R_FEET_AIR_TIME, s)
+  }
+  if (p.reward_active[LGK_R_FEET_CONTACT_FORCES]) {                   // LR:966-969
+    float s = 0.f;
+    for (int f = 0; f < p.num_feet; ++f) {
+      const float* c = contact + 3 * p.feet_idx[f];
+      s += fmaxf(norm3(c[0], c[1], c[2]) - p.max_contact_force, 0.f);
+    }
+    LGK_TERM(LGK_R_FEET_CONTACT_FORCES, s)
+  }
+  LGK_TERM(LGK_R_LIN_VEL_Z, o.blv.z * o.blv.z)                        // LR:872-874
+  if (p.reward_active[LGK_R_NO_FLY]) {                                // CAS:43-46
+    int n = 0;
+    for (int f = 0; f < p.num_feet; ++f) n += contact[3 * p.feet_idx[f] + 2] > 0.1f ? 1 : 0;
+    LGK_TERM(LGK_R_NO_FLY, n == 1 ? 1.f : 0.f)
+  }
+  LGK_TERM(LGK_R_ORIENTATION, o.pg.x * o.pg.x + o.pg.y * o.pg.y)      // LR:880-882
+  if (p.reward_active[LGK_R_STAND_STILL]) {                           // LR:961-964
+    float s = 0.f;
+    for (int d = 0; d < kDof; ++d) s += fabsf(dof[2 * d] - p.default_dof_pos[d]);
+    LGK_TERM(LGK_R_STAND_STILL, s * (cmd_norm < 0.1f ? 1.f : 0.f))
+  }
+  if (p.reward_active[LGK_R_STUMBLE]) {                               // LR:956-959
+    bool any = false;
+    for (int f = 0; f < p.num_feet; ++f) {
+      const float* c = contact + 3 * p.feet_idx[f];
+      any = any || (norm2(c[0], c[1]) > 5.f * fabsf(c[2]));
+    }
+    LGK_TERM(LGK_R_STUMBLE, any ? 1.f : 0.f)
+  }
+  if (p.reward_active[LGK_R_TORQUE_LIMITS]) {                         // LR:927-930
+    float s = 0.f;
+    for (int d = 0; d < kDof; ++d) s += fmaxf(fabsf(tq[d]) - p.torque_limits[d] * p.soft_torque_limit, 0.f);
+    LGK_TERM(LGK_R_TORQUE_LIMITS, s)
+  }
+  if (p.reward_active[LGK_R_TORQUES]) {                               // LR:889-891
+    float s = 0.f;
+    for (int d = 0; d < kDof; ++d) s += tq[d] * tq[d];
+    LGK_TERM(LGK_R_TORQUES, s)
+  }
+  {                                                                   // LR:937-940
+    const float e = cmd[2] - o.bav.z;
+    LGK_TERM(LGK_R_TRACKING_ANG_VEL, expf(-(e * e) / p.tracking_sigma))
+  }
+  {                                                                   // LR:932-935
+    const float ex = cmd[0] - o.blv.x, ey = cmd[1] - o.blv.y;
+    LGK_TERM(LGK_R_TRACKING_LIN_VEL, expf(-(ex * ex + ey * ey) / p.tracking_sigma))
+  }
+  o.rew = rew;
+}
+
+// LR:204-210: positive clip, then the termination term
+LGK_HD float env_finish_reward(const LgkStepParams& p, float rew, bool reset, bool time_out, float* sums,
+                               int sums_stride) {
+  if (p.only_positive_rewards) rew = fmaxf(rew, 0.f);
+  if (p.reward_active[LGK_R_TERMINATION]) {
+    const float r_ = ((reset && !time_out) ? 1.f : 0.f) * p.reward_scale[LGK_R_TERMINATION];
+    rew += r_;
+    sums[(size_t)p.reward_slot[LGK_R_TERMINATION] * sums_stride] += r_;
+  }
+  return rew;
+}
+#undef LGK_TERM
+
+// ---- reset_idx for one env (LR:147-191) minus the cross-env means and the LSTM-state zeroing, which
+// the callers do cooperatively.  Mutates the env's staged rows; terrain tables are global.
+// Returns the env's (possibly updated) terrain level.
+LGK_HD void env_reset(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, float* root, float* dof,
+                      float* cmd, float* fat, long long& ep_len) {
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+  if (p.env_origins) { ox = p.env_origins[3 * env]; oy = p.env_origins[3 * env + 1]; oz = p.env_origins[3 * env + 2]; }
+  if (p.terrain_curriculum) {                                         // LR:446-469
+    const float dist = norm2(root[0] - ox, root[1] - oy);
+    const bool up = dist > p.half_env_length;
+    const bool down = (dist < norm2(cmd[0], cmd[1]) * p.max_episode_length_s * 0.5f) && !up;
+    long long lvl = p.terrain_levels[env] + (up ? 1 : 0) - (down ? 1 : 0);
+    if (lvl >= p.max_terrain_level) {
+      const U4 r = rng_block(key, genv, LGK_STREAM_TERRAIN, 0);
+      lvl = (long long)(r.x % (uint32_t)p.max_terrain_level);
+    } else if (lvl < 0) {
+      lvl = 0;
+    }
+    p.terrain_levels[env] = lvl;
+    const float* o = p.terrain_origins + 3 * ((size_t)lvl * p.terrain_num_cols + (size_t)p.terrain_types[env]);
+    ox = o[0]; oy = o[1]; oz = o[2];
+    p.env_origins[3 * env] = ox; p.env_origins[3 * env + 1] = oy; p.env_origins[3 * env + 2] = oz;
+  }
+  // _reset_dofs LR:397-407
+  for (int b = 0; b < 3; ++b) {
+    const U4 r = rng_block(key, genv, LGK_STREAM_RESET_DOF, b);
+    for (int i = 0; i < 4; ++i) {
+      const int d = 4 * b + i;
+      dof[2 * d] = f_mul(p.default_dof_pos[d], scale_uniform(1.0f, 0.5f, u32_to_uniform(pick(r, i))));
+      dof[2 * d + 1] = 0.f;
+    }
+  }
+  // _reset_root_states LR:414-432
+  const U4 r0 = rng_block(key, genv, LGK_STREAM_RESET_ROOT, 0);
+  const U4 r1 = rng_block(key, genv, LGK_STREAM_RESET_ROOT, 1);
+  for (int i = 0; i < 13; ++i) root[i] = p.base_init_state[i];
+  root[0] = f_add(root[0], ox); root[1] = f_add(root[1], oy); root[2] = f_add(root[2], oz);
+  if (p.custom_origins) {
+    root[0] = f_add(root[0], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.x)));
+    root[1] = f_add(root[1], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.y)));
+  }
+  root[7] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.z));
+  root[8] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.w));
+  root[9] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.x));
+  root[10] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.y));
+  root[11] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.z));
+  root[12] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.w));
+  resample_commands(p, cmd, rng_block(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170
+  for (int f = 0; f < p.num_feet; ++f) fat[f] = 0.f;                            // LR:175
+  ep_len = 0;                                                                   // LR:176
+}
+
+// LR:212-222: the 48 proprioceptive columns, before noise
+LGK_HD void env_obs_head(const LgkStepParams& p, const EnvScalars& s, const float* dof, const float* cmd,
+                         const float* act, float* out48) {
+  out48[0] = s.blv.x * p.obs_scale_lin_vel; out48[1] = s.blv.y * p.obs_scale_lin_vel; out48[2] = s.blv.z * p.obs_scale_lin_vel;
+  out48[3] = s.bav.x * p.obs_scale_ang_vel; out48[4] = s.bav.y * p.obs_scale_ang_vel; out48[5] = s.bav.z * p.obs_scale_ang_vel;
+  out48[6] = s.pg.x; out48[7] = s.pg.y; out48[8] = s.pg.z;
+  out48[9] = cmd[0] * p.obs_scale_lin_vel; out48[10] = cmd[1] * p.obs_scale_lin_vel; out48[11] = cmd[2] * p.obs_scale_ang_vel;
+  for (int d = 0; d < kDof; ++d) {
+    out48[12 + d] = (dof[2 * d] - p.default_dof_pos[d]) * p.obs_scale_dof_pos;
+    out48[24 + d] = dof[2 * d + 1] * p.obs_scale_dof_vel;
+    out48[36 + d] = act[d];
+  }
+}
+
+// LR:225-230 + LR:100-101 for one column: value (+ noise) clipped
+LGK_HD float obs_finish(const LgkStepParams& p, float v, float noise_scale, uint32_t word) {
+  if (p.add_noise) v = v + (2.0f * u32_to_uniform(word) - 1.0f) * noise_scale;
+  return clampf(v, -p.clip_obs, p.clip_obs);
+}
+
+LGK_HD float obs_height_col(const LgkStepParams& p, float root_z, float h) {
+  return clampf(root_z - 0.5f - h, -1.f, 1.f) * p.obs_scale_height;
+}
+
+}  // namespace lgk

@@ -1,0 +1,20 @@
+"""Registered tasks (mirror of reference legged_gym/envs/__init__.py:31-56).  The two hierarchical game tasks
+(high_level_game, dec_high_level_game) need a checkpoint and a forked rsl_rl that are not part of the reference tree
+ and are not registered."""
+from .base.legged_robot import LeggedRobot
+from .anymal_c.anymal import Anymal
+from .anymal_c.mixed_terrains.anymal_c_rough_config import AnymalCRoughCfg, AnymalCRoughCfgPPO
+from .anymal_c.flat.anymal_c_flat_config import AnymalCFlatCfg, AnymalCFlatCfgPPO
+from .anymal_b.anymal_b_config import AnymalBRoughCfg, AnymalBRoughCfgPPO
+from .cassie.cassie import Cassie
+from .cassie.cassie_config import CassieRoughCfg, CassieRoughCfgPPO
+from .a1.a1_config import A1RoughCfg, A1RoughCfgPPO
+from .a1_game.low_level_game_config import LowLevelGameCfg, LowLevelGamePPO
+
+from ..utils.task_registry import task_registry
+
+task_registry.register("anymal_c_rough", Anymal, AnymalCRoughCfg(), AnymalCRoughCfgPPO())
+task_registry.register("anymal_c_flat", Anymal, AnymalCFlatCfg(), AnymalCFlatCfgPPO())
+task_registry.register("anymal_b", Anymal, AnymalBRoughCfg(), AnymalBRoughCfgPPO())
+task_registry.register("a1", LeggedRobot, A1RoughCfg(), A1RoughCfgPPO())
+task_registry.register("cassie", Cassie, CassieRoughCfg(), CassieRoughCfgPPO())

@@ -1,0 +1,599 @@
+"""LeggedRobot -- host-side mirror of the reference env class (legged_gym/envs/base/legged_robot.py, "LR").
+
+Same constructor, attributes, tensor layouts and method names; every per-env computation of LR:80-230,
+329-508 and 831-969 is executed by liblgk.so (include/lgk.h) through ``_native``:
+
+    step()                -> 4 x lgk_compute_torques  +  lgk_post_physics(PRE|POST)  +  lgk_finalize_step
+    reset_idx(env_ids)    -> lgk_reset_idx + lgk_finalize_step
+    _get_heights()        -> lgk_height_scan
+
+Python keeps only what is host logic in the reference too: cfg parsing, buffer allocation, the push /
+curriculum step counters and the extension points.  Supported extension points for subclasses (README.md:29-32,
+56-66 of the reference): extra ``_reward_<name>`` terms written in torch (the step then runs PRE, the Python
+terms, POST), ``_compute_torques``, ``compute_observations`` (called after the fused step when overridden),
+``_get_noise_scale_vec``, ``_init_buffers``.  Overriding ``check_termination`` / ``_post_physics_step_callback``
+/ ``compute_reward`` is rejected at construction: those run inside the fused kernel.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ... import _native as nat
+from ...sim.asset_model import model_for_asset
+from ...sim.state_feeder import StateFeeder, SimBackend, synth_height_field, synth_terrain_origins
+from ...utils.helpers import class_to_dict
+from .base_task import BaseTask
+from .legged_robot_config import LeggedRobotCfg
+
+
+class _Terrain:
+    """What the hot path reads from the reference's Terrain object (utils/terrain.py:38-83): cfg, env_length,
+    env_origins [rows, cols, 3], heightsamples int16 [tot_rows, tot_cols].  Generation (terrain.py:85-187)
+    depends on isaacgym.terrain_utils and is out of scope: fields are synthetic unless a provider is given."""
+
+    def __init__(self, cfg, seed):
+        self.cfg = cfg
+        self.env_length = cfg.terrain_length
+        self.env_width = cfg.terrain_width
+        self.border = int(cfg.border_size / cfg.horizontal_scale)
+        self.tot_rows = int(cfg.num_rows * cfg.terrain_length / cfg.horizontal_scale) + 2 * self.border
+        self.tot_cols = int(cfg.num_cols * cfg.terrain_width / cfg.horizontal_scale) + 2 * self.border
+        self.heightsamples = synth_height_field(self.tot_rows, self.tot_cols, seed)
+        self.env_origins = synth_terrain_origins(cfg)
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class LeggedRobot(BaseTask):
+    _FUSED_HOOKS = ("check_termination", "_post_physics_step_callback", "compute_reward", "_resample_commands",
+                    "_push_robots", "_reset_dofs", "_reset_root_states", "_update_terrain_curriculum")
+
+    def __init__(self, cfg: LeggedRobotCfg, sim_params, physics_engine, sim_device, headless, sim_backend=None,
+                 terrain=None, init_terrain_levels=None):
+        self.cfg = cfg
+        self.sim_params = sim_params
+        self.height_samples = None
+        self.debug_viz = False
+        self.init_done = False
+        self._terrain_arg = terrain
+        self._init_levels_arg = init_terrain_levels
+        for name in self._FUSED_HOOKS:
+            if getattr(type(self), name) is not getattr(LeggedRobot, name):
+                raise NotImplementedError(
+                    f"{type(self).__name__}.{name} overrides a stage that runs inside the fused CUDA step; "
+                    "extend through _reward_<name>, compute_observations, _compute_torques or _init_buffers instead")
+        self._parse_cfg(self.cfg)
+        super().__init__(self.cfg, sim_params, physics_engine, sim_device, headless, sim_backend)
+        self._init_buffers()
+        self._prepare_reward_function()
+        self._build_native_params()
+        self.init_done = True
+
+    # ------------------------------------------------------------------ LR:80-104
+    def step(self, actions):
+        clip_actions = self.cfg.normalization.clip_actions
+        gym = self.gym
+        native_tq = self._native_torques
+        if native_tq:
+            tp = self._tq_params
+            tp.actions_in = actions.data_ptr()
+            if not (actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()):
+                actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+                tp.actions_in = actions.data_ptr()
+            tp.actions_clipped = self.actions.data_ptr()
+        else:
+            torch.clamp(actions.to(self.device), -clip_actions, clip_actions, out=self.actions)
+        self.render()
+        for k in range(self.cfg.control.decimation):
+            if native_tq:
+                nat.check(nat.lib.lgk_compute_torques(C.byref(tp), _stream_ptr()), "lgk_compute_torques")
+                if k == 0:      # later sub-steps read the clipped copy (clip is idempotent)
+                    tp.actions_in = self.actions.data_ptr()
+                    tp.actions_clipped = None
+            else:
+                self.torques[:] = self._compute_torques(self.actions).view(self.torques.shape)
+            gym.set_dof_actuation_force_tensor(self.torques)
+            gym.simulate()
+            gym.refresh_dof_state_tensor()
+        self.post_physics_step()
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # ------------------------------------------------------------------ LR:106-137
+    def post_physics_step(self):
+        gym = self.gym
+        gym.refresh_actor_root_state_tensor()
+        gym.refresh_net_contact_force_tensor()
+        self.common_step_counter += 1          # episode_length_buf += 1 happens in the kernel (LR:114)
+        p = self._params
+        p.step = self.common_step_counter & 0x7FFFFFFF
+        dr = self.cfg.domain_rand
+        p.do_push = int(bool(dr.push_robots) and (self.common_step_counter % dr.push_interval == 0))
+        if self.reset_buf.dtype != torch.bool:     # first step: long ones -> persistent bool buffer
+            self.reset_buf = self._reset_bool
+        st = _stream_ptr()
+        cmd_curr = self.cfg.commands.curriculum and (self.common_step_counter % self.max_episode_length == 0)
+        if self._python_reward_names or cmd_curr:
+            p.phase_mask = nat.PHASE_PRE
+            nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics(PRE)")
+            for name in self._python_reward_names:             # user terms, LR:199-203
+                rew = getattr(self, "_reward_" + name)() * self.reward_scales[name]
+                self.rew_buf += rew
+                self.episode_sums[name] += rew
+            if cmd_curr:
+                ids = self.reset_buf.nonzero(as_tuple=False).flatten()
+                if len(ids) > 0:
+                    self.update_command_curriculum(ids)
+            p.phase_mask = nat.PHASE_POST
+            nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics(POST)")
+        else:
+            p.phase_mask = nat.PHASE_PRE | nat.PHASE_POST
+            nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics")
+        self._finalize(st)
+        if p.do_push:
+            gym.set_actor_root_state_tensor(self.root_states)
+        gym.set_dof_state_tensor_indexed(self.dof_state, self.reset_env_ids, self.reset_count)
+        gym.set_actor_root_state_tensor_indexed(self.root_states, self.reset_env_ids, self.reset_count)
+        if self._obs_overridden:
+            self.compute_observations()
+            clip_obs = self.cfg.normalization.clip_observations
+            self.obs_buf = torch.clip(self.obs_buf, -clip_obs, clip_obs)
+
+    def _finalize(self, st):
+        nat.check(nat.lib.lgk_finalize_step(C.byref(self._params), self.reset_env_ids.data_ptr(),
+                                            self.reset_count.data_ptr(), self._episode_means.data_ptr(),
+                                            self._time_outs_extras.data_ptr(), st), "lgk_finalize_step")
+        # extras are refreshed only when something was reset (LR:157-158, 179-191): the kernel keeps the previous
+        # values otherwise.  One snapshot per step so that references a runner keeps stay valid.
+        means = self._episode_means.clone()
+        ep = {"rew_" + k: means[i] for i, k in enumerate(self._sum_names)}
+        if self.cfg.terrain.curriculum:
+            ep["terrain_level"] = means[len(self._sum_names)]
+        if self.cfg.commands.curriculum:
+            ep["max_command_x"] = self.command_ranges["lin_vel_x"][1]
+        self.extras["episode"] = ep
+        if self.cfg.env.send_timeouts:
+            self.extras["time_outs"] = self._time_outs_extras
+
+    # ------------------------------------------------------------------ stages that live in the kernel
+    def check_termination(self):
+        raise RuntimeError("check_termination runs inside lgk_post_physics")
+
+    def compute_reward(self):
+        raise RuntimeError("compute_reward runs inside lgk_post_physics")
+
+    def _post_physics_step_callback(self):
+        raise RuntimeError("_post_physics_step_callback runs inside lgk_post_physics")
+
+    def _resample_commands(self, env_ids):
+        raise RuntimeError("_resample_commands runs inside lgk_post_physics / lgk_reset_idx")
+
+    def _push_robots(self):
+        raise RuntimeError("_push_robots runs inside lgk_post_physics")
+
+    def _reset_dofs(self, env_ids):
+        raise RuntimeError("_reset_dofs runs inside lgk_post_physics / lgk_reset_idx")
+
+    def _reset_root_states(self, env_ids):
+        raise RuntimeError("_reset_root_states runs inside lgk_post_physics / lgk_reset_idx")
+
+    def _update_terrain_curriculum(self, env_ids):
+        raise RuntimeError("_update_terrain_curriculum runs inside lgk_post_physics / lgk_reset_idx")
+
+    # ------------------------------------------------------------------ LR:147-191 on an explicit id list
+    def reset_idx(self, env_ids):
+        if len(env_ids) == 0:
+            return
+        env_ids = env_ids.to(device=self.device, dtype=torch.long).contiguous()
+        if self.cfg.commands.curriculum and (self.common_step_counter % self.max_episode_length == 0):
+            self.update_command_curriculum(env_ids)
+        p = self._params
+        p.step = self.common_step_counter & 0x7FFFFFFF
+        if self.reset_buf.dtype != torch.bool:
+            self.reset_buf = self._reset_bool
+            self.reset_buf.fill_(True)
+        st = _stream_ptr()
+        saved = p.terrain_curriculum
+        if not self.init_done:
+            p.terrain_curriculum = 0            # "don't change on initial reset" (LR:453-455)
+        nat.check(nat.lib.lgk_reset_idx(C.byref(p), env_ids.data_ptr(), int(env_ids.numel()), st), "lgk_reset_idx")
+        p.terrain_curriculum = saved
+        self._finalize(st)
+        self.gym.set_dof_state_tensor_indexed(self.dof_state, self.reset_env_ids, self.reset_count)
+        self.gym.set_actor_root_state_tensor_indexed(self.root_states, self.reset_env_ids, self.reset_count)
+
+    # ------------------------------------------------------------------ LR:212-230 (torch version for overriders)
+    def compute_observations(self):
+        o = self.obs_scales
+        self.obs_buf = torch.cat((self.base_lin_vel * o.lin_vel, self.base_ang_vel * o.ang_vel, self.projected_gravity,
+                                  self.commands[:, :3] * self.commands_scale,
+                                  (self.dof_pos - self.default_dof_pos) * o.dof_pos, self.dof_vel * o.dof_vel,
+                                  self.actions), dim=-1)
+        if self.cfg.terrain.measure_heights:
+            heights = torch.clip(self.root_states[:, 2].unsqueeze(1) - 0.5 - self.measured_heights, -1, 1.) * o.height_measurements
+            self.obs_buf = torch.cat((self.obs_buf, heights), dim=-1)
+        if self.add_noise:
+            self.obs_buf += (2 * torch.rand_like(self.obs_buf) - 1) * self.noise_scale_vec
+
+    # ------------------------------------------------------------------ LR:232-251
+    def create_sim(self):
+        self.up_axis_idx = 2
+        mesh_type = self.cfg.terrain.mesh_type
+        if mesh_type in ("heightfield", "trimesh"):
+            self.terrain = self._terrain_arg if self._terrain_arg is not None else _Terrain(
+                self.cfg.terrain, getattr(self.cfg, "seed", 0) or 0)
+            self.height_samples = torch.from_numpy(np.ascontiguousarray(self.terrain.heightsamples)).view(
+                self.terrain.tot_rows, self.terrain.tot_cols).to(self.device)
+        elif mesh_type not in (None, "plane"):
+            raise ValueError("Terrain mesh type not recognised. Allowed types are [None, plane, heightfield, trimesh]")
+        self._create_envs()
+
+    # ------------------------------------------------------------------ LR:657-750 (asset tables instead of PhysX)
+    def _create_envs(self):
+        model = model_for_asset(self.cfg.asset)
+        self.robot_model = model
+        self.num_dof = self.num_dofs = model.num_dof
+        self.num_bodies = model.num_bodies
+        self.dof_names = list(model.dof_names)
+        if self.num_dof != nat.NUM_DOF:
+            raise ValueError(f"kernels are built for {nat.NUM_DOF} DOF, asset has {self.num_dof}")
+        dev = self.device
+        a = self.cfg.asset
+        self.feet_indices = torch.tensor(model.indices(a.foot_name), dtype=torch.long, device=dev)
+        self.penalised_contact_indices = torch.tensor(model.indices(list(a.penalize_contacts_on)), dtype=torch.long, device=dev)
+        self.termination_contact_indices = torch.tensor(model.indices(list(a.terminate_after_contacts_on)), dtype=torch.long, device=dev)
+        # _process_dof_props LR:299-313 (same fp32 op sequence)
+        self.dof_pos_limits = torch.zeros(self.num_dof, 2, dtype=torch.float, device="cpu")
+        self.dof_vel_limits = torch.zeros(self.num_dof, dtype=torch.float, device="cpu")
+        self.torque_limits = torch.zeros(self.num_dof, dtype=torch.float, device="cpu")
+        soft = self.cfg.rewards.soft_dof_pos_limit
+        for i in range(self.num_dof):
+            self.dof_pos_limits[i, 0] = float(np.float32(model.dof_lower[i]))
+            self.dof_pos_limits[i, 1] = float(np.float32(model.dof_upper[i]))
+            self.dof_vel_limits[i] = float(np.float32(model.dof_vel_limits[i]))
+            self.torque_limits[i] = float(np.float32(model.torque_limits[i]))
+            m = (self.dof_pos_limits[i, 0] + self.dof_pos_limits[i, 1]) / 2
+            r = self.dof_pos_limits[i, 1] - self.dof_pos_limits[i, 0]
+            self.dof_pos_limits[i, 0] = m - 0.5 * r * soft
+            self.dof_pos_limits[i, 1] = m + 0.5 * r * soft
+        self.dof_pos_limits = self.dof_pos_limits.to(dev)
+        self.dof_vel_limits = self.dof_vel_limits.to(dev)
+        self.torque_limits = self.torque_limits.to(dev)
+        ini = self.cfg.init_state
+        self.base_init_state = torch.tensor(ini.pos + ini.rot + ini.lin_vel + ini.ang_vel, dtype=torch.float, device=dev)
+        self._get_env_origins()
+        if self.gym is None:
+            self.gym = StateFeeder(self.num_envs, self.num_bodies, self.num_dof, device=dev,
+                                   seed=getattr(self.cfg, "seed", 0) or 0, actors_per_env=self._actors_per_env())
+
+    def _actors_per_env(self):
+        return 1
+
+    # ------------------------------------------------------------------ LR:752-779
+    def _get_env_origins(self):
+        dev, N, t = self.device, self.num_envs, self.cfg.terrain
+        self.env_origins = torch.zeros(N, 3, device=dev, requires_grad=False)
+        if t.mesh_type in ("heightfield", "trimesh"):
+            self.custom_origins = True
+            max_init_level = t.max_init_terrain_level
+            if not t.curriculum:
+                max_init_level = t.num_rows - 1
+            if self._init_levels_arg is not None:
+                self.terrain_levels = torch.as_tensor(self._init_levels_arg, dtype=torch.long).to(dev).clone()
+            else:
+                self.terrain_levels = torch.randint(0, max_init_level + 1, (N,), device=dev)
+            self.terrain_types = torch.div(torch.arange(N, device=dev), (N / t.num_cols), rounding_mode="floor").to(torch.long)
+            self.max_terrain_level = t.num_rows
+            self.terrain_origins = torch.from_numpy(np.asarray(self.terrain.env_origins)).to(dev).to(torch.float).contiguous()
+            self.env_origins[:] = self.terrain_origins[self.terrain_levels, self.terrain_types]
+        else:
+            self.custom_origins = False
+            num_cols = np.floor(np.sqrt(N))
+            num_rows = np.ceil(N / num_cols)
+            xx, yy = torch.meshgrid(torch.arange(num_rows), torch.arange(num_cols), indexing="ij")
+            spacing = self.cfg.env.env_spacing
+            self.env_origins[:, 0] = (spacing * xx.flatten()[:N]).to(dev)
+            self.env_origins[:, 1] = (spacing * yy.flatten()[:N]).to(dev)
+            self.env_origins[:, 2] = 0.
+
+    # ------------------------------------------------------------------ LR:781-791
+    def _parse_cfg(self, cfg):
+        self.dt = self.cfg.control.decimation * self.sim_params.dt
+        self.obs_scales = self.cfg.normalization.obs_scales
+        self.reward_scales = class_to_dict(self.cfg.rewards.scales)
+        self.command_ranges = class_to_dict(self.cfg.commands.ranges)
+        if self.cfg.terrain.mesh_type not in ["heightfield", "trimesh"]:
+            self.cfg.terrain.curriculum = False
+        self.max_episode_length_s = self.cfg.env.episode_length_s
+        self.max_episode_length = np.ceil(self.max_episode_length_s / self.dt)
+        self.cfg.domain_rand.push_interval = np.ceil(self.cfg.domain_rand.push_interval_s / self.dt)
+
+    # ------------------------------------------------------------------ LR:485-508
+    def _get_noise_scale_vec(self, cfg):
+        noise_vec = torch.zeros_like(self.obs_buf[0])
+        self.add_noise = self.cfg.noise.add_noise
+        ns, lvl, o = self.cfg.noise.noise_scales, self.cfg.noise.noise_level, self.obs_scales
+        noise_vec[:3] = ns.lin_vel * lvl * o.lin_vel
+        noise_vec[3:6] = ns.ang_vel * lvl * o.ang_vel
+        noise_vec[6:9] = ns.gravity * lvl
+        noise_vec[9:12] = 0.
+        noise_vec[12:24] = ns.dof_pos * lvl * o.dof_pos
+        noise_vec[24:36] = ns.dof_vel * lvl * o.dof_vel
+        noise_vec[36:48] = 0.
+        if self.cfg.terrain.measure_heights:
+            noise_vec[48:235] = ns.height_measurements * lvl * o.height_measurements
+        return noise_vec
+
+    # ------------------------------------------------------------------ LR:511-581
+    def _init_buffers(self):
+        dev, N, D = self.device, self.num_envs, self.num_dof
+        gym = self.gym
+        self.root_states = gym.acquire_actor_root_state_tensor()
+        self.dof_state = gym.acquire_dof_state_tensor()
+        net_contact_forces = gym.acquire_net_contact_force_tensor()
+        gym.refresh_dof_state_tensor()
+        gym.refresh_actor_root_state_tensor()
+        gym.refresh_net_contact_force_tensor()
+        self.dof_pos = self.dof_state.view(N, D, 2)[..., 0]
+        self.dof_vel = self.dof_state.view(N, D, 2)[..., 1]
+        self.base_quat = self.root_states[self._root_rows(), 3:7]
+        self.contact_forces = net_contact_forces.view(N, -1, 3)
+        self.common_step_counter = 0
+        self.extras = {}
+        self.noise_scale_vec = self._get_noise_scale_vec(self.cfg).contiguous()
+        self.gravity_vec = torch.tensor([0., 0., -1.], device=dev).repeat((N, 1))
+        self.forward_vec = torch.tensor([1., 0., 0.], device=dev).repeat((N, 1))
+        z = lambda *s, dt=torch.float: torch.zeros(*s, dtype=dt, device=dev, requires_grad=False)
+        self.torques = z(N, self.num_actions)
+        self.p_gains = z(self.num_actions)
+        self.d_gains = z(self.num_actions)
+        self.actions = z(N, self.num_actions)
+        self.last_actions = z(N, self.num_actions)
+        self.last_dof_vel = z(N, D)
+        self.last_root_vel = z(N, 6)
+        self.commands = z(N, self.cfg.commands.num_commands)
+        self.commands_scale = torch.tensor([self.obs_scales.lin_vel, self.obs_scales.lin_vel, self.obs_scales.ang_vel], device=dev)
+        F = self.feet_indices.shape[0]
+        self.feet_air_time = z(N, F)
+        self.last_contacts = z(N, F, dt=torch.bool)
+        self.base_lin_vel = z(N, 3)
+        self.base_ang_vel = z(N, 3)
+        self.projected_gravity = z(N, 3)
+        if self.cfg.terrain.measure_heights:
+            self.height_points = self._init_height_points()
+            self.measured_heights = z(N, self.num_height_points)
+        else:
+            self.num_height_points = 0
+            self.measured_heights = 0
+        self.default_dof_pos = torch.zeros(D, dtype=torch.float, device="cpu")
+        pg, dg = torch.zeros(D), torch.zeros(D)
+        for i, name in enumerate(self.dof_names):
+            self.default_dof_pos[i] = self.cfg.init_state.default_joint_angles[name]
+            found = False
+            for key in self.cfg.control.stiffness.keys():
+                if key in name:
+                    pg[i] = self.cfg.control.stiffness[key]
+                    dg[i] = self.cfg.control.damping[key]
+                    found = True
+            if not found and self.cfg.control.control_type in ["P", "V"]:
+                print(f"PD gain of joint {name} were not defined, setting them to zero")
+        self.p_gains.copy_(pg)
+        self.d_gains.copy_(dg)
+        self.default_dof_pos = self.default_dof_pos.to(dev).unsqueeze(0)
+        # kernel-side persistent buffers
+        self._reset_bool = z(N, dt=torch.bool)
+        self._time_outs_extras = z(N, dt=torch.bool)
+        self.reset_env_ids = z(N, dt=torch.int32)
+        self.reset_count = z(1, dt=torch.int32)
+
+    def _root_rows(self):
+        return slice(None)
+
+    # ------------------------------------------------------------------ LR:583-607
+    def _prepare_reward_function(self):
+        for key in list(self.reward_scales.keys()):
+            if self.reward_scales[key] == 0:
+                self.reward_scales.pop(key)
+            else:
+                self.reward_scales[key] *= self.dt
+        self.reward_functions, self.reward_names = [], []
+        for name in self.reward_scales.keys():
+            if name == "termination":
+                continue
+            self.reward_names.append(name)
+            self.reward_functions.append(getattr(self, "_reward_" + name))     # AttributeError like LR:602
+        self._sum_names = list(self.reward_scales.keys())
+        K = max(len(self._sum_names), 1)
+        self._episode_sums_buf = torch.zeros(K, self.num_envs, dtype=torch.float, device=self.device)
+        self.episode_sums = {n: self._episode_sums_buf[i] for i, n in enumerate(self._sum_names)}
+        self._episode_means = torch.zeros(K + 1, dtype=torch.float, device=self.device)
+        self._reset_stats = torch.zeros(2, K + 2, dtype=torch.float, device=self.device)
+        # terms whose implementation is the class's own (native in the kernel) vs user-written torch terms
+        self._python_reward_names = []
+        for name in self.reward_names:
+            fn = getattr(type(self), "_reward_" + name)
+            native_owner = getattr(fn, "_lgk_native", False)
+            if not (native_owner and name in nat.REWARD_TERMS):
+                self._python_reward_names.append(name)
+
+    # ------------------------------------------------------------------ native parameter blocks
+    def _build_native_params(self):
+        cfg, N = self.cfg, self.num_envs
+        cls = type(self)
+        self._native_torques = getattr(cls._compute_torques, "_lgk_native", False)
+        self._obs_overridden = cls.compute_observations is not LeggedRobot.compute_observations
+        f = lambda t: [float(x) for x in t.detach().flatten().cpu().tolist()]
+        # ---- torques (LR:371-395)
+        tp = nat.TorqueParams()
+        tp.num_envs = N
+        ct = cfg.control.control_type
+        if ct not in nat.CTRL:
+            raise NameError(f"Unknown controller type: {ct}")
+        tp.control_type = nat.CTRL[ct]
+        tp.use_lstm = 0
+        tp.action_scale = cfg.control.action_scale
+        tp.clip_actions = cfg.normalization.clip_actions
+        tp.sim_dt = self.sim_params.dt
+        tp.p_gains[:] = f(self.p_gains)
+        tp.d_gains[:] = f(self.d_gains)
+        tp.torque_limits[:] = f(self.torque_limits)
+        tp.default_dof_pos[:] = f(self.default_dof_pos)
+        tp.dof_state = self.dof_state.data_ptr()
+        tp.last_dof_vel = self.last_dof_vel.data_ptr()
+        tp.torques = self.torques.data_ptr()
+        self._tq_params = tp
+        # ---- step
+        p = nat.StepParams()
+        p.num_envs, p.num_bodies, p.num_obs = N, self.num_bodies, self.num_obs
+        mh = bool(cfg.terrain.measure_heights)
+        p.num_height_points = self.num_height_points if mh else 0
+        p.actors_per_env, p.root_actor_offset = self._actors_per_env(), 0
+        p.seed = int(getattr(cfg, "seed", 0) or 0) & 0xFFFFFFFFFFFFFFFF
+        p.env_id_offset = int(getattr(self, "env_id_offset", 0))
+        p.heading_command = int(bool(cfg.commands.heading_command))
+        p.measure_heights = int(mh)
+        p.terrain_is_plane = int(cfg.terrain.mesh_type == "plane")
+        if mh and cfg.terrain.mesh_type == "none":
+            raise NameError("Can't measure height with terrain mesh type 'none'")
+        p.add_noise = int(bool(self.add_noise))
+        p.only_positive_rewards = int(bool(cfg.rewards.only_positive_rewards))
+        p.terrain_curriculum = int(bool(cfg.terrain.curriculum))
+        p.custom_origins = int(self.custom_origins)
+        p.send_timeouts = int(bool(cfg.env.send_timeouts))
+        p.zero_lstm_on_reset = 0
+        p.dt = self.dt
+        p.resample_period = int(cfg.commands.resampling_time / self.dt)
+        p.max_episode_length = float(self.max_episode_length)
+        p.max_episode_length_s = float(self.max_episode_length_s)
+        p.max_push_vel = cfg.domain_rand.max_push_vel_xy
+        self._refresh_command_ranges()
+        o = self.obs_scales
+        p.obs_scale_lin_vel, p.obs_scale_ang_vel, p.obs_scale_dof_pos = o.lin_vel, o.ang_vel, o.dof_pos
+        p.obs_scale_dof_vel, p.obs_scale_height = o.dof_vel, o.height_measurements
+        p.clip_obs = cfg.normalization.clip_observations
+        r = cfg.rewards
+        p.tracking_sigma, p.base_height_target, p.max_contact_force = r.tracking_sigma, r.base_height_target, r.max_contact_force
+        p.soft_dof_vel_limit, p.soft_torque_limit = r.soft_dof_vel_limit, r.soft_torque_limit
+        t = cfg.terrain
+        p.border_size, p.horizontal_scale, p.vertical_scale = t.border_size, t.horizontal_scale, t.vertical_scale
+        p.default_dof_pos[:] = f(self.default_dof_pos)
+        p.dof_pos_lo[:] = f(self.dof_pos_limits[:, 0])
+        p.dof_pos_hi[:] = f(self.dof_pos_limits[:, 1])
+        p.dof_vel_limits[:] = f(self.dof_vel_limits)
+        p.torque_limits[:] = f(self.torque_limits)
+        p.base_init_state[:] = f(self.base_init_state)
+        for name, arr, cap in (("feet", self.feet_indices, nat.MAX_FEET), ("pen", self.penalised_contact_indices, nat.MAX_PEN),
+                               ("term", self.termination_contact_indices, nat.MAX_TERM)):
+            idx = [int(i) for i in arr.cpu().tolist()]
+            if len(idx) > cap:
+                raise ValueError(f"too many {name} bodies ({len(idx)} > {cap})")
+            setattr(p, "num_" + name, len(idx))
+            getattr(p, name + "_idx")[:len(idx)] = idx
+        for k, name in enumerate(nat.REWARD_TERMS):
+            active = name in self.reward_scales and name not in self._python_reward_names
+            p.reward_active[k] = int(active)
+            p.reward_scale[k] = float(self.reward_scales[name]) if active else 0.0
+            p.reward_slot[k] = self._sum_names.index(name) if active else -1
+        p.num_reward_slots = len(self._sum_names)
+        ptr = lambda x: x.data_ptr()
+        p.root_states, p.dof_state, p.contact_forces = ptr(self.root_states), ptr(self.dof_state), ptr(self.contact_forces)
+        p.actions, p.torques, p.commands = ptr(self.actions), ptr(self.torques), ptr(self.commands)
+        p.episode_length_buf, p.last_actions, p.last_dof_vel = ptr(self.episode_length_buf), ptr(self.last_actions), ptr(self.last_dof_vel)
+        p.last_root_vel, p.feet_air_time, p.last_contacts = ptr(self.last_root_vel), ptr(self.feet_air_time), ptr(self.last_contacts)
+        p.episode_sums = ptr(self._episode_sums_buf)
+        p.env_origins = ptr(self.env_origins)
+        if self.custom_origins:
+            p.terrain_levels, p.terrain_types, p.terrain_origins = ptr(self.terrain_levels), ptr(self.terrain_types), ptr(self.terrain_origins)
+            p.half_env_length = self.terrain.env_length / 2
+            p.max_terrain_level = int(self.max_terrain_level)
+            p.terrain_num_cols = int(self.terrain_origins.shape[1])
+        p.base_lin_vel, p.base_ang_vel, p.projected_gravity = ptr(self.base_lin_vel), ptr(self.base_ang_vel), ptr(self.projected_gravity)
+        p.obs_buf, p.rew_buf = ptr(self.obs_buf), ptr(self.rew_buf)
+        p.reset_buf, p.time_out_buf = ptr(self._reset_bool), ptr(self.time_out_buf)
+        p.noise_scale_vec = ptr(self.noise_scale_vec)
+        p.reset_stats = ptr(self._reset_stats)
+        if mh:
+            p.measured_heights = ptr(self.measured_heights)
+            if not p.terrain_is_plane:
+                hs = self.height_samples
+                p.hf_rows, p.hf_cols = int(hs.shape[0]), int(hs.shape[1])
+                self._height_min3 = torch.empty_like(hs)
+                nat.check(nat.lib.lgk_height_min3(hs.data_ptr(), self._height_min3.data_ptr(), p.hf_rows, p.hf_cols,
+                                                  _stream_ptr()), "lgk_height_min3")
+                self._height_points_xy = self.height_points[0, :, :2].contiguous()
+                p.height_min3 = ptr(self._height_min3)
+                p.height_points_xy = ptr(self._height_points_xy)
+        self._params = p
+
+    def _refresh_command_ranges(self):
+        """(lo, float(hi - lo)) per command, as torch_rand_float evaluates them (LR:353-366)."""
+        p = getattr(self, "_params", None)
+        if p is None:
+            return
+        r = self.command_ranges
+        for i, k in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw", "heading")):
+            p.cmd_lo[i] = float(r[k][0])
+            p.cmd_range[i] = float(r[k][1] - r[k][0])
+
+    # ------------------------------------------------------------------ LR:471-483
+    def update_command_curriculum(self, env_ids):
+        if torch.mean(self.episode_sums["tracking_lin_vel"][env_ids]) / self.max_episode_length > \
+                0.8 * self.reward_scales["tracking_lin_vel"]:
+            r, mc = self.command_ranges["lin_vel_x"], self.cfg.commands.max_curriculum
+            r[0] = np.clip(r[0] - 0.5, -mc, 0.)
+            r[1] = np.clip(r[1] + 0.5, 0., mc)
+            self._refresh_command_ranges()
+
+    # ------------------------------------------------------------------ LR:371-395
+    def _compute_torques(self, actions):
+        tp = self._tq_params
+        a = actions if (actions.is_cuda and actions.is_contiguous() and actions.dtype == torch.float32) else \
+            actions.to(device=self.device, dtype=torch.float32).contiguous()
+        tp.actions_in = a.data_ptr()
+        tp.actions_clipped = None
+        nat.check(nat.lib.lgk_compute_torques(C.byref(tp), _stream_ptr()), "lgk_compute_torques")
+        return self.torques
+    _compute_torques._lgk_native = True
+
+    # ------------------------------------------------------------------ LR:815-829
+    def _init_height_points(self):
+        y = torch.tensor(self.cfg.terrain.measured_points_y, device=self.device, requires_grad=False)
+        x = torch.tensor(self.cfg.terrain.measured_points_x, device=self.device, requires_grad=False)
+        grid_x, grid_y = torch.meshgrid(x, y, indexing="ij")
+        self.num_height_points = grid_x.numel()
+        points = torch.zeros(self.num_envs, self.num_height_points, 3, device=self.device, requires_grad=False)
+        points[:, :, 0] = grid_x.flatten()
+        points[:, :, 1] = grid_y.flatten()
+        return points
+
+    # ------------------------------------------------------------------ LR:831-869
+    def _get_heights(self, env_ids=None):
+        if self.cfg.terrain.mesh_type == "plane":
+            return torch.zeros(self.num_envs, self.num_height_points, device=self.device, requires_grad=False)
+        elif self.cfg.terrain.mesh_type == "none":
+            raise NameError("Can't measure height with terrain mesh type 'none'")
+        p = self._params
+        out = torch.empty(self.num_envs, self.num_height_points, device=self.device)
+        nat.check(nat.lib.lgk_height_scan(self.root_states.data_ptr(), p.actors_per_env, p.root_actor_offset,
+                                          self.num_envs, p.height_points_xy, self.num_height_points, p.height_min3,
+                                          p.hf_rows, p.hf_cols, p.border_size, p.horizontal_scale, p.vertical_scale,
+                                          out.data_ptr(), None, None, _stream_ptr()), "lgk_height_scan")
+        return out if not env_ids else out[env_ids]
+
+
+def _native_reward(name):
+    def fn(self):
+        raise RuntimeError(f"_reward_{name} is evaluated inside lgk_post_physics; it has no Python body")
+    fn.__name__ = "_reward_" + name
+    fn._lgk_native = True
+    return fn
+
+
+# the 19 terms of LR:872-969 exist as attributes (so _prepare_reward_function finds them, LR:602) but are computed
+# by the kernel.  ``stumble`` keeps the reference's naming quirk: the cfg scale is ``feet_stumble`` (no method).
+for _n in nat.REWARD_TERMS:
+    if _n not in ("termination", "no_fly"):
+        setattr(LeggedRobot, "_reward_" + _n, _native_reward(_n))
+setattr(LeggedRobot, "_reward_termination", _native_reward("termination"))

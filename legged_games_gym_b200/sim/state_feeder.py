@@ -12,14 +12,14 @@ import numpy as np
 import torch
 
 
-def synth_state(num_envs, num_bodies, num_dof=12, seed=0, p_contact=0.3, actors_per_env=1):
+def synth_state(num_envs, num_bodies, num_dof=12, seed=0, p_contact=0.3, actors_per_env=1, xy_max=(83., 163.)):
     """numpy dict of seeded synthetic inputs (PCG64: stable across torch versions)."""
     g = np.random.default_rng(seed)
     N = num_envs
     na = N * actors_per_env
     root = np.zeros((na, 13), dtype=np.float32)
-    root[:, 0] = g.uniform(-2., 83., na)
-    root[:, 1] = g.uniform(-2., 163., na)
+    root[:, 0] = g.uniform(-2., xy_max[0], na)
+    root[:, 1] = g.uniform(-2., xy_max[1], na)
     root[:, 2] = g.normal(0.5, 0.1, na)
     q = g.normal(0., 1., (na, 4))
     q[:, :2] *= 0.3

@@ -47,14 +47,14 @@ def apply_overrides(cfg, overrides):
         setattr(obj, parts[-1], val)
 
 
-def build_case(task, num_envs, seed=0, overrides=None, hf_shape=None):
+def build_case(task, num_envs, seed=0, overrides=None, hf_shape=None, xy_max=(83., 163.)):
     """Returns dict(cfg, consts, state(np), height_samples(np int16|None), terrain_origins, init_levels)."""
     from legged_games_gym_b200.sim.asset_model import model_for_asset
     from legged_games_gym_b200.sim.state_feeder import synth_state, synth_height_field, synth_terrain_origins
     cfg = product_cfg(task, num_envs, overrides)
     model = model_for_asset(cfg.asset)
     consts = model.consts(cfg.asset)
-    st = synth_state(num_envs, model.num_bodies, model.num_dof, seed)
+    st = synth_state(num_envs, model.num_bodies, model.num_dof, seed, xy_max=xy_max)
     rough = cfg.terrain.mesh_type in ("heightfield", "trimesh")
     hs = None
     origins = None
@@ -97,18 +97,57 @@ def step_tables(seed, step, num_envs, num_obs, num_dof=12, env_offset=0):
         philox.STREAM_RESET_ROOT: philox.uniforms(seed, step, ids, philox.STREAM_RESET_ROOT, 8),
         philox.STREAM_RESET_CMD: philox.uniforms(seed, step, ids, philox.STREAM_RESET_CMD, 3),
         philox.STREAM_TERRAIN: philox.raw_u32(seed, step, ids, philox.STREAM_TERRAIN, 1),
-        philox.STREAM_OBS: philox.uniforms(seed, step, ids, philox.STREAM_OBS, num_obs),
+        philox.STREAM_OBS: philox.obs_uniforms(seed, step, ids, num_obs),
     }
 
 
-def perturb_state(state, step, seed):
-    """Cheap deterministic stand-in for a physics step between env steps: new dof/contact/root
-    velocities so consecutive steps are not identical.  Applied identically to every implementation."""
+def make_noise(case, step, seed):
+    """Deterministic stand-in for a physics step between env steps (new dof / contact / root velocities so that
+    consecutive steps differ).  Returned as arrays so fixtures can store them."""
     g = np.random.default_rng(seed * 1000003 + step)
+    st = case["state"]
+    return dict(dof_state=g.normal(0., 0.05, st["dof_state"].shape).astype(np.float32),
+                contact_forces=g.normal(0., 0.05, st["contact_forces"].shape).astype(np.float32),
+                root_vel=g.normal(0., 0.05, (st["root_states"].shape[0], 6)).astype(np.float32),
+                root_xy=g.normal(0., 0.02, (st["root_states"].shape[0], 2)).astype(np.float32))
+
+
+def apply_noise(state, noise):
+    """state: dict of torch tensors (any device), mutated in place.  Same arithmetic for every implementation."""
     for k in ("dof_state", "contact_forces"):
         t = state[k]
-        noise = g.normal(0., 0.05, tuple(t.shape)).astype(np.float32)
-        t += torch.from_numpy(noise).to(t.device) * (t != 0)
+        t += torch.from_numpy(noise[k]).to(t.device) * (t != 0)
     r = state["root_states"]
-    r[:, 7:13] += torch.from_numpy(g.normal(0., 0.05, (r.shape[0], 6)).astype(np.float32)).to(r.device)
-    r[:, 0:2] += torch.from_numpy(g.normal(0., 0.02, (r.shape[0], 2)).astype(np.float32)).to(r.device)
+    r[:, 7:13] += torch.from_numpy(noise["root_vel"]).to(r.device)
+    r[:, 0:2] += torch.from_numpy(noise["root_xy"]).to(r.device)
+
+
+def perturb_state(state, step, seed):
+    g = np.random.default_rng(seed * 1000003 + step)
+    noise = dict(dof_state=g.normal(0., 0.05, tuple(state["dof_state"].shape)).astype(np.float32),
+                 contact_forces=g.normal(0., 0.05, tuple(state["contact_forces"].shape)).astype(np.float32),
+                 root_vel=g.normal(0., 0.05, (state["root_states"].shape[0], 6)).astype(np.float32),
+                 root_xy=g.normal(0., 0.02, (state["root_states"].shape[0], 2)).astype(np.float32))
+    apply_noise(state, noise)
+
+
+def snapshot(env):
+    """Comparable view of an env (reference instance, OracleEnv, or the product LeggedRobot): name -> CPU tensor."""
+    names = ["obs_buf", "rew_buf", "reset_buf", "time_out_buf", "episode_length_buf", "commands", "base_lin_vel",
+             "base_ang_vel", "projected_gravity", "last_actions", "last_dof_vel", "last_root_vel", "feet_air_time",
+             "last_contacts", "root_states", "dof_state", "torques", "env_origins"]
+    d = {n: getattr(env, n).detach().cpu().clone() for n in names}
+    if isinstance(env.measured_heights, torch.Tensor):
+        d["measured_heights"] = env.measured_heights.detach().cpu().clone()
+    for k, v in env.episode_sums.items():
+        d["sum_" + k] = v.detach().cpu().clone()
+    for k, v in env.extras.get("episode", {}).items():
+        d["ex_" + k] = torch.as_tensor(v).detach().cpu().clone().float()
+    if "time_outs" in env.extras:
+        d["ex_time_outs"] = env.extras["time_outs"].detach().cpu().clone()
+    if hasattr(env, "terrain_levels"):
+        d["terrain_levels"] = env.terrain_levels.detach().cpu().clone()
+    if hasattr(env, "sea_hidden_state") and env.cfg.control.use_actuator_network:
+        d["sea_h"] = env.sea_hidden_state.detach().cpu().clone()
+        d["sea_c"] = env.sea_cell_state.detach().cpu().clone()
+    return d

@@ -69,6 +69,24 @@ def uniforms(seed, step, env_ids, stream, count):
     return (w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
 
 
+def obs_uniforms(seed, step, env_ids, num_obs):
+    """OBS stream: column j uses word (j//32)%4 of block 32*(j//128) + j%32, so that one warp lane owns one
+    Philox block per 128 columns and writes coalesced row segments (csrc/lgk_step_device.cuh obs_block_of)."""
+    env_ids = np.asarray(env_ids, dtype=np.uint32)
+    nsuper = (num_obs + 127) // 128
+    nblk = 32 * nsuper
+    ctr = np.zeros((env_ids.shape[0], nblk, 4), dtype=np.uint32)
+    ctr[..., 0] = env_ids[:, None]
+    ctr[..., 1] = np.arange(nblk, dtype=np.uint32)[None, :]
+    ctr[..., 2] = np.uint32(STREAM_OBS)
+    ctr[..., 3] = np.uint32(step & 0xFFFFFFFF)
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    words = philox4x32_10(ctr, key)                      # [n, nblk, 4]
+    j = np.arange(num_obs)
+    w = words[:, 32 * (j // 128) + (j % 32), (j // 32) % 4]
+    return (w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
 def normals(seed, step, env_ids, count):
     """Box-Muller on the ACT stream: pair (2i, 2i+1) of uniforms -> normals (2i, 2i+1).
     u1 is mapped to (0,1] so the log is finite.  fp32 arithmetic like the kernel

@@ -1,0 +1,55 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/lgk.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lgk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lgk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from legged_games_gym_b200 import _native
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), f"liblgk.so does not export {s}"
+    assert sorted(_native.EXPORTS) == syms
+
+
+def test_struct_mirrors_match():
+    from legged_games_gym_b200 import _native as nat
+    for which, cls in enumerate((nat.TorqueParams, nat.LstmWeights, nat.StepParams, nat.PolicyParams)):
+        assert nat.lib.lgk_struct_size(which) == ctypes.sizeof(cls)
+    assert nat.lib.lgk_abi_version() == 1
+
+
+def test_argument_errors_are_codes_not_crashes():
+    from legged_games_gym_b200 import _native as nat
+    p = nat.StepParams()
+    rc = nat.lib.lgk_post_physics(ctypes.byref(p), None)
+    assert rc == 1 and b"num_envs" in nat.lib.lgk_last_error_string()
+    t = nat.TorqueParams()
+    assert nat.lib.lgk_compute_torques(ctypes.byref(t), None) == 1
+
+
+def test_reward_order_is_alphabetical():
+    from legged_games_gym_b200 import _native as nat
+    assert nat.REWARD_TERMS == sorted(nat.REWARD_TERMS)
+
+
+def test_env_fails_loudly_without_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.utils.helpers import get_args
+    import copy
+    with pytest.raises(RuntimeError):
+        task_registry.make_env("a1", get_args([]), env_cfg=copy.deepcopy(task_registry.env_cfgs["a1"]))

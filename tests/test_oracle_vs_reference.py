@@ -1,0 +1,75 @@
+"""Pin the oracle restatement (oracle/legged_oracle.py) BIT-FOR-BIT against the unmodified reference executed through
+oracle/ref_loader.py.  Needs /root/reference, so it runs in the build container only (skipped on the GPU box, where the
+committed fixtures of tests/test_golden.py carry the pin)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import harness, ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not mounted")
+
+CASES = [("anymal_c_flat", 64, None), ("anymal_c_rough", 128, None), ("a1", 128, None), ("cassie", 96, None),
+         ("anymal_b", 64, None), ("anymal_c_flat", 64, {"control.use_actuator_network": False}),
+         ("a1", 96, {"commands.curriculum": True, "domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1}),
+         ("a1", 64, {"control.control_type": "V"}), ("a1", 64, {"control.control_type": "T"})]
+
+
+@pytest.mark.parametrize("task,n,ov", CASES)
+def test_oracle_is_bit_exact_with_reference(task, n, ov):
+    case = harness.build_case(task, n, seed=3, overrides=ov)
+    st_ref, st_or = harness.torch_state(case), harness.torch_state(case)
+    hs = None if case["height_samples"] is None else torch.from_numpy(case["height_samples"].copy())
+    ref = ref_loader.make_ref_env(task, n, case["consts"], st_ref, height_samples=hs, cfg_overrides=ov,
+                                  init_levels=case["init_levels"])
+    ref.episode_length_buf[:] = torch.from_numpy(case["state"]["episode_length_buf"])
+    tap = ref_loader.attach_tap(ref)
+    orc = harness.make_oracle(case, st_or)
+    assert ref.reward_names == orc.reward_names
+    for step in range(1, 6):
+        tables = harness.step_tables(case["seed"], step, n, ref.num_obs)
+        acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (n, 12)).astype(np.float32))
+        tap.set_tables(tables)
+        with tap.active():
+            ref.step(acts.clone())
+        orc.step(acts.clone(), tables)
+        a, b = harness.snapshot(ref), harness.snapshot(orc)
+        assert a.keys() == b.keys()
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"{task} step {step}: {k} differs from the reference"
+        harness.perturb_state(st_ref, step, 5)
+        harness.perturb_state(st_or, step, 5)
+
+
+def test_product_cfgs_equal_reference_cfgs():
+    """The cfg mirror (dict-spec built classes) must carry exactly the reference's values."""
+    ref_loader.load_reference()
+    from legged_gym.utils.task_registry import task_registry as ref_reg
+    from legged_gym.utils.helpers import class_to_dict as ref_c2d
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.utils.helpers import class_to_dict
+    for name in ("anymal_c_rough", "anymal_c_flat", "anymal_b", "a1", "cassie"):
+        for mine, theirs in ((task_registry.env_cfgs[name], ref_reg.env_cfgs[name]),
+                             (task_registry.train_cfgs[name], ref_reg.train_cfgs[name])):
+            a, b = class_to_dict(mine), ref_c2d(theirs)
+            a.pop("seed", None), b.pop("seed", None)
+            assert a == b, f"cfg mismatch for {name}"
+    from legged_games_gym_b200.envs import LowLevelGameCfg, LowLevelGamePPO
+    assert class_to_dict(LowLevelGameCfg()) == {k: v for k, v in ref_c2d(ref_reg.env_cfgs["low_level_game"]).items() if k != "seed"}
+    assert class_to_dict(LowLevelGamePPO()) == ref_c2d(ref_reg.train_cfgs["low_level_game"])
+
+
+def test_lstm_plain_restatement_matches_aten_lstm():
+    w = harness.lstm_weights()
+    from oracle.legged_oracle import ActuatorLSTM
+    net = ActuatorLSTM(w)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4096, 1, 2, generator=g)
+    h, c = torch.randn(2, 4096, 8, generator=g) * 0.5, torch.randn(2, 4096, 8, generator=g) * 0.5
+    a, ha, ca = net.forward(x, h.clone(), c.clone())
+    b, hb, cb = net.forward_plain(x, h.clone(), c.clone())
+    assert torch.allclose(a, b, rtol=1e-5, atol=5e-5) and torch.allclose(ha, hb, atol=1e-6) and torch.allclose(ca, cb, atol=1e-6)
+    ref = torch.jit.load(ref_loader.REFERENCE_ROOT + "/resources/actuator_nets/anydrive_v3_lstm.pt")
+    with torch.inference_mode():
+        r, (hr, cr) = ref(x, (h.clone(), c.clone()))
+    assert torch.equal(r, a) and torch.equal(hr, ha) and torch.equal(cr, ca)

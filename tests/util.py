@@ -1,0 +1,78 @@
+"""Shared helpers for the parity tests: build the PRODUCT env (CUDA kernels through the C ABI) on the same seeded
+inputs the oracle / the golden fixtures use."""
+import copy
+import types
+
+import numpy as np
+import torch
+
+from oracle import harness
+
+
+def product_env(case, device="cuda:0"):
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.sim.state_feeder import SimBackend
+    from legged_games_gym_b200.utils.helpers import SimParams
+
+    class ExplicitFeeder(SimBackend):
+        def __init__(self, st):
+            self.root_states = torch.from_numpy(st["root_states"].copy()).to(device)
+            self.dof_state = torch.from_numpy(st["dof_state"].copy()).to(device)
+            self.contact_forces = torch.from_numpy(st["contact_forces"].copy()).to(device)
+
+        def acquire_actor_root_state_tensor(self):
+            return self.root_states
+
+        def acquire_dof_state_tensor(self):
+            return self.dof_state
+
+        def acquire_net_contact_force_tensor(self):
+            return self.contact_forces
+
+    cfg = copy.deepcopy(case["cfg"])
+    cfg.seed = case["seed"]
+    terrain = None
+    if case["height_samples"] is not None:
+        hs = case["height_samples"]
+        terrain = types.SimpleNamespace(cfg=cfg.terrain, env_length=cfg.terrain.terrain_length,
+                                        env_width=cfg.terrain.terrain_width, heightsamples=hs, tot_rows=hs.shape[0],
+                                        tot_cols=hs.shape[1], env_origins=case["terrain_origins"])
+    cls = task_registry.get_task_class(case["task"])
+    feeder = ExplicitFeeder(case["state"])
+    env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
+              sim_device=device, headless=True, sim_backend=feeder, terrain=terrain,
+              init_terrain_levels=case["init_levels"])
+    env.episode_length_buf[:] = torch.from_numpy(case["state"]["episode_length_buf"]).to(device)
+    return env, feeder
+
+
+def feeder_state(feeder):
+    return dict(root_states=feeder.root_states, dof_state=feeder.dof_state, contact_forces=feeder.contact_forces)
+
+
+FLOAT_RTOL, FLOAT_ATOL = 1e-5, 1e-5      # north_star: within 1e-5 relative for fp32 obs / rewards / torques
+
+
+def assert_snapshots_close(got, want, step, exact=("reset_buf", "time_out_buf", "episode_length_buf", "last_contacts",
+                                                   "terrain_levels", "ex_time_outs"), atol_scale=None, skip=()):
+    """bit-exact on masks / counters / levels; rtol 1e-5 (+ atol 1e-5 * scale of the quantity) on fp32."""
+    atol_scale = atol_scale or {}
+    bad = []
+    for k, w in want.items():
+        if k in skip:
+            continue
+        assert k in got, f"step {step}: product snapshot lacks {k}"
+        g = got[k]
+        g = g.numpy() if isinstance(g, torch.Tensor) else np.asarray(g)
+        w = w.numpy() if isinstance(w, torch.Tensor) else np.asarray(w)
+        if k in exact or w.dtype == np.bool_ or np.issubdtype(w.dtype, np.integer):
+            if not np.array_equal(g.astype(np.int64), w.astype(np.int64)):
+                bad.append(f"{k}: {int((g.astype(np.int64) != w.astype(np.int64)).sum())} of {w.size} differ (exact)")
+            continue
+        scale = atol_scale.get(k, max(1.0, float(np.abs(w).max()) if w.size else 1.0))
+        err = np.abs(g.astype(np.float64) - w.astype(np.float64))
+        tol = FLOAT_ATOL * scale + FLOAT_RTOL * np.abs(w)
+        if not np.all(err <= tol):
+            i = int(np.argmax(err - tol))
+            bad.append(f"{k}: max excess at flat {i}: got {g.flat[i]!r} want {w.flat[i]!r} (|err| {err.flat[i]:.3e}, tol {tol.flat[i]:.3e})")
+    assert not bad, f"step {step} mismatches:\n  " + "\n  ".join(bad)

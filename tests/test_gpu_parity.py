@@ -1,0 +1,306 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (ctypes -> liblgk.so), against the CPU oracle on
+identical seeded inputs, and against the golden fixtures produced by the reference itself.
+
+Bars (BASELINE.json north_star): bit-exact for reset / time-out masks, height-sample indices, episode counters,
+terrain levels and command resampling under the shared Philox stream; rtol 1e-5 (atol 1e-5 x scale) for fp32
+observations, rewards, torques; 1e-3 for policy outputs and GAE."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import harness, philox
+from oracle.make_golden import CASES, GOLDEN_DIR, build
+from tests.util import product_env, feeder_state, assert_snapshots_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def nat():
+    from legged_games_gym_b200 import _native
+    return _native
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------- RNG tap
+@pytest.mark.parametrize("sid,count", [(philox.STREAM_CMD, 3), (philox.STREAM_RESET_DOF, 12), (philox.STREAM_RESET_ROOT, 8),
+                                       (philox.STREAM_TERRAIN, 1), (philox.STREAM_OBS, 235), (philox.STREAM_OBS, 48)])
+def test_rng_dump_bit_exact(sid, count):
+    n, seed, step, off = 257, 0x1234567890ABCDEF, 77, 1000
+    ids = np.arange(off, off + n)
+    out = torch.empty(n, count, dtype=torch.int32, device=DEV)
+    nat().check(nat().lib.lgk_rng_dump(seed, step, off, n, sid, count, 1, out.data_ptr(), stream()))
+    if sid == philox.STREAM_OBS:
+        u_want = philox.obs_uniforms(seed, step, ids, count)
+    else:
+        want = philox.raw_u32(seed, step, ids, sid, count)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want)
+        u_want = philox.uniforms(seed, step, ids, sid, count)
+    u = torch.empty(n, count, dtype=torch.float32, device=DEV)
+    nat().check(nat().lib.lgk_rng_dump(seed, step, off, n, sid, count, 0, u.data_ptr(), stream()))
+    assert np.array_equal(u.cpu().numpy(), u_want)
+
+
+def test_rng_normals_close():
+    n, seed, step = 300, 5, 9
+    z = torch.empty(n, 12, dtype=torch.float32, device=DEV)
+    nat().check(nat().lib.lgk_rng_dump(seed, step, 0, n, philox.STREAM_ACT, 12, 2, z.data_ptr(), stream()))
+    want = philox.normals(seed, step, np.arange(n), 12)
+    assert np.allclose(z.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- height scan
+@pytest.mark.parametrize("task,n", [("anymal_c_rough", 64), ("cassie", 100), ("anymal_c_rough", 4096)])
+def test_height_scan_indices_bit_exact(task, n):
+    case = harness.build_case(task, n, seed=21)
+    orc = harness.make_oracle(case)
+    want_h = orc.get_heights()
+    P = orc.num_height_points
+    hs = torch.from_numpy(case["height_samples"]).to(DEV)
+    m3 = torch.empty_like(hs)
+    L = nat().lib
+    nat().check(L.lgk_height_min3(hs.data_ptr(), m3.data_ptr(), hs.shape[0], hs.shape[1], stream()))
+    # min3 against its definition (integer work: exact)
+    h = case["height_samples"].astype(np.int32)
+    ref3 = h.copy()
+    ref3[:-1, :-1] = np.minimum(np.minimum(h[:-1, :-1], h[1:, :-1]), h[:-1, 1:])
+    assert np.array_equal(m3.cpu().numpy().astype(np.int32), ref3)
+    root = torch.from_numpy(case["state"]["root_states"]).to(DEV)
+    pts = orc.height_points[0, :, :2].contiguous().to(DEV)
+    out = torch.empty(n, P, device=DEV)
+    px = torch.empty(n, P, dtype=torch.int32, device=DEV)
+    py = torch.empty(n, P, dtype=torch.int32, device=DEV)
+    t = case["cfg"].terrain
+    nat().check(L.lgk_height_scan(root.data_ptr(), 1, 0, n, pts.data_ptr(), P, m3.data_ptr(), hs.shape[0], hs.shape[1],
+                                  t.border_size, t.horizontal_scale, t.vertical_scale, out.data_ptr(), px.data_ptr(),
+                                  py.data_ptr(), stream()))
+    assert np.array_equal(px.cpu().numpy().reshape(-1), orc.last_px.numpy())
+    assert np.array_equal(py.cpu().numpy().reshape(-1), orc.last_py.numpy())
+    assert np.array_equal(out.cpu().numpy(), want_h.numpy())
+    frac_clipped = float(((orc.last_px == 0) | (orc.last_px == hs.shape[0] - 2)).float().mean())
+    assert 0.0 < frac_clipped < 0.5       # the clip path is exercised, but not only the clip path
+
+
+# ---------------------------------------------------------------------------------------------- torques
+@pytest.mark.parametrize("ct", ["P", "V", "T"])
+def test_pd_torques_bit_exact(ct):
+    case = harness.build_case("a1", 200, seed=31, overrides={"control.control_type": ct})
+    orc = harness.make_oracle(case)
+    env, feeder = product_env(case)
+    acts = torch.from_numpy(np.random.default_rng(1).normal(0, 40, (200, 12)).astype(np.float32))   # some beyond +-100
+    acts[0, 0], acts[1, 1] = 250., -250.
+    orc.last_dof_vel[:] = torch.from_numpy(np.random.default_rng(2).normal(0, 1, (200, 12)).astype(np.float32))
+    env.last_dof_vel.copy_(orc.last_dof_vel.to(DEV))
+    want = orc.compute_torques(torch.clip(acts, -100, 100))
+    got = env._compute_torques(acts.to(DEV))
+    assert np.array_equal(got.cpu().numpy(), want.numpy())
+
+
+def test_lstm_torques_and_state():
+    case = harness.build_case("anymal_c_flat", 320, seed=32)
+    orc = harness.make_oracle(case)
+    env, feeder = product_env(case)
+    st_or = {"dof_state": orc.dof_state}
+    worst = 0.0
+    for k in range(6):
+        acts = torch.from_numpy(np.random.default_rng(10 + k).normal(0, 1, (320, 12)).astype(np.float32))
+        want = orc.compute_torques(acts).view(320, 12)
+        got = env._compute_torques(acts.to(DEV))
+        scale = float(want.abs().max())
+        err = (got.cpu() - want).abs()
+        worst = max(worst, float(err.max()))
+        assert torch.all(err <= 1e-5 * scale + 1e-5 * want.abs()), f"substep {k}: max err {float(err.max()):.3e} (scale {scale:.1f})"
+        assert torch.allclose(env.sea_hidden_state.cpu(), orc.sea_hidden_state, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(env.sea_cell_state.cpu(), orc.sea_cell_state, rtol=1e-5, atol=1e-5)
+        noise = torch.from_numpy(np.random.default_rng(50 + k).normal(0, 0.3, tuple(orc.dof_state.shape)).astype(np.float32))
+        orc.dof_state += noise
+        feeder.dof_state += noise.to(DEV)
+    print(f"LSTM torque max abs err over 6 sub-steps: {worst:.3e}")
+
+
+# ---------------------------------------------------------------------------------------------- full step
+STEP_CASES = [("anymal_c_flat", 64, None), ("anymal_c_rough", 256, None), ("anymal_c_rough", 1000, None),
+              ("a1", 512, None), ("cassie", 130, None), ("anymal_b", 96, None),
+              ("anymal_c_flat", 64, {"control.use_actuator_network": False}),
+              ("a1", 160, {"commands.curriculum": True, "domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1}),
+              ("a1", 64, {"noise.add_noise": False, "rewards.only_positive_rewards": False}),
+              ("anymal_c_rough", 96, {"rewards.scales.base_height": -1.0, "rewards.scales.dof_vel": -1e-4,
+                                      "rewards.scales.stand_still": -0.1, "rewards.scales.orientation": -1.0,
+                                      "rewards.scales.termination": -5.0, "rewards.scales.feet_contact_forces": -0.01,
+                                      "rewards.scales.dof_vel_limits": -0.5, "rewards.scales.torque_limits": -0.01,
+                                      "rewards.scales.dof_pos_limits": -2.0, "rewards.max_contact_force": 1.5})]
+
+
+@pytest.mark.parametrize("task,n,ov", STEP_CASES)
+def test_env_step_matches_oracle(task, n, ov):
+    case = harness.build_case(task, n, seed=3, overrides=ov)
+    st_or = harness.torch_state(case)
+    orc = harness.make_oracle(case, st_or)
+    env, feeder = product_env(case)
+    st_gpu = feeder_state(feeder)
+    assert env.reward_names == orc.reward_names
+    for step in range(1, 7):
+        tables = harness.step_tables(case["seed"], step, n, orc.num_obs)
+        acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (n, 12)).astype(np.float32))
+        orc.step(acts.clone(), tables)
+        env.step(acts.to(DEV))
+        torch.cuda.synchronize()
+        ids = env.reset_env_ids[: int(env.reset_count.item())].cpu().numpy()
+        assert np.array_equal(ids, orc.reset_buf.nonzero().flatten().numpy()), "reset id list must equal nonzero() order"
+        scales = {"torques": max(1.0, float(orc.torques.abs().max())), "sea_h": 1.0, "sea_c": 1.0}
+        assert_snapshots_close(harness.snapshot(env), harness.snapshot(orc), step, atol_scale=scales)
+        noise = harness.make_noise(case, step, 5)
+        harness.apply_noise(st_or, noise)
+        harness.apply_noise(st_gpu, noise)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_env_step_matches_reference_fixture(name):
+    spec = CASES[name]
+    fx = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    case = build(spec)
+    for k in ("root_states", "dof_state", "contact_forces", "episode_length_buf"):
+        case["state"][k] = fx["in_" + k]
+    env, feeder = product_env(case)
+    st_gpu = feeder_state(feeder)
+    for step in range(1, spec["steps"] + 1):
+        env.step(torch.from_numpy(fx[f"s{step}_actions"].copy()).to(DEV))
+        torch.cuda.synchronize()
+        snap = harness.snapshot(env)
+        want = {k: fx[f"s{step}_{k}"] for k in snap if f"s{step}_{k}" in fx.files}
+        missing = [k[len(f"s{step}_"):] for k in fx.files if k.startswith(f"s{step}_") and "noise_" not in k
+                   and k != f"s{step}_actions" and k[len(f"s{step}_"):] not in snap]
+        assert not missing, f"product env lacks outputs the reference has: {missing}"
+        scales = {"torques": max(1.0, float(np.abs(fx[f"s{step}_torques"]).max()))}
+        assert_snapshots_close(snap, want, step, atol_scale=scales)
+        harness.apply_noise(st_gpu, {k: fx[f"s{step}_noise_{k}"] for k in ("dof_state", "contact_forces", "root_vel", "root_xy")})
+
+
+def test_explicit_reset_idx_and_reset():
+    """BaseTask.reset(): reset_idx(arange(N)) then one zero-action step (base_task.py:114-118)."""
+    case = harness.build_case("anymal_c_rough", 200, seed=8)
+    st_or = harness.torch_state(case)
+    orc = harness.make_oracle(case, st_or)
+    env, feeder = product_env(case)
+    # oracle: same sequence with explicit tables; the reset uses step counter 0, the step uses 1
+    orc.tables = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in harness.step_tables(case["seed"], 0, 200, orc.num_obs).items()}
+    orc.reset_buf = torch.ones(200, dtype=torch.bool)
+    orc.reset_idx(torch.arange(200))
+    obs_o, *_ = orc.step(torch.zeros(200, 12), harness.step_tables(case["seed"], 1, 200, orc.num_obs))
+    obs_g, _ = env.reset()
+    torch.cuda.synchronize()
+    assert_snapshots_close(harness.snapshot(env), harness.snapshot(orc), 1,
+                           atol_scale={"torques": max(1.0, float(orc.torques.abs().max()))})
+    assert torch.allclose(obs_g.cpu(), obs_o, rtol=1e-5, atol=1e-5)
+
+
+def test_user_reward_term_runs_split_phases():
+    """A subclass adds a torch-written _reward_<name>: the step runs PRE, the Python term, POST (LR:199-203 order)."""
+    from legged_games_gym_b200.envs import LeggedRobot, task_registry
+    from legged_games_gym_b200.envs.a1.a1_config import A1RoughCfg
+    from legged_games_gym_b200.envs.base.base_config import cfg_from_spec
+
+    class MyEnv(LeggedRobot):
+        def _reward_zz_height_bonus(self):
+            return torch.exp(-torch.square(self.root_states[:, 2] - 0.4))
+
+    case = harness.build_case("a1", 96, seed=4)
+    case["cfg"].rewards.scales.zz_height_bonus = 0.3
+    task_registry.register("a1_custom", MyEnv, A1RoughCfg(), None)
+    case["task"] = "a1_custom"
+    st_or = harness.torch_state(case)
+    orc = harness.make_oracle(case, st_or)
+    orc._r_zz_height_bonus = lambda: torch.exp(-torch.square(orc.root_states[:, 2] - 0.4))
+    env, feeder = product_env(case)
+    assert env._python_reward_names == ["zz_height_bonus"]
+    for step in range(1, 4):
+        tables = harness.step_tables(case["seed"], step, 96, orc.num_obs)
+        acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (96, 12)).astype(np.float32))
+        orc.step(acts.clone(), tables)
+        env.step(acts.to(DEV))
+        torch.cuda.synchronize()
+        assert_snapshots_close(harness.snapshot(env), harness.snapshot(orc), step,
+                               atol_scale={"torques": max(1.0, float(orc.torques.abs().max()))})
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties():
+    """BASELINE config sizes (oracle too slow to sweep every step here): size-independent properties."""
+    for task, n in (("anymal_c_rough", 4096), ("a1", 16384)):
+        case = harness.build_case(task, n, seed=2)
+        env, feeder = product_env(case)
+        for step in range(3):
+            obs, _, rew, reset, extras = env.step(feeder_actions(n, step))
+        torch.cuda.synchronize()
+        cnt = int(env.reset_count.item())
+        ids = env.reset_env_ids[:cnt].long()
+        assert torch.equal(ids, reset.nonzero().flatten()), "ids ascending == nonzero()"
+        assert torch.all(env.episode_length_buf[ids] == 0) and torch.all(env.episode_length_buf[~reset] > 0)
+        assert float(obs.abs().max()) <= 100.0 and bool(torch.isfinite(obs).all()) and bool(torch.isfinite(rew).all())
+        assert torch.all(rew >= 0)                                      # only_positive_rewards, no termination term
+        assert torch.equal(env.last_actions, env.actions)
+        assert torch.equal(env.last_dof_vel, env.dof_vel) and torch.all(env.dof_vel[reset] == 0)
+        assert torch.all(env.time_out_buf <= reset)
+        for k, v in env.episode_sums.items():
+            assert torch.all(v[reset] == 0), k
+        # one-shot oracle check of the last step's pure functions at full size: heights
+        orc_case = harness.build_case(task, n, seed=2)
+        orc_case["state"]["root_states"] = feeder.root_states.cpu().numpy()
+        orc = harness.make_oracle(orc_case)
+        assert torch.equal(env._get_heights().cpu(), orc.get_heights())
+
+
+def feeder_actions(n, step):
+    return torch.from_numpy(np.random.default_rng(100 + step).normal(0, 1, (n, 12)).astype(np.float32)).to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------- rsl_rl pieces
+@pytest.mark.parametrize("T,N", [(24, 4096), (24, 100), (5, 33)])
+def test_gae_matches_restated_rsl_rl(T, N):
+    from oracle.rsl_oracle import compute_returns
+    g = torch.Generator().manual_seed(0)
+    rewards, values = torch.randn(T, N, 1, generator=g), torch.randn(T, N, 1, generator=g)
+    dones = (torch.rand(T, N, 1, generator=g) < 0.1).to(torch.uint8)
+    last = torch.randn(N, 1, generator=g)
+    want_r, want_a = compute_returns(rewards, values, dones, last, 0.99, 0.95)
+    d = lambda t: t.to(DEV).contiguous()
+    r, v, dn, lv = d(rewards), d(values), d(dones), d(last)
+    ret, adv = torch.empty_like(r), torch.empty_like(r)
+    scratch = torch.zeros(4, dtype=torch.float64, device=DEV)
+    nat().check(nat().lib.lgk_gae(r.data_ptr(), v.data_ptr(), dn.data_ptr(), lv.data_ptr(), T, N, 0.99, 0.95,
+                                  ret.data_ptr(), adv.data_ptr(), scratch.data_ptr(), stream()))
+    assert torch.allclose(ret.cpu(), want_r, rtol=1e-3, atol=1e-3)      # north_star tolerance for GAE returns
+    assert torch.allclose(adv.cpu(), want_a, rtol=1e-3, atol=1e-3)
+    assert torch.allclose(ret.cpu(), want_r, rtol=1e-5, atol=1e-5)      # and in fact fp32-tight
+
+
+@pytest.mark.parametrize("n,nobs,hidden", [(4096, 235, (512, 256, 128)), (100, 48, (128, 64, 32)), (777, 169, (512, 256, 128))])
+def test_policy_act_matches_restated_rsl_rl(n, nobs, hidden):
+    from oracle.rsl_oracle import ActorCriticOracle
+    from legged_games_gym_b200.rsl_rl.modules import ActorCritic
+    torch.manual_seed(0)
+    orc = ActorCriticOracle(nobs, nobs, 12, hidden, hidden)
+    with torch.no_grad():
+        orc.std.copy_(torch.linspace(0.5, 1.5, 12))
+    ac = ActorCritic(nobs, nobs, 12, list(hidden), list(hidden)).to(DEV)
+    ac.load_state_dict(orc.state_dict())
+    obs = torch.randn(n, nobs) * 2
+    seed, step = 17, 5
+    eps = torch.from_numpy(philox.normals(seed, step, np.arange(n), 12))
+    a, v, lp, mu, sg = orc.act(obs, obs, eps)
+    ac.set_rng(seed, step)
+    got_a = ac.act(obs.to(DEV))
+    got_v = ac.evaluate(obs.to(DEV))
+    torch.cuda.synchronize()
+    tol = dict(rtol=1e-3, atol=1e-3)
+    assert torch.allclose(ac.action_mean.cpu(), mu, **tol)
+    assert torch.allclose(got_a.cpu(), a, **tol)
+    assert torch.allclose(got_v.cpu(), v, **tol)
+    assert torch.allclose(ac.action_std.cpu(), sg, **tol)
+    assert torch.allclose(ac.get_actions_log_prob(got_a).cpu(), lp, rtol=1e-3, atol=5e-3)

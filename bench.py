@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the legged_gym per-environment step on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic state: clip actions -> 4 x actuator-net (LSTM)
+torques -> fused post-physics (rotations, 187-point height scan, rewards, termination, reset, observations) for
+anymal_c_rough, through the public API ``LeggedRobot.step`` (which calls liblgk.so through the C ABI).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--num-envs 4096] [--impl reference]
+
+Own arm, one JSON line on rank 0:
+  value     whole-job env-steps/s with the state tensors resident in HBM (CUDA-event time, max over ranks)
+  e2e       same metric with the sim state in pinned HOST memory: every step copies dof/root/contact state H2D and
+            torques / observations / rewards / resets D2H inside the timed region
+  roofline  dominant kernel (LSTM torque kernel, 84 % of the algorithmic bytes of a step): algorithmic bytes per
+            launch / CUDA-event time per launch, against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the oracle (torch-CPU restatement of the reference, bit-exact with it) on this box's host cores
+``--impl reference`` times that CPU path alone (the reference itself is Python + Isaac Gym and cannot travel).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TASK = "anymal_c_rough"
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+L2_FLUSH_BYTES = 256 << 20
+# algorithmic bytes per env per call (restated in DESIGN.md)
+BYTES_TORQUE_LSTM = 3264
+BYTES_TORQUE_PD = 192
+BYTES_POST_ROUGH = 2561
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--num-envs", type=int, default=4096, help="envs per GPU (weak scaling)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm (oracle)
+def cpu_arm(num_envs, steps, warmup):
+    """Time the oracle (reference algorithm, torch CPU, all host threads) on the same workload."""
+    import numpy as np
+    import torch
+    from oracle import harness
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    case = harness.build_case(TASK, num_envs, seed=0)
+    orc = harness.make_oracle(case)
+    acts = torch.from_numpy(case["state"]["actions"].copy())
+    tables = harness.step_tables(0, 1, num_envs, orc.num_obs)   # uniforms precomputed: RNG is not on the timed path
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.step(acts, tables)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(value=num_envs / med, unit=UNIT, cores=cores, kind="port", ms_per_step=med * 1e3,
+                best_ms=times[0] * 1e3,
+                sample=f"{steps} timed + {warmup} warm-up steps of {TASK} at {num_envs} envs (median), torch CPU {cores} threads")
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def make_env(num_envs, device, host_sim=False, env_id_offset=0):
+    import copy
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.sim.state_feeder import StateFeeder, HostStateFeeder
+    from legged_games_gym_b200.sim.asset_model import model_for_asset
+    from legged_games_gym_b200.utils.helpers import SimParams
+    cfg = copy.deepcopy(task_registry.env_cfgs[TASK])
+    cfg.env.num_envs = num_envs
+    cfg.seed = 1
+    model = model_for_asset(cfg.asset)
+    feeder_cls = HostStateFeeder if host_sim else StateFeeder
+    feeder = feeder_cls(num_envs, model.num_bodies, model.num_dof, device=device, seed=env_id_offset)
+    cls = task_registry.get_task_class(TASK)
+    env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
+              sim_device=device, headless=True, sim_backend=feeder)
+    env.env_id_offset = env_id_offset
+    env._params.env_id_offset = env_id_offset
+    env.episode_length_buf.copy_(feeder.synthetic_episode_length)
+    return env, feeder
+
+
+def time_steps(env, actions, steps, warmup, flush, dist_barrier):
+    """K steps, each bracketed by CUDA events on the launch stream, L2 flushed between steps (outside the events)."""
+    import torch
+    from legged_games_gym_b200 import _native as nat
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(warmup):
+        env.step(actions)
+        nat.lib.lgk_l2_flush(flush.data_ptr(), flush.numel(), st)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    dist_barrier()
+    torch.cuda.synchronize()
+    l0 = nat.launch_count()
+    for a, b in ev:
+        a.record()
+        env.step(actions)
+        b.record()
+        nat.lib.lgk_l2_flush(flush.data_ptr(), flush.numel(), st)
+    torch.cuda.synchronize()
+    dist_barrier()
+    launches = nat.launch_count() - l0
+    return sum(a.elapsed_time(b) for a, b in ev) / 1e3, launches   # seconds
+
+
+def time_kernel(fn, reps, flush):
+    """average CUDA-event duration of one launch, L2 flushed before every launch"""
+    import torch
+    from legged_games_gym_b200 import _native as nat
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        fn()
+    tot = 0.0
+    evs = []
+    for _ in range(reps):
+        nat.lib.lgk_l2_flush(flush.data_ptr(), flush.numel(), st)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return sum(ts) / len(ts) / 1e3, ts[len(ts) // 2] / 1e3
+
+
+def kernel_rooflines(env, actions, flush, peak_gbs, reps=200):
+    import ctypes as C
+    import torch
+    from legged_games_gym_b200 import _native as nat
+    n = env.num_envs
+    st = torch.cuda.current_stream().cuda_stream
+    env._tq_params.actions_in = actions.data_ptr()
+    env._tq_params.actions_clipped = None
+    tq = lambda: nat.lib.lgk_compute_torques(C.byref(env._tq_params), st)
+    p = env._params
+    p.phase_mask = nat.PHASE_PRE | nat.PHASE_POST
+    pp = lambda: nat.lib.lgk_post_physics(C.byref(p), st)
+    out = {}
+    for name, fn, bpe in (("torque_lstm", tq, BYTES_TORQUE_LSTM), ("post_physics", pp, BYTES_POST_ROUGH)):
+        mean_s, med_s = time_kernel(fn, reps, flush)
+        gbs = bpe * n / mean_s / 1e9
+        out[name] = dict(bound="hbm", achieved=round(gbs, 1), peak=peak_gbs, unit="GB/s", frac=round(gbs / peak_gbs, 4),
+                         us_per_launch=round(mean_s * 1e6, 2), median_us=round(med_s * 1e6, 2),
+                         algorithmic_bytes_per_launch=bpe * n)
+    return out
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    from legged_games_gym_b200 import _native as nat
+    N = args.num_envs
+    peak_gbs, peak_src = peaks()
+    env, feeder = make_env(N, dev, env_id_offset=rank * N)
+    actions = feeder.synthetic_actions
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    with ClockSampler(local) as clk:
+        secs, launches = time_steps(env, actions, args.steps, args.warmup, flush, barrier)
+    t = torch.tensor([secs], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    value = world * N * args.steps / secs
+
+    # ---- e2e: sim state in pinned host memory, actions from host, results read back (rank-local, max over ranks)
+    env_h, feeder_h = make_env(N, dev, host_sim=True, env_id_offset=rank * N)
+    h_actions = feeder_h.synthetic_actions.cpu().pin_memory()
+    d_actions = torch.empty_like(feeder_h.synthetic_actions)
+    h_obs = torch.empty(env_h.obs_buf.shape).pin_memory()
+    h_rew = torch.empty(N).pin_memory()
+    h_reset = torch.empty(N, dtype=torch.bool).pin_memory()
+    e2e_steps = max(10, min(args.steps, 200))
+
+    def e2e_step():
+        d_actions.copy_(h_actions, non_blocking=True)
+        obs, _, rew, reset, _ = env_h.step(d_actions)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_reset.copy_(reset, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(5):
+        e2e_step()
+    feeder_h.h2d_bytes = feeder_h.d2h_bytes = 0
+    barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    torch.cuda.synchronize()
+    e2e_secs = torch.tensor([a.elapsed_time(b) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
+    h2d = feeder_h.h2d_bytes // e2e_steps + d_actions.numel() * 4
+    d2h = feeder_h.d2h_bytes // e2e_steps + (h_obs.numel() + h_rew.numel()) * 4 + h_reset.numel()
+    e2e = dict(value=world * N * e2e_steps / float(e2e_secs.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
+               d2h_bytes_per_step=int(d2h), steps=e2e_steps)
+    del env_h, feeder_h
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---- rank 0 extras: per-kernel rooflines, size sweep, CPU baseline
+    roof = kernel_rooflines(env, actions, flush, peak_gbs)
+    sweep = {}
+    if not args.no_sweep and world == 1:
+        for n2 in (16384, 65536):
+            if n2 == N:
+                continue
+            env2, feeder2 = make_env(n2, dev)
+            s2, _ = time_steps(env2, feeder2.synthetic_actions, 100, 10, flush, lambda: None)
+            r2 = kernel_rooflines(env2, feeder2.synthetic_actions, flush, peak_gbs, reps=50)
+            sweep[str(n2)] = dict(value=n2 * 100 / s2, ms_per_step=s2 / 100 * 1e3,
+                                  roofline_torque_lstm=r2["torque_lstm"], roofline_post_physics=r2["post_physics"])
+            del env2, feeder2
+            torch.cuda.empty_cache()
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_arm(N, steps=10, warmup=3)
+    dom = dict(roof["torque_lstm"])
+    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=None)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{TASK}: {N} envs/GPU, 187-point height scan + 4x LSTM actuator-net torques + full reward set "
+                               "+ termination/reset/command resampling + noisy observations (BASELINE.json configs[1])",
+                   "num_envs_per_gpu": N, "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
+                   "timing": "per-step CUDA events on the launch stream, summed; barrier+synchronize both sides",
+                   "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu = cpu_arm(args.num_envs, steps=max(1, args.steps), warmup=max(1, args.warmup))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{TASK}: {args.num_envs} envs, reference algorithm (torch CPU, oracle port pinned bit-exact "
+                                   "to the reference), same step as the GPU arm"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        # bounded: the CPU path takes ~0.1 s per 4096-env step
+        a.steps, a.warmup = min(a.steps, 30), min(a.warmup, 5)
+        reference_arm(a)
+    else:
+        gpu_arm(a)

@@ -468,6 +468,7 @@ class LeggedRobot(BaseTask):
         p.max_episode_length = float(self.max_episode_length)
         p.max_episode_length_s = float(self.max_episode_length_s)
         p.max_push_vel = cfg.domain_rand.max_push_vel_xy
+        self._params = p
         self._refresh_command_ranges()
         o = self.obs_scales
         p.obs_scale_lin_vel, p.obs_scale_ang_vel, p.obs_scale_dof_pos = o.lin_vel, o.ang_vel, o.dof_pos

@@ -59,6 +59,12 @@ def test_rng_normals_close():
 @pytest.mark.parametrize("task,n", [("anymal_c_rough", 64), ("cassie", 100), ("anymal_c_rough", 4096)])
 def test_height_scan_indices_bit_exact(task, n):
     case = harness.build_case(task, n, seed=21)
+    # out-of-field roots exercise the index clip (LR:860-861): far negative, far positive, and huge
+    r = case["state"]["root_states"]
+    r[0, :2] = (-100., -100.)
+    r[1, :2] = (500., 500.)
+    r[2, :2] = (-24.96, 184.93)
+    r[3, :2] = (3.0e9, -3.0e9)
     orc = harness.make_oracle(case)
     want_h = orc.get_heights()
     P = orc.num_height_points
@@ -85,6 +91,7 @@ def test_height_scan_indices_bit_exact(task, n):
     assert np.array_equal(out.cpu().numpy(), want_h.numpy())
     frac_clipped = float(((orc.last_px == 0) | (orc.last_px == hs.shape[0] - 2)).float().mean())
     assert 0.0 < frac_clipped < 0.5       # the clip path is exercised, but not only the clip path
+    assert int(orc.last_py.max()) == hs.shape[1] - 2 and int(orc.last_py.min()) == 0
 
 
 # ---------------------------------------------------------------------------------------------- torques
@@ -295,12 +302,15 @@ def test_policy_act_matches_restated_rsl_rl(n, nobs, hidden):
     eps = torch.from_numpy(philox.normals(seed, step, np.arange(n), 12))
     a, v, lp, mu, sg = orc.act(obs, obs, eps)
     ac.set_rng(seed, step)
-    got_a = ac.act(obs.to(DEV))
-    got_v = ac.evaluate(obs.to(DEV))
+    with torch.inference_mode():      # rollout context of rsl_rl's runner: the fused kernel path
+        o = obs.to(DEV)
+        got_a = ac.act(o)
+        got_v = ac.evaluate(o)
+        got_lp = ac.get_actions_log_prob(got_a)
     torch.cuda.synchronize()
     tol = dict(rtol=1e-3, atol=1e-3)
     assert torch.allclose(ac.action_mean.cpu(), mu, **tol)
     assert torch.allclose(got_a.cpu(), a, **tol)
     assert torch.allclose(got_v.cpu(), v, **tol)
     assert torch.allclose(ac.action_std.cpu(), sg, **tol)
-    assert torch.allclose(ac.get_actions_log_prob(got_a).cpu(), lp, rtol=1e-3, atol=5e-3)
+    assert torch.allclose(got_lp.cpu(), lp, rtol=1e-3, atol=5e-3)

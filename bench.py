@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--tile", type=int, default=0, help="envs per CTA of the fused kernel (0 = auto)")
+    ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
+                    help="rotate: cycle over env replicas whose buffers exceed L2; flush: write 256 MiB between steps")
+    ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
 
 
@@ -129,6 +133,18 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+TILE, USE_GRAPH = 0, True
+
+
+def replica_bytes(env):
+    import torch
+    tot = 0
+    for v in list(vars(env).values()) + list(vars(env.gym).values()):
+        if isinstance(v, torch.Tensor) and v.is_cuda:
+            tot += v.numel() * v.element_size()
+    return tot
+
+
 def make_env(num_envs, device, host_sim=False, env_id_offset=0):
     import copy
     from legged_games_gym_b200.envs import task_registry
@@ -141,7 +157,8 @@ def make_env(num_envs, device, host_sim=False, env_id_offset=0):
     model = model_for_asset(cfg.asset)
     feeder_cls = HostStateFeeder if host_sim else StateFeeder
     feeder = feeder_cls(num_envs, model.num_bodies, model.num_dof, device=device, seed=env_id_offset)
-    cls = task_registry.get_task_class(TASK)
+    base = task_registry.get_task_class(TASK)
+    cls = type(base.__name__ + "Bench", (base,), {"tile_envs": TILE, "use_cuda_graph": USE_GRAPH})
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
               sim_device=device, headless=True, sim_backend=feeder)
     env.env_id_offset = env_id_offset
@@ -150,27 +167,59 @@ def make_env(num_envs, device, host_sim=False, env_id_offset=0):
     return env, feeder
 
 
-def time_steps(env, actions, steps, warmup, flush, dist_barrier):
-    """K steps, each bracketed by CUDA events on the launch stream, L2 flushed between steps (outside the events)."""
+def time_steps(envs, actions, steps, warmup, flush, dist_barrier):
+    """K steps bracketed by CUDA events on the launch stream.  `envs` is a list of independent env replicas stepped
+    round-robin: with more than one replica their combined buffers exceed L2, so every step starts cold without a
+    flush; with one replica the L2 is flushed between steps (outside the per-step events)."""
     import torch
     from legged_games_gym_b200 import _native as nat
     st = torch.cuda.current_stream().cuda_stream
-    for _ in range(warmup):
-        env.step(actions)
-        nat.lib.lgk_l2_flush(flush.data_ptr(), flush.numel(), st)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    rotate = len(envs) > 1
+    for i in range(max(warmup, 3 * len(envs))):
+        envs[i % len(envs)].step(actions[i % len(envs)])
+        if not rotate:
+            nat.lib.lgk_l2_flush(flush.data_ptr(), flush.numel(), st)
     dist_barrier()
     torch.cuda.synchronize()
     l0 = nat.launch_count()
-    for a, b in ev:
+    if rotate:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        env.step(actions)
+        for i in range(steps):
+            envs[i % len(envs)].step(actions[i % len(envs)])
         b.record()
-        nat.lib.lgk_l2_flush(flush.data_ptr(), flush.numel(), st)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        secs = a.elapsed_time(b) / 1e3
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            a.record()
+            envs[0].step(actions[0])
+            b.record()
+            nat.lib.lgk_l2_flush(flush.data_ptr(), flush.numel(), st)
+        torch.cuda.synchronize()
+        secs = sum(a.elapsed_time(b) for a, b in ev) / 1e3
     dist_barrier()
     launches = nat.launch_count() - l0
-    return sum(a.elapsed_time(b) for a, b in ev) / 1e3, launches   # seconds
+    graphed = sum(1 for e in envs if getattr(e, "_graph", None) is not None)
+    if graphed:        # replayed graphs bypass the library's launch counter: 6 kernels per replayed step
+        launches += steps * 6
+    return secs, launches
+
+
+def make_replicas(num_envs, device, env_id_offset, l2_mode):
+    import torch
+    envs, feeders = [], []
+    env, feeder = make_env(num_envs, device, env_id_offset=env_id_offset)
+    envs.append(env); feeders.append(feeder)
+    per = replica_bytes(env)
+    n_rep = 1
+    if l2_mode == "rotate":
+        n_rep = max(2, -(-2 * 126 * (1 << 20) // per))
+        for r in range(1, n_rep):
+            e2, f2 = make_env(num_envs, device, env_id_offset=env_id_offset)
+            envs.append(e2); feeders.append(f2)
+    return envs, feeders, per
 
 
 def time_kernel(fn, reps, flush):
@@ -230,11 +279,18 @@ def gpu_arm(args):
     from legged_games_gym_b200 import _native as nat
     N = args.num_envs
     peak_gbs, peak_src = peaks()
-    env, feeder = make_env(N, dev, env_id_offset=rank * N)
+    global TILE, USE_GRAPH
+    TILE, USE_GRAPH = args.tile, not args.no_graph
+    envs, feeders, per_bytes = make_replicas(N, dev, rank * N, args.l2)
+    env, feeder = envs[0], feeders[0]
     actions = feeder.synthetic_actions
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     with ClockSampler(local) as clk:
-        secs, launches = time_steps(env, actions, args.steps, args.warmup, flush, barrier)
+        secs, launches = time_steps(envs, [f.synthetic_actions for f in feeders], args.steps, args.warmup, flush, barrier)
+    l2_note = (f"inputs larger than L2: {len(envs)} env replicas x {per_bytes / 2**20:.0f} MiB stepped round-robin"
+               if len(envs) > 1 else f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)")
+    del envs[1:], feeders[1:]
+    torch.cuda.empty_cache()
     t = torch.tensor([secs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,12 +346,13 @@ def gpu_arm(args):
         for n2 in (16384, 65536):
             if n2 == N:
                 continue
-            env2, feeder2 = make_env(n2, dev)
-            s2, _ = time_steps(env2, feeder2.synthetic_actions, 100, 10, flush, lambda: None)
+            envs2, feeders2, _ = make_replicas(n2, dev, 0, args.l2)
+            env2, feeder2 = envs2[0], feeders2[0]
+            s2, _ = time_steps(envs2, [f.synthetic_actions for f in feeders2], 100, 10, flush, lambda: None)
             r2 = kernel_rooflines(env2, feeder2.synthetic_actions, flush, peak_gbs, reps=50)
             sweep[str(n2)] = dict(value=n2 * 100 / s2, ms_per_step=s2 / 100 * 1e3,
                                   roofline_torque_lstm=r2["torque_lstm"], roofline_post_physics=r2["post_physics"])
-            del env2, feeder2
+            del env2, feeder2, envs2, feeders2
             torch.cuda.empty_cache()
     cpu = None
     if not args.no_cpu_baseline:
@@ -308,8 +365,8 @@ def gpu_arm(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{TASK}: {N} envs/GPU, 187-point height scan + 4x LSTM actuator-net torques + full reward set "
                                "+ termination/reset/command resampling + noisy observations (BASELINE.json configs[1])",
-                   "num_envs_per_gpu": N, "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
-                   "timing": "per-step CUDA events on the launch stream, summed; barrier+synchronize both sides",
+                   "num_envs_per_gpu": N, "l2": l2_note, "cuda_graph": bool(getattr(env, "_graph", None) is not None),
+                   "timing": "CUDA events on the launch stream around the K steps; barrier+synchronize both sides",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
         "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep,

@@ -102,6 +102,8 @@ typedef struct LgkStepParams {
   int32_t actors_per_env;             /* root_states rows per env (1; 2 in low_level_game, LLG:532) */
   int32_t root_actor_offset;          /* row of the robot inside the env's actor group (prey index) */
   int32_t phase_mask;                 /* LGK_PHASE_* */
+  int32_t tile_envs;                  /* envs per CTA: 0 = auto, or 8 / 16 / 32 */
+  int32_t push_interval;              /* used with step_counter_dev: push when step % interval == 0 (0 = never) */
   int32_t step;                       /* common_step_counter AFTER the += 1 of LR:115 (RNG counter) */
   uint64_t seed;
   int64_t env_id_offset;              /* global id of env 0 (multi-GPU sharding keeps streams disjoint) */
@@ -185,6 +187,11 @@ typedef struct LgkStepParams {
    * per-term sum of episode_sums over the envs reset this step, then reset count, then
    * sum(terrain_levels) over all envs (LR:181-186) */
   float* reset_stats;
+  /* optional device-resident step counter (number of completed steps).  When non-NULL it overrides `step`
+   * (post_physics / finalize(advance=1) use counter+1, reset_idx uses counter) and `do_push` (derived from
+   * push_interval), and finalize(advance=1) stores counter+1: a whole env step then has no per-step host-side
+   * parameter and can be replayed as one CUDA graph. */
+  int32_t* step_counter_dev;
 } LgkStepParams;
 
 int lgk_post_physics(const LgkStepParams* p, void* stream);
@@ -199,7 +206,7 @@ int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int32_t num_id
  * episode_means[slot] = sum/count/max_episode_length_s, episode_means[nslots] = mean terrain level, and a copy
  * of time_out_buf into time_outs_extras; (c) clears the other ping-pong slot of reset_stats. */
 int lgk_finalize_step(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset_count,
-                      float* episode_means, uint8_t* time_outs_extras, void* stream);
+                      float* episode_means, uint8_t* time_outs_extras, int32_t advance, void* stream);
 
 /* ------------------------------------------------------------------ height field (LR:831-869) */
 /* min3[r,c] = min(hs[r,c], hs[r+1,c], hs[r,c+1]) for r<=rows-2, c<=cols-2 (the three samples LR:863-867

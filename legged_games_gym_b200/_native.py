@@ -40,7 +40,8 @@ class LstmWeights(C.Structure):
 class StepParams(C.Structure):
     _fields_ = [
         ("num_envs", i32), ("num_bodies", i32), ("num_obs", i32), ("num_height_points", i32),
-        ("actors_per_env", i32), ("root_actor_offset", i32), ("phase_mask", i32), ("step", i32),
+        ("actors_per_env", i32), ("root_actor_offset", i32), ("phase_mask", i32), ("tile_envs", i32),
+        ("push_interval", i32), ("step", i32),
         ("seed", u64), ("env_id_offset", i64),
         ("heading_command", i32), ("measure_heights", i32), ("terrain_is_plane", i32), ("do_push", i32),
         ("add_noise", i32), ("only_positive_rewards", i32), ("terrain_curriculum", i32), ("custom_origins", i32),
@@ -67,7 +68,8 @@ class StepParams(C.Structure):
         ("env_origins", vp), ("sea_hidden_state", vp), ("sea_cell_state", vp),
         ("base_lin_vel", vp), ("base_ang_vel", vp), ("projected_gravity", vp), ("measured_heights", vp),
         ("obs_buf", vp), ("rew_buf", vp), ("reset_buf", vp), ("time_out_buf", vp),
-        ("height_min3", vp), ("height_points_xy", vp), ("noise_scale_vec", vp), ("reset_stats", vp)]
+        ("height_min3", vp), ("height_points_xy", vp), ("noise_scale_vec", vp), ("reset_stats", vp),
+        ("step_counter_dev", vp)]
 
 
 class PolicyParams(C.Structure):
@@ -96,7 +98,7 @@ def _load():
     lib.lgk_compute_torques.argtypes = [C.POINTER(TorqueParams), vp]
     lib.lgk_post_physics.argtypes = [C.POINTER(StepParams), vp]
     lib.lgk_reset_idx.argtypes = [C.POINTER(StepParams), vp, i32, vp]
-    lib.lgk_finalize_step.argtypes = [C.POINTER(StepParams), vp, vp, vp, vp, vp]
+    lib.lgk_finalize_step.argtypes = [C.POINTER(StepParams), vp, vp, vp, vp, i32, vp]
     lib.lgk_height_min3.argtypes = [vp, vp, i32, i32, vp]
     lib.lgk_height_scan.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, i32, f32, f32, f32, vp, vp, vp, vp]
     lib.lgk_rng_dump.argtypes = [u64, i32, i64, i32, i32, i32, i32, vp, vp]

@@ -19,7 +19,6 @@
 
 namespace lgk {
 
-constexpr int kTile = 32;
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 
@@ -59,12 +58,12 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ------------------------------------------------------------------ shared-memory carve-up (bytes, 16-aligned)
 struct TileLayout {
-  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, pts, yaw, misc, total;
+  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, pts, yaw, h16, hstride, misc, total;
 };
 
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int npts) {
+__host__ __device__ inline TileLayout make_layout(int kTile, int nb, int nfeet, int npts) {
   TileLayout L;
   int o = 0;
   L.root = o;    o += al16(kTile * 13 * 4);
@@ -84,6 +83,8 @@ __host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int npts) {
   L.lrv = o;     o += al16(kTile * 6 * 4);
   L.pts = o;     o += al16((npts > 0 ? npts : 1) * 2 * 4);
   L.yaw = o;     o += al16(kTile * 4 * 4);
+  L.hstride = (npts + 7) & ~7;                       // int16 samples per env row
+  L.h16 = o;     o += al16(kTile * (L.hstride > 0 ? L.hstride : 8) * 2);
   L.misc = o;    o += 64;   // mbarrier (8 B) + chunk counter + reset mask
   L.total = o;
   return L;
@@ -111,9 +112,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------ the kernel
+template <int kTile>
 __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_constant__ LgkStepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const TileLayout L = make_layout(p.num_bodies, p.num_feet, p.num_height_points);
+  const TileLayout L = make_layout(kTile, p.num_bodies, p.num_feet, p.num_height_points);
   float* s_root = reinterpret_cast<float*>(smem + L.root);
   float* s_dof = reinterpret_cast<float*>(smem + L.dof);
   float* s_contact = reinterpret_cast<float*>(smem + L.contact);
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
   float* s_lrv = reinterpret_cast<float*>(smem + L.lrv);
   float* s_pts = reinterpret_cast<float*>(smem + L.pts);
   YawFrame* s_yaw = reinterpret_cast<YawFrame*>(smem + L.yaw);
+  int16_t* s_h16 = reinterpret_cast<int16_t*>(smem + L.h16);
+  const int HS = L.hstride;
   Misc* misc = reinterpret_cast<Misc*>(smem + L.misc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,8 +144,10 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
   const bool pre = (p.phase_mask & LGK_PHASE_PRE) != 0, post = (p.phase_mask & LGK_PHASE_POST) != 0;
   const bool fat_active = p.reward_active[LGK_R_FEET_AIR_TIME] != 0 && F > 0;
   // bulk (TMA) path needs a full tile (sizes are then multiples of 16 B) and unit root stride
-  const bool bulk = (nval == kTile) && (p.actors_per_env == 1);
-  const RngKey key = make_key(p.seed, p.step);
+  const bool bulk = (nval == kTile) && (p.actors_per_env == 1) && ((kTile * F) % 16 == 0);
+  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
+  const bool do_push = p.step_counter_dev ? (p.push_interval > 0 && step_eff % p.push_interval == 0) : (p.do_push != 0);
+  const RngKey key = make_key(p.seed, step_eff);
 
   // ---------------- stage the tile
   if (tid == 0) {
@@ -202,26 +208,44 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
   __syncthreads();
 
   // ---------------- height scan: dynamic 32-point chunks (env e, points 32c..32c+31)
+  // one work item = one env: all ceil(P/32) point chunks of the env are indexed first, then their gathers are
+  // issued back to back (memory-level parallelism), then stored.  Items are claimed dynamically so warp 0 can
+  // join after its scalar phase.
   auto height_scan = [&]() {
+    constexpr int kMaxChunks = 8;                       // P <= 256
     const int cpe = (P + 31) >> 5;
-    const int nchunks = nval * cpe;
     while (true) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(&misc->chunk_counter, 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      if (c >= nchunks) break;
-      const int e = c / cpe, j = ((c - e * cpe) << 5) + lane;
-      if (j < P) {
-        int ix, iy;
-        height_index(s_yaw[e], s_pts[2 * j], s_pts[2 * j + 1], p.border_size, p.horizontal_scale, p.hf_rows,
-                     p.hf_cols, ix, iy);
-        const int16_t h = __ldg(p.height_min3 + (size_t)ix * p.hf_cols + iy);
-        p.measured_heights[(size_t)(env0 + e) * P + j] = f_mul((float)h, p.vertical_scale);   // LR:869
+      int e = 0;
+      if (lane == 0) e = atomicAdd(&misc->chunk_counter, 1);
+      e = __shfl_sync(0xffffffffu, e, 0);
+      if (e >= nval) break;
+      const YawFrame yf = s_yaw[e];
+      int off[kMaxChunks];
+#pragma unroll
+      for (int c = 0; c < kMaxChunks; ++c) {
+        const int j = (c << 5) + lane;
+        off[c] = -1;
+        if (c < cpe && j < P) {
+          int ix, iy;
+          height_index(yf, s_pts[2 * j], s_pts[2 * j + 1], p.border_size, p.horizontal_scale, p.hf_rows, p.hf_cols, ix, iy);
+          off[c] = ix * p.hf_cols + iy;
+        }
+      }
+      int16_t h[kMaxChunks];
+#pragma unroll
+      for (int c = 0; c < kMaxChunks; ++c) h[c] = off[c] >= 0 ? __ldg(p.height_min3 + off[c]) : (int16_t)0;
+#pragma unroll
+      for (int c = 0; c < kMaxChunks; ++c) {
+        if (off[c] >= 0) {
+          const int j = (c << 5) + lane;
+          s_h16[e * HS + j] = h[c];
+          p.measured_heights[(size_t)(env0 + e) * P + j] = f_mul((float)h[c], p.vertical_scale);   // LR:869
+        }
       }
     }
   };
   if (pre && p.measure_heights && p.terrain_is_plane)      // LR:844-845: zeros
-    for (int i = tid; i < nval * P; i += kThreads) p.measured_heights[(size_t)env0 * P + i] = 0.f;
+    for (int i = tid; i < nval * P; i += kThreads) { p.measured_heights[(size_t)env0 * P + i] = 0.f; s_h16[(i / P) * HS + (i % P)] = 0; }
   if (heights_first) {
     height_scan();
     __syncthreads();
@@ -245,13 +269,13 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
         float mh = 0.f;
         if (p.reward_active[LGK_R_BASE_HEIGHT]) {        // mean_p(z - h_p), LR:886
           if (p.measure_heights) {
-            for (int j = 0; j < P; ++j) mh += root[2] - p.measured_heights[(size_t)env * P + j];
+            for (int j = 0; j < P; ++j) mh += root[2] - f_mul((float)s_h16[e * HS + j], p.vertical_scale);
             mh /= (float)P;
           } else {
             mh = root[2];                                 // measured_heights is the int 0 (LR:562)
           }
         }
-        env_pre(p, key, genv, root, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12, s_lact + e * 12,
+        env_pre(p, do_push, key, genv, root, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12, s_lact + e * 12,
                 s_ldv + e * 12, cmd, fat, lc, sums, N, p.episode_length_buf[env], mh, s);
         s_blv[3 * e] = s.blv.x; s_blv[3 * e + 1] = s.blv.y; s_blv[3 * e + 2] = s.blv.z;
         s_bav[3 * e] = s.bav.x; s_bav[3 * e + 1] = s.bav.y; s_bav[3 * e + 2] = s.bav.z;
@@ -282,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
     const uint32_t rmask = __ballot_sync(0xffffffffu, valid && s.reset && post);
     // extras["episode"] sums over the reset set + zeroing (LR:179-183), terrain-level mean (LR:186)
     if (post) {
-      float* stats = p.reset_stats + (size_t)(p.step & 1) * (p.num_reward_slots + 2);
+      float* stats = p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2);
       if (rmask != 0) {
         for (int k = 0; k < p.num_reward_slots; ++k) {
           float v = 0.f;
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
         bulk_s2g(p.base_lin_vel + (size_t)env0 * 3, s_blv, kTile * 3 * 4);
         bulk_s2g(p.base_ang_vel + (size_t)env0 * 3, s_bav, kTile * 3 * 4);
         bulk_s2g(p.projected_gravity + (size_t)env0 * 3, s_pg, kTile * 3 * 4);
-        if (p.do_push && !post) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
+        if (do_push && !post) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
       }
       if (pre || post) bulk_s2g(p.commands + (size_t)env0 * 4, s_cmd, kTile * 4 * 4);
       if (fat_active || (post && F > 0)) {
@@ -322,7 +346,7 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
         bulk_s2g(p.last_actions + (size_t)env0 * 12, s_act, kTile * 12 * 4);
         bulk_s2g(p.last_dof_vel + (size_t)env0 * 12, s_ldv, kTile * 12 * 4);
         bulk_s2g(p.last_root_vel + (size_t)env0 * 6, s_lrv, kTile * 6 * 4);
-        if (p.do_push && pre) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
+        if (do_push && pre) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
       }
       bulk_commit();
     }
@@ -342,7 +366,7 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
       copy_f32(p.last_dof_vel + (size_t)env0 * 12, s_ldv, nval * 12, tid);
       copy_f32(p.last_root_vel + (size_t)env0 * 6, s_lrv, nval * 6, tid);
     }
-    if (p.do_push) {
+    if (do_push) {
       for (int i = tid; i < nval * 13; i += kThreads) {
         const int e = i / 13, c = i - e * 13;
         if (c == 7 || c == 8)
@@ -392,7 +416,7 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
           if (j < O) {
             float v;
             if (j < 48) v = s_head[e * 48 + j];
-            else v = hcols ? obs_height_col(p, rz, hrow[j - 48]) : 0.f;
+            else v = !hcols ? 0.f : obs_height_col(p, rz, pre ? f_mul((float)s_h16[e * HS + (j - 48)], p.vertical_scale) : hrow[j - 48]);
             orow[j] = obs_finish(p, v, p.add_noise ? __ldg(p.noise_scale_vec + j) : 0.f, pick(r, k));
           }
         }
@@ -413,7 +437,8 @@ __global__ void __launch_bounds__(128) reset_idx_kernel(const __grid_constant__ 
   const bool live = i < n;
   const int env = live ? (int)ids[i] : 0;
   const int N = p.num_envs, F = p.num_feet;
-  const RngKey key = make_key(p.seed, p.step);
+  const int step_eff = p.step_counter_dev ? *p.step_counter_dev : p.step;
+  const RngKey key = make_key(p.seed, step_eff);
   const size_t rrow = ((size_t)env * p.actors_per_env + p.root_actor_offset) * 13;
   if (live) {
     if (lane < 13) s_root[w][lane] = p.root_states[rrow + lane];
@@ -429,7 +454,7 @@ __global__ void __launch_bounds__(128) reset_idx_kernel(const __grid_constant__ 
     p.reset_buf[env] = 1;                                   // LR:177
   }
   __syncwarp();
-  float* stats = p.reset_stats + (size_t)(p.step & 1) * (p.num_reward_slots + 2);
+  float* stats = p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2);
   if (live) {
     if (lane < 13) p.root_states[rrow + lane] = s_root[w][lane];
     if (lane < 24) p.dof_state[(size_t)env * 24 + lane] = s_dof[w][lane];
@@ -458,7 +483,8 @@ __global__ void terrain_level_sum_kernel(const __grid_constant__ LgkStepParams p
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.num_envs; i += gridDim.x * blockDim.x)
     v += (float)p.terrain_levels[i];
   v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) atomicAdd(p.reset_stats + (size_t)(p.step & 1) * (p.num_reward_slots + 2) + p.num_reward_slots + 1, v);
+  const int step_eff = p.step_counter_dev ? *p.step_counter_dev : p.step;
+  if ((threadIdx.x & 31) == 0) atomicAdd(p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2) + p.num_reward_slots + 1, v);
 }
 
 // ------------------------------------------------------------------ finalize: id compaction + extras
@@ -466,7 +492,7 @@ __global__ void terrain_level_sum_kernel(const __grid_constant__ LgkStepParams p
 // covers 16384 envs; ids come out in ascending order like reset_buf.nonzero() (LR:128).
 __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ LgkStepParams p, int32_t* reset_ids,
                                                         int32_t* reset_count, float* episode_means,
-                                                        uint8_t* time_outs_extras) {
+                                                        uint8_t* time_outs_extras, int advance) {
   __shared__ int s_warp[32];
   __shared__ int s_base, s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -510,8 +536,9 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ 
   }
   const int count = s_base;
   const int ns = p.num_reward_slots;
-  float* cur = p.reset_stats + (size_t)(p.step & 1) * (ns + 2);
-  float* other = p.reset_stats + (size_t)((p.step + 1) & 1) * (ns + 2);
+  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + (advance ? 1 : 0)) : p.step;
+  float* cur = p.reset_stats + (size_t)(step_eff & 1) * (ns + 2);
+  float* other = p.reset_stats + (size_t)((step_eff + 1) & 1) * (ns + 2);
   if (tid == 0 && reset_count) *reset_count = count;
   if (count > 0) {     // the reference refreshes extras only inside reset_idx with a non-empty id list
     if (episode_means) {
@@ -522,6 +549,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ 
       for (int i = tid; i < N; i += 1024) time_outs_extras[i] = p.time_out_buf[i];
   }
   for (int k = tid; k < ns + 2; k += 1024) other[k] = 0.f;
+  if (advance && p.step_counter_dev && tid == 0) *p.step_counter_dev = step_eff;
 }
 
 }  // namespace lgk
@@ -562,20 +590,33 @@ static int validate_step(const LgkStepParams* p) {
   return LGK_OK;
 }
 
-extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
-  if (int rc = validate_step(p)) return rc;
-  LGK_REQUIRE((p->phase_mask & (LGK_PHASE_PRE | LGK_PHASE_POST)) != 0, "phase_mask selects nothing");
-  const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_height_points);
+template <int kTile>
+static int launch_post_physics(const LgkStepParams* p, cudaStream_t st) {
+  const TileLayout L = make_layout(kTile, p->num_bodies, p->num_feet, p->num_height_points);
   static int smem_set = 0;
   if (L.total > smem_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(post_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
+    if (int rc = check_cuda(cudaFuncSetAttribute(post_physics_kernel<kTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
                             "cudaFuncSetAttribute(post_physics_kernel)")) return rc;
     smem_set = L.total;
   }
   const int tiles = (p->num_envs + kTile - 1) / kTile;
-  post_physics_kernel<<<tiles, kThreads, L.total, (cudaStream_t)stream>>>(*p);
+  post_physics_kernel<kTile><<<tiles, kThreads, L.total, st>>>(*p);
   count_launch();
   return check_cuda(cudaGetLastError(), "post_physics_kernel launch");
+}
+
+extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
+  if (int rc = validate_step(p)) return rc;
+  LGK_REQUIRE((p->phase_mask & (LGK_PHASE_PRE | LGK_PHASE_POST)) != 0, "phase_mask selects nothing");
+  LGK_REQUIRE(p->num_height_points <= 256, "at most 256 height points");
+  int tile = p->tile_envs;
+  if (tile == 0) tile = p->num_envs <= 16384 ? 8 : 16;     // small batches: more, shorter CTAs (latency-bound regime)
+  switch (tile) {
+    case 8: return launch_post_physics<8>(p, (cudaStream_t)stream);
+    case 16: return launch_post_physics<16>(p, (cudaStream_t)stream);
+    case 32: return launch_post_physics<32>(p, (cudaStream_t)stream);
+    default: return set_error(LGK_ERR_ARG, "tile_envs must be 0 (auto), 8, 16 or 32");
+  }
 }
 
 extern "C" int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int32_t num_ids, void* stream) {
@@ -593,9 +634,9 @@ extern "C" int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int
 }
 
 extern "C" int lgk_finalize_step(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset_count,
-                                 float* episode_means, uint8_t* time_outs_extras, void* stream) {
+                                 float* episode_means, uint8_t* time_outs_extras, int32_t advance, void* stream) {
   if (int rc = validate_step(p)) return rc;
-  finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*p, reset_ids, reset_count, episode_means, time_outs_extras);
+  finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*p, reset_ids, reset_count, episode_means, time_outs_extras, advance);
   count_launch();
   return check_cuda(cudaGetLastError(), "finalize_kernel launch");
 }

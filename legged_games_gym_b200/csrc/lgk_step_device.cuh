@@ -23,7 +23,7 @@ struct EnvScalars {
 // reward sum.  root/dof/contact/... are the env's rows inside the staged tile (read+write).
 // `sums` points at episode_sums[0*N + env]; row stride = num_envs.
 // `mean_height_err` = mean_p(z - h_p) when the base_height term is active, else unused.
-LGK_HD void env_pre(const LgkStepParams& p, const RngKey& key, uint32_t genv, float* root, const float* dof,
+LGK_HD void env_pre(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, float* root, const float* dof,
                     const float* contact, const float* act, const float* tq, const float* lact,
                     const float* ldv, float* cmd, float* fat, uint8_t* lc, float* sums, int sums_stride,
                     long long ep_in, float mean_height_err, EnvScalars& o) {
@@ -39,7 +39,7 @@ LGK_HD void env_pre(const LgkStepParams& p, const RngKey& key, uint32_t genv, fl
     const float h = heading_of(qx, qy, qz, qw);
     cmd[2] = clampf(0.5f * wrap_to_pi(cmd[3] - h), -1.f, 1.f);
   }
-  if (p.do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
+  if (do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
     const U4 r = rng_block(key, genv, LGK_STREAM_PUSH, 0);
     const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
     root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));

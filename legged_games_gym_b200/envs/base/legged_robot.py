@@ -47,6 +47,22 @@ def _stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _Extras(dict):
+    """extras dict whose "episode" entry is produced on read (see LeggedRobot._finalize)."""
+
+    def arm_episode(self, producer):
+        self._producer = producer
+        dict.__setitem__(self, "episode", None)
+
+    def __getitem__(self, key):
+        if key == "episode" and getattr(self, "_producer", None) is not None and dict.__getitem__(self, key) is None:
+            return self._producer()
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+
 class LeggedRobot(BaseTask):
     _FUSED_HOOKS = ("check_termination", "_post_physics_step_callback", "compute_reward", "_resample_commands",
                     "_push_robots", "_reset_dofs", "_reset_root_states", "_update_terrain_curriculum")
@@ -74,6 +90,32 @@ class LeggedRobot(BaseTask):
 
     # ------------------------------------------------------------------ LR:80-104
     def step(self, actions):
+        if self._graph_ok and not self._needs_host_logic_next_step():
+            return self._step_graphed(actions)
+        return self._step_eager(actions)
+
+    def _needs_host_logic_next_step(self):
+        return bool(self.cfg.commands.curriculum) and ((self.common_step_counter + 1) % self.max_episode_length == 0)
+
+    def _step_graphed(self, actions):
+        """The whole step (4 torque launches, fused post-physics, finalize) replayed as ONE CUDA graph: every
+        per-step parameter (step counter, push flag) lives in device memory, so nothing is patched between replays."""
+        self._actions_in.copy_(actions, non_blocking=True)
+        if self._graph is None:
+            if self._eager_steps < 1:              # first step eager: sets kernel attributes, warms the allocator
+                self._eager_steps += 1
+                return self._step_eager(self._actions_in)
+            g = torch.cuda.CUDAGraph()
+            counter = self.common_step_counter
+            with torch.cuda.graph(g):
+                self._step_eager(self._actions_in)
+            self.common_step_counter = counter     # capture ran the Python side once without executing kernels
+            self._graph = g
+        self._graph.replay()
+        self.common_step_counter += 1
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _step_eager(self, actions):
         clip_actions = self.cfg.normalization.clip_actions
         gym = self.gym
         native_tq = self._native_torques
@@ -108,9 +150,8 @@ class LeggedRobot(BaseTask):
         gym.refresh_net_contact_force_tensor()
         self.common_step_counter += 1          # episode_length_buf += 1 happens in the kernel (LR:114)
         p = self._params
-        p.step = self.common_step_counter & 0x7FFFFFFF
         dr = self.cfg.domain_rand
-        p.do_push = int(bool(dr.push_robots) and (self.common_step_counter % dr.push_interval == 0))
+        do_push = bool(dr.push_robots) and (self.common_step_counter % dr.push_interval == 0)   # device derives the same
         if self.reset_buf.dtype != torch.bool:     # first step: long ones -> persistent bool buffer
             self.reset_buf = self._reset_bool
         st = _stream_ptr()
@@ -131,8 +172,8 @@ class LeggedRobot(BaseTask):
         else:
             p.phase_mask = nat.PHASE_PRE | nat.PHASE_POST
             nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics")
-        self._finalize(st)
-        if p.do_push:
+        self._finalize(st, advance=1)
+        if do_push:
             gym.set_actor_root_state_tensor(self.root_states)
         gym.set_dof_state_tensor_indexed(self.dof_state, self.reset_env_ids, self.reset_count)
         gym.set_actor_root_state_tensor_indexed(self.root_states, self.reset_env_ids, self.reset_count)
@@ -141,21 +182,25 @@ class LeggedRobot(BaseTask):
             clip_obs = self.cfg.normalization.clip_observations
             self.obs_buf = torch.clip(self.obs_buf, -clip_obs, clip_obs)
 
-    def _finalize(self, st):
+    def _finalize(self, st, advance=0):
         nat.check(nat.lib.lgk_finalize_step(C.byref(self._params), self.reset_env_ids.data_ptr(),
                                             self.reset_count.data_ptr(), self._episode_means.data_ptr(),
-                                            self._time_outs_extras.data_ptr(), st), "lgk_finalize_step")
+                                            self._time_outs_extras.data_ptr(), advance, st), "lgk_finalize_step")
         # extras are refreshed only when something was reset (LR:157-158, 179-191): the kernel keeps the previous
-        # values otherwise.  One snapshot per step so that references a runner keeps stay valid.
+        # values otherwise.  extras["episode"] is materialised (one clone of the means vector) when it is READ, so a
+        # runner that keeps the dicts of several steps gets distinct tensors and a step that nobody logs costs nothing.
+        self.extras.arm_episode(self._episode_snapshot)
+        if self.cfg.env.send_timeouts:
+            dict.__setitem__(self.extras, "time_outs", self._time_outs_extras)
+
+    def _episode_snapshot(self):
         means = self._episode_means.clone()
         ep = {"rew_" + k: means[i] for i, k in enumerate(self._sum_names)}
         if self.cfg.terrain.curriculum:
             ep["terrain_level"] = means[len(self._sum_names)]
         if self.cfg.commands.curriculum:
             ep["max_command_x"] = self.command_ranges["lin_vel_x"][1]
-        self.extras["episode"] = ep
-        if self.cfg.env.send_timeouts:
-            self.extras["time_outs"] = self._time_outs_extras
+        return ep
 
     # ------------------------------------------------------------------ stages that live in the kernel
     def check_termination(self):
@@ -190,7 +235,6 @@ class LeggedRobot(BaseTask):
         if self.cfg.commands.curriculum and (self.common_step_counter % self.max_episode_length == 0):
             self.update_command_curriculum(env_ids)
         p = self._params
-        p.step = self.common_step_counter & 0x7FFFFFFF
         if self.reset_buf.dtype != torch.bool:
             self.reset_buf = self._reset_bool
             self.reset_buf.fill_(True)
@@ -200,7 +244,7 @@ class LeggedRobot(BaseTask):
             p.terrain_curriculum = 0            # "don't change on initial reset" (LR:453-455)
         nat.check(nat.lib.lgk_reset_idx(C.byref(p), env_ids.data_ptr(), int(env_ids.numel()), st), "lgk_reset_idx")
         p.terrain_curriculum = saved
-        self._finalize(st)
+        self._finalize(st, advance=0)
         self.gym.set_dof_state_tensor_indexed(self.dof_state, self.reset_env_ids, self.reset_count)
         self.gym.set_actor_root_state_tensor_indexed(self.root_states, self.reset_env_ids, self.reset_count)
 
@@ -341,7 +385,7 @@ class LeggedRobot(BaseTask):
         self.base_quat = self.root_states[self._root_rows(), 3:7]
         self.contact_forces = net_contact_forces.view(N, -1, 3)
         self.common_step_counter = 0
-        self.extras = {}
+        self.extras = _Extras()
         self.noise_scale_vec = self._get_noise_scale_vec(self.cfg).contiguous()
         self.gravity_vec = torch.tensor([0., 0., -1.], device=dev).repeat((N, 1))
         self.forward_vec = torch.tensor([1., 0., 0.], device=dev).repeat((N, 1))
@@ -387,6 +431,9 @@ class LeggedRobot(BaseTask):
         self._time_outs_extras = z(N, dt=torch.bool)
         self.reset_env_ids = z(N, dt=torch.int32)
         self.reset_count = z(1, dt=torch.int32)
+        self._step_counter_dev = z(1, dt=torch.int32)      # completed steps, advanced by lgk_finalize_step
+        self._actions_in = z(N, self.num_actions)          # staging for the graph-replayed step
+        self._graph, self._eager_steps = None, 0
 
     def _root_rows(self):
         return slice(None)
@@ -424,6 +471,10 @@ class LeggedRobot(BaseTask):
         cls = type(self)
         self._native_torques = getattr(cls._compute_torques, "_lgk_native", False)
         self._obs_overridden = cls.compute_observations is not LeggedRobot.compute_observations
+        # whole-step CUDA graph: needs the native torque path, no torch-written reward terms, the built-in
+        # observations and a sim backend whose hooks enqueue nothing between the kernels
+        self._graph_ok = (self._native_torques and not self._python_reward_names and not self._obs_overridden
+                          and getattr(self.gym, "graph_safe", False) and getattr(self, "use_cuda_graph", True))
         f = lambda t: [float(x) for x in t.detach().flatten().cpu().tolist()]
         # ---- torques (LR:371-395)
         tp = nat.TorqueParams()
@@ -515,6 +566,10 @@ class LeggedRobot(BaseTask):
         p.reset_buf, p.time_out_buf = ptr(self._reset_bool), ptr(self.time_out_buf)
         p.noise_scale_vec = ptr(self.noise_scale_vec)
         p.reset_stats = ptr(self._reset_stats)
+        p.step_counter_dev = ptr(self._step_counter_dev)
+        dr = cfg.domain_rand
+        p.push_interval = int(dr.push_interval) if dr.push_robots else 0
+        p.tile_envs = int(getattr(self, "tile_envs", 0))
         if mh:
             p.measured_heights = ptr(self.measured_heights)
             if not p.terrain_is_plane:

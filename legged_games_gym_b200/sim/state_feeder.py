@@ -95,6 +95,7 @@ class SimBackend:
 
 class StateFeeder(SimBackend):
     """Device-resident synthetic state (inputs already in HBM when a step starts)."""
+    graph_safe = True       # its hooks enqueue no work, so a whole env step can be captured into one CUDA graph
 
     def __init__(self, num_envs, num_bodies, num_dof=12, device="cuda", seed=0, p_contact=0.3,
                  actors_per_env=1):
@@ -117,6 +118,8 @@ class StateFeeder(SimBackend):
 
 
 class HostStateFeeder(StateFeeder):
+    graph_safe = False
+
     """Sim state lives in pinned host memory (the reference's ``sim_device=cpu`` pipeline: PhysX
     results are host tensors).  refresh_* = H2D copy; set_* = D2H copy.  Byte counters feed bench.py's
     ``e2e.h2d_bytes_per_step`` / ``d2h_bytes_per_step``."""

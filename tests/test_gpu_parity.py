@@ -167,6 +167,33 @@ def test_env_step_matches_oracle(task, n, ov):
         harness.apply_noise(st_gpu, noise)
 
 
+@pytest.mark.parametrize("task,n,tile", [("anymal_c_rough", 300, 8), ("anymal_c_rough", 300, 16), ("anymal_c_rough", 300, 32),
+                                         ("cassie", 77, 32), ("a1", 1000, 16)])
+def test_env_step_cuda_graph_and_tiles(task, n, tile):
+    """Same parity bar with the whole step replayed as one CUDA graph (device-side step counter) and for every
+    tile size of the fused kernel; pushes every 2nd step so the device-derived push flag is exercised."""
+    ov = {"domain_rand.push_interval_s": 0.04}
+    case = harness.build_case(task, n, seed=6, overrides=ov)
+    st_or = harness.torch_state(case)
+    orc = harness.make_oracle(case, st_or)
+    env, feeder = product_env(case, graph=True, tile=tile)
+    assert env._graph_ok
+    st_gpu = feeder_state(feeder)
+    for step in range(1, 8):
+        tables = harness.step_tables(case["seed"], step, n, orc.num_obs)
+        acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (n, 12)).astype(np.float32))
+        orc.step(acts.clone(), tables)
+        env.step(acts.to(DEV))
+        torch.cuda.synchronize()
+        assert int(env._step_counter_dev.item()) == step == env.common_step_counter
+        assert_snapshots_close(harness.snapshot(env), harness.snapshot(orc), step,
+                               atol_scale={"torques": max(1.0, float(orc.torques.abs().max()))})
+        noise = harness.make_noise(case, step, 5)
+        harness.apply_noise(st_or, noise)
+        harness.apply_noise(st_gpu, noise)
+    assert env._graph is not None
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_env_step_matches_reference_fixture(name):
     spec = CASES[name]

@@ -9,12 +9,14 @@ import torch
 from oracle import harness
 
 
-def product_env(case, device="cuda:0"):
+def product_env(case, device="cuda:0", graph=False, tile=0):
     from legged_games_gym_b200.envs import task_registry
     from legged_games_gym_b200.sim.state_feeder import SimBackend
     from legged_games_gym_b200.utils.helpers import SimParams
 
     class ExplicitFeeder(SimBackend):
+        graph_safe = graph
+
         def __init__(self, st):
             self.root_states = torch.from_numpy(st["root_states"].copy()).to(device)
             self.dof_state = torch.from_numpy(st["dof_state"].copy()).to(device)
@@ -39,6 +41,8 @@ def product_env(case, device="cuda:0"):
                                         tot_cols=hs.shape[1], env_origins=case["terrain_origins"])
     cls = task_registry.get_task_class(case["task"])
     feeder = ExplicitFeeder(case["state"])
+    if tile:
+        cls = type(cls.__name__ + f"Tile{tile}", (cls,), {"tile_envs": tile})
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
               sim_device=device, headless=True, sim_backend=feeder, terrain=terrain,
               init_terrain_levels=case["init_levels"])

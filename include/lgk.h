@@ -132,6 +132,8 @@ typedef struct LgkStepParams {
   float tracking_sigma, base_height_target, max_contact_force;
   float soft_dof_vel_limit, soft_torque_limit;
   float border_size, horizontal_scale, vertical_scale;   /* LR:856-857, 869 */
+  float horizontal_scale_recip;       /* RN(1/horizontal_scale) when the FMA division is proven exact for that scale
+                                         (oracle/divcheck.c: 0.1f, 0.05f, 0.25f); 0 = use IEEE division */
   int32_t hf_rows, hf_cols;           /* height_samples.shape */
   float half_env_length;              /* terrain.env_length / 2 (LR:458) */
   int32_t max_terrain_level;          /* LR:766 */

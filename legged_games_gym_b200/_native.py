@@ -52,7 +52,7 @@ class StepParams(C.Structure):
         ("obs_scale_dof_vel", f32), ("obs_scale_height", f32), ("clip_obs", f32),
         ("tracking_sigma", f32), ("base_height_target", f32), ("max_contact_force", f32),
         ("soft_dof_vel_limit", f32), ("soft_torque_limit", f32),
-        ("border_size", f32), ("horizontal_scale", f32), ("vertical_scale", f32),
+        ("border_size", f32), ("horizontal_scale", f32), ("vertical_scale", f32), ("horizontal_scale_recip", f32),
         ("hf_rows", i32), ("hf_cols", i32), ("half_env_length", f32), ("max_terrain_level", i32),
         ("terrain_num_cols", i32),
         ("default_dof_pos", f32 * NUM_DOF), ("dof_pos_lo", f32 * NUM_DOF), ("dof_pos_hi", f32 * NUM_DOF),

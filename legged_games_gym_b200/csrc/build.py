@@ -16,13 +16,16 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "--expt-relaxed-constexpr"]
 
 
+PER_FILE_FLAGS = {}
+
+
 def _digest():
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:
         p = os.path.join(HERE, f)
         if os.path.exists(p):
             h.update(open(p, "rb").read())
-    h.update(" ".join(FLAGS).encode())
+    h.update((" ".join(FLAGS) + repr(sorted(PER_FILE_FLAGS.items()))).encode())
     return h.hexdigest()
 
 
@@ -39,7 +42,8 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(HERE, "build", os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = PER_FILE_FLAGS.get(os.path.basename(s), [])
+        cmd = [nvcc] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, pr in procs:
         out, _ = pr.communicate()

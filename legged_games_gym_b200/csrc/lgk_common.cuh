@@ -31,6 +31,18 @@ LGK_HD float f_sqrt(float a) { return sqrtf(a); }
 LGK_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
 
+#if defined(__CUDACC__)
+// ---- Blackwell packed-fp32 (f32x2) helpers: one issue slot, two individually IEEE-rounded fp32 results
+namespace lgk {
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f2_t r, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+}  // namespace lgk
+#endif
+
 namespace lgk {
 
 constexpr int kWarp = 32;

@@ -61,15 +61,69 @@ LGK_HD void height_index(const YawFrame& f, float bx, float by, float border, fl
   px = f_add(f_add(px, f.rx), border);            // + root pos (LR:853-854), + border_size (LR:856)
   py = f_add(f_add(py, f.ry), border);
   const float qx = f_div(px, hscale), qy = f_div(py, hscale);   // LR:857, then .long() = trunc
+  // x86 float->int64 conversion (what .long() compiles to) returns INT64_MIN for NaN, inf and |q| >= 2^63; the
+  // clip then maps those to 0.  In-range values saturate harmlessly to int32 before the same clip.
 #if defined(__CUDA_ARCH__)
-  ix = __float2int_rz(qx); iy = __float2int_rz(qy);             // saturating; NaN -> 0
+  ix = qx < 9.2233720368547758e18f ? __float2int_rz(qx) : 0;    // saturating; NaN -> 0
+  iy = qy < 9.2233720368547758e18f ? __float2int_rz(qy) : 0;
 #else
-  ix = (qx != qx) ? 0 : (qx >= 2147483520.f ? 2147483647 : (qx <= -2147483648.f ? (-2147483647 - 1) : (int)qx));
-  iy = (qy != qy) ? 0 : (qy >= 2147483520.f ? 2147483647 : (qy <= -2147483648.f ? (-2147483647 - 1) : (int)qy));
+  ix = (qx != qx || qx >= 9.2233720368547758e18f) ? 0 : (qx >= 2147483520.f ? 2147483647 : (qx <= -2147483648.f ? (-2147483647 - 1) : (int)qx));
+  iy = (qy != qy || qy >= 9.2233720368547758e18f) ? 0 : (qy >= 2147483520.f ? 2147483647 : (qy <= -2147483648.f ? (-2147483647 - 1) : (int)qy));
 #endif
   ix = ix < 0 ? 0 : (ix > rows - 2 ? rows - 2 : ix);            // LR:860-861
   iy = iy < 0 ? 0 : (iy > cols - 2 ? cols - 2 : iy);
 }
+
+#if defined(__CUDACC__)
+// ---- packed variant of the index path (device only).  Same individually-rounded fp32 operations as
+// height_index(), issued two-at-a-time as f32x2 instructions (x and y coordinate in one register pair), and the
+// IEEE division by the horizontal scale c replaced by the FMA sequence  q0 = x*r; q = fma(fma(-q0, c, x), r, q0)
+// with r = RN(1/c), which oracle/divcheck.c proves bit-identical to x / c for EVERY fp32 x in [1e-20, 1e20) for
+// c in {0.1f, 0.05f, 0.25f} (outside that range the clipped index is 0 or rows-2 either way).
+struct YawFrame2 {
+  f2_t T;    // (-2zn, +2zn): times (by, bx) gives (t0, t1)
+  f2_t Ts;   // (+2zn, -2zn): times (bx, by) gives (t1, t0)
+  f2_t W;    // (wn, wn)
+  f2_t Zn;   // (-zn, +zn)
+  f2_t R;    // (root_x, root_y)
+};
+
+__device__ __forceinline__ YawFrame2 yaw_frame2(const YawFrame& f) {
+  const float z2 = f_mul(f.zn, 2.0f);      // exact doubling: fl(2zn*b) == 2*fl(zn*b)
+  return YawFrame2{pack2(-z2, z2), pack2(z2, -z2), pack2(f.wn, f.wn), pack2(-f.zn, f.zn), pack2(f.rx, f.ry)};
+}
+
+// B = (bx, by), Bs = (by, bx)
+template <bool kRecipDiv>
+__device__ __forceinline__ void height_index2(const YawFrame2& f, f2_t B, f2_t Bs, float border, float hscale,
+                                              float hrecip, float one, int rows, int cols, int& ix, int& iy) {
+  const f2_t T = mul2(f.T, Bs);                 // (t0, t1) = (-(2zn*by), 2zn*bx)
+  const f2_t Tsw = mul2(f.Ts, B);               // (t1, t0)
+  // (bx + wn*t0) + (-(zn*t1)),  (by + wn*t1) + zn*t0.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it
+  // honours .rn only on scalar f32, and -fmad=false does not reach it), which flips truncated indices; writing
+  // each "product + addend" as fma(product, 1, addend) keeps the product individually rounded.
+  // `one` must be a RUN-TIME 1.0f (the compiler folds fma(x, 1.0f, y) back into x + y and contracts again).
+  const f2_t One = pack2(one, one);
+  f2_t Pp = fma2(mul2(f.Zn, Tsw), One, fma2(mul2(f.W, T), One, B));
+  Pp = add2(add2(Pp, f.R), pack2(border, border));
+  float qx, qy;
+  if (kRecipDiv) {
+    const f2_t Rr = pack2(hrecip, hrecip);
+    const f2_t Q0 = mul2(Pp, Rr);
+    const f2_t Rem = fma2(Q0, pack2(-hscale, -hscale), Pp);
+    unpack2(fma2(Rem, Rr, Q0), qx, qy);
+  } else {
+    float px, py;
+    unpack2(Pp, px, py);
+    qx = f_div(px, hscale); qy = f_div(py, hscale);
+  }
+  // .long(): truncation; x86 turns NaN / inf / |q| >= 2^63 into INT64_MIN, which the clip maps to 0
+  ix = qx < 9.2233720368547758e18f ? __float2int_rz(qx) : 0;
+  iy = qy < 9.2233720368547758e18f ? __float2int_rz(qy) : 0;
+  ix = min(max(ix, 0), rows - 2);
+  iy = min(max(iy, 0), cols - 2);
+}
+#endif
 
 // torch.norm(dim=-1) over 3 / 2 elements on CPU: sqrt(fma(z,z,fma(y,y,x*x)))
 LGK_HD float norm3(float x, float y, float z) { return f_sqrt(f_fma(z, z, f_fma(y, y, f_mul(x, x)))); }

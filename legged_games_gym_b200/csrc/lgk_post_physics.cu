@@ -81,8 +81,8 @@ __host__ __device__ inline TileLayout make_layout(int kTile, int nb, int nfeet, 
   L.bav = o;     o += al16(kTile * 3 * 4);
   L.pg = o;      o += al16(kTile * 3 * 4);
   L.lrv = o;     o += al16(kTile * 6 * 4);
-  L.pts = o;     o += al16((npts > 0 ? npts : 1) * 2 * 4);
-  L.yaw = o;     o += al16(kTile * 4 * 4);
+  L.pts = o;     o += al16((npts > 0 ? npts : 1) * 4 * 4);   // (bx, by, by, bx) per point
+  L.yaw = o;     o += al16(kTile * 40);                     // YawFrame2 per env
   L.hstride = (npts + 7) & ~7;                       // int16 samples per env row
   L.h16 = o;     o += al16(kTile * (L.hstride > 0 ? L.hstride : 8) * 2);
   L.misc = o;    o += 64;   // mbarrier (8 B) + chunk counter + reset mask
@@ -113,7 +113,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ------------------------------------------------------------------ the kernel
 template <int kTile>
-__global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_constant__ LgkStepParams p) {
+__global__ void __launch_bounds__(kThreads, 8) post_physics_kernel(const __grid_constant__ LgkStepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const TileLayout L = make_layout(kTile, p.num_bodies, p.num_feet, p.num_height_points);
   float* s_root = reinterpret_cast<float*>(smem + L.root);
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
   float* s_pg = reinterpret_cast<float*>(smem + L.pg);
   float* s_lrv = reinterpret_cast<float*>(smem + L.lrv);
   float* s_pts = reinterpret_cast<float*>(smem + L.pts);
-  YawFrame* s_yaw = reinterpret_cast<YawFrame*>(smem + L.yaw);
+  YawFrame2* s_yaw = reinterpret_cast<YawFrame2*>(smem + L.yaw);
   int16_t* s_h16 = reinterpret_cast<int16_t*>(smem + L.h16);
   const int HS = L.hstride;
   Misc* misc = reinterpret_cast<Misc*>(smem + L.misc);
@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
   }
   // constants that are not part of the tile: height grid -> smem (P*2 floats, L2-resident)
   if (p.measure_heights && !p.terrain_is_plane)
-    for (int i = tid; i < 2 * P; i += kThreads) s_pts[i] = p.height_points_xy[i];
+    for (int i = tid; i < P; i += kThreads) {
+      const float bx = p.height_points_xy[2 * i], by = p.height_points_xy[2 * i + 1];
+      *reinterpret_cast<float4*>(s_pts + 4 * i) = make_float4(bx, by, by, bx);
+    }
   if (bulk) mbar_wait(&misc->bar, 0);
   __syncthreads();
 
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
   const bool scan = pre && p.measure_heights && !p.terrain_is_plane && P > 0;
   if (warp == 0 && lane < nval && scan) {
     const float* r = s_root + lane * 13;
-    s_yaw[lane] = yaw_frame(r[5], r[6], r[0], r[1]);
+    s_yaw[lane] = yaw_frame2(yaw_frame(r[5], r[6], r[0], r[1]));
   }
   const bool heights_first = scan && p.reward_active[LGK_R_BASE_HEIGHT];
   __syncthreads();
@@ -211,6 +214,8 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
   // one work item = one env: all ceil(P/32) point chunks of the env are indexed first, then their gathers are
   // issued back to back (memory-level parallelism), then stored.  Items are claimed dynamically so warp 0 can
   // join after its scalar phase.
+  const bool recip_div = p.horizontal_scale_recip != 0.f;
+  const float rt_one = __int_as_float(0x3f800000u | ((uint32_t)p.num_envs >> 31));   // 1.0f the compiler cannot see
   auto height_scan = [&]() {
     constexpr int kMaxChunks = 8;                       // P <= 256
     const int cpe = (P + 31) >> 5;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
       if (lane == 0) e = atomicAdd(&misc->chunk_counter, 1);
       e = __shfl_sync(0xffffffffu, e, 0);
       if (e >= nval) break;
-      const YawFrame yf = s_yaw[e];
+      const YawFrame2 yf = s_yaw[e];
       int off[kMaxChunks];
 #pragma unroll
       for (int c = 0; c < kMaxChunks; ++c) {
@@ -227,7 +232,9 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
         off[c] = -1;
         if (c < cpe && j < P) {
           int ix, iy;
-          height_index(yf, s_pts[2 * j], s_pts[2 * j + 1], p.border_size, p.horizontal_scale, p.hf_rows, p.hf_cols, ix, iy);
+          const ulonglong2 pt = *reinterpret_cast<const ulonglong2*>(s_pts + 4 * j);
+          if (recip_div) height_index2<true>(yf, pt.x, pt.y, p.border_size, p.horizontal_scale, p.horizontal_scale_recip, rt_one, p.hf_rows, p.hf_cols, ix, iy);
+          else height_index2<false>(yf, pt.x, pt.y, p.border_size, p.horizontal_scale, 0.f, rt_one, p.hf_rows, p.hf_cols, ix, iy);
           off[c] = ix * p.hf_cols + iy;
         }
       }
@@ -400,24 +407,45 @@ __global__ void __launch_bounds__(kThreads) post_physics_kernel(const __grid_con
     }
 
     // ---------------- observation rows (LR:212-230 + clip LR:100-101): warp w takes envs w, w+4, ...
+    // Lane l owns columns l + 32m; its noise scales are loop-invariant and live in registers.
+    constexpr int kMaxSuper = 3;                       // O <= 48 + 256
     const bool hcols = p.measure_heights != 0;
+    const bool noisy = p.add_noise != 0;
+    const float clip = p.clip_obs, vs = p.vertical_scale, hsc = p.obs_scale_height;
+    float nz[kMaxSuper][4];
+#pragma unroll
+    for (int sc = 0; sc < kMaxSuper; ++sc)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = sc * 128 + 32 * k + lane;
+        nz[sc][k] = (noisy && j < O) ? __ldg(p.noise_scale_vec + j) : 0.f;
+      }
     for (int e = warp; e < nval; e += kWarps) {
       const int env = env0 + e;
       const uint32_t genv = (uint32_t)(p.env_id_offset + env);
-      const float rz = s_root[e * 13 + 2];                        // post-reset root z
+      const float rz = s_root[e * 13 + 2] - 0.5f;                 // post-reset root z, LR:225
       float* orow = p.obs_buf + (size_t)env * O;
-      const float* hrow = p.measured_heights + (size_t)env * P;   // written above by this CTA (plain loads)
-      for (int base = 0; base < O; base += 128) {
-        U4 r = U4{0, 0, 0, 0};
-        if (p.add_noise) r = rng_block(key, genv, LGK_STREAM_OBS, obs_block_of(base + lane));
+      const float* hrow = p.measured_heights + (size_t)env * P;   // split mode only (PRE ran in another launch)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = base + 32 * k + lane;
-          if (j < O) {
-            float v;
-            if (j < 48) v = s_head[e * 48 + j];
-            else v = !hcols ? 0.f : obs_height_col(p, rz, pre ? f_mul((float)s_h16[e * HS + (j - 48)], p.vertical_scale) : hrow[j - 48]);
-            orow[j] = obs_finish(p, v, p.add_noise ? __ldg(p.noise_scale_vec + j) : 0.f, pick(r, k));
+      for (int sc = 0; sc < kMaxSuper; ++sc) {
+        if (sc * 128 < O) {
+          U4 r = U4{0, 0, 0, 0};
+          if (noisy) r = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = sc * 128 + 32 * k + lane;
+            if (j < O) {
+              float v;
+              if (sc == 0 && k < 2 && j < 48) {
+                v = s_head[e * 48 + j];
+              } else {
+                float h = 0.f;
+                if (hcols) h = pre ? f_mul((float)s_h16[e * HS + (j - 48)], vs) : hrow[j - 48];
+                v = hcols ? clampf(rz - h, -1.f, 1.f) * hsc : 0.f;
+              }
+              v = v + (2.0f * u32_to_uniform(pick(r, k)) - 1.0f) * nz[sc][k];
+              orow[j] = clampf(v, -clip, clip);
+            }
           }
         }
       }
@@ -608,7 +636,7 @@ static int launch_post_physics(const LgkStepParams* p, cudaStream_t st) {
 extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
   if (int rc = validate_step(p)) return rc;
   LGK_REQUIRE((p->phase_mask & (LGK_PHASE_PRE | LGK_PHASE_POST)) != 0, "phase_mask selects nothing");
-  LGK_REQUIRE(p->num_height_points <= 256, "at most 256 height points");
+  LGK_REQUIRE(p->num_height_points <= 256 && p->num_obs <= 384, "at most 256 height points");
   int tile = p->tile_envs;
   if (tile == 0) tile = p->num_envs <= 16384 ? 8 : 16;     // small batches: more, shorter CTAs (latency-bound regime)
   switch (tile) {

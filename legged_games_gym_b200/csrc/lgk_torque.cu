@@ -25,16 +25,6 @@ __constant__ LstmDev c_lstm;
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long r, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kTanhClamp = 43.0f;   // = 2*log2(e)*14.9: tanh saturates in fp32 long before, keeps 1 - 2^x finite
 
@@ -84,7 +74,7 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 }
 
 template <bool LSTM>
-__global__ void __launch_bounds__(128) torque_kernel(const __grid_constant__ LgkTorqueParams p) {
+__global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_constant__ LgkTorqueParams p) {
   const int idx = blockIdx.x * 128 + threadIdx.x;
   const int total = p.num_envs * kDof;
   if (idx >= total) return;

@@ -530,6 +530,10 @@ class LeggedRobot(BaseTask):
         p.soft_dof_vel_limit, p.soft_torque_limit = r.soft_dof_vel_limit, r.soft_torque_limit
         t = cfg.terrain
         p.border_size, p.horizontal_scale, p.vertical_scale = t.border_size, t.horizontal_scale, t.vertical_scale
+        # FMA-based exact division: only for scales proven bit-identical to IEEE division (oracle/divcheck.c)
+        hs32 = np.float32(t.horizontal_scale)
+        if any(hs32 == np.float32(c) for c in (0.1, 0.05, 0.25)):
+            p.horizontal_scale_recip = float(np.float32(1.0 / float(hs32)))
         p.default_dof_pos[:] = f(self.default_dof_pos)
         p.dof_pos_lo[:] = f(self.dof_pos_limits[:, 0])
         p.dof_pos_hi[:] = f(self.dof_pos_limits[:, 1])

@@ -102,7 +102,7 @@ typedef struct LgkStepParams {
   int32_t actors_per_env;             /* root_states rows per env (1; 2 in low_level_game, LLG:532) */
   int32_t root_actor_offset;          /* row of the robot inside the env's actor group (prey index) */
   int32_t phase_mask;                 /* LGK_PHASE_* */
-  int32_t tile_envs;                  /* envs per CTA: 0 = auto, or 8 / 16 / 32 */
+  int32_t tile_envs;                  /* reserved (tile size is fixed at 32 envs per warp) */
   int32_t push_interval;              /* used with step_counter_dev: push when step % interval == 0 (0 = never) */
   int32_t step;                       /* common_step_counter AFTER the += 1 of LR:115 (RNG counter) */
   uint64_t seed;
@@ -189,6 +189,9 @@ typedef struct LgkStepParams {
    * per-term sum of episode_sums over the envs reset this step, then reset count, then
    * sum(terrain_levels) over all envs (LR:181-186) */
   float* reset_stats;
+  /* [N,8] fp32 scratch handed from the scalar kernel to the scan/observation kernel: pre-reset yaw frame
+   * (zn, wn, root_x, root_y) and post-reset (root_z - 0.5); required when measure_heights on a height field */
+  float* scan_frames;
   /* optional device-resident step counter (number of completed steps).  When non-NULL it overrides `step`
    * (post_physics / finalize(advance=1) use counter+1, reset_idx uses counter) and `do_push` (derived from
    * push_interval), and finalize(advance=1) stores counter+1: a whole env step then has no per-step host-side

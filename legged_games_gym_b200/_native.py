@@ -69,7 +69,7 @@ class StepParams(C.Structure):
         ("base_lin_vel", vp), ("base_ang_vel", vp), ("projected_gravity", vp), ("measured_heights", vp),
         ("obs_buf", vp), ("rew_buf", vp), ("reset_buf", vp), ("time_out_buf", vp),
         ("height_min3", vp), ("height_points_xy", vp), ("noise_scale_vec", vp), ("reset_stats", vp),
-        ("step_counter_dev", vp)]
+        ("scan_frames", vp), ("step_counter_dev", vp)]
 
 
 class PolicyParams(C.Structure):

@@ -1,26 +1,26 @@
-// lgk_post_physics.cu -- fused post-physics step (reference LR:106-230, 329-508, 831-969) for sm_100a.
+// lgk_post_physics.cu -- post-physics step (reference LR:106-230, 329-508, 831-969) for sm_100a, one kernel per phase:
 //
-// One CTA (4 warps) owns a TILE of 32 consecutive environments.  Because every reference tensor is
-// env-major row-major, the tile's slice of root_states / dof_state / contact_forces / actions / torques /
-// last_actions / last_dof_vel / commands / feet_air_time is ONE contiguous chunk per tensor: each is
-// fetched with a single TMA bulk copy (cp.async.bulk.shared::cluster.global, completion on an mbarrier)
-// and the whole-tile results (commands, feet_air_time, last_*, base_*) leave through bulk stores
-// (cp.async.bulk.global.shared::cta).  Compute threads only touch shared memory:
-//   warp 0, lane = env : all per-env scalar work (rotations, commands, termination, the reward terms in
-//                        the reference's alphabetical order, reset_idx, the 48 proprioceptive columns)
-//   warps 1-3 (+ warp 0 when done): the 187-point height scan, 32 points per warp-step, one int16 gather
-//                        per point from the precomputed min3 field (lgk_height_min3)
-//   all warps          : observation rows (height columns + in-kernel Philox noise + clip), coalesced
-//                        128-byte row segments; cooperative write-back of reset rows and LSTM-state zeroing
-// Cross-env sums for extras["episode"] go through warp shuffles + one atomicAdd per tile into a
-// ping-pong accumulator consumed by lgk_finalize_step.
+//  K1  post_scalar_kernel   one WARP per tile of 32 consecutive envs, lane = env.  Every reference tensor is env-major
+//      row-major, so the tile's slice of root_states / dof_state / contact_forces / actions / torques / last_actions /
+//      last_dof_vel / commands / feet_air_time is ONE contiguous chunk per tensor: each arrives by a single TMA bulk copy
+//      (cp.async.bulk.shared::cluster.global, mbarrier completion) and whole-tile results (commands, feet_air_time,
+//      last_*, base_*, scan frames) leave by bulk stores.  The lane does all per-env scalar work: rotations, command
+//      resampling / heading, push, termination, the reward terms in the reference's alphabetical order, reset_idx,
+//      the 48 proprioceptive observation columns (un-noised).  Reset rows + LSTM-state zeroing are written
+//      cooperatively; cross-env sums for extras["episode"] use warp shuffles + one atomicAdd per tile.
+//  K2  scan_obs_kernel      one WARP per env, lanes over columns: the 187-point height scan (packed f32x2 op-exact
+//      index path, all int16 gathers of the env issued back to back from the precomputed min3 field), measured_heights,
+//      and the finished observation row: height columns, in-kernel Philox noise, clip -- lane l owns columns l+32m, so
+//      one Philox block serves four coalesced 128-byte row segments.  Persistent CTAs keep the point grid in shared
+//      memory and the noise scales in registers.
+//
+// lgk_post_physics orders them (K1 then K2; when the base_height reward is active the scan runs first) and runs the
+// PRE / POST phases of K1 separately when Python code has to run in between.
 #include "lgk_step_device.cuh"
-#include <cooperative_groups.h>
 
 namespace lgk {
 
-constexpr int kThreads = 128;
-constexpr int kWarps = kThreads / 32;
+constexpr int kTile = 32;          // envs per K1 warp
 
 // ------------------------------------------------------------------ PTX helpers (TMA bulk copy + mbarrier)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -56,19 +56,21 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ------------------------------------------------------------------ shared-memory carve-up (bytes, 16-aligned)
+// ------------------------------------------------------------------ K1 shared-memory carve-up (bytes, 16-aligned)
 struct TileLayout {
-  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, pts, yaw, h16, hstride, misc, total;
+  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, frame, sums, ep, rew, flags, misc, total;
 };
 
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline TileLayout make_layout(int kTile, int nb, int nfeet, int npts) {
+__host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots) {
   TileLayout L;
   int o = 0;
   L.root = o;    o += al16(kTile * 13 * 4);
   L.dof = o;     o += al16(kTile * 24 * 4);
-  L.contact = o; o += al16(kTile * nb * 3 * 4);
+  // the 48-column observation head (row stride 49: conflict-free lane-per-env writes) reuses the contact tile, which
+  // is dead once env_pre has run (a __syncwarp separates the two uses)
+  { const int c = al16(kTile * nb * 3 * 4), h = al16(kTile * 49 * 4); L.contact = o; L.head = o; o += c > h ? c : h; }
   L.act = o;     o += al16(kTile * 12 * 4);
   L.tq = o;      o += al16(kTile * 12 * 4);
   L.lact = o;    o += al16(kTile * 12 * 4);
@@ -76,33 +78,25 @@ __host__ __device__ inline TileLayout make_layout(int kTile, int nb, int nfeet, 
   L.cmd = o;     o += al16(kTile * 4 * 4);
   L.fat = o;     o += al16(kTile * (nfeet > 0 ? nfeet : 1) * 4);
   L.lc = o;      o += al16(kTile * (nfeet > 0 ? nfeet : 1));
-  L.head = o;    o += al16(kTile * 48 * 4);
   L.blv = o;     o += al16(kTile * 3 * 4);
   L.bav = o;     o += al16(kTile * 3 * 4);
   L.pg = o;      o += al16(kTile * 3 * 4);
   L.lrv = o;     o += al16(kTile * 6 * 4);
-  L.pts = o;     o += al16((npts > 0 ? npts : 1) * 4 * 4);   // (bx, by, by, bx) per point
-  L.yaw = o;     o += al16(kTile * 40);                     // YawFrame2 per env
-  L.hstride = (npts + 7) & ~7;                       // int16 samples per env row
-  L.h16 = o;     o += al16(kTile * (L.hstride > 0 ? L.hstride : 8) * 2);
-  L.misc = o;    o += 64;   // mbarrier (8 B) + chunk counter + reset mask
+  L.frame = o;   o += al16(kTile * 8 * 4);
+  L.sums = o;    o += al16((nslots > 0 ? nslots : 1) * kTile * 4);   // episode_sums rows of the tile: [K][32]
+  L.ep = o;      o += al16(kTile * 8);                                // episode_length_buf (int64)
+  L.rew = o;     o += al16(kTile * 4);
+  L.flags = o;   o += al16(kTile * 2);                                // reset flags [32] then time_out flags [32]
+  L.misc = o;    o += 16;   // mbarrier
   L.total = o;
   return L;
 }
 
-struct Misc {
-  uint64_t bar;
-  int chunk_counter;
-  uint32_t reset_mask;
-  uint32_t valid_mask;
-};
-
-// cooperative copy helpers for the non-bulk (partial tile / strided root) path
-__device__ __forceinline__ void copy_f32(float* dst, const float* src, int n, int tid) {
-  for (int i = tid; i < n; i += kThreads) dst[i] = src[i];
+__device__ __forceinline__ void copy_f32(float* dst, const float* src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
-__device__ __forceinline__ void copy_u8(uint8_t* dst, const uint8_t* src, int n, int tid) {
-  for (int i = tid; i < n; i += kThreads) dst[i] = src[i];
+__device__ __forceinline__ void copy_u8(uint8_t* dst, const uint8_t* src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -111,11 +105,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// ------------------------------------------------------------------ the kernel
-template <int kTile>
-__global__ void __launch_bounds__(kThreads, 8) post_physics_kernel(const __grid_constant__ LgkStepParams p) {
+// scan frame of one env: [zn, wn, root_x, root_y] (pre-reset yaw frame, LR:853-854) + [root_z_post_reset - 0.5] (LR:225)
+constexpr int kFrameFloats = 8;
+
+// ------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__ LgkStepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const TileLayout L = make_layout(kTile, p.num_bodies, p.num_feet, p.num_height_points);
+  const TileLayout L = make_layout(p.num_bodies, p.num_feet, p.num_reward_slots);
   float* s_root = reinterpret_cast<float*>(smem + L.root);
   float* s_dof = reinterpret_cast<float*>(smem + L.dof);
   float* s_contact = reinterpret_cast<float*>(smem + L.contact);
@@ -131,220 +127,170 @@ __global__ void __launch_bounds__(kThreads, 8) post_physics_kernel(const __grid_
   float* s_bav = reinterpret_cast<float*>(smem + L.bav);
   float* s_pg = reinterpret_cast<float*>(smem + L.pg);
   float* s_lrv = reinterpret_cast<float*>(smem + L.lrv);
-  float* s_pts = reinterpret_cast<float*>(smem + L.pts);
-  YawFrame2* s_yaw = reinterpret_cast<YawFrame2*>(smem + L.yaw);
-  int16_t* s_h16 = reinterpret_cast<int16_t*>(smem + L.h16);
-  const int HS = L.hstride;
-  Misc* misc = reinterpret_cast<Misc*>(smem + L.misc);
+  float* s_frame = reinterpret_cast<float*>(smem + L.frame);
+  float* s_sums = reinterpret_cast<float*>(smem + L.sums);
+  long long* s_ep = reinterpret_cast<long long*>(smem + L.ep);
+  float* s_rew = reinterpret_cast<float*>(smem + L.rew);
+  uint8_t* s_flags = smem + L.flags;
+  const int K = p.num_reward_slots;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.misc);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x;
   const int env0 = blockIdx.x * kTile;
-  const int nval = min(kTile, p.num_envs - env0);     // valid envs in this tile
+  const int nval = min(kTile, p.num_envs - env0);
   const int NB = p.num_bodies, F = p.num_feet, P = p.num_height_points, O = p.num_obs, N = p.num_envs;
   const bool pre = (p.phase_mask & LGK_PHASE_PRE) != 0, post = (p.phase_mask & LGK_PHASE_POST) != 0;
   const bool fat_active = p.reward_active[LGK_R_FEET_AIR_TIME] != 0 && F > 0;
   // bulk (TMA) path needs a full tile (sizes are then multiples of 16 B) and unit root stride
-  const bool bulk = (nval == kTile) && (p.actors_per_env == 1) && ((kTile * F) % 16 == 0);
+  const bool bulk = (nval == kTile) && (p.actors_per_env == 1) && (p.num_envs % 4 == 0);   // 16-B aligned rows
   const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
   const bool do_push = p.step_counter_dev ? (p.push_interval > 0 && step_eff % p.push_interval == 0) : (p.do_push != 0);
   const RngKey key = make_key(p.seed, step_eff);
 
   // ---------------- stage the tile
-  if (tid == 0) {
-    misc->chunk_counter = 0;
-    misc->reset_mask = 0;
-    mbar_init(&misc->bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
   if (bulk) {
-    if (tid == 0) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       uint32_t bytes = kTile * (13 + 24 + 3 * NB + 12 + 12 + 12 + 12 + 4) * 4;
       if (F > 0) bytes += kTile * F * 4 + kTile * F;
-      mbar_expect_tx(&misc->bar, bytes);
-      bulk_g2s(s_root, p.root_states + (size_t)env0 * 13, kTile * 13 * 4, &misc->bar);
-      bulk_g2s(s_dof, p.dof_state + (size_t)env0 * 24, kTile * 24 * 4, &misc->bar);
-      bulk_g2s(s_contact, p.contact_forces + (size_t)env0 * NB * 3, kTile * NB * 3 * 4, &misc->bar);
-      bulk_g2s(s_act, p.actions + (size_t)env0 * 12, kTile * 12 * 4, &misc->bar);
-      bulk_g2s(s_tq, p.torques + (size_t)env0 * 12, kTile * 12 * 4, &misc->bar);
-      bulk_g2s(s_lact, p.last_actions + (size_t)env0 * 12, kTile * 12 * 4, &misc->bar);
-      bulk_g2s(s_ldv, p.last_dof_vel + (size_t)env0 * 12, kTile * 12 * 4, &misc->bar);
-      bulk_g2s(s_cmd, p.commands + (size_t)env0 * 4, kTile * 4 * 4, &misc->bar);
+      bytes += K * kTile * 4 + kTile * 8;
+      mbar_expect_tx(bar, bytes);
+      for (int k = 0; k < K; ++k) bulk_g2s(s_sums + k * kTile, p.episode_sums + (size_t)k * N + env0, kTile * 4, bar);
+      bulk_g2s(s_ep, p.episode_length_buf + env0, kTile * 8, bar);
+      bulk_g2s(s_root, p.root_states + (size_t)env0 * 13, kTile * 13 * 4, bar);
+      bulk_g2s(s_dof, p.dof_state + (size_t)env0 * 24, kTile * 24 * 4, bar);
+      bulk_g2s(s_contact, p.contact_forces + (size_t)env0 * NB * 3, kTile * NB * 3 * 4, bar);
+      bulk_g2s(s_act, p.actions + (size_t)env0 * 12, kTile * 12 * 4, bar);
+      bulk_g2s(s_tq, p.torques + (size_t)env0 * 12, kTile * 12 * 4, bar);
+      bulk_g2s(s_lact, p.last_actions + (size_t)env0 * 12, kTile * 12 * 4, bar);
+      bulk_g2s(s_ldv, p.last_dof_vel + (size_t)env0 * 12, kTile * 12 * 4, bar);
+      bulk_g2s(s_cmd, p.commands + (size_t)env0 * 4, kTile * 4 * 4, bar);
       if (F > 0) {
-        bulk_g2s(s_fat, p.feet_air_time + (size_t)env0 * F, kTile * F * 4, &misc->bar);
-        bulk_g2s(s_lc, p.last_contacts + (size_t)env0 * F, kTile * F, &misc->bar);
+        bulk_g2s(s_fat, p.feet_air_time + (size_t)env0 * F, kTile * F * 4, bar);
+        bulk_g2s(s_lc, p.last_contacts + (size_t)env0 * F, kTile * F, bar);
       }
     }
+    __syncwarp();
+    mbar_wait(bar, 0);
   } else {
-    for (int i = tid; i < nval * 13; i += kThreads) {
+    for (int i = lane; i < nval * 13; i += 32) {
       const int e = i / 13, c = i - e * 13;
       s_root[i] = p.root_states[((size_t)(env0 + e) * p.actors_per_env + p.root_actor_offset) * 13 + c];
     }
-    copy_f32(s_dof, p.dof_state + (size_t)env0 * 24, nval * 24, tid);
-    copy_f32(s_contact, p.contact_forces + (size_t)env0 * NB * 3, nval * NB * 3, tid);
-    copy_f32(s_act, p.actions + (size_t)env0 * 12, nval * 12, tid);
-    copy_f32(s_tq, p.torques + (size_t)env0 * 12, nval * 12, tid);
-    copy_f32(s_lact, p.last_actions + (size_t)env0 * 12, nval * 12, tid);
-    copy_f32(s_ldv, p.last_dof_vel + (size_t)env0 * 12, nval * 12, tid);
-    copy_f32(s_cmd, p.commands + (size_t)env0 * 4, nval * 4, tid);
+    copy_f32(s_dof, p.dof_state + (size_t)env0 * 24, nval * 24, lane);
+    copy_f32(s_contact, p.contact_forces + (size_t)env0 * NB * 3, nval * NB * 3, lane);
+    copy_f32(s_act, p.actions + (size_t)env0 * 12, nval * 12, lane);
+    copy_f32(s_tq, p.torques + (size_t)env0 * 12, nval * 12, lane);
+    copy_f32(s_lact, p.last_actions + (size_t)env0 * 12, nval * 12, lane);
+    copy_f32(s_ldv, p.last_dof_vel + (size_t)env0 * 12, nval * 12, lane);
+    copy_f32(s_cmd, p.commands + (size_t)env0 * 4, nval * 4, lane);
     if (F > 0) {
-      copy_f32(s_fat, p.feet_air_time + (size_t)env0 * F, nval * F, tid);
-      copy_u8(s_lc, p.last_contacts + (size_t)env0 * F, nval * F, tid);
+      copy_f32(s_fat, p.feet_air_time + (size_t)env0 * F, nval * F, lane);
+      copy_u8(s_lc, p.last_contacts + (size_t)env0 * F, nval * F, lane);
     }
-  }
-  // constants that are not part of the tile: height grid -> smem (P*2 floats, L2-resident)
-  if (p.measure_heights && !p.terrain_is_plane)
-    for (int i = tid; i < P; i += kThreads) {
-      const float bx = p.height_points_xy[2 * i], by = p.height_points_xy[2 * i + 1];
-      *reinterpret_cast<float4*>(s_pts + 4 * i) = make_float4(bx, by, by, bx);
-    }
-  if (bulk) mbar_wait(&misc->bar, 0);
-  __syncthreads();
-
-  // ---------------- yaw frames for the height scan (pre-reset root pose, LR:853-854)
-  const bool scan = pre && p.measure_heights && !p.terrain_is_plane && P > 0;
-  if (warp == 0 && lane < nval && scan) {
-    const float* r = s_root + lane * 13;
-    s_yaw[lane] = yaw_frame2(yaw_frame(r[5], r[6], r[0], r[1]));
-  }
-  const bool heights_first = scan && p.reward_active[LGK_R_BASE_HEIGHT];
-  __syncthreads();
-
-  // ---------------- height scan: dynamic 32-point chunks (env e, points 32c..32c+31)
-  // one work item = one env: all ceil(P/32) point chunks of the env are indexed first, then their gathers are
-  // issued back to back (memory-level parallelism), then stored.  Items are claimed dynamically so warp 0 can
-  // join after its scalar phase.
-  const bool recip_div = p.horizontal_scale_recip != 0.f;
-  const float rt_one = __int_as_float(0x3f800000u | ((uint32_t)p.num_envs >> 31));   // 1.0f the compiler cannot see
-  auto height_scan = [&]() {
-    constexpr int kMaxChunks = 8;                       // P <= 256
-    const int cpe = (P + 31) >> 5;
-    while (true) {
-      int e = 0;
-      if (lane == 0) e = atomicAdd(&misc->chunk_counter, 1);
-      e = __shfl_sync(0xffffffffu, e, 0);
-      if (e >= nval) break;
-      const YawFrame2 yf = s_yaw[e];
-      int off[kMaxChunks];
-#pragma unroll
-      for (int c = 0; c < kMaxChunks; ++c) {
-        const int j = (c << 5) + lane;
-        off[c] = -1;
-        if (c < cpe && j < P) {
-          int ix, iy;
-          const ulonglong2 pt = *reinterpret_cast<const ulonglong2*>(s_pts + 4 * j);
-          if (recip_div) height_index2<true>(yf, pt.x, pt.y, p.border_size, p.horizontal_scale, p.horizontal_scale_recip, rt_one, p.hf_rows, p.hf_cols, ix, iy);
-          else height_index2<false>(yf, pt.x, pt.y, p.border_size, p.horizontal_scale, 0.f, rt_one, p.hf_rows, p.hf_cols, ix, iy);
-          off[c] = ix * p.hf_cols + iy;
-        }
-      }
-      int16_t h[kMaxChunks];
-#pragma unroll
-      for (int c = 0; c < kMaxChunks; ++c) h[c] = off[c] >= 0 ? __ldg(p.height_min3 + off[c]) : (int16_t)0;
-#pragma unroll
-      for (int c = 0; c < kMaxChunks; ++c) {
-        if (off[c] >= 0) {
-          const int j = (c << 5) + lane;
-          s_h16[e * HS + j] = h[c];
-          p.measured_heights[(size_t)(env0 + e) * P + j] = f_mul((float)h[c], p.vertical_scale);   // LR:869
-        }
-      }
-    }
-  };
-  if (pre && p.measure_heights && p.terrain_is_plane)      // LR:844-845: zeros
-    for (int i = tid; i < nval * P; i += kThreads) { p.measured_heights[(size_t)env0 * P + i] = 0.f; s_h16[(i / P) * HS + (i % P)] = 0; }
-  if (heights_first) {
-    height_scan();
-    __syncthreads();
+    for (int k = 0; k < K; ++k) if (lane < nval) s_sums[k * kTile + lane] = p.episode_sums[(size_t)k * N + env0 + lane];
+    if (lane < nval) s_ep[lane] = p.episode_length_buf[env0 + lane];
+    __syncwarp();
   }
 
-  // ---------------- warp 0: per-env scalar work, lane = env
-  if (warp == 0) {
-    const int e = lane, env = env0 + e;
-    const bool valid = e < nval;
-    const uint32_t genv = (uint32_t)(p.env_id_offset + env);
-    EnvScalars s;
-    s.reset = false; s.time_out = false; s.rew = 0.f; s.ep_len = 0;
-    float* root = s_root + e * 13;
-    float* dof = s_dof + e * 24;
-    float* cmd = s_cmd + e * 4;
-    float* fat = s_fat + e * F;
-    uint8_t* lc = s_lc + e * F;
-    float* sums = p.episode_sums + env;
-    if (valid) {
-      if (pre) {
-        float mh = 0.f;
-        if (p.reward_active[LGK_R_BASE_HEIGHT]) {        // mean_p(z - h_p), LR:886
-          if (p.measure_heights) {
-            for (int j = 0; j < P; ++j) mh += root[2] - f_mul((float)s_h16[e * HS + j], p.vertical_scale);
-            mh /= (float)P;
-          } else {
-            mh = root[2];                                 // measured_heights is the int 0 (LR:562)
-          }
+  // ---------------- per-env scalar work, lane = env
+  const int e = lane, env = env0 + e;
+  const bool valid = e < nval;
+  const uint32_t genv = (uint32_t)(p.env_id_offset + env);
+  EnvScalars s;
+  s.reset = false; s.time_out = false; s.rew = 0.f; s.ep_len = 0;
+  float* root = s_root + e * 13;
+  float* dof = s_dof + e * 24;
+  float* cmd = s_cmd + e * 4;
+  float* fat = s_fat + e * F;
+  uint8_t* lc = s_lc + e * F;
+  float* sums = s_sums + e;                 // tile-local episode sums, row stride kTile
+  const bool want_frames = p.measure_heights && !p.terrain_is_plane && p.scan_frames != nullptr;
+  if (valid) {
+    if (pre) {
+      if (want_frames) {     // pre-reset yaw frame for K2 (LR:853-854 uses the pose of THIS step before reset_idx)
+        const YawFrame yf = yaw_frame(root[5], root[6], root[0], root[1]);
+        s_frame[e * kFrameFloats + 0] = yf.zn; s_frame[e * kFrameFloats + 1] = yf.wn;
+        s_frame[e * kFrameFloats + 2] = yf.rx; s_frame[e * kFrameFloats + 3] = yf.ry;
+      }
+      float mh = 0.f;
+      if (p.reward_active[LGK_R_BASE_HEIGHT]) {        // mean_p(z - h_p), LR:886 (the scan ran before this kernel)
+        if (p.measure_heights) {
+          for (int j = 0; j < P; ++j) mh += root[2] - p.measured_heights[(size_t)env * P + j];
+          mh /= (float)P;
+        } else {
+          mh = root[2];                                 // measured_heights is the int 0 (LR:562)
         }
-        env_pre(p, do_push, key, genv, root, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12, s_lact + e * 12,
-                s_ldv + e * 12, cmd, fat, lc, sums, N, p.episode_length_buf[env], mh, s);
-        s_blv[3 * e] = s.blv.x; s_blv[3 * e + 1] = s.blv.y; s_blv[3 * e + 2] = s.blv.z;
-        s_bav[3 * e] = s.bav.x; s_bav[3 * e + 1] = s.bav.y; s_bav[3 * e + 2] = s.bav.z;
-        s_pg[3 * e] = s.pg.x; s_pg[3 * e + 1] = s.pg.y; s_pg[3 * e + 2] = s.pg.z;
-      } else {   // split mode: PRE ran in an earlier launch, pick its results up from global memory
-        s.blv = V3{p.base_lin_vel[3 * env], p.base_lin_vel[3 * env + 1], p.base_lin_vel[3 * env + 2]};
-        s.bav = V3{p.base_ang_vel[3 * env], p.base_ang_vel[3 * env + 1], p.base_ang_vel[3 * env + 2]};
-        s.pg = V3{p.projected_gravity[3 * env], p.projected_gravity[3 * env + 1], p.projected_gravity[3 * env + 2]};
-        s.ep_len = p.episode_length_buf[env];
-        s.reset = p.reset_buf[env] != 0;
-        s.time_out = p.time_out_buf[env] != 0;
-        s.rew = p.rew_buf[env];
       }
-      if (post) {
-        s.rew = env_finish_reward(p, s.rew, s.reset, s.time_out, sums, N);
-        if (s.reset) env_reset(p, key, genv, env, root, dof, cmd, fat, s.ep_len);
-        env_obs_head(p, s, dof, cmd, s_act + e * 12, s_head + e * 48);
-        for (int d = 0; d < 12; ++d) s_ldv[e * 12 + d] = dof[2 * d + 1];    // LR:133 (post-reset dof_vel)
-        for (int i = 0; i < 6; ++i) s_lrv[e * 6 + i] = root[7 + i];         // LR:134 (post push/reset)
-      }
-      p.rew_buf[env] = s.rew;
-      p.episode_length_buf[env] = s.ep_len;
-      if (pre) {
-        p.reset_buf[env] = s.reset ? 1 : 0;
-        p.time_out_buf[env] = s.time_out ? 1 : 0;
-      }
+      env_pre(p, do_push, key, genv, root, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12, s_lact + e * 12,
+              s_ldv + e * 12, cmd, fat, lc, sums, kTile, s_ep[e], mh, s);
+      s_blv[3 * e] = s.blv.x; s_blv[3 * e + 1] = s.blv.y; s_blv[3 * e + 2] = s.blv.z;
+      s_bav[3 * e] = s.bav.x; s_bav[3 * e + 1] = s.bav.y; s_bav[3 * e + 2] = s.bav.z;
+      s_pg[3 * e] = s.pg.x; s_pg[3 * e + 1] = s.pg.y; s_pg[3 * e + 2] = s.pg.z;
+    } else {   // split mode: PRE ran in an earlier launch, pick its results up from global memory
+      s.blv = V3{p.base_lin_vel[3 * env], p.base_lin_vel[3 * env + 1], p.base_lin_vel[3 * env + 2]};
+      s.bav = V3{p.base_ang_vel[3 * env], p.base_ang_vel[3 * env + 1], p.base_ang_vel[3 * env + 2]};
+      s.pg = V3{p.projected_gravity[3 * env], p.projected_gravity[3 * env + 1], p.projected_gravity[3 * env + 2]};
+      s.ep_len = s_ep[e];
+      s.reset = p.reset_buf[env] != 0;
+      s.time_out = p.time_out_buf[env] != 0;
+      s.rew = p.rew_buf[env];
     }
-    const uint32_t rmask = __ballot_sync(0xffffffffu, valid && s.reset && post);
-    // extras["episode"] sums over the reset set + zeroing (LR:179-183), terrain-level mean (LR:186)
     if (post) {
-      float* stats = p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2);
-      if (rmask != 0) {
-        for (int k = 0; k < p.num_reward_slots; ++k) {
-          float v = 0.f;
-          if (valid && s.reset) { v = sums[(size_t)k * N]; sums[(size_t)k * N] = 0.f; }
-          v = warp_sum(v);
-          if (lane == 0) atomicAdd(stats + k, v);
-        }
-        if (lane == 0) atomicAdd(stats + p.num_reward_slots, (float)__popc(rmask));
-      }
-      if (p.terrain_curriculum) {
-        float lv = valid ? (float)p.terrain_levels[env] : 0.f;
-        lv = warp_sum(lv);
-        if (lane == 0) atomicAdd(stats + p.num_reward_slots + 1, lv);
-      }
+      s.rew = env_finish_reward(p, s.rew, s.reset, s.time_out, sums, kTile);
+      if (s.reset) env_reset(p, key, genv, env, root, dof, cmd, fat, s.ep_len);
     }
-    if (lane == 0) misc->reset_mask = rmask;
   }
-  if (scan && !heights_first) height_scan();     // warps 1-3 start immediately; warp 0 joins when done
+  __syncwarp();          // every lane is done with its contact rows: the region now holds the observation head
+  if (valid) {
+    if (post) {
+      env_obs_head(p, s, dof, cmd, s_act + e * 12, s_head + e * 49);
+      for (int d = 0; d < 12; ++d) s_ldv[e * 12 + d] = dof[2 * d + 1];    // LR:133 (post-reset dof_vel)
+      for (int i = 0; i < 6; ++i) s_lrv[e * 6 + i] = root[7 + i];         // LR:134 (post push/reset)
+      if (p.scan_frames) p.scan_frames[(size_t)env * kFrameFloats + 4] = root[2] - 0.5f;   // post-reset z
+    }
+    s_rew[e] = s.rew;
+    s_ep[e] = s.ep_len;
+    s_flags[e] = s.reset ? 1 : 0;
+    s_flags[kTile + e] = s.time_out ? 1 : 0;
+  }
+  const uint32_t rmask = __ballot_sync(0xffffffffu, valid && s.reset && post);
+  // extras["episode"] sums over the reset set + zeroing (LR:179-183), terrain-level mean (LR:186)
+  if (post) {
+    float* stats = p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2);
+    if (rmask != 0) {
+      for (int k = 0; k < p.num_reward_slots; ++k) {
+        float v = 0.f;
+        if (valid && s.reset) { v = sums[k * kTile]; sums[k * kTile] = 0.f; }
+        v = warp_sum(v);
+        if (lane == 0) atomicAdd(stats + k, v);
+      }
+      if (lane == 0) atomicAdd(stats + p.num_reward_slots, (float)__popc(rmask));
+    }
+    if (p.terrain_curriculum) {
+      float lv = valid ? (float)p.terrain_levels[env] : 0.f;
+      lv = warp_sum(lv);
+      if (lane == 0) atomicAdd(stats + p.num_reward_slots + 1, lv);
+    }
+  }
   fence_async_smem();
-  __syncthreads();
+  __syncwarp();
 
   // ---------------- whole-tile write-backs
   if (bulk) {
-    if (tid == 0) {
+    if (lane == 0) {
       if (pre) {
         bulk_s2g(p.base_lin_vel + (size_t)env0 * 3, s_blv, kTile * 3 * 4);
         bulk_s2g(p.base_ang_vel + (size_t)env0 * 3, s_bav, kTile * 3 * 4);
         bulk_s2g(p.projected_gravity + (size_t)env0 * 3, s_pg, kTile * 3 * 4);
         if (do_push && !post) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
       }
-      if (pre || post) bulk_s2g(p.commands + (size_t)env0 * 4, s_cmd, kTile * 4 * 4);
+      bulk_s2g(p.commands + (size_t)env0 * 4, s_cmd, kTile * 4 * 4);
+      for (int k = 0; k < K; ++k) bulk_s2g(p.episode_sums + (size_t)k * N + env0, s_sums + k * kTile, kTile * 4);
+      bulk_s2g(p.episode_length_buf + env0, s_ep, kTile * 8);
+      bulk_s2g(p.rew_buf + env0, s_rew, kTile * 4);
+      if (pre) { bulk_s2g(p.reset_buf + env0, s_flags, kTile); bulk_s2g(p.time_out_buf + env0, s_flags + kTile, kTile); }
       if (fat_active || (post && F > 0)) {
         bulk_s2g(p.feet_air_time + (size_t)env0 * F, s_fat, kTile * F * 4);
         if (pre) bulk_s2g(p.last_contacts + (size_t)env0 * F, s_lc, kTile * F);
@@ -359,91 +305,185 @@ __global__ void __launch_bounds__(kThreads, 8) post_physics_kernel(const __grid_
     }
   } else {
     if (pre) {
-      copy_f32(p.base_lin_vel + (size_t)env0 * 3, s_blv, nval * 3, tid);
-      copy_f32(p.base_ang_vel + (size_t)env0 * 3, s_bav, nval * 3, tid);
-      copy_f32(p.projected_gravity + (size_t)env0 * 3, s_pg, nval * 3, tid);
+      copy_f32(p.base_lin_vel + (size_t)env0 * 3, s_blv, nval * 3, lane);
+      copy_f32(p.base_ang_vel + (size_t)env0 * 3, s_bav, nval * 3, lane);
+      copy_f32(p.projected_gravity + (size_t)env0 * 3, s_pg, nval * 3, lane);
     }
-    copy_f32(p.commands + (size_t)env0 * 4, s_cmd, nval * 4, tid);
+    copy_f32(p.commands + (size_t)env0 * 4, s_cmd, nval * 4, lane);
+    if (lane < nval) {
+      for (int k = 0; k < K; ++k) p.episode_sums[(size_t)k * N + env0 + lane] = s_sums[k * kTile + lane];
+      p.episode_length_buf[env0 + lane] = s_ep[lane];
+      p.rew_buf[env0 + lane] = s_rew[lane];
+      if (pre) { p.reset_buf[env0 + lane] = s_flags[lane]; p.time_out_buf[env0 + lane] = s_flags[kTile + lane]; }
+    }
     if (fat_active || (post && F > 0)) {
-      copy_f32(p.feet_air_time + (size_t)env0 * F, s_fat, nval * F, tid);
-      if (pre) copy_u8(p.last_contacts + (size_t)env0 * F, s_lc, nval * F, tid);
+      copy_f32(p.feet_air_time + (size_t)env0 * F, s_fat, nval * F, lane);
+      if (pre) copy_u8(p.last_contacts + (size_t)env0 * F, s_lc, nval * F, lane);
     }
     if (post) {
-      copy_f32(p.last_actions + (size_t)env0 * 12, s_act, nval * 12, tid);
-      copy_f32(p.last_dof_vel + (size_t)env0 * 12, s_ldv, nval * 12, tid);
-      copy_f32(p.last_root_vel + (size_t)env0 * 6, s_lrv, nval * 6, tid);
+      copy_f32(p.last_actions + (size_t)env0 * 12, s_act, nval * 12, lane);
+      copy_f32(p.last_dof_vel + (size_t)env0 * 12, s_ldv, nval * 12, lane);
+      copy_f32(p.last_root_vel + (size_t)env0 * 6, s_lrv, nval * 6, lane);
     }
     if (do_push) {
-      for (int i = tid; i < nval * 13; i += kThreads) {
-        const int e = i / 13, c = i - e * 13;
+      for (int i = lane; i < nval * 13; i += 32) {
+        const int ee = i / 13, c = i - ee * 13;
         if (c == 7 || c == 8)
-          p.root_states[((size_t)(env0 + e) * p.actors_per_env + p.root_actor_offset) * 13 + c] = s_root[i];
+          p.root_states[((size_t)(env0 + ee) * p.actors_per_env + p.root_actor_offset) * 13 + c] = s_root[i];
       }
     }
+  }
+  // scan frames (pose part): 4 floats per env, strided rows of 8
+  if (pre && want_frames && valid) {
+    *reinterpret_cast<float4*>(p.scan_frames + (size_t)env * kFrameFloats) =
+        *reinterpret_cast<const float4*>(s_frame + e * kFrameFloats);
   }
 
   if (post) {
     // ---------------- reset rows: dof_state / root_states write-back + LSTM state zeroing (ANY:56-60)
-    uint32_t rm = misc->reset_mask;
-    int idx = 0;
+    uint32_t rm = rmask;
     while (rm) {
-      const int e = __ffs(rm) - 1;
+      const int ee = __ffs(rm) - 1;
       rm &= rm - 1;
-      if ((idx++ & (kWarps - 1)) != warp) continue;
-      const int env = env0 + e;
-      if (lane < 24) p.dof_state[(size_t)env * 24 + lane] = s_dof[e * 24 + lane];
+      const int en = env0 + ee;
+      if (lane < 24) p.dof_state[(size_t)en * 24 + lane] = s_dof[ee * 24 + lane];
       if (lane < 13)
-        p.root_states[((size_t)env * p.actors_per_env + p.root_actor_offset) * 13 + lane] = s_root[e * 13 + lane];
+        p.root_states[((size_t)en * p.actors_per_env + p.root_actor_offset) * 13 + lane] = s_root[ee * 13 + lane];
       if (p.zero_lstm_on_reset && p.sea_hidden_state) {
         // [2, N*12, 8]: per layer the env's 12 joints x 8 = 96 contiguous floats
         const size_t layer = (size_t)N * 96;
-        float4* h0 = reinterpret_cast<float4*>(p.sea_hidden_state + (size_t)env * 96);
-        float4* h1 = reinterpret_cast<float4*>(p.sea_hidden_state + layer + (size_t)env * 96);
-        float4* c0 = reinterpret_cast<float4*>(p.sea_cell_state + (size_t)env * 96);
-        float4* c1 = reinterpret_cast<float4*>(p.sea_cell_state + layer + (size_t)env * 96);
+        float4* h0 = reinterpret_cast<float4*>(p.sea_hidden_state + (size_t)en * 96);
+        float4* h1 = reinterpret_cast<float4*>(p.sea_hidden_state + layer + (size_t)en * 96);
+        float4* c0 = reinterpret_cast<float4*>(p.sea_cell_state + (size_t)en * 96);
+        float4* c1 = reinterpret_cast<float4*>(p.sea_cell_state + layer + (size_t)en * 96);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane < 24) { h0[lane] = z; h1[lane] = z; c0[lane] = z; c1[lane] = z; }
       }
     }
+    // ---------------- the 48 proprioceptive columns, un-noised (K2 adds noise + clip): coalesced row segments
+    for (int ee = 0; ee < nval; ++ee) {
+      float* orow = p.obs_buf + (size_t)(env0 + ee) * O;
+      orow[lane] = s_head[ee * 49 + lane];
+      if (lane < 16) orow[32 + lane] = s_head[ee * 49 + 32 + lane];
+    }
+  }
+  if (bulk && lane == 0) bulk_wait_read0();
+}
 
-    // ---------------- observation rows (LR:212-230 + clip LR:100-101): warp w takes envs w, w+4, ...
-    // Lane l owns columns l + 32m; its noise scales are loop-invariant and live in registers.
-    constexpr int kMaxSuper = 3;                       // O <= 48 + 256
-    const bool hcols = p.measure_heights != 0;
-    const bool noisy = p.add_noise != 0;
-    const float clip = p.clip_obs, vs = p.vertical_scale, hsc = p.obs_scale_height;
-    float nz[kMaxSuper][4];
+// ------------------------------------------------------------------ K2
+enum { kScan = 1, kObs = 2 };
+constexpr int kK2Threads = 128;
+constexpr int kMaxGroupsAny = 12;  // 32-column groups per row: O <= 384
+
+template <int kMaxGroups>
+__global__ void __launch_bounds__(kK2Threads, 8) scan_obs_kernel(const __grid_constant__ LgkStepParams p, int mode) {
+  extern __shared__ __align__(16) float s_pts[];       // (bx, by, by, bx) per height point
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.num_envs, P = p.num_height_points, O = p.num_obs;
+  const bool scan = (mode & kScan) != 0 && p.measure_heights && !p.terrain_is_plane && P > 0;
+  const bool obs = (mode & kObs) != 0;
+  const bool hcols = p.measure_heights != 0;
+  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
+  const RngKey key = make_key(p.seed, step_eff);
+  if (scan) {
+    for (int i = tid; i < P; i += kK2Threads) {
+      const float bx = p.height_points_xy[2 * i], by = p.height_points_xy[2 * i + 1];
+      *reinterpret_cast<float4*>(s_pts + 4 * i) = make_float4(bx, by, by, bx);
+    }
+  }
+  __syncthreads();
+  const bool recip_div = p.horizontal_scale_recip != 0.f;
+  const float rt_one = __int_as_float(0x3f800000u | ((uint32_t)p.num_envs >> 31));   // 1.0f the compiler cannot see
+  const bool noisy = p.add_noise != 0;
+  const float clip = p.clip_obs, vs = p.vertical_scale, hsc = p.obs_scale_height;
+  // lane l owns columns l + 32g; its noise scales are loop-invariant
+  float nz[kMaxGroups];
 #pragma unroll
-    for (int sc = 0; sc < kMaxSuper; ++sc)
+  for (int g = 0; g < kMaxGroups; ++g) {
+    const int j = 32 * g + lane;
+    nz[g] = (obs && noisy && j < O) ? __ldg(p.noise_scale_vec + j) : 0.f;
+  }
+  const int ngroups = obs ? (O + 31) >> 5 : ((48 + P + 31) >> 5);
+
+  // per-env inputs (frame from K1 or the root pose, the two head segments) are fetched one env AHEAD of their use
+  struct EnvIn { float4 f; float rz, head0, head1; };
+  auto fetch = [&](int env) {
+    EnvIn in;
+    in.f = make_float4(0.f, 0.f, 0.f, 0.f); in.rz = 0.f; in.head0 = 0.f; in.head1 = 0.f;
+    if (env >= N) return in;
+    const float* r = p.root_states + ((size_t)env * p.actors_per_env + p.root_actor_offset) * 13;
+    if (scan) {
+      if (p.scan_frames && obs) in.f = __ldg(reinterpret_cast<const float4*>(p.scan_frames + (size_t)env * kFrameFloats));
+      else in.f = make_float4(r[5], r[6], r[0], r[1]);       // scan-only pass before K1: current root pose
+    }
+    if (obs && hcols) in.rz = p.scan_frames ? p.scan_frames[(size_t)env * kFrameFloats + 4] : r[2] - 0.5f;
+    if (obs) {
+      const float* orow = p.obs_buf + (size_t)env * O;
+      in.head0 = orow[lane];                         // columns 0..31, written un-noised by K1
+      if (lane < 16) in.head1 = orow[32 + lane];     // columns 32..47
+    }
+    return in;
+  };
+  const int stride = gridDim.x * (kK2Threads / 32);
+  int env = blockIdx.x * (kK2Threads / 32) + warp;
+  EnvIn nxt = fetch(env);
+  for (; env < N; env += stride) {
+    const EnvIn cur = nxt;
+    nxt = fetch(env + stride);
+    YawFrame2 yf;
+    if (scan) {
+      if (p.scan_frames && obs) yf = yaw_frame2(YawFrame{cur.f.x, cur.f.y, cur.f.z, cur.f.w});   // K1's pre-reset frame
+      else yf = yaw_frame2(yaw_frame(cur.f.x, cur.f.y, cur.f.z, cur.f.w));
+    }
+    const float rz = cur.rz;
+    float* orow = p.obs_buf + (size_t)env * O;
+    float* hrow = p.measured_heights + (size_t)env * P;
+    const uint32_t genv = (uint32_t)(p.env_id_offset + env);
+
+    // ---- pass 1: sample offsets of every height column this lane owns (column j <-> point j - 48)
+    int off[kMaxGroups];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = sc * 128 + 32 * k + lane;
-        nz[sc][k] = (noisy && j < O) ? __ldg(p.noise_scale_vec + j) : 0.f;
+    for (int g = 0; g < kMaxGroups; ++g) {
+      off[g] = -1;
+      const int pt = 32 * g + lane - 48;
+      if (scan && g >= 1 && g < ngroups && pt >= 0 && pt < P) {
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(s_pts + 4 * pt);
+        int ix, iy;
+        if (recip_div) height_index2<true>(yf, q.x, q.y, p.border_size, p.horizontal_scale, p.horizontal_scale_recip, rt_one, p.hf_rows, p.hf_cols, ix, iy);
+        else height_index2<false>(yf, q.x, q.y, p.border_size, p.horizontal_scale, 0.f, rt_one, p.hf_rows, p.hf_cols, ix, iy);
+        off[g] = ix * p.hf_cols + iy;
       }
-    for (int e = warp; e < nval; e += kWarps) {
-      const int env = env0 + e;
-      const uint32_t genv = (uint32_t)(p.env_id_offset + env);
-      const float rz = s_root[e * 13 + 2] - 0.5f;                 // post-reset root z, LR:225
-      float* orow = p.obs_buf + (size_t)env * O;
-      const float* hrow = p.measured_heights + (size_t)env * P;   // split mode only (PRE ran in another launch)
+    }
+    // ---- pass 2: all gathers back to back (memory-level parallelism)
+    float h[kMaxGroups];
 #pragma unroll
-      for (int sc = 0; sc < kMaxSuper; ++sc) {
-        if (sc * 128 < O) {
-          U4 r = U4{0, 0, 0, 0};
-          if (noisy) r = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
+    for (int g = 0; g < kMaxGroups; ++g) {
+      h[g] = 0.f;
+      const int pt = 32 * g + lane - 48;
+      if (g >= 1 && g < ngroups && pt >= 0 && pt < P) {
+        if (scan) h[g] = f_mul((float)__ldg(p.height_min3 + off[g]), vs);               // LR:869
+        else if (obs && hcols && !p.terrain_is_plane) h[g] = hrow[pt];                    // scan ran in an earlier launch
+      }
+    }
+    // ---- pass 3: measured_heights + finished observation columns
+    const float head0 = cur.head0, head1 = cur.head1;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int j = sc * 128 + 32 * k + lane;
-            if (j < O) {
+    for (int sc = 0; sc < (kMaxGroups + 3) / 4; ++sc) {
+      if (sc * 4 < ngroups) {
+        U4 r = U4{0, 0, 0, 0};
+        if (obs && noisy) r = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int g = sc * 4 + k;
+          const int j = 32 * g + lane, pt = j - 48;
+          if (g < kMaxGroups && g < ngroups) {
+            if ((scan || (p.terrain_is_plane && (mode & kScan) && hcols)) && pt >= 0 && pt < P) hrow[pt] = h[g];
+            if (obs && j < O) {
               float v;
-              if (sc == 0 && k < 2 && j < 48) {
-                v = s_head[e * 48 + j];
-              } else {
-                float h = 0.f;
-                if (hcols) h = pre ? f_mul((float)s_h16[e * HS + (j - 48)], vs) : hrow[j - 48];
-                v = hcols ? clampf(rz - h, -1.f, 1.f) * hsc : 0.f;
-              }
-              v = v + (2.0f * u32_to_uniform(pick(r, k)) - 1.0f) * nz[sc][k];
+              if (g == 0) v = head0;
+              else if (g == 1 && lane < 16) v = head1;
+              else v = hcols ? clampf(rz - h[g], -1.f, 1.f) * hsc : 0.f;
+              v = v + (2.0f * u32_to_uniform(pick(r, k)) - 1.0f) * nz[g];
               orow[j] = clampf(v, -clip, clip);
             }
           }
@@ -451,7 +491,6 @@ __global__ void __launch_bounds__(kThreads, 8) post_physics_kernel(const __grid_
       }
     }
   }
-  if (bulk && tid == 0) bulk_wait_read0();
 }
 
 // ------------------------------------------------------------------ reset_idx on an explicit id list
@@ -582,7 +621,6 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ 
 
 }  // namespace lgk
 
-// ====================================================================== C ABI
 using namespace lgk;
 
 static int validate_step(const LgkStepParams* p) {
@@ -618,33 +656,59 @@ static int validate_step(const LgkStepParams* p) {
   return LGK_OK;
 }
 
-template <int kTile>
-static int launch_post_physics(const LgkStepParams* p, cudaStream_t st) {
-  const TileLayout L = make_layout(kTile, p->num_bodies, p->num_feet, p->num_height_points);
+static int launch_k1(const LgkStepParams* p, cudaStream_t st) {
+  const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_reward_slots);
   static int smem_set = 0;
   if (L.total > smem_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(post_physics_kernel<kTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
-                            "cudaFuncSetAttribute(post_physics_kernel)")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(post_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
+                            "cudaFuncSetAttribute(post_scalar_kernel)")) return rc;
     smem_set = L.total;
+    // one warp per CTA, ~15 KB of staged tiles each: ask for the largest shared-memory carve-out so that a whole
+    // 65k-env grid (2048 CTAs) is resident in a single wave
+    cudaFuncSetAttribute(post_scalar_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
-  const int tiles = (p->num_envs + kTile - 1) / kTile;
-  post_physics_kernel<kTile><<<tiles, kThreads, L.total, st>>>(*p);
+  post_scalar_kernel<<<(p->num_envs + kTile - 1) / kTile, 32, L.total, st>>>(*p);
   count_launch();
-  return check_cuda(cudaGetLastError(), "post_physics_kernel launch");
+  return check_cuda(cudaGetLastError(), "post_scalar_kernel launch");
+}
+
+static int launch_k2(const LgkStepParams* p, int mode, cudaStream_t st) {
+  const int wpb = kK2Threads / 32;
+  int blocks = (p->num_envs + wpb - 1) / wpb;
+  const int cap = 148 * 16;                          // persistent beyond one full wave of resident CTAs
+  if (blocks > cap) blocks = cap;
+  const size_t smem = (size_t)(p->num_height_points > 0 ? p->num_height_points : 1) * 16;
+  const int groups = (48 + p->num_height_points + 31) / 32;
+  if (groups <= 2) scan_obs_kernel<2><<<blocks, kK2Threads, smem, st>>>(*p, mode);
+  else if (groups <= 8) scan_obs_kernel<8><<<blocks, kK2Threads, smem, st>>>(*p, mode);
+  else scan_obs_kernel<12><<<blocks, kK2Threads, smem, st>>>(*p, mode);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "scan_obs_kernel launch");
 }
 
 extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
   if (int rc = validate_step(p)) return rc;
   LGK_REQUIRE((p->phase_mask & (LGK_PHASE_PRE | LGK_PHASE_POST)) != 0, "phase_mask selects nothing");
-  LGK_REQUIRE(p->num_height_points <= 256 && p->num_obs <= 384, "at most 256 height points");
-  int tile = p->tile_envs;
-  if (tile == 0) tile = p->num_envs <= 16384 ? 8 : 16;     // small batches: more, shorter CTAs (latency-bound regime)
-  switch (tile) {
-    case 8: return launch_post_physics<8>(p, (cudaStream_t)stream);
-    case 16: return launch_post_physics<16>(p, (cudaStream_t)stream);
-    case 32: return launch_post_physics<32>(p, (cudaStream_t)stream);
-    default: return set_error(LGK_ERR_ARG, "tile_envs must be 0 (auto), 8, 16 or 32");
+  LGK_REQUIRE(p->num_height_points <= 256 && p->num_obs <= 32 * kMaxGroupsAny, "at most 256 height points");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool pre = (p->phase_mask & LGK_PHASE_PRE) != 0, post = (p->phase_mask & LGK_PHASE_POST) != 0;
+  const bool heights = p->measure_heights != 0;
+  // the base_height reward needs this step's heights inside K1 (LR:884-887): run the scan first in that case
+  const bool scan_first = heights && p->reward_active[LGK_R_BASE_HEIGHT] != 0;
+  if (heights && !p->terrain_is_plane) LGK_REQUIRE(p->scan_frames != nullptr, "scan_frames buffer is null");
+  if (pre && post) {              // fused step
+    if (scan_first)
+      if (int rc = launch_k2(p, kScan, st)) return rc;
+    if (int rc = launch_k1(p, st)) return rc;
+    return launch_k2(p, scan_first ? kObs : (kScan | kObs), st);
   }
+  if (pre) {                      // Python code follows (user reward terms may read measured_heights): scan now
+    if (heights)
+      if (int rc = launch_k2(p, kScan, st)) return rc;
+    return launch_k1(p, st);
+  }
+  if (int rc = launch_k1(p, st)) return rc;      // POST only
+  return launch_k2(p, kObs, st);
 }
 
 extern "C" int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int32_t num_ids, void* stream) {

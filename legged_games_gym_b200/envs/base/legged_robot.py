@@ -571,6 +571,8 @@ class LeggedRobot(BaseTask):
         p.noise_scale_vec = ptr(self.noise_scale_vec)
         p.reset_stats = ptr(self._reset_stats)
         p.step_counter_dev = ptr(self._step_counter_dev)
+        self._scan_frames = torch.zeros(N, 8, dtype=torch.float, device=self.device)
+        p.scan_frames = ptr(self._scan_frames)
         dr = cfg.domain_rand
         p.push_interval = int(dr.push_interval) if dr.push_robots else 0
         p.tile_envs = int(getattr(self, "tile_envs", 0))

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 
-def synth_state(num_envs, num_bodies, num_dof=12, seed=0, p_contact=0.3, actors_per_env=1, xy_max=(83., 163.)):
+def synth_state(num_envs, num_bodies, num_dof=12, seed=0, p_contact=0.3, actors_per_env=1, xy_max=(83., 163.),
+                p_contact_body0=None):
     """numpy dict of seeded synthetic inputs (PCG64: stable across torch versions)."""
     g = np.random.default_rng(seed)
     N = num_envs
@@ -27,8 +28,12 @@ def synth_state(num_envs, num_bodies, num_dof=12, seed=0, p_contact=0.3, actors_
     root[:, 3:7] = q
     root[:, 7:13] = g.normal(0., 1., (na, 6))
     dof = g.normal(0., 1., (N * num_dof, 2)).astype(np.float32)
-    contact = (g.normal(0., 2., (N * num_bodies, 3)) *
-               (g.uniform(0., 1., (N * num_bodies, 1)) < p_contact)).astype(np.float32)
+    force = g.normal(0., 2., (N * num_bodies, 3))          # draw order (force, then gate) is part of the fixtures
+    gate = g.uniform(0., 1., (N * num_bodies, 1))
+    thresh = np.full((N, num_bodies, 1), p_contact)
+    if p_contact_body0 is not None:          # body 0 is the base/pelvis: its contact terminates the episode (LR:142)
+        thresh[:, 0, :] = p_contact_body0
+    contact = (force * (gate < thresh.reshape(-1, 1))).astype(np.float32)
     actions = g.normal(0., 1., (N, num_dof)).astype(np.float32)
     ep_len = g.integers(0, 1000, N).astype(np.int64)
     return dict(root_states=root, dof_state=dof, contact_forces=contact, actions=actions,
@@ -98,8 +103,8 @@ class StateFeeder(SimBackend):
     graph_safe = True       # its hooks enqueue no work, so a whole env step can be captured into one CUDA graph
 
     def __init__(self, num_envs, num_bodies, num_dof=12, device="cuda", seed=0, p_contact=0.3,
-                 actors_per_env=1):
-        s = synth_state(num_envs, num_bodies, num_dof, seed, p_contact, actors_per_env)
+                 actors_per_env=1, p_contact_body0=None):
+        s = synth_state(num_envs, num_bodies, num_dof, seed, p_contact, actors_per_env, p_contact_body0=p_contact_body0)
         self.device = torch.device(device)
         self.root_states = torch.from_numpy(s["root_states"]).to(self.device)
         self.dof_state = torch.from_numpy(s["dof_state"]).to(self.device)

@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="rotate: cycle over env replicas whose buffers exceed L2; flush: write 256 MiB between steps")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--lstm-variant", type=int, default=0, help="0 auto, 1 thread-per-sequence, 2 role-split")
     return ap.parse_args()
 
 
@@ -133,7 +134,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-TILE, USE_GRAPH = 0, True
+TILE, USE_GRAPH, LSTM_VARIANT = 0, True, 0
 # probability that the base body reports a contact (=> termination, LR:142) in the synthetic state; the other 16 bodies
 # keep the survey's 0.3.  ~2 % of the envs reset every step (a 20 s episode alone gives 0.1 %), instead of 28 %.
 P_TERMINATE = 0.02
@@ -166,6 +167,7 @@ def make_env(num_envs, device, host_sim=False, env_id_offset=0):
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
               sim_device=device, headless=True, sim_backend=feeder)
     env.env_id_offset = env_id_offset
+    env._tq_params.lstm_variant = LSTM_VARIANT
     env._params.env_id_offset = env_id_offset
     env.episode_length_buf.copy_(feeder.synthetic_episode_length)
     return env, feeder
@@ -283,8 +285,8 @@ def gpu_arm(args):
     from legged_games_gym_b200 import _native as nat
     N = args.num_envs
     peak_gbs, peak_src = peaks()
-    global TILE, USE_GRAPH
-    TILE, USE_GRAPH = args.tile, not args.no_graph
+    global TILE, USE_GRAPH, LSTM_VARIANT
+    TILE, USE_GRAPH, LSTM_VARIANT = args.tile, not args.no_graph, args.lstm_variant
     envs, feeders, per_bytes = make_replicas(N, dev, rank * N, args.l2)
     env, feeder = envs[0], feeders[0]
     actions = feeder.synthetic_actions

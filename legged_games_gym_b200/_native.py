@@ -24,7 +24,7 @@ f32, i32, i64, u64, vp = C.c_float, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
 class TorqueParams(C.Structure):
     _fields_ = [("num_envs", i32), ("control_type", i32), ("use_lstm", i32), ("action_scale", f32),
-                ("clip_actions", f32), ("inv_sim_dt_unused", f32), ("sim_dt", f32),
+                ("clip_actions", f32), ("lstm_variant", i32), ("sim_dt", f32),
                 ("p_gains", f32 * NUM_DOF), ("d_gains", f32 * NUM_DOF), ("torque_limits", f32 * NUM_DOF),
                 ("default_dof_pos", f32 * NUM_DOF),
                 ("actions_in", vp), ("actions_clipped", vp), ("dof_state", vp), ("last_dof_vel", vp),

@@ -7,6 +7,7 @@
 // Gate nonlinearities use MUFU ex2/rcp with the products sigma(i)*tanh(g) and sigma(o)*tanh(c') sharing one
 // reciprocal each (8 MUFU per hidden unit instead of 10) -- the MUFU pipe, not HBM, is the next limiter.
 #include "lgk_math.cuh"
+#include <cstdlib>
 
 namespace lgk {
 
@@ -20,6 +21,10 @@ struct LstmDev {
   float w_ih0[2 * 32], w_hh0[8 * 32], b0[32];
   float w_ih1[8 * 32], w_hh1[8 * 32], b1[32];
   float lin_w[8], lin_b;
+  // per-role copies for torque_lstm_split_kernel: role r owns gate rows 8g + 2r + {0,1}; for each input k the 8 floats
+  // [g][2] are contiguous, so a role's slice of a matrix row is two LDCU.128 with compile-time offsets
+  float role_w[4][(2 + 8 + 8 + 8) * 8];     // w_ih0 (k<2) | w_hh0 | w_ih1 | w_hh1
+  float role_b[4][2][8];                     // layer 0 / layer 1 biases [g][2]
 };
 __constant__ LstmDev c_lstm;
 
@@ -116,6 +121,133 @@ __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_
   }
 }
 
+
+// ------------------------------------------------------------------ role-split variant (small and medium batches)
+// CTA = 4 warps x 32 sequences.  Warp w owns hidden units {2w, 2w+1} of BOTH layers, i.e. the 8 gate rows
+// {2w, 2w+1} + {0, 8, 16, 24}: four packed (FFMA2) accumulators per layer, a quarter of the matvec and of the
+// MUFU work per thread.  The 32 floats of h/c state per sequence enter and leave through shared memory with fully
+// coalesced 128-bit global accesses; the new h vectors are exchanged through shared memory between the layers.
+// Per-thread instruction stream is ~4x shorter than in torque_kernel<true> (and the code ~4x smaller), which is what
+// matters when the batch cannot fill the machine (4096 envs = 49k sequences).
+constexpr int kSeqPerCta = 32;
+
+__device__ __forceinline__ void gates_to_state(const f2_t (&acc)[4], float (&c)[2], float (&h)[2]) {
+  float gi[2], gf[2], gg[2], go[2];
+  unpack2(acc[0], gi[0], gi[1]); unpack2(acc[1], gf[0], gf[1]); unpack2(acc[2], gg[0], gg[1]); unpack2(acc[3], go[0], go[1]);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const float ei = ex2_approx(gi[u]), ef = ex2_approx(gf[u]), eo = ex2_approx(go[u]);
+    const float eg = ex2_approx(fminf(gg[u], kTanhClamp));
+    const float cn = fmaf(c[u], rcp_approx(1.0f + ef), (1.0f - eg) * rcp_approx((1.0f + ei) * (1.0f + eg)));
+    const float ec = ex2_approx(fminf(cn * (-2.0f * kLog2e), kTanhClamp));
+    c[u] = cn;
+    h[u] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+  }
+}
+
+// acc[g] += W_role[k][g][0..1] * x[k] for the four gates g; W points at the role's [k][8] slice (compile-time offsets)
+template <int IN>
+__device__ __forceinline__ void role_matvec(const float* __restrict__ W, const float (&x)[IN], f2_t (&acc)[4]) {
+#pragma unroll
+  for (int k = 0; k < IN; ++k) {
+    const f2_t xx = pack2(x[k], x[k]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) acc[g] = fma2(pack2(W[k * 8 + 2 * g], W[k * 8 + 2 * g + 1]), xx, acc[g]);
+  }
+}
+
+// both layers for role R; shared-memory exchange of the new layer-0 hidden vector in the middle
+template <int R>
+__device__ __forceinline__ void role_body(const float (&x)[2], int lane, float (*s_state)[kSeqPerCta][8],
+                                          float (*s_hnew)[kSeqPerCta][8]) {
+  constexpr int w2 = 2 * R;
+  const float* W = c_lstm.role_w[R];
+  float hin[8], c[2], h[2];
+  f2_t acc[4];
+  // ---- layer 0
+  *reinterpret_cast<float4*>(hin) = *reinterpret_cast<const float4*>(&s_state[0][lane][0]);
+  *reinterpret_cast<float4*>(hin + 4) = *reinterpret_cast<const float4*>(&s_state[0][lane][4]);
+  c[0] = s_state[2][lane][w2]; c[1] = s_state[2][lane][w2 + 1];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) acc[g] = pack2(c_lstm.role_b[R][0][2 * g], c_lstm.role_b[R][0][2 * g + 1]);
+  role_matvec<2>(W, x, acc);
+  role_matvec<8>(W + 2 * 8, hin, acc);
+  gates_to_state(acc, c, h);
+  s_hnew[0][lane][w2] = h[0]; s_hnew[0][lane][w2 + 1] = h[1];
+  const float c0n0 = c[0], c0n1 = c[1];
+  // ---- layer 1: the recurrent part does not depend on layer 0 and goes first
+  float h1in[8];
+  *reinterpret_cast<float4*>(h1in) = *reinterpret_cast<const float4*>(&s_state[1][lane][0]);
+  *reinterpret_cast<float4*>(h1in + 4) = *reinterpret_cast<const float4*>(&s_state[1][lane][4]);
+  c[0] = s_state[3][lane][w2]; c[1] = s_state[3][lane][w2 + 1];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) acc[g] = pack2(c_lstm.role_b[R][1][2 * g], c_lstm.role_b[R][1][2 * g + 1]);
+  role_matvec<8>(W + (2 + 8 + 8) * 8, h1in, acc);
+  __syncthreads();                                        // s_hnew[0] complete; every role has read its old state
+  *reinterpret_cast<float4*>(hin) = *reinterpret_cast<const float4*>(&s_hnew[0][lane][0]);
+  *reinterpret_cast<float4*>(hin + 4) = *reinterpret_cast<const float4*>(&s_hnew[0][lane][4]);
+  role_matvec<8>(W + (2 + 8) * 8, hin, acc);
+  gates_to_state(acc, c, h);
+  s_hnew[1][lane][w2] = h[0]; s_hnew[1][lane][w2 + 1] = h[1];
+  // new cell states overwrite the staged old ones (each role only ever touches its own two units)
+  s_state[2][lane][w2] = c0n0; s_state[2][lane][w2 + 1] = c0n1;
+  s_state[3][lane][w2] = c[0]; s_state[3][lane][w2 + 1] = c[1];
+}
+
+__global__ void __launch_bounds__(128) torque_lstm_split_kernel(const __grid_constant__ LgkTorqueParams p) {
+  // [array: h0, h1, c0, c1][seq 32][8]
+  __shared__ __align__(16) float s_state[4][kSeqPerCta][8];
+  __shared__ __align__(16) float s_hnew[2][kSeqPerCta][8];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int total = p.num_envs * kDof;
+  const int seq0 = blockIdx.x * kSeqPerCta;
+  const int nseq = min(kSeqPerCta, total - seq0);
+  const size_t layer = (size_t)total * 8;
+  // ---- coalesced state load: 4 arrays x (32 seq x 8 floats) = 4 x 64 float4
+  for (int i = tid; i < 4 * 64; i += 128) {
+    const int arr = i >> 6, q = i & 63;                   // q = float4 index inside the 32x8 block
+    if ((q >> 1) < nseq) {
+      const float* src = ((arr & 2) ? p.sea_cell_state : p.sea_hidden_state) + (size_t)(arr & 1) * layer + (size_t)seq0 * 8;
+      reinterpret_cast<float4*>(&s_state[arr][0][0])[q] = reinterpret_cast<const float4*>(src)[q];
+    }
+  }
+  const int idx = seq0 + lane;
+  const bool live = lane < nseq;
+  float x[2] = {0.f, 0.f};
+  if (live) {
+    const int d = idx % kDof;
+    float a = p.actions_in[idx];
+    a = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);                     // LR:86-87
+    if (p.actions_clipped && w == 0) p.actions_clipped[idx] = a;
+    const float2 qs = *reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx);
+    x[0] = f_sub(f_add(f_mul(a, p.action_scale), p.default_dof_pos[d]), qs.x);   // ANY:75 (in_scale folded into w_ih0)
+    x[1] = qs.y;                                                                 // ANY:76
+  }
+  __syncthreads();
+  switch (w) {            // warp-uniform: each role runs its own copy with compile-time weight offsets
+    case 0: role_body<0>(x, lane, s_state, s_hnew); break;
+    case 1: role_body<1>(x, lane, s_state, s_hnew); break;
+    case 2: role_body<2>(x, lane, s_state, s_hnew); break;
+    default: role_body<3>(x, lane, s_state, s_hnew); break;
+  }
+  __syncthreads();
+  // ---- output layer (warp 0) and coalesced state store
+  if (w == 0 && live) {
+    float y = c_lstm.lin_b;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y = fmaf(c_lstm.lin_w[k], s_hnew[1][lane][k], y);
+    p.torques[idx] = y;                                   // out_scale folded; no clip on this path (ANY:77-78)
+  }
+  for (int i = tid; i < 4 * 64; i += 128) {
+    const int arr = i >> 6, q = i & 63;
+    if ((q >> 1) < nseq) {
+      float* dst = ((arr & 2) ? p.sea_cell_state : p.sea_hidden_state) + (size_t)(arr & 1) * layer + (size_t)seq0 * 8;
+      const float* src = (arr & 2) ? &s_state[arr][0][0] : &s_hnew[arr & 1][0][0];
+      reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(src)[q];
+    }
+  }
+}
+
 }  // namespace lgk
 
 using namespace lgk;
@@ -138,6 +270,20 @@ extern "C" int lgk_set_lstm_weights(const LgkLstmWeights* w, void* stream) {
   }
   for (int k = 0; k < 8; ++k) img.lin_w[k] = (float)((double)w->out_scale[0] * (double)w->lin_w[k]);
   img.lin_b = (float)((double)w->out_scale[0] * (double)w->lin_b[0]);
+  for (int r = 0; r < 4; ++r) {
+    const float* mats[4] = {img.w_ih0, img.w_hh0, img.w_ih1, img.w_hh1};
+    const int ks[4] = {2, 8, 8, 8};
+    int o = 0;
+    for (int m = 0; m < 4; ++m)
+      for (int k = 0; k < ks[m]; ++k)
+        for (int g = 0; g < 4; ++g)
+          for (int h = 0; h < 2; ++h) img.role_w[r][o++] = mats[m][k * 32 + 8 * g + 2 * r + h];
+    for (int g = 0; g < 4; ++g)
+      for (int h = 0; h < 2; ++h) {
+        img.role_b[r][0][2 * g + h] = img.b0[8 * g + 2 * r + h];
+        img.role_b[r][1][2 * g + h] = img.b1[8 * g + 2 * r + h];
+      }
+  }
   return check_cuda(cudaMemcpyToSymbolAsync(c_lstm, &img, sizeof(LstmDev), 0, cudaMemcpyHostToDevice,
                                             (cudaStream_t)stream), "cudaMemcpyToSymbolAsync(c_lstm)");
 }
@@ -154,7 +300,12 @@ extern "C" int lgk_compute_torques(const LgkTorqueParams* p, void* stream) {
   }
   if ((reinterpret_cast<uintptr_t>(p->dof_state) & 7u) != 0) return set_error(LGK_ERR_ALIGN, "dof_state must be 8-byte aligned");
   const int blocks = (p->num_envs * kDof + 127) / 128;
-  if (p->use_lstm) torque_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(*p);
+  LGK_REQUIRE(p->lstm_variant >= 0 && p->lstm_variant <= 2, "lstm_variant must be 0, 1 or 2");
+  // auto = one thread per sequence: measured faster at 4096, 16384 and 65536 envs (bench.py --lstm-variant 2 to compare)
+  const bool split = p->lstm_variant == 2;
+  if (p->use_lstm && split)
+    torque_lstm_split_kernel<<<(p->num_envs * kDof + kSeqPerCta - 1) / kSeqPerCta, 128, 0, (cudaStream_t)stream>>>(*p);
+  else if (p->use_lstm) torque_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(*p);
   else torque_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(*p);
   count_launch();
   return check_cuda(cudaGetLastError(), "torque_kernel launch");

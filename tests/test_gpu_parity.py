@@ -109,15 +109,18 @@ def test_pd_torques_bit_exact(ct):
     assert np.array_equal(got.cpu().numpy(), want.numpy())
 
 
-def test_lstm_torques_and_state():
-    case = harness.build_case("anymal_c_flat", 320, seed=32)
+@pytest.mark.parametrize("variant", [1, 2])
+def test_lstm_torques_and_state(variant):
+    """both actuator-net kernels: 1 = one thread per (env, joint) sequence, 2 = role-split CTA (4 warps x 32 sequences)"""
+    case = harness.build_case("anymal_c_flat", 323, seed=32)       # 3876 sequences: not a multiple of 32 or 128
     orc = harness.make_oracle(case)
     env, feeder = product_env(case)
+    env._tq_params.lstm_variant = variant
     st_or = {"dof_state": orc.dof_state}
     worst = 0.0
     for k in range(6):
-        acts = torch.from_numpy(np.random.default_rng(10 + k).normal(0, 1, (320, 12)).astype(np.float32))
-        want = orc.compute_torques(acts).view(320, 12)
+        acts = torch.from_numpy(np.random.default_rng(10 + k).normal(0, 1, (323, 12)).astype(np.float32))
+        want = orc.compute_torques(acts).view(323, 12)
         got = env._compute_torques(acts.to(DEV))
         scale = float(want.abs().max())
         err = (got.cpu() - want).abs()

@@ -228,46 +228,49 @@ def make_replicas(num_envs, device, env_id_offset, l2_mode):
     return envs, feeders, per
 
 
-def time_kernel(fn, reps, flush):
-    """average CUDA-event duration of one launch, L2 flushed before every launch"""
+def time_kernel(fns, reps):
+    """average duration of one launch: `reps` launches between two CUDA events on the launch stream, cycling over the
+    env replicas in `fns` (their combined buffers exceed L2, so every launch streams its state from HBM and no dirty
+    flush-buffer lines compete for write-back); best of 5 batches and the mean over all of them are reported"""
     import torch
-    from legged_games_gym_b200 import _native as nat
-    st = torch.cuda.current_stream().cuda_stream
-    for _ in range(3):
-        fn()
-    tot = 0.0
-    evs = []
-    for _ in range(reps):
-        nat.lib.lgk_l2_flush(flush.data_ptr(), flush.numel(), st)
+    for i in range(3 * len(fns)):
+        fns[i % len(fns)]()
+    torch.cuda.synchronize()
+    batches = []
+    for _ in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for i in range(reps):
+            fns[i % len(fns)]()
         b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) for a, b in evs)
-    return sum(ts) / len(ts) / 1e3, ts[len(ts) // 2] / 1e3
+        torch.cuda.synchronize()
+        batches.append(a.elapsed_time(b) / 1e3 / reps)
+    return sum(batches) / len(batches), min(batches)
 
 
-def kernel_rooflines(env, actions, flush, peak_gbs, reps=200):
+def kernel_rooflines(envs, actions, peak_gbs, reps=200):
+    """per-kernel achieved bandwidth = algorithmic bytes per launch / average launch duration, kernels launched back to
+    back through the C ABI on replicas larger than L2 (launch gaps are inside the measured time)"""
     import ctypes as C
     import torch
     from legged_games_gym_b200 import _native as nat
-    n = env.num_envs
+    n = envs[0].num_envs
     st = torch.cuda.current_stream().cuda_stream
-    env._tq_params.actions_in = actions.data_ptr()
-    env._tq_params.actions_clipped = None
-    tq = lambda: nat.lib.lgk_compute_torques(C.byref(env._tq_params), st)
-    p = env._params
-    p.phase_mask = nat.PHASE_PRE | nat.PHASE_POST
-    pp = lambda: nat.lib.lgk_post_physics(C.byref(p), st)
+    tqs, pps = [], []
+    for env, act in zip(envs, actions):
+        env._tq_params.actions_in = act.data_ptr()
+        env._tq_params.actions_clipped = None
+        env._params.phase_mask = nat.PHASE_PRE | nat.PHASE_POST
+        tqs.append(lambda e=env: nat.lib.lgk_compute_torques(C.byref(e._tq_params), st))
+        pps.append(lambda e=env: nat.lib.lgk_post_physics(C.byref(e._params), st))
     out = {}
-    for name, fn, bpe in (("torque_lstm", tq, BYTES_TORQUE_LSTM), ("post_physics", pp, BYTES_POST_ROUGH)):
-        mean_s, med_s = time_kernel(fn, reps, flush)
+    for name, fns, bpe in (("torque_lstm", tqs, BYTES_TORQUE_LSTM), ("post_physics", pps, BYTES_POST_ROUGH)):
+        with ClockSampler(torch.cuda.current_device()) as clk:
+            mean_s, best_s = time_kernel(fns, reps)
         gbs = bpe * n / mean_s / 1e9
         out[name] = dict(bound="hbm", achieved=round(gbs, 1), peak=peak_gbs, unit="GB/s", frac=round(gbs / peak_gbs, 4),
-                         us_per_launch=round(mean_s * 1e6, 2), median_us=round(med_s * 1e6, 2),
-                         algorithmic_bytes_per_launch=bpe * n)
+                         us_per_launch=round(mean_s * 1e6, 2), best_batch_us=round(best_s * 1e6, 2),
+                         algorithmic_bytes_per_launch=bpe * n, sm_mhz=clk.summary()["sm_mhz"])
     return out
 
 
@@ -295,8 +298,6 @@ def gpu_arm(args):
         secs, launches = time_steps(envs, [f.synthetic_actions for f in feeders], args.steps, args.warmup, flush, barrier)
     l2_note = (f"inputs larger than L2: {len(envs)} env replicas x {per_bytes / 2**20:.0f} MiB stepped round-robin"
                if len(envs) > 1 else f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)")
-    del envs[1:], feeders[1:]
-    torch.cuda.empty_cache()
     t = torch.tensor([secs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,7 +347,9 @@ def gpu_arm(args):
             dist.destroy_process_group()
         return
     # ---- rank 0 extras: per-kernel rooflines, size sweep, CPU baseline
-    roof = kernel_rooflines(env, actions, flush, peak_gbs)
+    roof = kernel_rooflines(envs, [f.synthetic_actions for f in feeders], peak_gbs)
+    del envs[1:], feeders[1:]
+    torch.cuda.empty_cache()
     sweep = {}
     if not args.no_sweep and world == 1:
         for n2 in (16384, 65536):
@@ -355,7 +358,7 @@ def gpu_arm(args):
             envs2, feeders2, _ = make_replicas(n2, dev, 0, args.l2)
             env2, feeder2 = envs2[0], feeders2[0]
             s2, _ = time_steps(envs2, [f.synthetic_actions for f in feeders2], 100, 10, flush, lambda: None)
-            r2 = kernel_rooflines(env2, feeder2.synthetic_actions, flush, peak_gbs, reps=50)
+            r2 = kernel_rooflines(envs2, [f.synthetic_actions for f in feeders2], peak_gbs, reps=50)
             sweep[str(n2)] = dict(value=n2 * 100 / s2, ms_per_step=s2 / 100 * 1e3,
                                   roofline_torque_lstm=r2["torque_lstm"], roofline_post_physics=r2["post_physics"])
             del env2, feeder2, envs2, feeders2

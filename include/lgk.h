@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LGK_ABI_VERSION 1
+#define LGK_ABI_VERSION 2
 #define LGK_NUM_DOF 12          /* every registered task has 12 DOF = 12 actions */
 #define LGK_MAX_FEET 4
 #define LGK_MAX_PEN 16
@@ -235,7 +235,11 @@ int lgk_rng_dump(uint64_t seed, int32_t step, int64_t env_id_offset, int32_t num
 /* ------------------------------------------------------------------ rsl_rl: ActorCritic.act / evaluate */
 /* Fused actor + critic MLP forward (ELU), Normal(mean, std).sample(), log_prob.sum(-1)
  * (rsl_rl ActorCritic.act / evaluate / get_actions_log_prob; PPO.act).  Weights are nn.Linear layout
- * [out,in] fp32.  Hidden layers run on tcgen05 tensor cores in TF32 with FP32 accumulation in TMEM. */
+ * [out,in] fp32.  The three hidden layers run on tcgen05 tensor cores (TF32 operands rounded to nearest, FP32
+ * accumulation in TMEM, one CTA per 128-env tile and network, activations never leave the SM); the last layer,
+ * biases, ELU and the distribution epilogue are FP32.  Shapes the tensor-core kernel does not cover (hidden[0] not a
+ * multiple of 64 or > 512, hidden[1] > hidden[0]/2, hidden[2] > 128, obs wider than 256, > 16 actions) run an FP32
+ * tiled-GEMM path with the same results to 1e-3. */
 typedef struct LgkPolicyParams {
   int32_t num_envs, num_obs, num_critic_obs, num_actions;
   int32_t hidden[3];                  /* actor and critic hidden sizes (must match pairwise) */
@@ -254,10 +258,21 @@ typedef struct LgkPolicyParams {
   float* values;                      /* [N,1] */
   float* actions_log_prob;            /* [N] */
   void* workspace; int64_t workspace_bytes;   /* see lgk_policy_workspace_bytes */
+  /* 0: weights are re-packed (TF32, swizzled tiles) into the workspace on every call.  Non-zero: a caller-maintained
+   * version of the weight tensors; the packed image in `workspace` is reused while version, workspace and shapes
+   * are unchanged (the Python ActorCritic passes the sum of the parameters' torch version counters + 1). */
+  int64_t weights_version;
 } LgkPolicyParams;
 
 int64_t lgk_policy_workspace_bytes(const LgkPolicyParams* p);
 int lgk_policy_act(const LgkPolicyParams* p, void* stream);
+/* 0 = auto (tcgen05 when the shape fits), 1 = force the FP32 path, 2 = require tcgen05 (error if the shape does not
+ * fit).  Process-wide; returns the previous value.  For tests and benchmarks. */
+int lgk_policy_set_variant(int variant);
+/* Profiling hook: when non-NULL, CTA (0,0) of the tcgen05 kernel writes %globaltimer stamps (ns) of its phases into
+ * device_buf16[0..9] (setup, obs staged, L1 done, drain 1, L2a done, drain 2, L2b done, drain 3, L3 done, outputs).
+ * flags (profiling experiments only, results are then meaningless): bit 0 skips the weight-tile copies, bit 1 the MMAs. */
+int lgk_policy_debug_timeline(int64_t* device_buf16, int flags);
 
 /* ------------------------------------------------------------------ rsl_rl: RolloutStorage.compute_returns */
 /* Reverse GAE scan over [T,N] + global advantage normalisation (unbiased std, +1e-8).

@@ -78,7 +78,7 @@ class PolicyParams(C.Structure):
                 ("actor_w", vp * 4), ("actor_b", vp * 4), ("critic_w", vp * 4), ("critic_b", vp * 4),
                 ("std", vp), ("seed", u64), ("step", i32), ("env_id_offset", i64), ("sample", i32),
                 ("actions", vp), ("action_mean", vp), ("action_sigma", vp), ("values", vp),
-                ("actions_log_prob", vp), ("workspace", vp), ("workspace_bytes", i64)]
+                ("actions_log_prob", vp), ("workspace", vp), ("workspace_bytes", i64), ("weights_version", i64)]
 
 
 class LgkError(RuntimeError):
@@ -104,6 +104,8 @@ def _load():
     lib.lgk_rng_dump.argtypes = [u64, i32, i64, i32, i32, i32, i32, vp, vp]
     lib.lgk_policy_workspace_bytes.argtypes = [C.POINTER(PolicyParams)]
     lib.lgk_policy_act.argtypes = [C.POINTER(PolicyParams), vp]
+    lib.lgk_policy_set_variant.argtypes = [C.c_int]
+    lib.lgk_policy_debug_timeline.argtypes = [vp, C.c_int]
     lib.lgk_gae.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp]
     lib.lgk_l2_flush.argtypes = [vp, i64, vp]
     lib.lgk_struct_size.argtypes = [C.c_int]
@@ -111,7 +113,7 @@ def _load():
         n = lib.lgk_struct_size(which)
         if n != C.sizeof(cls):
             raise ImportError(f"liblgk.so struct {cls.__name__} is {n} bytes, ctypes mirror is {C.sizeof(cls)}: rebuild")
-    if lib.lgk_abi_version() != 1:
+    if lib.lgk_abi_version() != 2:
         raise ImportError("liblgk.so ABI version mismatch")
     return lib
 
@@ -119,7 +121,7 @@ def _load():
 lib = _load()
 
 EXPORTS = ["lgk_set_lstm_weights", "lgk_compute_torques", "lgk_post_physics", "lgk_reset_idx", "lgk_finalize_step",
-           "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act",
+           "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline",
            "lgk_gae", "lgk_last_error_string", "lgk_abi_version", "lgk_l2_flush", "lgk_launch_count",
            "lgk_struct_size"]
 

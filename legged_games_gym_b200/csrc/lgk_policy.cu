@@ -3,10 +3,11 @@
 //   actor  = Linear(O,h0) ELU Linear(h0,h1) ELU Linear(h1,h2) ELU Linear(h2,A)
 //   critic = Linear(Oc,h0) ELU ... Linear(h2,1);  a ~ Normal(mu, std);  logp = sum log N(a; mu, std)
 //
-// v1 (this file): fp32 FFMA tiles -- a 64x64x16 shared-memory GEMM with fused bias+ELU epilogue per layer and a
-// sampling/log-prob epilogue kernel.  Hidden activations go through the caller-provided workspace.
-// The tcgen05 (TF32, TMEM accumulators) version of the three hidden layers replaces gemm_bias_act below.
-#include "lgk_math.cuh"
+// lgk_policy_act dispatches to the tcgen05 kernel (lgk_policy_tc.cu) whenever the shape fits it.  This file holds the
+// FP32 path for every other shape: a 64x64x16 shared-memory FFMA GEMM with fused bias+ELU epilogue per layer and a
+// sampling/log-prob epilogue kernel; hidden activations go through the caller-provided workspace.
+#include "lgk_policy_common.cuh"
+#include "lgk_policy_tc_plan.h"
 
 namespace lgk {
 
@@ -92,11 +93,32 @@ __global__ void sample_kernel(const __grid_constant__ LgkPolicyParams p) {
 
 using namespace lgk;
 
-extern "C" int64_t lgk_policy_workspace_bytes(const LgkPolicyParams* p) {
-  if (!p) return -1;
+static int g_variant = 0;
+
+extern "C" int lgk_policy_set_variant(int variant) {
+  const int prev = g_variant;
+  if (variant >= 0 && variant <= 2) g_variant = variant;
+  return prev;
+}
+
+extern "C" int lgk_policy_debug_timeline(int64_t* device_buf16, int flags) {
+  policy_tc_set_timeline(reinterpret_cast<long long*>(device_buf16), flags);
+  return LGK_OK;
+}
+
+static int64_t fp32_workspace_bytes(const LgkPolicyParams* p) {
   const int64_t hmax = p->hidden[0] > p->hidden[1] ? (p->hidden[0] > p->hidden[2] ? p->hidden[0] : p->hidden[2])
                                                     : (p->hidden[1] > p->hidden[2] ? p->hidden[1] : p->hidden[2]);
   return (int64_t)2 * p->num_envs * hmax * (int64_t)sizeof(float);
+}
+
+// large enough for either path, so that switching variants never needs a new workspace
+extern "C" int64_t lgk_policy_workspace_bytes(const LgkPolicyParams* p) {
+  if (!p) return -1;
+  int64_t need = fp32_workspace_bytes(p);
+  TcPlan pl;
+  if (policy_tc_plan(p, &pl)) { const int64_t t = policy_tc_workspace_bytes(pl); if (t > need) need = t; }
+  return need;
 }
 
 template <bool ELU>
@@ -114,7 +136,13 @@ extern "C" int lgk_policy_act(const LgkPolicyParams* p, void* stream) {
   LGK_REQUIRE(p->workspace_bytes >= lgk_policy_workspace_bytes(p), "policy: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int N = p->num_envs;
-  const int64_t hmax = lgk_policy_workspace_bytes(p) / (2 * (int64_t)N * (int64_t)sizeof(float));
+  {
+    TcPlan pl;
+    const bool fits = policy_tc_plan(p, &pl);
+    LGK_REQUIRE(g_variant != 2 || fits, "policy: shape does not fit the tcgen05 kernel");
+    if (fits && g_variant != 1) return policy_tc_launch(p, pl, st);
+  }
+  const int64_t hmax = fp32_workspace_bytes(p) / (2 * (int64_t)N * (int64_t)sizeof(float));
   float* w0 = reinterpret_cast<float*>(p->workspace);
   float* w1 = w0 + (size_t)N * hmax;
   for (int net = 0; net < 2; ++net) {

@@ -1,0 +1,538 @@
+// lgk_policy_tc.cu -- ActorCritic.act on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// rsl_rl ActorCritic (not vendored in the reference; call sites utils/task_registry.py:37-38,154):
+//   actor / critic = Linear(O,h0) ELU Linear(h0,h1) ELU Linear(h1,h2) ELU Linear(h2,A|1)
+//
+// One CTA owns a tile of 128 environments (= the 128 TMEM lanes) of ONE network and carries it through all four layers
+// without touching global memory in between:
+//
+//   warps 0-15 stage the observation tile into shared memory (TF32, 128-byte swizzled K-major chunks of 32 columns),
+//              later drain accumulators TMEM -> registers (tcgen05.ld 32x32b; warp w reads lane quadrant w%4, the four
+//              warps of a quadrant split the columns), add bias, ELU, round to TF32 and write the next layer's A
+//              operand back into the same chunks; the last drain feeds the h2->A layer on FP32 FFMA, then Normal
+//              sampling (Philox ACT stream) / log-prob / value.
+//   warp 16    streams pre-packed weight tiles (<=128 rows x 32 k, already swizzled + TF32-rounded by
+//              policy_pack_kernel) through a 5-stage 16 KB ring with TMA bulk copies (cp.async.bulk + mbarrier tx).
+//   warp 17    owns TMEM (512 columns) and issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=128, K=8) from one
+//              thread; tcgen05.commit releases ring stages and signals finished accumulations.
+//
+// Accumulator schedule in TMEM (fp32, one column per output feature), default 512-256-128 nets:
+//   L1 -> cols [0,h0)   drain cols [0,h0/2) -> A   L2a (k < h0/2) -> cols [0,h1)
+//                       drain cols [h0/2,h0) -> A  L2b (k >= h0/2) accumulates into cols [0,h1)
+//   drain [0,h1) -> A   L3 -> cols [h0/2, h0/2+h2)  final drain.
+// The A buffer (128 rows x 256 k x 4 B = 128 KB) is reused by every layer; 128 KB A + 80 KB ring + 14 KB constants
+// fit the 227 KB of one SM.
+//
+// Numerics: TF32 operands rounded to nearest (cvt.rna), FP32 accumulation in TMEM, biases / ELU / last layer / sampling
+// in FP32: within the north_star's 1e-3 for policy outputs (tests/test_gpu_parity.py).
+#include "lgk_policy_common.cuh"
+#include "lgk_policy_tc_plan.h"
+
+namespace lgk {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;                     // fp32 per 128-byte swizzle row
+constexpr int kChunkBytes = kTileM * 128;       // one A chunk: [128 rows][32 k] = 16 KB
+constexpr int kMaxChunks = 8;                   // K <= 256 per accumulation phase
+constexpr int kStageBytes = 16384;              // one weight tile: <= 128 rows x 128 B
+constexpr int kStages = 5;
+constexpr int kColSplit = 4;                     // warps per TMEM lane quadrant: they split the accumulator columns
+constexpr int kEpiWarps = 4 * kColSplit, kEpiThreads = 32 * kEpiWarps;
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kTcThreads = 32 * (kEpiWarps + 2);
+constexpr int kMaxH2 = 128;
+constexpr int kMaxOut = 16;
+constexpr int kTmemCols = 512;
+
+// shared-memory carve-up (offsets from a 1024-byte aligned base)
+constexpr int kOffA = 0;
+constexpr int kOffRing = kOffA + kMaxChunks * kChunkBytes;            // 131072
+constexpr int kOffW4 = kOffRing + kStages * kStageBytes;              // 212992: [h2][16] fp32, transposed last layer
+constexpr int kOffBias = kOffW4 + kMaxH2 * kMaxOut * 4;               // b1[512] b2[256] b3[128] b4[16] std[16]
+constexpr int kBiasFloats = 512 + 256 + 128 + 16 + 16;
+constexpr int kOffBar = kOffBias + kBiasFloats * 4;
+constexpr int kSmemBytes = kOffBar + 128 + 1024;                      // + barriers + alignment slack
+
+static inline int tile_rows(int n) { return n < 128 ? n : 128; }
+
+// returns false when the shape does not fit this kernel (the FP32 path in lgk_policy.cu handles it)
+bool policy_tc_plan(const LgkPolicyParams* p, TcPlan* pl) {
+  const int h0 = p->hidden[0], h1 = p->hidden[1], h2 = p->hidden[2];
+  if (h0 <= 0 || h1 <= 0 || h2 <= 0) return false;
+  if (h0 % 64 != 0 || h0 > 512) return false;
+  const int half = h0 / 2;
+  if (h1 % 32 != 0 || h1 > half) return false;
+  if (h2 % 32 != 0 || h2 > kMaxH2 || half + h2 > kTmemCols) return false;
+  if (p->num_actions < 1 || p->num_actions > kMaxOut) return false;
+  if (p->num_obs < 1 || p->num_obs > kMaxChunks * kChunkK || p->num_critic_obs < 1 || p->num_critic_obs > kMaxChunks * kChunkK) return false;
+  const int nb1 = tile_rows(half), nb2 = tile_rows(h1), nb3 = tile_rows(h2);
+  if (half % nb1 || h1 % nb2 || h2 % nb3 || nb1 % 16 || nb2 % 16 || nb3 % 16) return false;
+  pl->o[0] = p->num_obs; pl->o[1] = p->num_critic_obs;
+  pl->h0 = h0; pl->h1 = h1; pl->h2 = h2; pl->half = half; pl->nact = p->num_actions;
+  pl->nb1 = nb1; pl->nb2 = nb2; pl->nb3 = nb3;
+  pl->t2 = 2 * (h1 / nb2) * (half / kChunkK);
+  pl->t3 = (h2 / nb3) * (h1 / kChunkK);
+  long long off = 0;
+  for (int net = 0; net < 2; ++net) {
+    pl->kc1[net] = (pl->o[net] + kChunkK - 1) / kChunkK;
+    pl->t1[net] = 2 * (half / nb1) * pl->kc1[net];
+    pl->net_bytes[net] = 128LL * ((long long)pl->t1[net] * nb1 + (long long)pl->t2 * nb2 + (long long)pl->t3 * nb3);
+    pl->net_off[net] = off;
+    off += pl->net_bytes[net];
+  }
+  return true;
+}
+
+long long policy_tc_workspace_bytes(const TcPlan& pl) { return pl.net_off[1] + pl.net_bytes[1] + 1024; }
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B (layout type 2), 8-row groups 1024 B apart, descriptor version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+
+// ------------------------------------------------------------------ weight packing
+// job j = net*3 + layer.  Tile order == the order the MMA warp consumes tiles:
+//   layer 0 : half (0,1) | n-block | k-chunk              rows nb1, K = O
+//   layer 1 : k-part (0,1) | n-block | k-chunk in part    rows nb2, K = h0
+//   layer 2 : n-block | k-chunk                           rows nb3, K = h1
+// A tile is the shared-memory image itself: row r holds 32 consecutive k as eight 16-byte chunks, logical chunk c at
+// physical chunk c ^ (r & 7) (128-byte swizzle), values rounded to TF32, zero beyond K.
+struct PackJobs {
+  const float* w[6];
+  float* dst[6];
+  int n[6], k[6], nb[6], tiles[6], kchunks[6], nblks[6];
+};
+
+__global__ void __launch_bounds__(256) policy_pack_kernel(const __grid_constant__ PackJobs jobs) {
+  const int j = blockIdx.y, layer = j % 3;
+  const int nb = jobs.nb[j], K = jobs.k[j], kch = jobs.kchunks[j], nblks = jobs.nblks[j];
+  const long long total = (long long)jobs.tiles[j] * nb * kChunkK;
+  const float* __restrict__ W = jobs.w[j];
+  float* __restrict__ dst = jobs.dst[j];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % (nb * kChunkK)), t = (int)(i / (nb * kChunkK));
+    const int row = e >> 5, pc = (e >> 2) & 7, w = e & 3;
+    const int lc = pc ^ (row & 7);
+    const int outer = t / (nblks * kch), rem = t % (nblks * kch);     // half (layer 0) / k-part (layer 1) / 0 (layer 2)
+    const int nblk = rem / kch, kc = rem % kch;
+    int n, k;
+    if (layer == 0) { n = outer * (nblks * nb) + nblk * nb + row; k = kc * kChunkK + lc * 4 + w; }
+    else if (layer == 1) { n = nblk * nb + row; k = (outer * kch + kc) * kChunkK + lc * 4 + w; }
+    else { n = nblk * nb + row; k = kc * kChunkK + lc * 4 + w; }
+    dst[i] = (k < K) ? to_tf32(W[(size_t)n * K + k]) : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ the fused forward
+struct TcArgs {
+  LgkPolicyParams p;
+  TcPlan pl;
+  const uint8_t* packed;      // workspace base (1024-byte aligned)
+  long long* timeline;        // optional [16] globaltimer stamps of CTA (0,0) (lgk_policy_debug_timeline)
+  int dbg_flags;              // bit 0: skip the weight copies, bit 1: skip the MMAs (profiling experiments only)
+};
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+// ELU with one MUFU: exp(x) - 1 = 2^(x*log2e) - 1 for x <= 0 (absolute error ~1e-7, far inside the TF32 rounding that follows)
+__device__ __forceinline__ float elu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.f ? x : e - 1.0f;
+}
+
+// drain accumulator column blocks cb = part, part + kColSplit, ... (32 columns each) of `ncols` columns starting at TMEM
+// column col0 into A chunks cb: + bias, ELU, round to TF32, 128-byte swizzled row
+__device__ __forceinline__ void drain_to_a(uint32_t tmem_lane_base, int part, int row, int col0, int ncols,
+                                           uint32_t bias_addr, uint32_t abuf_addr) {
+  for (int cb = part; cb < ncols / 32; cb += kColSplit) {
+    uint32_t v[32];
+    tmem_ld32(tmem_lane_base + (uint32_t)(col0 + cb * 32), v);
+    const uint32_t rowp = abuf_addr + cb * kChunkBytes + row * 128;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = lds_f4(bias_addr + (cb * 32 + 4 * q) * 4);
+      float4 o;
+      o.x = to_tf32(elu_fast(__uint_as_float(v[4 * q + 0]) + b.x));
+      o.y = to_tf32(elu_fast(__uint_as_float(v[4 * q + 1]) + b.y));
+      o.z = to_tf32(elu_fast(__uint_as_float(v[4 * q + 2]) + b.z));
+      o.w = to_tf32(elu_fast(__uint_as_float(v[4 * q + 3]) + b.w));
+      sts_f4(rowp + ((q ^ (row & 7)) << 4), o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);     // 128-byte swizzle atoms need 1024-byte alignment
+  const uint32_t s_base = smem_addr(smem);
+  const uint32_t abuf = s_base + kOffA, ring = s_base + kOffRing;
+  float* s_w4t = reinterpret_cast<float*>(smem + kOffW4);
+  float* s_b1 = reinterpret_cast<float*>(smem + kOffBias);
+  float* s_b2 = s_b1 + 512;
+  float* s_b3 = s_b2 + 256;
+  float* s_b4 = s_b3 + 128;
+  float* s_std = s_b4 + 16;
+  const uint32_t a_b1 = s_base + kOffBias, a_b2 = a_b1 + 512 * 4, a_b3 = a_b2 + 256 * 4, a_w4t = s_base + kOffW4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  const uint32_t bar_full = smem_addr(bars), bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_acc = bar_full + 16 * kStages, bar_a = bar_acc + 8;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+
+  const LgkPolicyParams& p = a.p;
+  const TcPlan& pl = a.pl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int net = blockIdx.y;                     // 0 actor, 1 critic
+  const int m0 = blockIdx.x * kTileM;
+  const int N = p.num_envs;
+  const int O = pl.o[net], kc1 = pl.kc1[net];
+  const int h0 = pl.h0, h1 = pl.h1, h2 = pl.h2, half = pl.half;
+  const int nout = net ? 1 : pl.nact;
+  const float* const* Wg = net ? p.critic_w : p.actor_w;
+  const float* const* Bg = net ? p.critic_b : p.actor_b;
+
+  // ---- one-time setup
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_a, kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"((uint32_t)kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // constants: biases, transposed last layer [k][16]
+  for (int i = tid; i < h0; i += kTcThreads) s_b1[i] = Bg[0][i];
+  for (int i = tid; i < h1; i += kTcThreads) s_b2[i] = Bg[1][i];
+  for (int i = tid; i < h2; i += kTcThreads) s_b3[i] = Bg[2][i];
+  if (tid < kMaxOut) { s_b4[tid] = tid < nout ? Bg[3][tid] : 0.f; s_std[tid] = (net == 0 && tid < nout) ? p.std[tid] : 1.f; }
+  for (int i = tid; i < h2 * kMaxOut; i += kTcThreads) {
+    const int k = i >> 4, o = i & 15;
+    s_w4t[i] = o < nout ? Wg[3][(size_t)o * h2 + k] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  // phase stamps of CTA (0,0): 0 setup done | 1 obs staged | 2 L1 done | 3 drain 1 | 4 L2a done | 5 drain 2 | 6 L2b done |
+  // 7 drain 3 | 8 L3 done | 9 outputs written
+  auto stamp = [&](int slot) {
+    if (a.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0)) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.timeline[slot] = (long long)t;
+    }
+  };
+  stamp(0);
+
+  if (warp < kEpiWarps) {
+    // ================= staging + epilogue warps =================
+    // TMEM lane quadrant = warp % 4 (hardware rule); the kColSplit warps of a quadrant split the column blocks
+    const int quad = warp & 3, part = warp >> 2;
+    const int row = quad * 32 + lane;                       // TMEM lane == row of the tile
+    const uint32_t tmem_lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    {   // observation tile -> A chunks (coalesced 128-byte row segments; lane = k inside the chunk); four rows per pass
+        // so that up to 32 independent loads are in flight per thread
+      const float* __restrict__ X = net ? p.critic_obs : p.obs;
+      constexpr int kRowsPerWarp = kTileM / kEpiWarps, kRowsPerPass = 4;
+      for (int r0 = warp * kRowsPerWarp; r0 < (warp + 1) * kRowsPerWarp; r0 += kRowsPerPass) {
+        float vals[kRowsPerPass][kMaxChunks];
+#pragma unroll
+        for (int i = 0; i < kRowsPerPass; ++i) {
+          const int n = m0 + r0 + i;
+          const float* src = X + (size_t)n * O;
+#pragma unroll
+          for (int kc = 0; kc < kMaxChunks; ++kc) {
+            const int k = kc * kChunkK + lane;
+            vals[i][kc] = (kc < kc1 && n < N && k < O) ? __ldg(src + k) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kRowsPerPass; ++i) {
+          const int r = r0 + i;
+          const uint32_t dstp = abuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
+#pragma unroll
+          for (int kc = 0; kc < kMaxChunks; ++kc)
+            if (kc < kc1) sts_f1(dstp + kc * kChunkBytes, to_tf32(vals[i][kc]));
+        }
+      }
+    }
+    stamp(1);
+    fence_proxy_async();
+    mbar_arrive(bar_a);                                     // A ready #0 (layer-1 input)
+
+    mbar_wait(bar_acc, 0);                                  // L1 done (both halves)
+    tc_fence_after();
+    stamp(2);
+    drain_to_a(tmem_lane_base, part, row, 0, half, a_b1, abuf);
+    fence_proxy_async(); tc_fence_before();
+    stamp(3);
+    mbar_arrive(bar_a);                                     // A ready #1 (h1 columns [0, half))
+
+    mbar_wait(bar_acc, 1);                                  // L2a done: A consumed, cols [0,h1) hold partial sums
+    tc_fence_after();
+    stamp(4);
+    drain_to_a(tmem_lane_base, part, row, half, half, a_b1 + half * 4, abuf);
+    fence_proxy_async(); tc_fence_before();
+    stamp(5);
+    mbar_arrive(bar_a);                                     // A ready #2 (h1 columns [half, h0))
+
+    mbar_wait(bar_acc, 0);                                  // L2b done
+    tc_fence_after();
+    stamp(6);
+    drain_to_a(tmem_lane_base, part, row, 0, h1, a_b2, abuf);
+    fence_proxy_async(); tc_fence_before();
+    stamp(7);
+    mbar_arrive(bar_a);                                     // A ready #3 (layer-3 input)
+
+    mbar_wait(bar_acc, 1);                                  // L3 done: the A buffer is free again
+    tc_fence_after();
+    stamp(8);
+    // ---- last layer (h2 -> nout) on FP32 FFMA: every part sums its column blocks, parts 1.. hand their partial sums
+    //      to part 0 through the (now idle) A buffer, laid out [part-1][output][row]
+    float acc[kMaxOut];
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.f;
+    for (int cb = part; cb < h2 / 32; cb += kColSplit) {
+      uint32_t v[32];
+      tmem_ld32(tmem_lane_base + (uint32_t)(half + cb * 32), v);
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 4) {
+        const float4 b = lds_f4(a_b3 + (cb * 32 + jj) * 4);
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float h = elu_fast(__uint_as_float(v[jj + u]) + bb[u]);
+          const uint32_t wr = a_w4t + (cb * 32 + jj + u) * kMaxOut * 4;
+          const float4 w0 = lds_f4(wr), w1 = lds_f4(wr + 16), w2 = lds_f4(wr + 32), w3 = lds_f4(wr + 48);
+          acc[0] = fmaf(h, w0.x, acc[0]); acc[1] = fmaf(h, w0.y, acc[1]); acc[2] = fmaf(h, w0.z, acc[2]); acc[3] = fmaf(h, w0.w, acc[3]);
+          acc[4] = fmaf(h, w1.x, acc[4]); acc[5] = fmaf(h, w1.y, acc[5]); acc[6] = fmaf(h, w1.z, acc[6]); acc[7] = fmaf(h, w1.w, acc[7]);
+          acc[8] = fmaf(h, w2.x, acc[8]); acc[9] = fmaf(h, w2.y, acc[9]); acc[10] = fmaf(h, w2.z, acc[10]); acc[11] = fmaf(h, w2.w, acc[11]);
+          acc[12] = fmaf(h, w3.x, acc[12]); acc[13] = fmaf(h, w3.y, acc[13]); acc[14] = fmaf(h, w3.z, acc[14]); acc[15] = fmaf(h, w3.w, acc[15]);
+        }
+      }
+    }
+    tc_fence_before();
+    if (part > 0) {
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) sts_f1(abuf + (((part - 1) * kMaxOut + o) * kTileM + row) * 4, acc[o]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    if (part == 0) {
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) {
+        float t = acc[o] + s_b4[o];
+#pragma unroll
+        for (int q = 0; q < kColSplit - 1; ++q) t += lds_f1(abuf + ((q * kMaxOut + o) * kTileM + row) * 4);
+        acc[o] = t;
+      }
+      const int n = m0 + row;
+      if (n < N) {
+        if (net == 1) p.values[n] = acc[0];
+        else policy_finish_row<kMaxOut, true>(p, n, acc, s_std);
+      }
+    }
+    stamp(9);
+  } else if (warp == kProducerWarp) {
+    // ================= weight-tile producer =================
+    if (lane == 0) {
+      const uint8_t* src = a.packed + pl.net_off[net];
+      const int ntiles[3] = {pl.t1[net], pl.t2, pl.t3};
+      const int bytes[3] = {pl.nb1 * 128, pl.nb2 * 128, pl.nb3 * 128};
+      int i = 0;
+      for (int ph = 0; ph < 3; ++ph) {
+        for (int t = 0; t < ntiles[ph]; ++t, ++i) {
+          const int s = i % kStages;
+          mbar_wait(bar_empty + 8 * s, ((i / kStages) & 1) ^ 1);
+          if (a.dbg_flags & 1) {
+            mbar_arrive(bar_full + 8 * s);
+          } else {
+            mbar_expect_tx(bar_full + 8 * s, (uint32_t)bytes[ph]);
+            bulk_g2s(ring + s * kStageBytes, src, (uint32_t)bytes[ph], bar_full + 8 * s);
+          }
+          src += bytes[ph];
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int i = 0;
+      uint32_t a_par = 0;
+      const bool skip_mma = (a.dbg_flags & 2) != 0;
+      // one weight tile = one n-block x one 32-wide k-chunk: `ksteps` MMAs of K = 8
+      auto tile_mma = [&](int a_chunk, uint32_t d_col, int nb, bool first_k, int ksteps) {
+        const int s = i % kStages;
+        mbar_wait(bar_full + 8 * s, (i / kStages) & 1);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(nb);
+        if (!skip_mma) {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ad = make_smem_desc(abuf + a_chunk * kChunkBytes + ks * 32);
+            const uint64_t bd = make_smem_desc(ring + s * kStageBytes + ks * 32);
+            mma_tf32(tmem_base + d_col, ad, bd, idesc, (first_k && ks == 0) ? 0u : 1u);
+          }
+        }
+        tc_commit(bar_empty + 8 * s);                       // stage is free once these MMAs have read it
+        ++i;
+      };
+      // ---- L1: both halves into cols [0, h0)
+      mbar_wait(bar_a, a_par); a_par ^= 1; tc_fence_after();
+      const int last_ks = (O - (kc1 - 1) * kChunkK + 7) / 8;     // K-steps of the (zero-padded) last chunk that hold data
+      for (int hb = 0; hb < 2; ++hb)
+        for (int nb = 0; nb < half / pl.nb1; ++nb)
+          for (int kc = 0; kc < kc1; ++kc)
+            tile_mma(kc, (uint32_t)(hb * half + nb * pl.nb1), pl.nb1, kc == 0, kc == kc1 - 1 ? last_ks : 4);
+      tc_commit(bar_acc);
+      // ---- L2: two k-parts into cols [0, h1)
+      for (int part = 0; part < 2; ++part) {
+        mbar_wait(bar_a, a_par); a_par ^= 1; tc_fence_after();
+        for (int nb = 0; nb < h1 / pl.nb2; ++nb)
+          for (int kc = 0; kc < half / kChunkK; ++kc)
+            tile_mma(kc, (uint32_t)(nb * pl.nb2), pl.nb2, part == 0 && kc == 0, 4);
+        tc_commit(bar_acc);
+      }
+      // ---- L3 into cols [half, half + h2)
+      mbar_wait(bar_a, a_par); a_par ^= 1; tc_fence_after();
+      for (int nb = 0; nb < h2 / pl.nb3; ++nb)
+        for (int kc = 0; kc < h1 / kChunkK; ++kc)
+          tile_mma(kc, (uint32_t)(half + nb * pl.nb3), pl.nb3, kc == 0, 4);
+      tc_commit(bar_acc);
+    }
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct PackCache { const void* ws; long long version; int shape[8]; const void* w[8]; };
+static PackCache g_pack = {nullptr, 0, {0}, {nullptr}};
+static long long* g_timeline = nullptr;
+static int g_dbg_flags = 0;
+void policy_tc_set_timeline(long long* dev, int flags) { g_timeline = dev; g_dbg_flags = flags; }
+
+int policy_tc_launch(const LgkPolicyParams* p, const TcPlan& pl, cudaStream_t st) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)p->workspace + 1023) & ~(uintptr_t)1023);
+  const int shape[8] = {pl.o[0], pl.o[1], pl.h0, pl.h1, pl.h2, pl.nact, 0, 0};
+  const void* wptr[8];
+  for (int i = 0; i < 4; ++i) { wptr[i] = p->actor_w[i]; wptr[4 + i] = p->critic_w[i]; }
+  const bool cached = p->weights_version != 0 && g_pack.ws == p->workspace && g_pack.version == p->weights_version &&
+                      memcmp(shape, g_pack.shape, sizeof(shape)) == 0 && memcmp(wptr, g_pack.w, sizeof(wptr)) == 0;
+  if (!cached) {
+    PackJobs jobs;
+    for (int net = 0; net < 2; ++net) {
+      const float* const* W = net ? p->critic_w : p->actor_w;
+      float* dst = reinterpret_cast<float*>(base + pl.net_off[net]);
+      const int nbs[3] = {pl.nb1, pl.nb2, pl.nb3};
+      const int tiles[3] = {pl.t1[net], pl.t2, pl.t3};
+      const int ns[3] = {pl.h0, pl.h1, pl.h2}, ks[3] = {pl.o[net], pl.h0, pl.h1};
+      const int kch[3] = {pl.kc1[net], pl.half / kChunkK, pl.h1 / kChunkK};
+      const int nblks[3] = {pl.half / pl.nb1, pl.h1 / pl.nb2, pl.h2 / pl.nb3};
+      for (int l = 0; l < 3; ++l) {
+        const int j = net * 3 + l;
+        jobs.w[j] = W[l]; jobs.dst[j] = dst; jobs.n[j] = ns[l]; jobs.k[j] = ks[l]; jobs.nb[j] = nbs[l];
+        jobs.tiles[j] = tiles[l]; jobs.kchunks[j] = kch[l]; jobs.nblks[j] = nblks[l];
+        dst += (size_t)tiles[l] * nbs[l] * kChunkK;
+      }
+    }
+    policy_pack_kernel<<<dim3(74, 6), 256, 0, st>>>(jobs);
+    count_launch();
+    if (int rc = check_cuda(cudaGetLastError(), "policy_pack_kernel launch")) return rc;
+    g_pack.ws = p->workspace; g_pack.version = p->weights_version;
+    memcpy(g_pack.shape, shape, sizeof(shape));
+    memcpy(g_pack.w, wptr, sizeof(wptr));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
+                            "cudaFuncSetAttribute(policy_tc_kernel)")) return rc;
+    attr_set = true;
+  }
+  TcArgs args;
+  args.p = *p; args.pl = pl; args.packed = base; args.timeline = g_timeline; args.dbg_flags = g_dbg_flags;
+  policy_tc_kernel<<<dim3((p->num_envs + kTileM - 1) / kTileM, 2), kTcThreads, kSmemBytes, st>>>(args);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "policy_tc_kernel launch");
+}
+
+}  // namespace lgk

@@ -93,7 +93,11 @@ class ActorCritic(nn.Module):
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         p.workspace, p.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        # torch bumps a tensor's version counter on every in-place update (optimizer.step, load_state_dict): the packed
+        # TF32 weight image inside the workspace is rebuilt only when this sum moves
+        p.weights_version = 1 + sum(int(q._version) for q in self.parameters())
         nat.check(nat.lib.lgk_policy_act(C.byref(p), torch.cuda.current_stream().cuda_stream), "lgk_policy_act")
+        self._last_params, self._last_inputs = p, (obs, critic_obs)      # keeps the launch's buffers alive
         self._fused = out
         return out
 

@@ -317,11 +317,16 @@ def test_gae_matches_restated_rsl_rl(T, N):
     assert torch.allclose(ret.cpu(), want_r, rtol=1e-5, atol=1e-5)      # and in fact fp32-tight
 
 
-@pytest.mark.parametrize("n,nobs,hidden", [(4096, 235, (512, 256, 128)), (100, 48, (128, 64, 32)), (777, 169, (512, 256, 128))])
-def test_policy_act_matches_restated_rsl_rl(n, nobs, hidden):
+# variant 2 = tcgen05 kernel (TF32 operands, FP32 accumulation in TMEM), 1 = FP32 FFMA path; (96, 64, 32) does not fit the
+# tensor-core kernel's tiling and must take the FP32 path on its own under variant 0 (auto)
+@pytest.mark.parametrize("n,nobs,hidden,variant", [
+    (4096, 235, (512, 256, 128), 2), (100, 48, (128, 64, 32), 2), (777, 169, (512, 256, 128), 2), (129, 235, (256, 128, 64), 2),
+    (4096, 235, (512, 256, 128), 1), (100, 48, (128, 64, 32), 1), (300, 48, (96, 64, 32), 0)])
+def test_policy_act_matches_restated_rsl_rl(n, nobs, hidden, variant):
     from oracle.rsl_oracle import ActorCriticOracle
     from legged_games_gym_b200.rsl_rl.modules import ActorCritic
     torch.manual_seed(0)
+    nat().lib.lgk_policy_set_variant(variant)
     orc = ActorCriticOracle(nobs, nobs, 12, hidden, hidden)
     with torch.no_grad():
         orc.std.copy_(torch.linspace(0.5, 1.5, 12))
@@ -344,3 +349,8 @@ def test_policy_act_matches_restated_rsl_rl(n, nobs, hidden):
     assert torch.allclose(got_v.cpu(), v, **tol)
     assert torch.allclose(ac.action_std.cpu(), sg, **tol)
     assert torch.allclose(got_lp.cpu(), lp, rtol=1e-3, atol=5e-3)
+    # a second call reuses the packed weight image (same torch version counters) and must reproduce the first
+    with torch.inference_mode():
+        again = ac.act(o)
+    assert torch.equal(again, got_a)
+    nat().lib.lgk_policy_set_variant(0)

@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="rotate: cycle over env replicas whose buffers exceed L2; flush: write 256 MiB between steps")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launch")
     ap.add_argument("--lstm-variant", type=int, default=0, help="0 auto, 1 thread-per-sequence, 2 role-split")
     return ap.parse_args()
 
@@ -181,6 +182,10 @@ def time_steps(envs, actions, steps, warmup, flush, dist_barrier):
     from legged_games_gym_b200 import _native as nat
     st = torch.cuda.current_stream().cuda_stream
     rotate = len(envs) > 1
+    # the step graph reads its actions from env.action_buffer: a policy writes them there directly (no per-step copy)
+    for e, a in zip(envs, actions):
+        e.action_buffer.copy_(a)
+    actions = [e.action_buffer for e in envs]
     for i in range(max(warmup, 3 * len(envs))):
         envs[i % len(envs)].step(actions[i % len(envs)])
         if not rotate:
@@ -288,6 +293,8 @@ def gpu_arm(args):
     from legged_games_gym_b200 import _native as nat
     N = args.num_envs
     peak_gbs, peak_src = peaks()
+    if args.no_pdl:
+        nat.lib.lgk_set_pdl(0)
     global TILE, USE_GRAPH, LSTM_VARIANT
     TILE, USE_GRAPH, LSTM_VARIANT = args.tile, not args.no_graph, args.lstm_variant
     envs, feeders, per_bytes = make_replicas(N, dev, rank * N, args.l2)
@@ -307,11 +314,12 @@ def gpu_arm(args):
     # ---- e2e: sim state in pinned host memory, actions from host, results read back (rank-local, max over ranks)
     env_h, feeder_h = make_env(N, dev, host_sim=True, env_id_offset=rank * N)
     h_actions = feeder_h.synthetic_actions.cpu().pin_memory()
-    d_actions = torch.empty_like(feeder_h.synthetic_actions)
     h_obs = torch.empty(env_h.obs_buf.shape).pin_memory()
     h_rew = torch.empty(N).pin_memory()
     h_reset = torch.empty(N, dtype=torch.bool).pin_memory()
     e2e_steps = max(10, min(args.steps, 200))
+
+    d_actions = env_h.action_buffer
 
     def e2e_step():
         d_actions.copy_(h_actions, non_blocking=True)
@@ -321,9 +329,11 @@ def gpu_arm(args):
         h_reset.copy_(reset, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    feeder_h.h2d_bytes = feeder_h.d2h_bytes = 0
+    e2e_step()                                  # the env's first step runs eagerly: count the sim-side bytes of one step
+    sim_h2d, sim_d2h = feeder_h.h2d_bytes, feeder_h.d2h_bytes
     for _ in range(5):
         e2e_step()
-    feeder_h.h2d_bytes = feeder_h.d2h_bytes = 0
     barrier()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -335,8 +345,8 @@ def gpu_arm(args):
     e2e_secs = torch.tensor([a.elapsed_time(b) / 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
-    h2d = feeder_h.h2d_bytes // e2e_steps + d_actions.numel() * 4
-    d2h = feeder_h.d2h_bytes // e2e_steps + (h_obs.numel() + h_rew.numel()) * 4 + h_reset.numel()
+    h2d = sim_h2d + d_actions.numel() * 4
+    d2h = sim_d2h + (h_obs.numel() + h_rew.numel()) * 4 + h_reset.numel()
     e2e = dict(value=world * N * e2e_steps / float(e2e_secs.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
                d2h_bytes_per_step=int(d2h), steps=e2e_steps)
     del env_h, feeder_h
@@ -374,7 +384,7 @@ def gpu_arm(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{TASK}: {N} envs/GPU, 187-point height scan + 4x LSTM actuator-net torques + full reward set "
                                "+ termination/reset/command resampling + noisy observations (BASELINE.json configs[1])",
-                   "num_envs_per_gpu": N, "resets_per_step": float(env.reset_buf.float().mean()), "l2": l2_note, "cuda_graph": bool(getattr(env, "_graph", None) is not None),
+                   "num_envs_per_gpu": N, "resets_per_step": float(env.reset_buf.float().mean()), "l2": l2_note, "cuda_graph": bool(getattr(env, "_graph", None) is not None), "pdl": not args.no_pdl,
                    "timing": "CUDA events on the launch stream around the K steps; barrier+synchronize both sides",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),

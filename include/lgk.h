@@ -285,6 +285,10 @@ int lgk_gae(const float* rewards, const float* values, const uint8_t* dones, con
 /* ------------------------------------------------------------------ misc */
 const char* lgk_last_error_string(void);
 int lgk_abi_version(void);
+/* Programmatic dependent launch for the kernels of the env step (default on): each kernel of the chain may begin its
+ * prologue while its predecessor on the stream drains, and waits (griddepcontrol.wait) before touching memory.
+ * Returns the previous setting. */
+int lgk_set_pdl(int enable);
 /* Write `bytes` of a scratch buffer (L2 flush between timed iterations; bench only). */
 int lgk_l2_flush(void* scratch, int64_t bytes, void* stream);
 /* number of kernel launches issued through this library since load (bench's gpu_launches). */

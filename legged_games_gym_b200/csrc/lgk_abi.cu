@@ -8,6 +8,7 @@ namespace lgk {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+int g_pdl = 1;
 
 int set_error(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -59,6 +60,7 @@ using namespace lgk;
 
 extern "C" const char* lgk_last_error_string(void) { return g_err; }
 extern "C" int lgk_abi_version(void) { return LGK_ABI_VERSION; }
+extern "C" int lgk_set_pdl(int enable) { const int prev = g_pdl; g_pdl = enable ? 1 : 0; return prev; }
 extern "C" int64_t lgk_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" int lgk_struct_size(int which) {

@@ -8,9 +8,11 @@
 #if defined(__CUDACC__)
 #define LGK_HD __host__ __device__ __forceinline__
 #define LGK_D __device__ __forceinline__
+#define LGK_COLD static __device__ __noinline__
 #else
 #define LGK_HD inline
 #define LGK_D inline
+#define LGK_COLD static inline
 #endif
 
 // ---- individually-rounded fp32 ops (no FMA contraction).  On the device these are the _rn intrinsics;
@@ -52,6 +54,26 @@ constexpr int kDof = LGK_NUM_DOF;
 int set_error(int code, const char* msg);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+
+// ---- programmatic dependent launch (PDL): the kernels of one env step form a chain on one stream; launched with
+// programmatic stream serialization each may start (prologue, barrier init, constant staging) while its predecessor
+// drains, and blocks in pdl_wait() until the predecessor's writes are visible.  Works under stream capture (the edges
+// become programmatic graph edges).  lgk_set_pdl(0) switches back to plain launches.
+extern int g_pdl;
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 #define LGK_REQUIRE(cond, msg) do { if (!(cond)) return lgk::set_error(LGK_ERR_ARG, msg); } while (0)
 #define LGK_ALIGNED16(ptr, msg) do { if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return lgk::set_error(LGK_ERR_ALIGN, msg); } while (0)

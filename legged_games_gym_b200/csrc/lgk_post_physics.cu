@@ -92,10 +92,13 @@ __host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots)
   return L;
 }
 
-__device__ __forceinline__ void copy_f32(float* dst, const float* src, int n, int lane) {
+// used only by the partial-tile fallback path: kept out of line and rolled so the hot path stays compact
+__device__ __noinline__ void copy_f32(float* dst, const float* src, int n, int lane) {
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
-__device__ __forceinline__ void copy_u8(uint8_t* dst, const uint8_t* src, int n, int lane) {
+__device__ __noinline__ void copy_u8(uint8_t* dst, const uint8_t* src, int n, int lane) {
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
@@ -143,6 +146,8 @@ __global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__
   const bool fat_active = p.reward_active[LGK_R_FEET_AIR_TIME] != 0 && F > 0;
   // bulk (TMA) path needs a full tile (sizes are then multiples of 16 B) and unit root stride
   const bool bulk = (nval == kTile) && (p.actors_per_env == 1) && (p.num_envs % 4 == 0);   // 16-B aligned rows
+  pdl_launch_dependents();
+  pdl_wait();              // everything below reads state written by the previous kernels of the step
   const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
   const bool do_push = p.step_counter_dev ? (p.push_interval > 0 && step_eff % p.push_interval == 0) : (p.do_push != 0);
   const RngKey key = make_key(p.seed, step_eff);
@@ -383,8 +388,7 @@ __global__ void __launch_bounds__(kK2Threads, 8) scan_obs_kernel(const __grid_co
   const bool scan = (mode & kScan) != 0 && p.measure_heights && !p.terrain_is_plane && P > 0;
   const bool obs = (mode & kObs) != 0;
   const bool hcols = p.measure_heights != 0;
-  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
-  const RngKey key = make_key(p.seed, step_eff);
+  pdl_launch_dependents();
   if (scan) {
     for (int i = tid; i < P; i += kK2Threads) {
       const float bx = p.height_points_xy[2 * i], by = p.height_points_xy[2 * i + 1];
@@ -404,6 +408,9 @@ __global__ void __launch_bounds__(kK2Threads, 8) scan_obs_kernel(const __grid_co
     nz[g] = (obs && noisy && j < O) ? __ldg(p.noise_scale_vec + j) : 0.f;
   }
   const int ngroups = obs ? (O + 31) >> 5 : ((48 + P + 31) >> 5);
+  pdl_wait();              // constants above (point grid, noise scales) never change; everything below is per-step state
+  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
+  const RngKey key = make_key(p.seed, step_eff);
 
   // per-env inputs (frame from K1 or the root pose, the two head segments) are fetched one env AHEAD of their use
   struct EnvIn { float4 f; float rz, head0, head1; };
@@ -555,53 +562,62 @@ __global__ void terrain_level_sum_kernel(const __grid_constant__ LgkStepParams p
 }
 
 // ------------------------------------------------------------------ finalize: id compaction + extras
-// Single CTA.  Each thread owns 16 consecutive envs per sweep (one 16-byte load of reset_buf), so a sweep
-// covers 16384 envs; ids come out in ascending order like reset_buf.nonzero() (LR:128).
+// Single CTA, single sweep: thread t owns the contiguous flag range [t*chunk, (t+1)*chunk) (chunk a multiple of 16 so
+// every load is one aligned 16-byte vector), counts it, one block-wide exclusive scan, then re-reads its (L1-resident)
+// range and emits the ids -- ascending like reset_buf.nonzero() (LR:128).
+__device__ __forceinline__ int count_flags16(uint4 v) {
+  // flags are 0/1 bytes (bool tensors): the byte sum is the popcount
+  return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+}
+
 __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ LgkStepParams p, int32_t* reset_ids,
                                                         int32_t* reset_count, float* episode_means,
                                                         uint8_t* time_outs_extras, int advance) {
   __shared__ int s_warp[32];
-  __shared__ int s_base, s_total;
+  __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.num_envs;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int start = 0; start < N; start += 16384) {
-    const int first = start + tid * 16;
-    uint8_t flags[16];
-    int c = 0;
-    if (first + 16 <= N) {
-      *reinterpret_cast<uint4*>(flags) = *reinterpret_cast<const uint4*>(p.reset_buf + first);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) c += flags[i] != 0;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { flags[i] = (first + i < N) ? p.reset_buf[first + i] : 0; c += flags[i] != 0; }
-    }
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const int v = s_warp[lane];
-      int wi = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-      s_warp[lane] = wi - v;
-      if (lane == 31) s_total = wi;
-    }
-    __syncthreads();
-    int off = s_base + s_warp[warp] + incl - c;
-    if (reset_ids && c) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (flags[i]) reset_ids[off++] = first + i;
-    }
-    __syncthreads();
-    if (tid == 0) s_base += s_total;
-    __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+  const int chunk = (((N + 1023) / 1024) + 15) & ~15;
+  const int first = tid * chunk, last = min(N, first + chunk);
+  const bool vec = (reinterpret_cast<uintptr_t>(p.reset_buf) & 15u) == 0;
+  int c = 0;
+  for (int i = first; i < last; i += 16) {
+    if (vec && i + 16 <= last) c += count_flags16(*reinterpret_cast<const uint4*>(p.reset_buf + i));
+    else for (int k = i; k < min(i + 16, last); ++k) c += p.reset_buf[k] != 0;
   }
-  const int count = s_base;
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int v = s_warp[lane];
+    int wi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+    s_warp[lane] = wi - v;
+    if (lane == 31) s_total = wi;
+  }
+  __syncthreads();
+  const int count = s_total;
+  if (reset_ids && c) {
+    int off = s_warp[warp] + incl - c;
+    for (int i = first; i < last; i += 16) {
+      if (vec && i + 16 <= last) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p.reset_buf + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t m = w[q];
+          while (m) { const int b = __ffs(m) - 1; m &= m - 1; reset_ids[off++] = i + 4 * q + (b >> 3); }
+        }
+      } else {
+        for (int k = i; k < min(i + 16, last); ++k) if (p.reset_buf[k]) reset_ids[off++] = k;
+      }
+    }
+  }
   const int ns = p.num_reward_slots;
   const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + (advance ? 1 : 0)) : p.step;
   float* cur = p.reset_stats + (size_t)(step_eff & 1) * (ns + 2);
@@ -612,8 +628,13 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const __grid_constant__ 
       for (int k = tid; k < ns; k += 1024) episode_means[k] = cur[k] / (float)count / p.max_episode_length_s;
       if (tid == 0) episode_means[ns] = p.terrain_curriculum ? cur[ns + 1] / (float)N : 0.f;
     }
-    if (p.send_timeouts && time_outs_extras)
-      for (int i = tid; i < N; i += 1024) time_outs_extras[i] = p.time_out_buf[i];
+    if (p.send_timeouts && time_outs_extras) {
+      const bool v16 = ((reinterpret_cast<uintptr_t>(p.time_out_buf) | reinterpret_cast<uintptr_t>(time_outs_extras)) & 15u) == 0;
+      const int n16 = v16 ? N / 16 : 0;
+      for (int i = tid; i < n16; i += 1024)
+        reinterpret_cast<uint4*>(time_outs_extras)[i] = reinterpret_cast<const uint4*>(p.time_out_buf)[i];
+      for (int i = n16 * 16 + tid; i < N; i += 1024) time_outs_extras[i] = p.time_out_buf[i];
+    }
   }
   for (int k = tid; k < ns + 2; k += 1024) other[k] = 0.f;
   if (advance && p.step_counter_dev && tid == 0) *p.step_counter_dev = step_eff;
@@ -667,9 +688,9 @@ static int launch_k1(const LgkStepParams* p, cudaStream_t st) {
     // 65k-env grid (2048 CTAs) is resident in a single wave
     cudaFuncSetAttribute(post_scalar_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
-  post_scalar_kernel<<<(p->num_envs + kTile - 1) / kTile, 32, L.total, st>>>(*p);
+  const cudaError_t e = launch_chained(post_scalar_kernel, dim3((p->num_envs + kTile - 1) / kTile), dim3(32), (size_t)L.total, st, *p);
   count_launch();
-  return check_cuda(cudaGetLastError(), "post_scalar_kernel launch");
+  return check_cuda(e, "post_scalar_kernel launch");
 }
 
 static int launch_k2(const LgkStepParams* p, int mode, cudaStream_t st) {
@@ -679,11 +700,12 @@ static int launch_k2(const LgkStepParams* p, int mode, cudaStream_t st) {
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)(p->num_height_points > 0 ? p->num_height_points : 1) * 16;
   const int groups = (48 + p->num_height_points + 31) / 32;
-  if (groups <= 2) scan_obs_kernel<2><<<blocks, kK2Threads, smem, st>>>(*p, mode);
-  else if (groups <= 8) scan_obs_kernel<8><<<blocks, kK2Threads, smem, st>>>(*p, mode);
-  else scan_obs_kernel<12><<<blocks, kK2Threads, smem, st>>>(*p, mode);
+  cudaError_t e;
+  if (groups <= 2) e = launch_chained(scan_obs_kernel<2>, dim3(blocks), dim3(kK2Threads), smem, st, *p, mode);
+  else if (groups <= 8) e = launch_chained(scan_obs_kernel<8>, dim3(blocks), dim3(kK2Threads), smem, st, *p, mode);
+  else e = launch_chained(scan_obs_kernel<12>, dim3(blocks), dim3(kK2Threads), smem, st, *p, mode);
   count_launch();
-  return check_cuda(cudaGetLastError(), "scan_obs_kernel launch");
+  return check_cuda(e, "scan_obs_kernel launch");
 }
 
 extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
@@ -728,7 +750,8 @@ extern "C" int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int
 extern "C" int lgk_finalize_step(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset_count,
                                  float* episode_means, uint8_t* time_outs_extras, int32_t advance, void* stream) {
   if (int rc = validate_step(p)) return rc;
-  finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*p, reset_ids, reset_count, episode_means, time_outs_extras, advance);
+  const cudaError_t e = launch_chained(finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, *p, reset_ids, reset_count,
+                                       episode_means, time_outs_extras, (int)advance);
   count_launch();
-  return check_cuda(cudaGetLastError(), "finalize_kernel launch");
+  return check_cuda(e, "finalize_kernel launch");
 }

@@ -1,5 +1,5 @@
-// lgk_step_device.cuh -- per-environment pieces of post_physics_step shared by the fused tile kernel,
-// the explicit reset_idx kernel and tests/hostcheck (host build; NOT a product path).
+// lgk_step_device.cuh -- per-environment pieces of post_physics_step shared by the scalar tile kernel and
+// the explicit reset_idx kernel (device code).
 // "tile-local" pointers address one env's row inside a staged tile (shared memory on the device).
 #pragma once
 #include "lgk_math.cuh"
@@ -12,6 +12,10 @@ namespace lgk {
 LGK_HD uint32_t obs_block_of(int j) { return (uint32_t)(32 * (j >> 7) + (j & 31)); }
 LGK_HD int obs_word_of(int j) { return (j >> 5) & 3; }
 
+// rng_block, NOT inlined: for the rarely-taken branches (resampling, pushes, resets) of kernels whose hot path must stay
+// small (each inlined Philox4x32-10 is ~100 instructions)
+LGK_COLD U4 rng_block_cold(const RngKey& k, uint32_t env, uint32_t stream, uint32_t blk) { return rng_block(k, env, stream, blk); }
+
 struct EnvScalars {
   V3 blv, bav, pg;       // base_lin_vel, base_ang_vel, projected_gravity (LR:119-121)
   long long ep_len;      // episode_length_buf after += 1 (LR:114)
@@ -23,7 +27,7 @@ struct EnvScalars {
 // reward sum.  root/dof/contact/... are the env's rows inside the staged tile (read+write).
 // `sums` points at episode_sums[0*N + env]; row stride = num_envs.
 // `mean_height_err` = mean_p(z - h_p) when the base_height term is active, else unused.
-LGK_HD void env_pre(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, float* root, const float* dof,
+LGK_D void env_pre(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, float* root, const float* dof,
                     const float* contact, const float* act, const float* tq, const float* lact,
                     const float* ldv, float* cmd, float* fat, uint8_t* lc, float* sums, int sums_stride,
                     long long ep_in, float mean_height_err, EnvScalars& o) {
@@ -34,13 +38,13 @@ LGK_HD void env_pre(const LgkStepParams& p, bool do_push, const RngKey& key, uin
   o.pg = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
   // _post_physics_step_callback LR:329-345
   if (o.ep_len % (long long)p.resample_period == 0)
-    resample_commands(p, cmd, rng_block(key, genv, LGK_STREAM_CMD, 0));
+    resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_CMD, 0));
   if (p.heading_command) {
     const float h = heading_of(qx, qy, qz, qw);
     cmd[2] = clampf(0.5f * wrap_to_pi(cmd[3] - h), -1.f, 1.f);
   }
   if (do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
-    const U4 r = rng_block(key, genv, LGK_STREAM_PUSH, 0);
+    const U4 r = rng_block_cold(key, genv, LGK_STREAM_PUSH, 0);
     const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
     root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));
     root[8] = scale_uniform(range, lo, u32_to_uniform(r.y));
@@ -169,7 +173,7 @@ LGK_HD void env_pre(const LgkStepParams& p, bool do_push, const RngKey& key, uin
 }
 
 // LR:204-210: positive clip, then the termination term
-LGK_HD float env_finish_reward(const LgkStepParams& p, float rew, bool reset, bool time_out, float* sums,
+LGK_D float env_finish_reward(const LgkStepParams& p, float rew, bool reset, bool time_out, float* sums,
                                int sums_stride) {
   if (p.only_positive_rewards) rew = fmaxf(rew, 0.f);
   if (p.reward_active[LGK_R_TERMINATION]) {
@@ -184,7 +188,8 @@ LGK_HD float env_finish_reward(const LgkStepParams& p, float rew, bool reset, bo
 // ---- reset_idx for one env (LR:147-191) minus the cross-env means and the LSTM-state zeroing, which
 // the callers do cooperatively.  Mutates the env's staged rows; terrain tables are global.
 // Returns the env's (possibly updated) terrain level.
-LGK_HD void env_reset(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, float* root, float* dof,
+// rare (a few % of the envs per step): kept out of line so that the hot path of the scalar kernel stays compact
+LGK_COLD void env_reset(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, float* root, float* dof,
                       float* cmd, float* fat, long long& ep_len) {
   float ox = 0.f, oy = 0.f, oz = 0.f;
   if (p.env_origins) { ox = p.env_origins[3 * env]; oy = p.env_origins[3 * env + 1]; oz = p.env_origins[3 * env + 2]; }
@@ -194,7 +199,7 @@ LGK_HD void env_reset(const LgkStepParams& p, const RngKey& key, uint32_t genv, 
     const bool down = (dist < norm2(cmd[0], cmd[1]) * p.max_episode_length_s * 0.5f) && !up;
     long long lvl = p.terrain_levels[env] + (up ? 1 : 0) - (down ? 1 : 0);
     if (lvl >= p.max_terrain_level) {
-      const U4 r = rng_block(key, genv, LGK_STREAM_TERRAIN, 0);
+      const U4 r = rng_block_cold(key, genv, LGK_STREAM_TERRAIN, 0);
       lvl = (long long)(r.x % (uint32_t)p.max_terrain_level);
     } else if (lvl < 0) {
       lvl = 0;
@@ -206,7 +211,7 @@ LGK_HD void env_reset(const LgkStepParams& p, const RngKey& key, uint32_t genv, 
   }
   // _reset_dofs LR:397-407
   for (int b = 0; b < 3; ++b) {
-    const U4 r = rng_block(key, genv, LGK_STREAM_RESET_DOF, b);
+    const U4 r = rng_block_cold(key, genv, LGK_STREAM_RESET_DOF, b);
     for (int i = 0; i < 4; ++i) {
       const int d = 4 * b + i;
       dof[2 * d] = f_mul(p.default_dof_pos[d], scale_uniform(1.0f, 0.5f, u32_to_uniform(pick(r, i))));
@@ -214,8 +219,8 @@ LGK_HD void env_reset(const LgkStepParams& p, const RngKey& key, uint32_t genv, 
     }
   }
   // _reset_root_states LR:414-432
-  const U4 r0 = rng_block(key, genv, LGK_STREAM_RESET_ROOT, 0);
-  const U4 r1 = rng_block(key, genv, LGK_STREAM_RESET_ROOT, 1);
+  const U4 r0 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 0);
+  const U4 r1 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 1);
   for (int i = 0; i < 13; ++i) root[i] = p.base_init_state[i];
   root[0] = f_add(root[0], ox); root[1] = f_add(root[1], oy); root[2] = f_add(root[2], oz);
   if (p.custom_origins) {
@@ -228,13 +233,13 @@ LGK_HD void env_reset(const LgkStepParams& p, const RngKey& key, uint32_t genv, 
   root[10] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.y));
   root[11] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.z));
   root[12] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.w));
-  resample_commands(p, cmd, rng_block(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170
+  resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170
   for (int f = 0; f < p.num_feet; ++f) fat[f] = 0.f;                            // LR:175
   ep_len = 0;                                                                   // LR:176
 }
 
 // LR:212-222: the 48 proprioceptive columns, before noise
-LGK_HD void env_obs_head(const LgkStepParams& p, const EnvScalars& s, const float* dof, const float* cmd,
+LGK_D void env_obs_head(const LgkStepParams& p, const EnvScalars& s, const float* dof, const float* cmd,
                          const float* act, float* out48) {
   out48[0] = s.blv.x * p.obs_scale_lin_vel; out48[1] = s.blv.y * p.obs_scale_lin_vel; out48[2] = s.blv.z * p.obs_scale_lin_vel;
   out48[3] = s.bav.x * p.obs_scale_ang_vel; out48[4] = s.bav.y * p.obs_scale_ang_vel; out48[5] = s.bav.z * p.obs_scale_ang_vel;

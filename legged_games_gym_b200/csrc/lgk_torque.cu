@@ -80,10 +80,12 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 
 template <bool LSTM>
 __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_constant__ LgkTorqueParams p) {
+  pdl_launch_dependents();
   const int idx = blockIdx.x * 128 + threadIdx.x;
   const int total = p.num_envs * kDof;
   if (idx >= total) return;
   const int d = idx % kDof;
+  pdl_wait();                       // the predecessor on the stream produced actions / dof state / LSTM state
   float a = p.actions_in[idx];
   a = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);                       // LR:86-87
   if (p.actions_clipped) p.actions_clipped[idx] = a;
@@ -198,9 +200,11 @@ __global__ void __launch_bounds__(128) torque_lstm_split_kernel(const __grid_con
   // [array: h0, h1, c0, c1][seq 32][8]
   __shared__ __align__(16) float s_state[4][kSeqPerCta][8];
   __shared__ __align__(16) float s_hnew[2][kSeqPerCta][8];
+  pdl_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int total = p.num_envs * kDof;
   const int seq0 = blockIdx.x * kSeqPerCta;
+  pdl_wait();
   const int nseq = min(kSeqPerCta, total - seq0);
   const size_t layer = (size_t)total * 8;
   // ---- coalesced state load: 4 arrays x (32 seq x 8 floats) = 4 x 64 float4
@@ -303,10 +307,11 @@ extern "C" int lgk_compute_torques(const LgkTorqueParams* p, void* stream) {
   LGK_REQUIRE(p->lstm_variant >= 0 && p->lstm_variant <= 2, "lstm_variant must be 0, 1 or 2");
   // auto = one thread per sequence: measured faster at 4096, 16384 and 65536 envs (bench.py --lstm-variant 2 to compare)
   const bool split = p->lstm_variant == 2;
+  cudaError_t e;
   if (p->use_lstm && split)
-    torque_lstm_split_kernel<<<(p->num_envs * kDof + kSeqPerCta - 1) / kSeqPerCta, 128, 0, (cudaStream_t)stream>>>(*p);
-  else if (p->use_lstm) torque_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(*p);
-  else torque_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(*p);
+    e = launch_chained(torque_lstm_split_kernel, dim3((p->num_envs * kDof + kSeqPerCta - 1) / kSeqPerCta), dim3(128), 0, (cudaStream_t)stream, *p);
+  else if (p->use_lstm) e = launch_chained(torque_kernel<true>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p);
+  else e = launch_chained(torque_kernel<false>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p);
   count_launch();
-  return check_cuda(cudaGetLastError(), "torque_kernel launch");
+  return check_cuda(e, "torque_kernel launch");
 }

@@ -94,13 +94,21 @@ class LeggedRobot(BaseTask):
             return self._step_graphed(actions)
         return self._step_eager(actions)
 
+    @property
+    def action_buffer(self):
+        """[num_envs, num_actions] fp32 device buffer the captured step graph reads its actions from.  A policy that
+        writes its actions here (ActorCritic's fused kernel takes an output pointer) and calls ``step(env.action_buffer)``
+        saves the per-step device-to-device copy."""
+        return self._actions_in
+
     def _needs_host_logic_next_step(self):
         return bool(self.cfg.commands.curriculum) and ((self.common_step_counter + 1) % self.max_episode_length == 0)
 
     def _step_graphed(self, actions):
         """The whole step (4 torque launches, fused post-physics, finalize) replayed as ONE CUDA graph: every
         per-step parameter (step counter, push flag) lives in device memory, so nothing is patched between replays."""
-        self._actions_in.copy_(actions, non_blocking=True)
+        if actions.data_ptr() != self._actions_in.data_ptr():     # callers that write into `action_buffer` skip this copy
+            self._actions_in.copy_(actions, non_blocking=True)
         if self._graph is None:
             if self._eager_steps < 1:              # first step eager: sets kernel attributes, warms the allocator
                 self._eager_steps += 1

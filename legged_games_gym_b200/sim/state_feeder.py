@@ -123,7 +123,9 @@ class StateFeeder(SimBackend):
 
 
 class HostStateFeeder(StateFeeder):
-    graph_safe = False
+    # every hook is a stream-ordered cudaMemcpyAsync between PINNED host memory and the device: capturable, so the whole
+    # step (copies + kernels) still replays as one CUDA graph
+    graph_safe = True
 
     """Sim state lives in pinned host memory (the reference's ``sim_device=cpu`` pipeline: PhysX
     results are host tensors).  refresh_* = H2D copy; set_* = D2H copy.  Byte counters feed bench.py's

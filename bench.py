@@ -279,6 +279,65 @@ def kernel_rooflines(envs, actions, peak_gbs, reps=200):
     return out
 
 
+def rollout_phase(dev, n_envs=4096, T=24, reps=20):
+    """BASELINE.json configs[3]: 24 x ActorCritic.act() (235 -> 512-256-128 -> 12 / 1, ELU) + GAE compute_returns,
+    kernels launched back to back through the C ABI on resident buffers; FLOPs = 2 * MACs of the eight Linear layers."""
+    import ctypes as C
+    import torch
+    from legged_games_gym_b200 import _native as nat
+    from legged_games_gym_b200.rsl_rl.modules import ActorCritic
+    torch.manual_seed(0)
+    hid = [512, 256, 128]
+    ac = ActorCritic(235, 235, 12, hid, hid).to(dev)
+    obs = [torch.randn(n_envs, 235, device=dev) for _ in range(4)]
+    with torch.inference_mode():
+        ac.act(obs[0])
+    p = ac._last_params
+    st = torch.cuda.current_stream().cuda_stream
+    rew, val = torch.randn(T, n_envs, 1, device=dev), torch.randn(T, n_envs, 1, device=dev)
+    dones = (torch.rand(T, n_envs, 1, device=dev) < 0.02).to(torch.uint8)
+    last = torch.randn(n_envs, 1, device=dev)
+    ret, adv = torch.empty_like(rew), torch.empty_like(rew)
+    scratch = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    def phase():
+        for t in range(T):
+            p.obs = p.critic_obs = obs[t % 4].data_ptr()
+            p.step = t
+            nat.check(nat.lib.lgk_policy_act(C.byref(p), st), "lgk_policy_act")
+        nat.check(nat.lib.lgk_gae(rew.data_ptr(), val.data_ptr(), dones.data_ptr(), last.data_ptr(), T, n_envs, 0.99, 0.95,
+                                  ret.data_ptr(), adv.data_ptr(), scratch.data_ptr(), st), "lgk_gae")
+    for _ in range(3):
+        phase()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        phase()
+    b.record()
+    torch.cuda.synchronize()
+    sec = a.elapsed_time(b) / 1e3 / reps
+    # act() alone, for the tensor-pipe figure
+    a.record()
+    for _ in range(reps * T):
+        nat.lib.lgk_policy_act(C.byref(p), st)
+    b.record()
+    torch.cuda.synchronize()
+    act_s = a.elapsed_time(b) / 1e3 / (reps * T)
+    macs = 2 * (235 * 512 + 512 * 256 + 256 * 128) + 128 * 13
+    tflops = 2.0 * macs * n_envs / act_s / 1e12
+    peak = None
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        peak = float(json.load(open(path))["bf16_tflops"]) / 2.0      # TF32 runs at half the bf16 tensor rate
+    return dict(workload=f"{T} x act() + GAE at {n_envs} envs (BASELINE.json configs[3])", ms_per_phase=sec * 1e3,
+                env_steps_per_sec=T * n_envs / sec, act_us=act_s * 1e6,
+                roofline_policy=dict(bound="tensor", achieved=round(tflops, 1), peak=peak, unit="TFLOP/s",
+                                     frac=(round(tflops / peak, 4) if peak else None), dtype="tf32 operands, f32 accumulate",
+                                     kernel="policy_tc_kernel (tcgen05.mma kind::tf32, TMEM accumulators)",
+                                     peak_source="MEASURED_PEAKS.json bf16_tflops / 2"))
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -373,6 +432,7 @@ def gpu_arm(args):
                                   roofline_torque_lstm=r2["torque_lstm"], roofline_post_physics=r2["post_physics"])
             del env2, feeder2, envs2, feeders2
             torch.cuda.empty_cache()
+    rollout = rollout_phase(dev)
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_arm(N, steps=10, warmup=3)
@@ -388,7 +448,7 @@ def gpu_arm(args):
                    "timing": "CUDA events on the launch stream around the K steps; barrier+synchronize both sides",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep,
+        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep, "rollout_phase": rollout,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -205,6 +205,11 @@ int lgk_post_physics(const LgkStepParams* p, void* stream);
  * Accumulates into the same reset_stats slot as a step with p->step. */
 int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int32_t num_ids, void* stream);
 
+/* Profiling hook: when non-NULL, CTA 0 of the scalar post-physics kernel writes %globaltimer stamps (ns) into
+ * device_buf16[0..8]: entry, step counter read, tile staged, rewards done, reset done, outputs staged, bulk stores issued,
+ * rows written, bulk stores drained. */
+int lgk_step_debug_timeline(int64_t* device_buf16);
+
 /* After lgk_post_physics / lgk_reset_idx: single-CTA pass that (a) compacts reset_buf into an ascending
  * int32 id list + count (what set_*_tensor_indexed needs, LR:409-412, 433-436), (b) if count > 0 writes the
  * extras the reference refreshes only when something was reset (LR:157-158, 179-191):

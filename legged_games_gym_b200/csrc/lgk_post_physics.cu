@@ -93,13 +93,13 @@ __host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots)
 }
 
 // used only by the partial-tile fallback path: kept out of line and rolled so the hot path stays compact
-__device__ __noinline__ void copy_f32(float* dst, const float* src, int n, int lane) {
+__device__ __noinline__ void copy_f32(float* dst, const float* src, int n, int tid) {
 #pragma unroll 1
-  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+  for (int i = tid; i < n; i += 4 * kTile) dst[i] = src[i];
 }
-__device__ __noinline__ void copy_u8(uint8_t* dst, const uint8_t* src, int n, int lane) {
+__device__ __noinline__ void copy_u8(uint8_t* dst, const uint8_t* src, int n, int tid) {
 #pragma unroll 1
-  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+  for (int i = tid; i < n; i += 4 * kTile) dst[i] = src[i];
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -112,7 +112,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int kFrameFloats = 8;
 
 // ------------------------------------------------------------------ K1
-__global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__ LgkStepParams p) {
+// CTA = 4 warps = one tile of 32 envs; four consecutive lanes (a "quad", roles 0..3) share an env, so a warp covers 8 envs.
+constexpr int kK1Threads = 4 * kTile;
+__device__ long long* g_k1_timeline = nullptr;     // profiling hook (lgk_step_debug_timeline): stamps of CTA 0
+__device__ __forceinline__ void k1_stamp(int slot) {
+  if (g_k1_timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_k1_timeline[slot] = (long long)t;
+  }
+}
+
+__global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_constant__ LgkStepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const TileLayout L = make_layout(p.num_bodies, p.num_feet, p.num_reward_slots);
   float* s_root = reinterpret_cast<float*>(smem + L.root);
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__
   const int K = p.num_reward_slots;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.misc);
 
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int env0 = blockIdx.x * kTile;
   const int nval = min(kTile, p.num_envs - env0);
   const int NB = p.num_bodies, F = p.num_feet, P = p.num_height_points, O = p.num_obs, N = p.num_envs;
@@ -147,16 +158,17 @@ __global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__
   // bulk (TMA) path needs a full tile (sizes are then multiples of 16 B) and unit root stride
   const bool bulk = (nval == kTile) && (p.actors_per_env == 1) && (p.num_envs % 4 == 0);   // 16-B aligned rows
   pdl_launch_dependents();
+  k1_stamp(0);
+  if (bulk && tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   pdl_wait();              // everything below reads state written by the previous kernels of the step
-  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
-  const bool do_push = p.step_counter_dev ? (p.push_interval > 0 && step_eff % p.push_interval == 0) : (p.do_push != 0);
-  const RngKey key = make_key(p.seed, step_eff);
 
   // ---------------- stage the tile
   if (bulk) {
-    if (lane == 0) {
-      mbar_init(bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (tid == 0) {
       uint32_t bytes = kTile * (13 + 24 + 3 * NB + 12 + 12 + 12 + 12 + 4) * 4;
       if (F > 0) bytes += kTile * F * 4 + kTile * F;
       bytes += K * kTile * 4 + kTile * 8;
@@ -176,32 +188,43 @@ __global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__
         bulk_g2s(s_lc, p.last_contacts + (size_t)env0 * F, kTile * F, bar);
       }
     }
-    __syncwarp();
+  }
+  // the device step counter is read while the tile loads are in flight
+  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
+  const bool do_push = p.step_counter_dev ? (p.push_interval > 0 && step_eff % p.push_interval == 0) : (p.do_push != 0);
+  const RngKey key = make_key(p.seed, step_eff);
+  k1_stamp(1);
+  if (bulk) {
     mbar_wait(bar, 0);
   } else {
-    for (int i = lane; i < nval * 13; i += 32) {
+    for (int i = tid; i < nval * 13; i += kK1Threads) {
       const int e = i / 13, c = i - e * 13;
       s_root[i] = p.root_states[((size_t)(env0 + e) * p.actors_per_env + p.root_actor_offset) * 13 + c];
     }
-    copy_f32(s_dof, p.dof_state + (size_t)env0 * 24, nval * 24, lane);
-    copy_f32(s_contact, p.contact_forces + (size_t)env0 * NB * 3, nval * NB * 3, lane);
-    copy_f32(s_act, p.actions + (size_t)env0 * 12, nval * 12, lane);
-    copy_f32(s_tq, p.torques + (size_t)env0 * 12, nval * 12, lane);
-    copy_f32(s_lact, p.last_actions + (size_t)env0 * 12, nval * 12, lane);
-    copy_f32(s_ldv, p.last_dof_vel + (size_t)env0 * 12, nval * 12, lane);
-    copy_f32(s_cmd, p.commands + (size_t)env0 * 4, nval * 4, lane);
+    copy_f32(s_dof, p.dof_state + (size_t)env0 * 24, nval * 24, tid);
+    copy_f32(s_contact, p.contact_forces + (size_t)env0 * NB * 3, nval * NB * 3, tid);
+    copy_f32(s_act, p.actions + (size_t)env0 * 12, nval * 12, tid);
+    copy_f32(s_tq, p.torques + (size_t)env0 * 12, nval * 12, tid);
+    copy_f32(s_lact, p.last_actions + (size_t)env0 * 12, nval * 12, tid);
+    copy_f32(s_ldv, p.last_dof_vel + (size_t)env0 * 12, nval * 12, tid);
+    copy_f32(s_cmd, p.commands + (size_t)env0 * 4, nval * 4, tid);
     if (F > 0) {
-      copy_f32(s_fat, p.feet_air_time + (size_t)env0 * F, nval * F, lane);
-      copy_u8(s_lc, p.last_contacts + (size_t)env0 * F, nval * F, lane);
+      copy_f32(s_fat, p.feet_air_time + (size_t)env0 * F, nval * F, tid);
+      copy_u8(s_lc, p.last_contacts + (size_t)env0 * F, nval * F, tid);
     }
-    for (int k = 0; k < K; ++k) if (lane < nval) s_sums[k * kTile + lane] = p.episode_sums[(size_t)k * N + env0 + lane];
-    if (lane < nval) s_ep[lane] = p.episode_length_buf[env0 + lane];
-    __syncwarp();
+    for (int i = tid; i < K * nval; i += kK1Threads) {
+      const int k = i / nval, e = i - k * nval;
+      s_sums[k * kTile + e] = p.episode_sums[(size_t)k * N + env0 + e];
+    }
+    if (tid < nval) s_ep[tid] = p.episode_length_buf[env0 + tid];
+    __syncthreads();
   }
 
-  // ---------------- per-env scalar work, lane = env
-  const int e = lane, env = env0 + e;
+  k1_stamp(2);
+  // ---------------- per-env scalar work: quad (4 lanes) per env
+  const int e = tid >> 2, role = tid & 3, env = env0 + e;
   const bool valid = e < nval;
+  const int envc = valid ? env : env0;        // clamped id for global reads of the (discarded) lanes of a partial tile
   const uint32_t genv = (uint32_t)(p.env_id_offset + env);
   EnvScalars s;
   s.reset = false; s.time_out = false; s.rew = 0.f; s.ep_len = 0;
@@ -212,79 +235,90 @@ __global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__
   uint8_t* lc = s_lc + e * F;
   float* sums = s_sums + e;                 // tile-local episode sums, row stride kTile
   const bool want_frames = p.measure_heights && !p.terrain_is_plane && p.scan_frames != nullptr;
-  if (valid) {
-    if (pre) {
-      if (want_frames) {     // pre-reset yaw frame for K2 (LR:853-854 uses the pose of THIS step before reset_idx)
-        const YawFrame yf = yaw_frame(root[5], root[6], root[0], root[1]);
-        s_frame[e * kFrameFloats + 0] = yf.zn; s_frame[e * kFrameFloats + 1] = yf.wn;
-        s_frame[e * kFrameFloats + 2] = yf.rx; s_frame[e * kFrameFloats + 3] = yf.ry;
-      }
-      float mh = 0.f;
-      if (p.reward_active[LGK_R_BASE_HEIGHT]) {        // mean_p(z - h_p), LR:886 (the scan ran before this kernel)
-        if (p.measure_heights) {
-          for (int j = 0; j < P; ++j) mh += root[2] - p.measured_heights[(size_t)env * P + j];
-          mh /= (float)P;
-        } else {
-          mh = root[2];                                 // measured_heights is the int 0 (LR:562)
-        }
-      }
-      env_pre(p, do_push, key, genv, root, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12, s_lact + e * 12,
-              s_ldv + e * 12, cmd, fat, lc, sums, kTile, s_ep[e], mh, s);
-      s_blv[3 * e] = s.blv.x; s_blv[3 * e + 1] = s.blv.y; s_blv[3 * e + 2] = s.blv.z;
-      s_bav[3 * e] = s.bav.x; s_bav[3 * e + 1] = s.bav.y; s_bav[3 * e + 2] = s.bav.z;
-      s_pg[3 * e] = s.pg.x; s_pg[3 * e + 1] = s.pg.y; s_pg[3 * e + 2] = s.pg.z;
-    } else {   // split mode: PRE ran in an earlier launch, pick its results up from global memory
-      s.blv = V3{p.base_lin_vel[3 * env], p.base_lin_vel[3 * env + 1], p.base_lin_vel[3 * env + 2]};
-      s.bav = V3{p.base_ang_vel[3 * env], p.base_ang_vel[3 * env + 1], p.base_ang_vel[3 * env + 2]};
-      s.pg = V3{p.projected_gravity[3 * env], p.projected_gravity[3 * env + 1], p.projected_gravity[3 * env + 2]};
-      s.ep_len = s_ep[e];
-      s.reset = p.reset_buf[env] != 0;
-      s.time_out = p.time_out_buf[env] != 0;
-      s.rew = p.rew_buf[env];
+  if (pre) {
+    if (want_frames && role == 3) {     // pre-reset yaw frame for K2 (LR:853-854 uses the pose of THIS step before reset_idx)
+      const YawFrame yf = yaw_frame(root[5], root[6], root[0], root[1]);
+      *reinterpret_cast<float4*>(s_frame + e * kFrameFloats) = make_float4(yf.zn, yf.wn, yf.rx, yf.ry);
     }
-    if (post) {
-      s.rew = env_finish_reward(p, s.rew, s.reset, s.time_out, sums, kTile);
-      if (s.reset) env_reset(p, key, genv, env, root, dof, cmd, fat, s.ep_len);
+    float mh = 0.f;
+    if (p.reward_active[LGK_R_BASE_HEIGHT]) {        // mean_p(z - h_p), LR:886 (the scan ran before this kernel)
+      if (p.measure_heights) {
+        for (int j = role; j < P; j += 4) mh += root[2] - p.measured_heights[(size_t)envc * P + j];
+        mh = quad_sum(mh) / (float)P;
+      } else {
+        mh = root[2];                                 // measured_heights is the int 0 (LR:562)
+      }
+    }
+    env_pre_quad(p, do_push, key, genv, lane, root, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12,
+                 s_lact + e * 12, s_ldv + e * 12, cmd, fat, lc, sums, kTile, s_ep[e], mh, s);
+    if (role < 3) {
+      const V3 v = role == 0 ? s.blv : (role == 1 ? s.bav : s.pg);
+      float* dst = (role == 0 ? s_blv : (role == 1 ? s_bav : s_pg)) + 3 * e;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
+    }
+  } else {   // split mode: PRE ran in an earlier launch, pick its results up from global memory
+    s.blv = V3{p.base_lin_vel[3 * envc], p.base_lin_vel[3 * envc + 1], p.base_lin_vel[3 * envc + 2]};
+    s.bav = V3{p.base_ang_vel[3 * envc], p.base_ang_vel[3 * envc + 1], p.base_ang_vel[3 * envc + 2]};
+    s.pg = V3{p.projected_gravity[3 * envc], p.projected_gravity[3 * envc + 1], p.projected_gravity[3 * envc + 2]};
+    s.ep_len = s_ep[e];
+    s.reset = p.reset_buf[envc] != 0;
+    s.time_out = p.time_out_buf[envc] != 0;
+    s.rew = p.rew_buf[envc];
+  }
+  k1_stamp(3);
+  if (post) {
+    if (p.only_positive_rewards) s.rew = fmaxf(s.rew, 0.f);                      // LR:204-205
+    if (p.reward_active[LGK_R_TERMINATION]) {                                    // LR:206-210
+      const float r_ = ((s.reset && !s.time_out) ? 1.f : 0.f) * p.reward_scale[LGK_R_TERMINATION];
+      s.rew += r_;
+      if (role == 0) sums[(size_t)p.reward_slot[LGK_R_TERMINATION] * kTile] += r_;
     }
   }
-  __syncwarp();          // every lane is done with its contact rows: the region now holds the observation head
-  if (valid) {
-    if (post) {
-      env_obs_head(p, s, dof, cmd, s_act + e * 12, s_head + e * 49);
-      for (int d = 0; d < 12; ++d) s_ldv[e * 12 + d] = dof[2 * d + 1];    // LR:133 (post-reset dof_vel)
-      for (int i = 0; i < 6; ++i) s_lrv[e * 6 + i] = root[7 + i];         // LR:134 (post push/reset)
-      if (p.scan_frames) p.scan_frames[(size_t)env * kFrameFloats + 4] = root[2] - 0.5f;   // post-reset z
+  // cross-env sums for extras["episode"] use the PRE-reset episode sums of the envs that reset (LR:179-183)
+  const bool resetting = post && valid && s.reset;
+  if (post) {
+    float* stats = p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2);
+    __syncwarp();                                     // role 0's sums[] updates are visible to the quad
+    const uint32_t wmask = __ballot_sync(0xffffffffu, resetting && role == 0);
+    if (wmask != 0) {
+      for (int k = 0; k < p.num_reward_slots; ++k) {
+        float v = 0.f;
+        if (resetting && role == 0) { v = sums[k * kTile]; sums[k * kTile] = 0.f; }
+        v = warp_sum(v);
+        if (lane == 0) atomicAdd(stats + k, v);
+      }
+      if (lane == 0) atomicAdd(stats + p.num_reward_slots, (float)__popc(wmask));
     }
+    if (resetting) env_reset_quad(p, key, genv, env, role, root, dof, cmd, fat, s.ep_len);
+    if (p.terrain_curriculum) {                       // mean terrain level over ALL envs (LR:186), after the level updates
+      __syncwarp();
+      float lv = (valid && role == 0) ? (float)p.terrain_levels[env] : 0.f;
+      lv = warp_sum(lv);
+      if (lane == 0) atomicAdd(stats + p.num_reward_slots + 1, lv);
+    }
+  }
+  k1_stamp(4);
+  __syncthreads();       // every quad is done with its contact rows (the region now holds the observation head) and resets
+  if (post) {
+    env_obs_head_quad(p, s, role, dof, cmd, s_act + e * 12, s_head + e * 49);
+#pragma unroll
+    for (int d = 3 * role; d < 3 * role + 3; ++d) s_ldv[e * 12 + d] = dof[2 * d + 1];   // LR:133 (post-reset dof_vel)
+    if (role == 1) { for (int i = 0; i < 6; ++i) s_lrv[e * 6 + i] = root[7 + i]; }      // LR:134 (post push/reset)
+    if (role == 2 && valid && p.scan_frames) p.scan_frames[(size_t)env * kFrameFloats + 4] = root[2] - 0.5f;   // post-reset z
+  }
+  if (role == 0) {
     s_rew[e] = s.rew;
     s_ep[e] = s.ep_len;
     s_flags[e] = s.reset ? 1 : 0;
     s_flags[kTile + e] = s.time_out ? 1 : 0;
   }
-  const uint32_t rmask = __ballot_sync(0xffffffffu, valid && s.reset && post);
-  // extras["episode"] sums over the reset set + zeroing (LR:179-183), terrain-level mean (LR:186)
-  if (post) {
-    float* stats = p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2);
-    if (rmask != 0) {
-      for (int k = 0; k < p.num_reward_slots; ++k) {
-        float v = 0.f;
-        if (valid && s.reset) { v = sums[k * kTile]; sums[k * kTile] = 0.f; }
-        v = warp_sum(v);
-        if (lane == 0) atomicAdd(stats + k, v);
-      }
-      if (lane == 0) atomicAdd(stats + p.num_reward_slots, (float)__popc(rmask));
-    }
-    if (p.terrain_curriculum) {
-      float lv = valid ? (float)p.terrain_levels[env] : 0.f;
-      lv = warp_sum(lv);
-      if (lane == 0) atomicAdd(stats + p.num_reward_slots + 1, lv);
-    }
-  }
   fence_async_smem();
-  __syncwarp();
+  __syncthreads();
+  k1_stamp(5);
 
   // ---------------- whole-tile write-backs
   if (bulk) {
-    if (lane == 0) {
+    if (tid == 0) {
       if (pre) {
         bulk_s2g(p.base_lin_vel + (size_t)env0 * 3, s_blv, kTile * 3 * 4);
         bulk_s2g(p.base_ang_vel + (size_t)env0 * 3, s_bav, kTile * 3 * 4);
@@ -310,28 +344,31 @@ __global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__
     }
   } else {
     if (pre) {
-      copy_f32(p.base_lin_vel + (size_t)env0 * 3, s_blv, nval * 3, lane);
-      copy_f32(p.base_ang_vel + (size_t)env0 * 3, s_bav, nval * 3, lane);
-      copy_f32(p.projected_gravity + (size_t)env0 * 3, s_pg, nval * 3, lane);
+      copy_f32(p.base_lin_vel + (size_t)env0 * 3, s_blv, nval * 3, tid);
+      copy_f32(p.base_ang_vel + (size_t)env0 * 3, s_bav, nval * 3, tid);
+      copy_f32(p.projected_gravity + (size_t)env0 * 3, s_pg, nval * 3, tid);
     }
-    copy_f32(p.commands + (size_t)env0 * 4, s_cmd, nval * 4, lane);
-    if (lane < nval) {
-      for (int k = 0; k < K; ++k) p.episode_sums[(size_t)k * N + env0 + lane] = s_sums[k * kTile + lane];
-      p.episode_length_buf[env0 + lane] = s_ep[lane];
-      p.rew_buf[env0 + lane] = s_rew[lane];
-      if (pre) { p.reset_buf[env0 + lane] = s_flags[lane]; p.time_out_buf[env0 + lane] = s_flags[kTile + lane]; }
+    copy_f32(p.commands + (size_t)env0 * 4, s_cmd, nval * 4, tid);
+    for (int i = tid; i < K * nval; i += kK1Threads) {
+      const int k = i / nval, ee = i - k * nval;
+      p.episode_sums[(size_t)k * N + env0 + ee] = s_sums[k * kTile + ee];
+    }
+    if (tid < nval) {
+      p.episode_length_buf[env0 + tid] = s_ep[tid];
+      p.rew_buf[env0 + tid] = s_rew[tid];
+      if (pre) { p.reset_buf[env0 + tid] = s_flags[tid]; p.time_out_buf[env0 + tid] = s_flags[kTile + tid]; }
     }
     if (fat_active || (post && F > 0)) {
-      copy_f32(p.feet_air_time + (size_t)env0 * F, s_fat, nval * F, lane);
-      if (pre) copy_u8(p.last_contacts + (size_t)env0 * F, s_lc, nval * F, lane);
+      copy_f32(p.feet_air_time + (size_t)env0 * F, s_fat, nval * F, tid);
+      if (pre) copy_u8(p.last_contacts + (size_t)env0 * F, s_lc, nval * F, tid);
     }
     if (post) {
-      copy_f32(p.last_actions + (size_t)env0 * 12, s_act, nval * 12, lane);
-      copy_f32(p.last_dof_vel + (size_t)env0 * 12, s_ldv, nval * 12, lane);
-      copy_f32(p.last_root_vel + (size_t)env0 * 6, s_lrv, nval * 6, lane);
+      copy_f32(p.last_actions + (size_t)env0 * 12, s_act, nval * 12, tid);
+      copy_f32(p.last_dof_vel + (size_t)env0 * 12, s_ldv, nval * 12, tid);
+      copy_f32(p.last_root_vel + (size_t)env0 * 6, s_lrv, nval * 6, tid);
     }
     if (do_push) {
-      for (int i = lane; i < nval * 13; i += 32) {
+      for (int i = tid; i < nval * 13; i += kK1Threads) {
         const int ee = i / 13, c = i - ee * 13;
         if (c == 7 || c == 8)
           p.root_states[((size_t)(env0 + ee) * p.actors_per_env + p.root_actor_offset) * 13 + c] = s_root[i];
@@ -339,16 +376,17 @@ __global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__
     }
   }
   // scan frames (pose part): 4 floats per env, strided rows of 8
-  if (pre && want_frames && valid) {
+  if (pre && want_frames && valid && role == 3) {
     *reinterpret_cast<float4*>(p.scan_frames + (size_t)env * kFrameFloats) =
         *reinterpret_cast<const float4*>(s_frame + e * kFrameFloats);
   }
 
+  k1_stamp(6);
   if (post) {
-    // ---------------- reset rows: dof_state / root_states write-back + LSTM state zeroing (ANY:56-60)
-    uint32_t rm = rmask;
+    // ---------------- reset rows of this warp's 8 envs: dof_state / root_states write-back + LSTM state zeroing (ANY:56-60)
+    uint32_t rm = __ballot_sync(0xffffffffu, resetting && role == 0);
     while (rm) {
-      const int ee = __ffs(rm) - 1;
+      const int ee = warp * 8 + ((__ffs(rm) - 1) >> 2);
       rm &= rm - 1;
       const int en = env0 + ee;
       if (lane < 24) p.dof_state[(size_t)en * 24 + lane] = s_dof[ee * 24 + lane];
@@ -366,13 +404,15 @@ __global__ void __launch_bounds__(32) post_scalar_kernel(const __grid_constant__
       }
     }
     // ---------------- the 48 proprioceptive columns, un-noised (K2 adds noise + clip): coalesced row segments
-    for (int ee = 0; ee < nval; ++ee) {
+    for (int ee = warp * 8; ee < min(warp * 8 + 8, nval); ++ee) {
       float* orow = p.obs_buf + (size_t)(env0 + ee) * O;
       orow[lane] = s_head[ee * 49 + lane];
       if (lane < 16) orow[32 + lane] = s_head[ee * 49 + 32 + lane];
     }
   }
-  if (bulk && lane == 0) bulk_wait_read0();
+  k1_stamp(7);
+  if (bulk && tid == 0) bulk_wait_read0();
+  k1_stamp(8);
 }
 
 // ------------------------------------------------------------------ K2
@@ -493,6 +533,121 @@ __global__ void __launch_bounds__(kK2Threads, 8) scan_obs_kernel(const __grid_co
               v = v + (2.0f * u32_to_uniform(pick(r, k)) - 1.0f) * nz[g];
               orow[j] = clampf(v, -clip, clip);
             }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K2, specialised
+// Same work split as scan_obs_kernel for the configurations that matter for throughput (height field present, or no height
+// columns at all), written branch-free: the column-group count G, the pass (scan / observations / both) and the division
+// variant are template parameters; every lane computes an in-range sample index for each of its G columns whether or not
+// the column is a height point (the clip of LR:860-861 makes any input a valid index), so the only predication left is on
+// the stores.  Per-lane constants (grid points, noise scales, column masks) live in registers across the env loop.
+template <int G, int MODE, bool RECIP>
+__global__ void __launch_bounds__(kK2Threads, 5) scan_obs_fast_kernel(const __grid_constant__ LgkStepParams p) {
+  constexpr bool SCAN = (MODE & kScan) != 0, OBS = (MODE & kObs) != 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.num_envs, P = p.num_height_points, O = p.num_obs;
+  pdl_launch_dependents();
+  // ---- lane constants
+  f2_t Bv[G], Bsv[G];
+  float nz[G];
+  uint32_t pmask = 0, omask = 0;      // bit g: column 32g+lane is a height point / an observation column
+  const bool noisy = OBS && p.add_noise != 0;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int j = 32 * g + lane, pt = j - 48;
+    const bool isp = G > 2 && pt >= 0 && pt < P;
+    float bx = 0.f, by = 0.f;
+    if (isp && SCAN) { const float2 b = __ldg(reinterpret_cast<const float2*>(p.height_points_xy) + pt); bx = b.x; by = b.y; }
+    Bv[g] = pack2(bx, by); Bsv[g] = pack2(by, bx);
+    pmask |= (isp ? 1u : 0u) << g;
+    omask |= ((OBS && j < O) ? 1u : 0u) << g;
+    nz[g] = (noisy && j < O) ? __ldg(p.noise_scale_vec + j) : 0.f;
+  }
+  const float rt_one = __int_as_float(0x3f800000u | ((uint32_t)p.num_envs >> 31));   // 1.0f the compiler cannot see
+  const float clip = p.clip_obs, vs = p.vertical_scale, hsc = p.obs_scale_height;
+  const float border = p.border_size, hscale = p.horizontal_scale, hrecip = p.horizontal_scale_recip;
+  const int rows = p.hf_rows, cols = p.hf_cols;
+  const bool k1_frames = OBS && p.scan_frames != nullptr;     // K1 ran before this pass: use its pre-reset yaw frame
+  pdl_wait();
+  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
+  const RngKey key = make_key(p.seed, step_eff);
+
+  struct EnvIn { float4 f; float rz, head0, head1; };
+  auto fetch = [&](int env) {
+    EnvIn in;
+    in.f = make_float4(0.f, 0.f, 0.f, 0.f); in.rz = 0.f; in.head0 = 0.f; in.head1 = 0.f;
+    if (env >= N) return in;
+    const float* r = p.root_states + ((size_t)env * p.actors_per_env + p.root_actor_offset) * 13;
+    if (G > 2) {
+      if (k1_frames) {
+        in.f = __ldg(reinterpret_cast<const float4*>(p.scan_frames + (size_t)env * kFrameFloats));
+        in.rz = p.scan_frames[(size_t)env * kFrameFloats + 4];
+      } else {
+        in.f = make_float4(r[5], r[6], r[0], r[1]);
+        in.rz = r[2] - 0.5f;
+      }
+    }
+    if (OBS) {
+      const float* orow = p.obs_buf + (size_t)env * O;
+      in.head0 = orow[lane];                         // columns 0..31, written un-noised by K1
+      if (lane < 16) in.head1 = orow[32 + lane];     // columns 32..47
+    }
+    return in;
+  };
+  const int stride = gridDim.x * (kK2Threads / 32);
+  int env = blockIdx.x * (kK2Threads / 32) + warp;
+  EnvIn nxt = fetch(env);
+  for (; env < N; env += stride) {
+    const EnvIn cur = nxt;
+    nxt = fetch(env + stride);
+    float* orow = p.obs_buf + (size_t)env * O;
+    float* hrow = p.measured_heights + (size_t)env * P;
+    float h[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) h[g] = 0.f;
+    if (G > 2) {
+      if (SCAN) {
+        const YawFrame2 yf = k1_frames ? yaw_frame2(YawFrame{cur.f.x, cur.f.y, cur.f.z, cur.f.w})
+                                       : yaw_frame2(yaw_frame(cur.f.x, cur.f.y, cur.f.z, cur.f.w));
+        int off[G];
+#pragma unroll
+        for (int g = 1; g < G; ++g) {
+          int ix, iy;
+          height_index2<RECIP>(yf, Bv[g], Bsv[g], border, hscale, hrecip, rt_one, rows, cols, ix, iy);
+          off[g] = ix * cols + iy;
+        }
+#pragma unroll
+        for (int g = 1; g < G; ++g) h[g] = f_mul((float)__ldg(p.height_min3 + off[g]), vs);      // LR:869
+#pragma unroll
+        for (int g = 1; g < G; ++g) if ((pmask >> g) & 1u) hrow[32 * g + lane - 48] = h[g];
+      } else {
+#pragma unroll
+        for (int g = 1; g < G; ++g) if ((pmask >> g) & 1u) h[g] = hrow[32 * g + lane - 48];     // scan ran in an earlier launch
+      }
+    }
+    if (OBS) {
+      const uint32_t genv = (uint32_t)(p.env_id_offset + env);
+#pragma unroll
+      for (int sc = 0; sc < (G + 3) / 4; ++sc) {
+        U4 r = U4{0, 0, 0, 0};
+        if (noisy) r = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int g = sc * 4 + k;
+          if (g < G) {
+            float v;
+            if (g == 0) v = cur.head0;
+            else {
+              v = clampf(cur.rz - h[g], -1.f, 1.f) * hsc;
+              if (g == 1) v = lane < 16 ? cur.head1 : v;
+            }
+            v = v + (2.0f * u32_to_uniform(pick(r, k)) - 1.0f) * nz[g];
+            if ((omask >> g) & 1u) orow[32 * g + lane] = clampf(v, -clip, clip);
           }
         }
       }
@@ -688,7 +843,7 @@ static int launch_k1(const LgkStepParams* p, cudaStream_t st) {
     // 65k-env grid (2048 CTAs) is resident in a single wave
     cudaFuncSetAttribute(post_scalar_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
-  const cudaError_t e = launch_chained(post_scalar_kernel, dim3((p->num_envs + kTile - 1) / kTile), dim3(32), (size_t)L.total, st, *p);
+  const cudaError_t e = launch_chained(post_scalar_kernel, dim3((p->num_envs + kTile - 1) / kTile), dim3(kK1Threads), (size_t)L.total, st, *p);
   count_launch();
   return check_cuda(e, "post_scalar_kernel launch");
 }
@@ -701,6 +856,23 @@ static int launch_k2(const LgkStepParams* p, int mode, cudaStream_t st) {
   const size_t smem = (size_t)(p->num_height_points > 0 ? p->num_height_points : 1) * 16;
   const int groups = (48 + p->num_height_points + 31) / 32;
   cudaError_t e;
+  // specialised branch-free kernels for the throughput configurations: a height field behind every height column, or
+  // no height columns at all; everything else (plane terrain with measure_heights, ...) takes the generic kernel
+  const bool field = p->measure_heights && !p->terrain_is_plane && p->num_height_points > 0;
+  const bool flat = !p->measure_heights;
+  if (field || (flat && mode == kObs)) {
+    const int fblocks = blocks < 148 * 10 ? blocks : 148 * 10;
+    const bool rc = p->horizontal_scale_recip != 0.f;
+    const dim3 gd(fblocks), bd(kK2Threads);
+#define LGK_K2(GG, MM) (rc ? launch_chained(scan_obs_fast_kernel<GG, MM, true>, gd, bd, 0, st, *p) \
+                           : launch_chained(scan_obs_fast_kernel<GG, MM, false>, gd, bd, 0, st, *p))
+    if (flat) e = launch_chained(scan_obs_fast_kernel<2, kObs, false>, gd, bd, 0, st, *p);
+    else if (groups <= 8) e = mode == kScan ? LGK_K2(8, kScan) : (mode == kObs ? LGK_K2(8, kObs) : LGK_K2(8, kScan | kObs));
+    else e = mode == kScan ? LGK_K2(12, kScan) : (mode == kObs ? LGK_K2(12, kObs) : LGK_K2(12, kScan | kObs));
+#undef LGK_K2
+    count_launch();
+    return check_cuda(e, "scan_obs_fast_kernel launch");
+  }
   if (groups <= 2) e = launch_chained(scan_obs_kernel<2>, dim3(blocks), dim3(kK2Threads), smem, st, *p, mode);
   else if (groups <= 8) e = launch_chained(scan_obs_kernel<8>, dim3(blocks), dim3(kK2Threads), smem, st, *p, mode);
   else e = launch_chained(scan_obs_kernel<12>, dim3(blocks), dim3(kK2Threads), smem, st, *p, mode);
@@ -731,6 +903,11 @@ extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
   }
   if (int rc = launch_k1(p, st)) return rc;      // POST only
   return launch_k2(p, kObs, st);
+}
+
+extern "C" int lgk_step_debug_timeline(int64_t* device_buf16) {
+  long long* ptr = reinterpret_cast<long long*>(device_buf16);
+  return check_cuda(cudaMemcpyToSymbol(g_k1_timeline, &ptr, sizeof(ptr)), "cudaMemcpyToSymbol(g_k1_timeline)");
 }
 
 extern "C" int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int32_t num_ids, void* stream) {

@@ -172,6 +172,266 @@ LGK_D void env_pre(const LgkStepParams& p, bool do_push, const RngKey& key, uint
   o.rew = rew;
 }
 
+// ------------------------------------------------------------------ quad-cooperative variants (scalar kernel)
+// Four consecutive lanes ("roles" 0..3) share one environment: role r owns joints {3r,3r+1,3r+2}, foot r, the
+// penalised bodies {r, r+4, ...} and the termination bodies {r, r+4}; the three rotations and the heading are computed by
+// one role each and exchanged by shuffles, per-joint reward terms are reduced over the quad with two xor-shuffles.
+// Same reference lines as env_pre / env_reset / env_obs_head above; only the summation order inside a term differs
+// (fp32, within the 1e-5 bar).  All 32 lanes of the warp must call these together.
+#if defined(__CUDACC__)
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_bcast(float v, int lane, int role) { return __shfl_sync(0xffffffffu, v, (lane & ~3) | role); }
+__device__ __forceinline__ uint32_t quad_ballot(bool pred, int lane) {
+  return (__ballot_sync(0xffffffffu, pred) >> (lane & ~3)) & 0xFu;
+}
+
+LGK_D void env_pre_quad(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, int lane, float* root,
+                        const float* dof, const float* contact, const float* act, const float* tq, const float* lact,
+                        const float* ldv, float* cmd, float* fat, uint8_t* lc, float* sums, int sums_stride,
+                        long long ep_in, float mean_height_err, EnvScalars& o) {
+  const int role = lane & 3;
+  o.ep_len = ep_in + 1;
+  const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+  // roles 0,1,2: one rotation each (LR:119-121); role 3: heading (LR:338-339)
+  V3 mine = V3{0.f, 0.f, 0.f};
+  if (role == 0) mine = quat_rotate_inverse(qx, qy, qz, qw, V3{root[7], root[8], root[9]});
+  else if (role == 1) mine = quat_rotate_inverse(qx, qy, qz, qw, V3{root[10], root[11], root[12]});
+  else if (role == 2) mine = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
+  else if (p.heading_command) mine.x = heading_of(qx, qy, qz, qw);
+  o.blv = V3{quad_bcast(mine.x, lane, 0), quad_bcast(mine.y, lane, 0), quad_bcast(mine.z, lane, 0)};
+  o.bav = V3{quad_bcast(mine.x, lane, 1), quad_bcast(mine.y, lane, 1), quad_bcast(mine.z, lane, 1)};
+  o.pg = V3{quad_bcast(mine.x, lane, 2), quad_bcast(mine.y, lane, 2), quad_bcast(mine.z, lane, 2)};
+  const float heading = quad_bcast(mine.x, lane, 3);
+  // _post_physics_step_callback LR:329-345 (role 0 owns the env's command row and the push)
+  if (role == 0) {
+    if (o.ep_len % (long long)p.resample_period == 0)
+      resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_CMD, 0));
+    if (p.heading_command) cmd[2] = clampf(0.5f * wrap_to_pi(cmd[3] - heading), -1.f, 1.f);
+    if (do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
+      const U4 r = rng_block_cold(key, genv, LGK_STREAM_PUSH, 0);
+      const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
+      root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));
+      root[8] = scale_uniform(range, lo, u32_to_uniform(r.y));
+    }
+  }
+  __syncwarp();
+  const float c0 = cmd[0], c1 = cmd[1], c2 = cmd[2];
+  // check_termination LR:139-145
+  bool term = false;
+  for (int t = role; t < p.num_term; t += 4) {
+    const float* f = contact + 3 * p.term_idx[t];
+    term = term || (norm3(f[0], f[1], f[2]) > 1.0f);
+  }
+  term = quad_ballot(term, lane) != 0;
+  o.time_out = (float)o.ep_len > p.max_episode_length;
+  o.reset = term || o.time_out;
+
+  // compute_reward LR:193-210, terms in alphabetical order; every lane carries the full sum, role 0 books episode_sums
+  float rew = 0.f;
+  const float cmd_norm = norm2(c0, c1);
+  const int d0 = 3 * role;
+#undef LGK_TERM
+#define LGK_TERM(ID, EXPR)                                                      \
+  if (p.reward_active[ID]) {                                                    \
+    const float r_ = (EXPR) * p.reward_scale[ID];                               \
+    rew += r_;                                                                  \
+    if (role == 0) sums[(size_t)p.reward_slot[ID] * sums_stride] += r_;         \
+  }
+  if (p.reward_active[LGK_R_ACTION_RATE]) {                           // LR:901-903
+    float s = 0.f;
+#pragma unroll
+    for (int d = d0; d < d0 + 3; ++d) { const float e = lact[d] - act[d]; s += e * e; }
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_ACTION_RATE, s)
+  }
+  LGK_TERM(LGK_R_ANG_VEL_XY, o.bav.x * o.bav.x + o.bav.y * o.bav.y)   // LR:876-878
+  if (p.reward_active[LGK_R_BASE_HEIGHT]) {                           // LR:884-887
+    const float e = mean_height_err - p.base_height_target;
+    LGK_TERM(LGK_R_BASE_HEIGHT, e * e)
+  }
+  if (p.reward_active[LGK_R_COLLISION]) {                             // LR:905-908
+    float s = 0.f;
+    for (int b = role; b < p.num_pen; b += 4) {
+      const float* f = contact + 3 * p.pen_idx[b];
+      s += norm3(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f;
+    }
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_COLLISION, s)
+  }
+  if (p.reward_active[LGK_R_DOF_ACC]) {                               // LR:897-899
+    float s = 0.f;
+#pragma unroll
+    for (int d = d0; d < d0 + 3; ++d) { const float a = (ldv[d] - dof[2 * d + 1]) / p.dt; s += a * a; }
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_DOF_ACC, s)
+  }
+  if (p.reward_active[LGK_R_DOF_POS_LIMITS]) {                        // LR:914-918
+    float s = 0.f;
+#pragma unroll
+    for (int d = d0; d < d0 + 3; ++d) {
+      const float q = dof[2 * d];
+      s += -fminf(q - p.dof_pos_lo[d], 0.f) + fmaxf(q - p.dof_pos_hi[d], 0.f);
+    }
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_DOF_POS_LIMITS, s)
+  }
+  if (p.reward_active[LGK_R_DOF_VEL]) {                               // LR:893-895
+    float s = 0.f;
+#pragma unroll
+    for (int d = d0; d < d0 + 3; ++d) { const float v = dof[2 * d + 1]; s += v * v; }
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_DOF_VEL, s)
+  }
+  if (p.reward_active[LGK_R_DOF_VEL_LIMITS]) {                        // LR:920-925
+    float s = 0.f;
+#pragma unroll
+    for (int d = d0; d < d0 + 3; ++d)
+      s += clampf(fabsf(dof[2 * d + 1]) - p.dof_vel_limits[d] * p.soft_dof_vel_limit, 0.f, 1.f);
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_DOF_VEL_LIMITS, s)
+  }
+  const bool has_foot = role < p.num_feet;
+  const float* cf = contact + 3 * p.feet_idx[has_foot ? role : 0];    // this role's foot
+  if (p.reward_active[LGK_R_FEET_AIR_TIME]) {                         // LR:942-954 (stateful)
+    float s = 0.f;
+    if (has_foot) {
+      const int f = role;
+      const bool c = cf[2] > 1.0f;
+      const bool filt = c || (lc[f] != 0);
+      lc[f] = c ? 1 : 0;
+      const bool first = (fat[f] > 0.f) && filt;
+      const float air = fat[f] + p.dt;
+      s = (air - 0.5f) * (first ? 1.f : 0.f);
+      fat[f] = filt ? 0.f * air : air;     // air *= ~filt
+    }
+    s = quad_sum(s);
+    s *= cmd_norm > 0.1f ? 1.f : 0.f;
+    LGK_TERM(LGK_R_FEET_AIR_TIME, s)
+  }
+  if (p.reward_active[LGK_R_FEET_CONTACT_FORCES]) {                   // LR:966-969
+    float s = has_foot ? fmaxf(norm3(cf[0], cf[1], cf[2]) - p.max_contact_force, 0.f) : 0.f;
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_FEET_CONTACT_FORCES, s)
+  }
+  LGK_TERM(LGK_R_LIN_VEL_Z, o.blv.z * o.blv.z)                        // LR:872-874
+  if (p.reward_active[LGK_R_NO_FLY]) {                                // CAS:43-46
+    const int n = __popc(quad_ballot(has_foot && cf[2] > 0.1f, lane));
+    LGK_TERM(LGK_R_NO_FLY, n == 1 ? 1.f : 0.f)
+  }
+  LGK_TERM(LGK_R_ORIENTATION, o.pg.x * o.pg.x + o.pg.y * o.pg.y)      // LR:880-882
+  if (p.reward_active[LGK_R_STAND_STILL]) {                           // LR:961-964
+    float s = 0.f;
+#pragma unroll
+    for (int d = d0; d < d0 + 3; ++d) s += fabsf(dof[2 * d] - p.default_dof_pos[d]);
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_STAND_STILL, s * (cmd_norm < 0.1f ? 1.f : 0.f))
+  }
+  if (p.reward_active[LGK_R_STUMBLE]) {                               // LR:956-959
+    const bool any = quad_ballot(has_foot && (norm2(cf[0], cf[1]) > 5.f * fabsf(cf[2])), lane) != 0;
+    LGK_TERM(LGK_R_STUMBLE, any ? 1.f : 0.f)
+  }
+  if (p.reward_active[LGK_R_TORQUE_LIMITS]) {                         // LR:927-930
+    float s = 0.f;
+#pragma unroll
+    for (int d = d0; d < d0 + 3; ++d) s += fmaxf(fabsf(tq[d]) - p.torque_limits[d] * p.soft_torque_limit, 0.f);
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_TORQUE_LIMITS, s)
+  }
+  if (p.reward_active[LGK_R_TORQUES]) {                               // LR:889-891
+    float s = 0.f;
+#pragma unroll
+    for (int d = d0; d < d0 + 3; ++d) s += tq[d] * tq[d];
+    s = quad_sum(s);
+    LGK_TERM(LGK_R_TORQUES, s)
+  }
+  {                                                                   // LR:937-940
+    const float e = c2 - o.bav.z;
+    LGK_TERM(LGK_R_TRACKING_ANG_VEL, expf(-(e * e) / p.tracking_sigma))
+  }
+  {                                                                   // LR:932-935
+    const float ex = c0 - o.blv.x, ey = c1 - o.blv.y;
+    LGK_TERM(LGK_R_TRACKING_LIN_VEL, expf(-(ex * ex + ey * ey) / p.tracking_sigma))
+  }
+#undef LGK_TERM
+  o.rew = rew;
+}
+
+// reset_idx for one env, shared by its quad (LR:147-191): role 0 = terrain curriculum, root state, command resample;
+// roles 1..3 = the three Philox blocks of the joint positions (joints 4b..4b+3, b = role-1); role r clears foot r
+LGK_COLD void env_reset_quad(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, int role, float* root,
+                             float* dof, float* cmd, float* fat, long long& ep_len) {
+  if (role == 0) {
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (p.env_origins) { ox = p.env_origins[3 * env]; oy = p.env_origins[3 * env + 1]; oz = p.env_origins[3 * env + 2]; }
+    if (p.terrain_curriculum) {                                         // LR:446-469
+      const float dist = norm2(root[0] - ox, root[1] - oy);
+      const bool up = dist > p.half_env_length;
+      const bool down = (dist < norm2(cmd[0], cmd[1]) * p.max_episode_length_s * 0.5f) && !up;
+      long long lvl = p.terrain_levels[env] + (up ? 1 : 0) - (down ? 1 : 0);
+      if (lvl >= p.max_terrain_level) {
+        const U4 r = rng_block_cold(key, genv, LGK_STREAM_TERRAIN, 0);
+        lvl = (long long)(r.x % (uint32_t)p.max_terrain_level);
+      } else if (lvl < 0) {
+        lvl = 0;
+      }
+      p.terrain_levels[env] = lvl;
+      const float* o = p.terrain_origins + 3 * ((size_t)lvl * p.terrain_num_cols + (size_t)p.terrain_types[env]);
+      ox = o[0]; oy = o[1]; oz = o[2];
+      p.env_origins[3 * env] = ox; p.env_origins[3 * env + 1] = oy; p.env_origins[3 * env + 2] = oz;
+    }
+    // _reset_root_states LR:414-432
+    const U4 r0 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 0);
+    const U4 r1 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 1);
+    for (int i = 0; i < 13; ++i) root[i] = p.base_init_state[i];
+    root[0] = f_add(root[0], ox); root[1] = f_add(root[1], oy); root[2] = f_add(root[2], oz);
+    if (p.custom_origins) {
+      root[0] = f_add(root[0], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.x)));
+      root[1] = f_add(root[1], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.y)));
+    }
+    root[7] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.z));
+    root[8] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.w));
+    root[9] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.x));
+    root[10] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.y));
+    root[11] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.z));
+    root[12] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.w));
+    resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170 (after the curriculum read cmd)
+  } else {
+    // _reset_dofs LR:397-407
+    const int b = role - 1;
+    const U4 r = rng_block_cold(key, genv, LGK_STREAM_RESET_DOF, b);
+    for (int i = 0; i < 4; ++i) {
+      const int d = 4 * b + i;
+      dof[2 * d] = f_mul(p.default_dof_pos[d], scale_uniform(1.0f, 0.5f, u32_to_uniform(pick(r, i))));
+      dof[2 * d + 1] = 0.f;
+    }
+  }
+  if (role < p.num_feet) fat[role] = 0.f;                                         // LR:175
+  ep_len = 0;                                                                     // LR:176
+}
+
+// LR:212-222: the 48 proprioceptive columns, before noise -- role r writes the nine columns of its joints, role 0 the
+// twelve base / command columns
+LGK_D void env_obs_head_quad(const LgkStepParams& p, const EnvScalars& s, int role, const float* dof, const float* cmd,
+                             const float* act, float* out48) {
+  if (role == 0) {
+    out48[0] = s.blv.x * p.obs_scale_lin_vel; out48[1] = s.blv.y * p.obs_scale_lin_vel; out48[2] = s.blv.z * p.obs_scale_lin_vel;
+    out48[3] = s.bav.x * p.obs_scale_ang_vel; out48[4] = s.bav.y * p.obs_scale_ang_vel; out48[5] = s.bav.z * p.obs_scale_ang_vel;
+    out48[6] = s.pg.x; out48[7] = s.pg.y; out48[8] = s.pg.z;
+    out48[9] = cmd[0] * p.obs_scale_lin_vel; out48[10] = cmd[1] * p.obs_scale_lin_vel; out48[11] = cmd[2] * p.obs_scale_ang_vel;
+  }
+#pragma unroll
+  for (int d = 3 * role; d < 3 * role + 3; ++d) {
+    out48[12 + d] = (dof[2 * d] - p.default_dof_pos[d]) * p.obs_scale_dof_pos;
+    out48[24 + d] = dof[2 * d + 1] * p.obs_scale_dof_vel;
+    out48[36 + d] = act[d];
+  }
+}
+#endif
+
 // LR:204-210: positive clip, then the termination term
 LGK_D float env_finish_reward(const LgkStepParams& p, float rew, bool reset, bool time_out, float* sums,
                                int sums_stride) {

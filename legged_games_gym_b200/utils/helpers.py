@@ -108,6 +108,17 @@ def update_cfg_from_args(env_cfg, cfg_train, args):
     return env_cfg, cfg_train
 
 
+def export_policy_as_jit(actor_critic, path):
+    """reference legged_gym/utils/helpers.py:212-222: the actor MLP as TorchScript, <path>/policy_1.pt (run from C++)."""
+    import copy
+    import torch
+    os.makedirs(path, exist_ok=True)
+    path = os.path.join(path, "policy_1.pt")
+    model = copy.deepcopy(actor_critic.actor).to("cpu")
+    torch.jit.script(model).save(path)
+    return path
+
+
 def get_args(argv=None):
     p = argparse.ArgumentParser(description="RL Policy")
     p.add_argument("--task", type=str, default="anymal_c_flat")

@@ -164,9 +164,12 @@ def make_env(num_envs, device, host_sim=False, env_id_offset=0):
     feeder = feeder_cls(num_envs, model.num_bodies, model.num_dof, device=device, seed=env_id_offset,
                         p_contact_body0=P_TERMINATE)
     base = task_registry.get_task_class(TASK)
+    from legged_games_gym_b200.envs.base.legged_robot import SyntheticTerrain
     cls = type(base.__name__ + "Bench", (base,), {"tile_envs": TILE, "use_cuda_graph": USE_GRAPH})
+    # height field = SURVEY 8(d)'s synthetic input (uniform int16 heights): every sample differs from its neighbours,
+    # the worst case for the gather; the generated terrain (utils/terrain.py) is the library default
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
-              sim_device=device, headless=True, sim_backend=feeder)
+              sim_device=device, headless=True, sim_backend=feeder, terrain=SyntheticTerrain(cfg.terrain, cfg.seed))
     env.env_id_offset = env_id_offset
     env._tq_params.lstm_variant = LSTM_VARIANT
     env._params.env_id_offset = env_id_offset

@@ -24,13 +24,15 @@ from ...sim.asset_model import model_for_asset
 from ...sim.state_feeder import StateFeeder, SimBackend, synth_height_field, synth_terrain_origins
 from ...utils.helpers import class_to_dict
 from .base_task import BaseTask
+from ...utils.terrain import Terrain
 from .legged_robot_config import LeggedRobotCfg
 
 
-class _Terrain:
-    """What the hot path reads from the reference's Terrain object (utils/terrain.py:38-83): cfg, env_length,
-    env_origins [rows, cols, 3], heightsamples int16 [tot_rows, tot_cols].  Generation (terrain.py:85-187)
-    depends on isaacgym.terrain_utils and is out of scope: fields are synthetic unless a provider is given."""
+class SyntheticTerrain:
+    """Stand-in with the attributes the hot path reads from a Terrain object (utils/terrain.py: cfg, env_length,
+    env_origins [rows, cols, 3], heightsamples int16 [tot_rows, tot_cols]) filled with the seeded synthetic field of
+    SURVEY.md section 8(d) (uniform int16 heights): the benchmark / parity input.  Pass it as ``terrain=``; the default
+    is the generated terrain of utils/terrain.py, like the reference (LR:235)."""
 
     def __init__(self, cfg, seed):
         self.cfg = cfg
@@ -41,6 +43,9 @@ class _Terrain:
         self.tot_cols = int(cfg.num_cols * cfg.terrain_width / cfg.horizontal_scale) + 2 * self.border
         self.heightsamples = synth_height_field(self.tot_rows, self.tot_cols, seed)
         self.env_origins = synth_terrain_origins(cfg)
+
+
+_Terrain = SyntheticTerrain
 
 
 def _stream_ptr():
@@ -274,8 +279,7 @@ class LeggedRobot(BaseTask):
         self.up_axis_idx = 2
         mesh_type = self.cfg.terrain.mesh_type
         if mesh_type in ("heightfield", "trimesh"):
-            self.terrain = self._terrain_arg if self._terrain_arg is not None else _Terrain(
-                self.cfg.terrain, getattr(self.cfg, "seed", 0) or 0)
+            self.terrain = self._terrain_arg if self._terrain_arg is not None else Terrain(self.cfg.terrain, self.num_envs)
             self.height_samples = torch.from_numpy(np.ascontiguousarray(self.terrain.heightsamples)).view(
                 self.terrain.tot_rows, self.terrain.tot_cols).to(self.device)
         elif mesh_type not in (None, "plane"):

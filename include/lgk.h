@@ -47,7 +47,8 @@ enum {
  * counter = (global env id, word_index/4, stream, step)); uniform = (word >> 8) * 2^-24. */
 enum {
   LGK_STREAM_CMD = 0, LGK_STREAM_PUSH = 1, LGK_STREAM_RESET_DOF = 2, LGK_STREAM_RESET_ROOT = 3,
-  LGK_STREAM_RESET_CMD = 4, LGK_STREAM_TERRAIN = 5, LGK_STREAM_OBS = 6, LGK_STREAM_ACT = 7
+  LGK_STREAM_RESET_CMD = 4, LGK_STREAM_TERRAIN = 5, LGK_STREAM_OBS = 6, LGK_STREAM_ACT = 7,
+  LGK_STREAM_PREDATOR = 8
 };
 
 enum { LGK_CTRL_P = 0, LGK_CTRL_V = 1, LGK_CTRL_T = 2 };
@@ -119,6 +120,11 @@ typedef struct LgkStepParams {
   int32_t custom_origins;             /* LR:422 */
   int32_t send_timeouts;              /* LR:190 */
   int32_t zero_lstm_on_reset;         /* ANY:56-60 */
+  /* low_level_game (envs/a1_game/low_level_game.py:419-432): on reset the env's second actor (a sphere "predator") is
+   * re-spawned at prey_pos - sign * U(1,10)^3 with one random sign per env, z forced to 0.3; only its position columns
+   * are written.  predator_actor_offset = its row inside the env's actor group. */
+  int32_t predator_spawn;
+  int32_t predator_actor_offset;
 
   /* scalars */
   float dt;                           /* decimation * sim.dt (LR:782) */

@@ -45,7 +45,7 @@ class StepParams(C.Structure):
         ("seed", u64), ("env_id_offset", i64),
         ("heading_command", i32), ("measure_heights", i32), ("terrain_is_plane", i32), ("do_push", i32),
         ("add_noise", i32), ("only_positive_rewards", i32), ("terrain_curriculum", i32), ("custom_origins", i32),
-        ("send_timeouts", i32), ("zero_lstm_on_reset", i32),
+        ("send_timeouts", i32), ("zero_lstm_on_reset", i32), ("predator_spawn", i32), ("predator_actor_offset", i32),
         ("dt", f32), ("resample_period", i32), ("max_episode_length", f32), ("max_episode_length_s", f32),
         ("max_push_vel", f32), ("cmd_lo", f32 * 4), ("cmd_range", f32 * 4),
         ("obs_scale_lin_vel", f32), ("obs_scale_ang_vel", f32), ("obs_scale_dof_pos", f32),

@@ -807,6 +807,8 @@ static int validate_step(const LgkStepParams* p) {
   LGK_REQUIRE(p->num_pen >= 0 && p->num_pen <= LGK_MAX_PEN, "num_pen out of range");
   LGK_REQUIRE(p->num_term >= 0 && p->num_term <= LGK_MAX_TERM, "num_term out of range");
   LGK_REQUIRE(p->actors_per_env >= 1 && p->root_actor_offset >= 0 && p->root_actor_offset < p->actors_per_env, "bad actor layout");
+  LGK_REQUIRE(!p->predator_spawn || (p->predator_actor_offset >= 0 && p->predator_actor_offset < p->actors_per_env &&
+                                     p->predator_actor_offset != p->root_actor_offset), "bad predator actor offset");
   LGK_REQUIRE(p->num_obs == 48 + (p->measure_heights ? p->num_height_points : 0), "num_obs must be 48 + P");
   LGK_REQUIRE(p->resample_period > 0, "resample_period must be positive");
   LGK_REQUIRE(p->root_states && p->dof_state && p->contact_forces && p->actions && p->torques && p->commands &&

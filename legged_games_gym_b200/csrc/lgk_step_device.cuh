@@ -16,6 +16,16 @@ LGK_HD int obs_word_of(int j) { return (j >> 5) & 3; }
 // small (each inlined Philox4x32-10 is ~100 instructions)
 LGK_COLD U4 rng_block_cold(const RngKey& k, uint32_t env, uint32_t stream, uint32_t blk) { return rng_block(k, env, stream, blk); }
 
+// LLG:419-432: re-spawn the predator sphere relative to the freshly reset prey position (`root` = prey row)
+LGK_D void spawn_predator(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, const float* root) {
+  const U4 r = rng_block_cold(key, genv, LGK_STREAM_PREDATOR, 0);
+  const float sgn = u32_to_uniform(r.w) < 0.5f ? -1.f : 1.f;
+  float* pred = p.root_states + ((size_t)env * p.actors_per_env + p.predator_actor_offset) * 13;
+  pred[0] = f_sub(root[0], sgn * scale_uniform(9.0f, 1.0f, u32_to_uniform(r.x)));
+  pred[1] = f_sub(root[1], sgn * scale_uniform(9.0f, 1.0f, u32_to_uniform(r.y)));
+  pred[2] = 0.3f;          // the z offset (word r.z) is drawn and then overwritten, LLG:432
+}
+
 struct EnvScalars {
   V3 blv, bav, pg;       // base_lin_vel, base_ang_vel, projected_gravity (LR:119-121)
   long long ep_len;      // episode_length_buf after += 1 (LR:114)
@@ -398,6 +408,7 @@ LGK_COLD void env_reset_quad(const LgkStepParams& p, const RngKey& key, uint32_t
     root[10] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.y));
     root[11] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.z));
     root[12] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.w));
+    if (p.predator_spawn) spawn_predator(p, key, genv, env, root);
     resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170 (after the curriculum read cmd)
   } else {
     // _reset_dofs LR:397-407
@@ -493,6 +504,7 @@ LGK_COLD void env_reset(const LgkStepParams& p, const RngKey& key, uint32_t genv
   root[10] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.y));
   root[11] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.z));
   root[12] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.w));
+  if (p.predator_spawn) spawn_predator(p, key, genv, env, root);
   resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170
   for (int f = 0; f < p.num_feet; ++f) fat[f] = 0.f;                            // LR:175
   ep_len = 0;                                                                   // LR:176

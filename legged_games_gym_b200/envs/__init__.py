@@ -1,6 +1,6 @@
 """Registered tasks (mirror of reference legged_gym/envs/__init__.py:31-56).  The two hierarchical game tasks
-(high_level_game, dec_high_level_game) need a checkpoint and a forked rsl_rl that are not part of the reference tree
- and are not registered."""
+(high_level_game, dec_high_level_game) drive a pre-trained low-level policy through a checkpoint and a forked rsl_rl
+runner that are not part of the reference tree and are not registered."""
 from .base.legged_robot import LeggedRobot
 from .anymal_c.anymal import Anymal
 from .anymal_c.mixed_terrains.anymal_c_rough_config import AnymalCRoughCfg, AnymalCRoughCfgPPO
@@ -9,6 +9,7 @@ from .anymal_b.anymal_b_config import AnymalBRoughCfg, AnymalBRoughCfgPPO
 from .cassie.cassie import Cassie
 from .cassie.cassie_config import CassieRoughCfg, CassieRoughCfgPPO
 from .a1.a1_config import A1RoughCfg, A1RoughCfgPPO
+from .a1_game.low_level_game import LowLevelGame
 from .a1_game.low_level_game_config import LowLevelGameCfg, LowLevelGamePPO
 
 from ..utils.task_registry import task_registry
@@ -18,3 +19,4 @@ task_registry.register("anymal_c_flat", Anymal, AnymalCFlatCfg(), AnymalCFlatCfg
 task_registry.register("anymal_b", Anymal, AnymalBRoughCfg(), AnymalBRoughCfgPPO())
 task_registry.register("a1", LeggedRobot, A1RoughCfg(), A1RoughCfgPPO())
 task_registry.register("cassie", Cassie, CassieRoughCfg(), CassieRoughCfgPPO())
+task_registry.register("low_level_game", LowLevelGame, LowLevelGameCfg(), LowLevelGamePPO())

@@ -188,8 +188,7 @@ class LeggedRobot(BaseTask):
         self._finalize(st, advance=1)
         if do_push:
             gym.set_actor_root_state_tensor(self.root_states)
-        gym.set_dof_state_tensor_indexed(self.dof_state, self.reset_env_ids, self.reset_count)
-        gym.set_actor_root_state_tensor_indexed(self.root_states, self.reset_env_ids, self.reset_count)
+        self._push_resets_to_sim()
         if self._obs_overridden:
             self.compute_observations()
             clip_obs = self.cfg.normalization.clip_observations
@@ -258,8 +257,7 @@ class LeggedRobot(BaseTask):
         nat.check(nat.lib.lgk_reset_idx(C.byref(p), env_ids.data_ptr(), int(env_ids.numel()), st), "lgk_reset_idx")
         p.terrain_curriculum = saved
         self._finalize(st, advance=0)
-        self.gym.set_dof_state_tensor_indexed(self.dof_state, self.reset_env_ids, self.reset_count)
-        self.gym.set_actor_root_state_tensor_indexed(self.root_states, self.reset_env_ids, self.reset_count)
+        self._push_resets_to_sim()
 
     # ------------------------------------------------------------------ LR:212-230 (torch version for overriders)
     def compute_observations(self):
@@ -269,7 +267,7 @@ class LeggedRobot(BaseTask):
                                   (self.dof_pos - self.default_dof_pos) * o.dof_pos, self.dof_vel * o.dof_vel,
                                   self.actions), dim=-1)
         if self.cfg.terrain.measure_heights:
-            heights = torch.clip(self.root_states[:, 2].unsqueeze(1) - 0.5 - self.measured_heights, -1, 1.) * o.height_measurements
+            heights = torch.clip(self.root_states[self._root_rows(), 2].unsqueeze(1) - 0.5 - self.measured_heights, -1, 1.) * o.height_measurements
             self.obs_buf = torch.cat((self.obs_buf, heights), dim=-1)
         if self.add_noise:
             self.obs_buf += (2 * torch.rand_like(self.obs_buf) - 1) * self.noise_scale_vec
@@ -291,7 +289,7 @@ class LeggedRobot(BaseTask):
         model = model_for_asset(self.cfg.asset)
         self.robot_model = model
         self.num_dof = self.num_dofs = model.num_dof
-        self.num_bodies = model.num_bodies
+        self.num_bodies = model.num_bodies                     # robot links (LR:687); the contact view may hold more
         self.dof_names = list(model.dof_names)
         if self.num_dof != nat.NUM_DOF:
             raise ValueError(f"kernels are built for {nat.NUM_DOF} DOF, asset has {self.num_dof}")
@@ -321,11 +319,22 @@ class LeggedRobot(BaseTask):
         self.base_init_state = torch.tensor(ini.pos + ini.rot + ini.lin_vel + ini.ang_vel, dtype=torch.float, device=dev)
         self._get_env_origins()
         if self.gym is None:
-            self.gym = StateFeeder(self.num_envs, self.num_bodies, self.num_dof, device=dev,
+            self.gym = StateFeeder(self.num_envs, self.num_bodies + self._extra_bodies_per_env(), self.num_dof, device=dev,
                                    seed=getattr(self.cfg, "seed", 0) or 0, actors_per_env=self._actors_per_env())
 
     def _actors_per_env(self):
         return 1
+
+    def _extra_bodies_per_env(self):
+        return 0
+
+    def _configure_native(self, p):
+        """hook for subclasses that hand extra facts to the kernels (LowLevelGame: predator spawn)"""
+
+    def _push_resets_to_sim(self):
+        # LR:409-412, 433-436: indexed state writes for the envs that were reset
+        self.gym.set_dof_state_tensor_indexed(self.dof_state, self.reset_env_ids, self.reset_count)
+        self.gym.set_actor_root_state_tensor_indexed(self.root_states, self.reset_env_ids, self.reset_count)
 
     # ------------------------------------------------------------------ LR:752-779
     def _get_env_origins(self):
@@ -509,10 +518,11 @@ class LeggedRobot(BaseTask):
         self._tq_params = tp
         # ---- step
         p = nat.StepParams()
-        p.num_envs, p.num_bodies, p.num_obs = N, self.num_bodies, self.num_obs
+        p.num_envs, p.num_bodies, p.num_obs = N, int(self.contact_forces.shape[1]), self.num_obs      # bodies in the contact view (LR:529)
         mh = bool(cfg.terrain.measure_heights)
         p.num_height_points = self.num_height_points if mh else 0
         p.actors_per_env, p.root_actor_offset = self._actors_per_env(), 0
+        self._configure_native(p)
         p.seed = int(getattr(cfg, "seed", 0) or 0) & 0xFFFFFFFFFFFFFFFF
         p.env_id_offset = int(getattr(self, "env_id_offset", 0))
         p.heading_command = int(bool(cfg.commands.heading_command))

@@ -91,8 +91,9 @@ class SimBackend:
     def set_dof_state_tensor_indexed(self, dof_state, env_ids_int32, count):
         pass
 
-    def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count):
-        pass
+    def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count, actor_stride=1, actor_offset=0):
+        """env_ids_int32[:count] (device int32, ascending) name the ENVS whose actor `actor_stride * id + actor_offset` was
+        reset; the reference passes the actor ids themselves (LR:433-436, LLG:441-451)."""
 
     def set_actor_root_state_tensor(self, root_states):
         pass
@@ -165,8 +166,9 @@ class HostStateFeeder(StateFeeder):
     def set_dof_state_tensor_indexed(self, dof_state, env_ids_int32, count):
         self._d2h(self.h_dof, dof_state)
 
-    def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count):
-        self._d2h(self.h_root, root_states)
+    def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count, actor_stride=1, actor_offset=0):
+        if actor_offset == 0:          # one copy of the whole tensor covers every actor of the env
+            self._d2h(self.h_root, root_states)
 
     def set_actor_root_state_tensor(self, root_states):
         self._d2h(self.h_root, root_states)

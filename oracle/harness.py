@@ -22,6 +22,7 @@ TASKS = {
     "anymal_b": ("anymal", "envs.anymal_b.anymal_b_config", "AnymalBRoughCfg"),
     "a1": ("legged", "envs.a1.a1_config", "A1RoughCfg"),
     "cassie": ("cassie", "envs.cassie.cassie_config", "CassieRoughCfg"),
+    "low_level_game": ("llg", "envs.a1_game.low_level_game_config", "LowLevelGameCfg"),
 }
 
 
@@ -54,7 +55,9 @@ def build_case(task, num_envs, seed=0, overrides=None, hf_shape=None, xy_max=(83
     cfg = product_cfg(task, num_envs, overrides)
     model = model_for_asset(cfg.asset)
     consts = model.consts(cfg.asset)
-    st = synth_state(num_envs, model.num_bodies, model.num_dof, seed, xy_max=xy_max)
+    llg = TASKS[task][0] == "llg"        # two actors per env (robot + predator sphere), 18 bodies in the contact view
+    st = synth_state(num_envs, model.num_bodies + (1 if llg else 0), model.num_dof, seed, xy_max=xy_max,
+                     actors_per_env=2 if llg else 1)
     rough = cfg.terrain.mesh_type in ("heightfield", "trimesh")
     hs = None
     origins = None
@@ -98,6 +101,7 @@ def step_tables(seed, step, num_envs, num_obs, num_dof=12, env_offset=0):
         philox.STREAM_RESET_CMD: philox.uniforms(seed, step, ids, philox.STREAM_RESET_CMD, 3),
         philox.STREAM_TERRAIN: philox.raw_u32(seed, step, ids, philox.STREAM_TERRAIN, 1),
         philox.STREAM_OBS: philox.obs_uniforms(seed, step, ids, num_obs),
+        philox.STREAM_PREDATOR: philox.uniforms(seed, step, ids, philox.STREAM_PREDATOR, 4),
     }
 
 

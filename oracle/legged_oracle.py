@@ -168,10 +168,18 @@ class OracleEnv:
         self.env_length = cfg.terrain.terrain_length
         # ---- _init_buffers (LR:511-581)
         self.root_states = state["root_states"]
+        # low_level_game (LLG:123-125, 760-812): two actors per env, prey (robot) first, then the predator sphere
+        self.llg = kind == "llg"
+        if self.llg:
+            self.prey_indices = torch.arange(N) * 2
+            self.predator_indices = torch.arange(N) * 2 + 1
+            self.rows = self.prey_indices
+        else:
+            self.rows = slice(None)
         self.dof_state = state["dof_state"]
         self.dof_pos = self.dof_state.view(N, D, 2)[..., 0]
         self.dof_vel = self.dof_state.view(N, D, 2)[..., 1]
-        self.base_quat = self.root_states[:, 3:7]
+        self.base_quat = self.root_states[self.rows, 3:7]      # a copy for llg (advanced indexing), refreshed every step
         self.contact_forces = state["contact_forces"].view(N, -1, 3)
         self.common_step_counter = 0
         self.gravity_vec = torch.tensor([0., 0., -1.]).repeat((N, 1))
@@ -182,13 +190,13 @@ class OracleEnv:
         self.actions = torch.zeros(N, self.num_actions)
         self.last_actions = torch.zeros(N, self.num_actions)
         self.last_dof_vel = torch.zeros_like(self.dof_vel)
-        self.last_root_vel = torch.zeros_like(self.root_states[:, 7:13])
+        self.last_root_vel = torch.zeros_like(self.root_states[self.rows, 7:13])
         self.commands = torch.zeros(N, cfg.commands.num_commands)
         self.commands_scale = torch.tensor([self.obs_scales.lin_vel, self.obs_scales.lin_vel, self.obs_scales.ang_vel])
         self.feet_air_time = torch.zeros(N, self.feet.shape[0])
         self.last_contacts = torch.zeros(N, len(self.feet), dtype=torch.bool)
-        self.base_lin_vel = quat_rotate_inverse(self.base_quat, self.root_states[:, 7:10])
-        self.base_ang_vel = quat_rotate_inverse(self.base_quat, self.root_states[:, 10:13])
+        self.base_lin_vel = quat_rotate_inverse(self.base_quat, self.root_states[self.rows, 7:10])
+        self.base_ang_vel = quat_rotate_inverse(self.base_quat, self.root_states[self.rows, 10:13])
         self.projected_gravity = quat_rotate_inverse(self.base_quat, self.gravity_vec)
         self.measure_heights = cfg.terrain.measure_heights
         if self.measure_heights:
@@ -283,8 +291,10 @@ class OracleEnv:
         self.tables = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in tables.items()}
         self.episode_length_buf += 1
         self.common_step_counter += 1
-        self.base_lin_vel[:] = quat_rotate_inverse(self.base_quat, self.root_states[:, 7:10])
-        self.base_ang_vel[:] = quat_rotate_inverse(self.base_quat, self.root_states[:, 10:13])
+        if self.llg:
+            self.base_quat[:] = self.root_states[self.rows, 3:7]                  # LLG:123
+        self.base_lin_vel[:] = quat_rotate_inverse(self.base_quat, self.root_states[self.rows, 7:10])
+        self.base_ang_vel[:] = quat_rotate_inverse(self.base_quat, self.root_states[self.rows, 10:13])
         self.projected_gravity[:] = quat_rotate_inverse(self.base_quat, self.gravity_vec)
         self._callback()
         self.check_termination()
@@ -294,7 +304,7 @@ class OracleEnv:
         self.compute_observations()
         self.last_actions[:] = self.actions[:]
         self.last_dof_vel[:] = self.dof_vel[:]
-        self.last_root_vel[:] = self.root_states[:, 7:13]
+        self.last_root_vel[:] = self.root_states[self.rows, 7:13]
 
     # ------------------------------------------------------------------ LR:329-345
     def _callback(self):
@@ -310,7 +320,7 @@ class OracleEnv:
         if self.cfg.domain_rand.push_robots and (self.common_step_counter % self.push_interval == 0):
             mv = self.cfg.domain_rand.max_push_vel_xy                       # LR:438-444
             u = self.tables[philox.STREAM_PUSH][:, 0:2]
-            self.root_states[:, 7:9] = (mv - -mv) * u + -mv
+            self.root_states[self.rows, 7:9] = (mv - -mv) * u + -mv
 
     def _draw(self, lo, hi, stream, ids, c0, c1):
         return (hi - lo) * self.tables[stream][ids, c0:c1] + lo
@@ -333,7 +343,7 @@ class OracleEnv:
         if self.cfg.terrain.mesh_type == "none":
             raise NameError("Can't measure height with terrain mesh type 'none'")
         pts = yaw_only_apply(self.base_quat.repeat(1, self.num_height_points), self.height_points) + \
-            (self.root_states[:, :3]).unsqueeze(1)
+            (self.root_states[self.rows, :3]).unsqueeze(1)
         pts += self.cfg.terrain.border_size
         pts = (pts / self.cfg.terrain.horizontal_scale).long()
         px = torch.clip(pts[:, :, 0].view(-1), 0, self.height_samples.shape[0] - 2)
@@ -377,11 +387,22 @@ class OracleEnv:
         self.dof_pos[ids] = self.default_dof_pos * self._draw(0.5, 1.5, philox.STREAM_RESET_DOF, ids, 0, self.D)
         self.dof_vel[ids] = 0.
         # _reset_root_states LR:414-436
-        self.root_states[ids] = self.base_init_state
-        self.root_states[ids, :3] += self.env_origins[ids]
+        rid = self.rows[ids] if self.llg else ids
+        self.root_states[rid] = self.base_init_state
+        self.root_states[rid, :3] += self.env_origins[ids]
         if self.custom_origins:
-            self.root_states[ids, :2] += self._draw(-1., 1., philox.STREAM_RESET_ROOT, ids, 0, 2)
-        self.root_states[ids, 7:13] = self._draw(-0.5, 0.5, philox.STREAM_RESET_ROOT, ids, 2, 8)
+            self.root_states[rid, :2] += self._draw(-1., 1., philox.STREAM_RESET_ROOT, ids, 0, 2)
+        self.root_states[rid, 7:13] = self._draw(-0.5, 0.5, philox.STREAM_RESET_ROOT, ids, 2, 8)
+        if self.llg:                                                               # LLG:419-432
+            init_prey_pos = self.root_states[rid, :3].detach().clone()
+            rand_offset = self._draw(1.0, 10.0, philox.STREAM_PREDATOR, ids, 0, 3)
+            rand_sign = self.tables[philox.STREAM_PREDATOR][ids, 3].clone()
+            lo = rand_sign < 0.5
+            rand_sign[lo] = -1
+            rand_sign[~lo] = 1
+            offset = rand_sign.unsqueeze(1) * rand_offset
+            self.root_states[self.predator_indices[ids], :3] = init_prey_pos - offset
+            self.root_states[self.predator_indices[ids], 2] = 0.3
         self.resample_commands(ids, philox.STREAM_RESET_CMD)
         self.last_actions[ids] = 0.
         self.last_dof_vel[ids] = 0.
@@ -406,7 +427,7 @@ class OracleEnv:
     def _terrain_curriculum(self, ids):
         if not self.init_done:
             return
-        dist = torch.norm(self.root_states[ids, :2] - self.env_origins[ids, :2], dim=1)
+        dist = torch.norm(self.root_states[self.rows[ids] if self.llg else ids, :2] - self.env_origins[ids, :2], dim=1)
         up = dist > self.env_length / 2
         down = (dist < torch.norm(self.commands[ids, :2], dim=1) * self.max_episode_length_s * 0.5) * ~up
         self.terrain_levels[ids] += 1 * up - 1 * down
@@ -431,7 +452,7 @@ class OracleEnv:
                                   (self.dof_pos - self.default_dof_pos) * o.dof_pos,
                                   self.dof_vel * o.dof_vel, self.actions), dim=-1)
         if self.measure_heights:
-            h = torch.clip(self.root_states[:, 2].unsqueeze(1) - 0.5 - self.measured_heights, -1, 1.) * o.height_measurements
+            h = torch.clip(self.root_states[self.rows, 2].unsqueeze(1) - 0.5 - self.measured_heights, -1, 1.) * o.height_measurements
             self.obs_buf = torch.cat((self.obs_buf, h), dim=-1)
         if self.add_noise:
             self.obs_buf += (2 * self.tables[philox.STREAM_OBS].clone() - 1) * self.noise_scale_vec
@@ -447,7 +468,7 @@ class OracleEnv:
         return torch.sum(torch.square(self.projected_gravity[:, :2]), dim=1)
 
     def _r_base_height(self):
-        bh = torch.mean(self.root_states[:, 2].unsqueeze(1) - self.measured_heights, dim=1)
+        bh = torch.mean(self.root_states[self.rows, 2].unsqueeze(1) - self.measured_heights, dim=1)
         return torch.square(bh - self.cfg.rewards.base_height_target)
 
     def _r_torques(self):

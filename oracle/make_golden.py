@@ -29,6 +29,10 @@ CASES = {
                                                                     "domain_rand.push_interval_s": 0.04,
                                                                     "env.episode_length_s": 0.06})),
     "cassie_n40": dict(task="cassie", n=40, seed=15, steps=3, overrides=dict(SMALL_TERRAIN), xy_max=(18., 22.)),
+    # two actors per env, 18-body contact view, predator re-spawn on reset, pushes, time-outs
+    "low_level_game_n56": dict(task="low_level_game", n=56, seed=16, steps=5, xy_max=(18., 22.),
+                               overrides=dict(SMALL_TERRAIN, **{"domain_rand.push_interval_s": 0.04,
+                                                                "env.episode_length_s": 0.06})),
 }
 
 
@@ -72,9 +76,13 @@ def run_reference(name, spec):
 
 
 def main():
+    import sys
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
+    only = set(sys.argv[1:])
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         out = run_reference(name, spec)
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **out)

@@ -27,6 +27,7 @@ STREAM_RESET_CMD = 4   # command resample inside reset_idx: x, y, heading|yaw
 STREAM_TERRAIN = 5     # raw uint32 for the terrain-level wrap randint
 STREAM_OBS = 6         # observation noise, one uniform per obs column
 STREAM_ACT = 7         # policy action noise (Box-Muller pairs)
+STREAM_PREDATOR = 8    # low_level_game predator spawn: offset xyz (3) then the sign draw
 
 
 def philox4x32_10(counter, key):

@@ -216,6 +216,9 @@ def make_ref_env(task, num_envs, consts, state, height_samples=None, cfg_overrid
     if init_levels is not None and env.custom_origins:
         env.terrain_levels[:] = torch.as_tensor(init_levels, dtype=torch.long)
         env.env_origins[:] = env.terrain_origins[env.terrain_levels, env.terrain_types]
+    if cls.__name__ == "LowLevelGame":        # what its _create_envs records (low_level_game.py:760-812): prey first
+        env.prey_indices = torch.arange(num_envs, dtype=torch.long) * 2
+        env.predator_indices = torch.arange(num_envs, dtype=torch.long) * 2 + 1
     if cls.__name__ == "Anymal" and cfg.control.use_actuator_network:
         path = cfg.control.actuator_net_file.format(LEGGED_GYM_ROOT_DIR=REFERENCE_ROOT)
         env.actuator_network = torch.jit.load(path)
@@ -268,6 +271,18 @@ class RngTap:
     def _begin(self, stream, ids):
         self.stream, self.ids, self.col = stream, ids, 0
 
+    # low_level_game's predator spawn (low_level_game.py:421-422): Tensor.uniform_ on a [len(ids), 3] tensor, then
+    # torch.rand(len(ids)) -- served from the PREDATOR table, columns 0:3 and 3
+    def _uniform_(self, x, a=0.0, b=1.0):
+        u = self.tables[philox.STREAM_PREDATOR][self.ids, 0:x.shape[1]]
+        assert tuple(u.shape) == tuple(x.shape), (u.shape, x.shape)
+        x.copy_((b - a) * u + a)
+        return x
+
+    def _rand(self, n, **k):
+        assert n == len(self.ids)
+        return self.tables[philox.STREAM_PREDATOR][self.ids, 3].clone()
+
     def _wrap(self):
         env, tap = self.env, self
         cls = type(env)
@@ -317,16 +332,24 @@ class RngTap:
     @contextlib.contextmanager
     def active(self):
         g = self.mod.__dict__
-        saved = (g["torch_rand_float"], torch.rand_like, torch.randint_like)
+        saved = (g["torch_rand_float"], torch.rand_like, torch.randint_like, torch.rand, torch.Tensor.uniform_)
         g["torch_rand_float"] = self._rand_float
         torch.rand_like = self._rand_like
         torch.randint_like = self._randint_like
+        tap = self
+        if philox.STREAM_PREDATOR in (self.tables or {}) and type(self.env).__name__ == "LowLevelGame":
+            torch.rand = self._rand
+            torch.Tensor.uniform_ = lambda x, a=0.0, b=1.0: tap._uniform_(x, a, b)
         try:
             yield
         finally:
-            g["torch_rand_float"], torch.rand_like, torch.randint_like = saved
+            g["torch_rand_float"], torch.rand_like, torch.randint_like, torch.rand, torch.Tensor.uniform_ = saved
 
 
 def attach_tap(env):
-    import legged_gym.envs.base.legged_robot as lr_mod
-    return RngTap(env, lr_mod)
+    import importlib
+    # the draw helpers are module globals of the file that defines the class (LowLevelGame is a stand-alone copy of
+    # LeggedRobot, not a subclass)
+    mod = importlib.import_module(type(env).__module__) if type(env).__name__ == "LowLevelGame" else \
+        importlib.import_module("legged_gym.envs.base.legged_robot")
+    return RngTap(env, mod)

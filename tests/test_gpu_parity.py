@@ -140,6 +140,8 @@ STEP_CASES = [("anymal_c_flat", 64, None), ("anymal_c_rough", 256, None), ("anym
               ("anymal_c_flat", 64, {"control.use_actuator_network": False}),
               ("a1", 160, {"commands.curriculum": True, "domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1}),
               ("a1", 64, {"noise.add_noise": False, "rewards.only_positive_rewards": False}),
+              ("low_level_game", 200, None),
+              ("low_level_game", 90, {"domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1}),
               ("anymal_c_rough", 96, {"rewards.scales.base_height": -1.0, "rewards.scales.dof_vel": -1e-4,
                                       "rewards.scales.stand_still": -0.1, "rewards.scales.orientation": -1.0,
                                       "rewards.scales.termination": -5.0, "rewards.scales.feet_contact_forces": -0.01,

@@ -12,7 +12,10 @@ pytestmark = pytest.mark.skipif(not ref_loader.reference_available(), reason="/r
 CASES = [("anymal_c_flat", 64, None), ("anymal_c_rough", 128, None), ("a1", 128, None), ("cassie", 96, None),
          ("anymal_b", 64, None), ("anymal_c_flat", 64, {"control.use_actuator_network": False}),
          ("a1", 96, {"commands.curriculum": True, "domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1}),
-         ("a1", 64, {"control.control_type": "V"}), ("a1", 64, {"control.control_type": "T"})]
+         ("a1", 64, {"control.control_type": "V"}), ("a1", 64, {"control.control_type": "T"}),
+         # low_level_game: two actors per env (prey robot + predator sphere), 18-body contact view, predator re-spawn
+         ("low_level_game", 96, None),
+         ("low_level_game", 64, {"domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1})]
 
 
 @pytest.mark.parametrize("task,n,ov", CASES)

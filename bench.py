@@ -282,6 +282,23 @@ def kernel_rooflines(envs, actions, peak_gbs, reps=200):
     return out
 
 
+def ncu_traffic(num_envs, *kernels):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json, written by profiles/summarize.py); None when no capture exists for this size."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    table = json.load(open(path)).get(str(num_envs), {})
+    tot, found = 0, 0
+    for want in kernels:
+        for name, rec in table.items():
+            if want in name:
+                tot += int(rec["dram_bytes"])
+                found += 1
+                break
+    return tot if found == len(kernels) else None
+
+
 def rollout_phase(dev, n_envs=4096, T=24, reps=20):
     """BASELINE.json configs[3]: 24 x ActorCritic.act() (235 -> 512-256-128 -> 12 / 1, ELU) + GAE compute_returns,
     kernels launched back to back through the C ABI on resident buffers; FLOPs = 2 * MACs of the eight Linear layers."""
@@ -431,6 +448,8 @@ def gpu_arm(args):
             env2, feeder2 = envs2[0], feeders2[0]
             s2, _ = time_steps(envs2, [f.synthetic_actions for f in feeders2], 100, 10, flush, lambda: None)
             r2 = kernel_rooflines(envs2, [f.synthetic_actions for f in feeders2], peak_gbs, reps=50)
+            r2["torque_lstm"]["traffic"] = ncu_traffic(n2, "torque_kernel<1>")
+            r2["post_physics"]["traffic"] = ncu_traffic(n2, "post_scalar_kernel", "scan_obs_fast_kernel")
             sweep[str(n2)] = dict(value=n2 * 100 / s2, ms_per_step=s2 / 100 * 1e3,
                                   roofline_torque_lstm=r2["torque_lstm"], roofline_post_physics=r2["post_physics"])
             del env2, feeder2, envs2, feeders2
@@ -440,7 +459,8 @@ def gpu_arm(args):
     if not args.no_cpu_baseline:
         cpu = cpu_arm(N, steps=10, warmup=3)
     dom = dict(roof["torque_lstm"])
-    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=None)
+    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, "torque_kernel<1>"))
+    roof["post_physics"]["traffic"] = ncu_traffic(N, "post_scalar_kernel", "scan_obs_fast_kernel")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -140,6 +140,9 @@ STEP_CASES = [("anymal_c_flat", 64, None), ("anymal_c_rough", 256, None), ("anym
               ("anymal_c_flat", 64, {"control.use_actuator_network": False}),
               ("a1", 160, {"commands.curriculum": True, "domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1}),
               ("a1", 64, {"noise.add_noise": False, "rewards.only_positive_rewards": False}),
+              # ragged / minimal batches: one env, a partial tile, N not a multiple of 4 (no 16-byte aligned rows -> the
+              # non-TMA staging path), one env more than a tile
+              ("a1", 1, None), ("anymal_c_rough", 33, None), ("anymal_c_flat", 3, None), ("cassie", 31, None),
               ("low_level_game", 200, None),
               ("low_level_game", 90, {"domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1}),
               ("anymal_c_rough", 96, {"rewards.scales.base_height": -1.0, "rewards.scales.dof_vel": -1e-4,
@@ -271,7 +274,7 @@ def test_user_reward_term_runs_split_phases():
 # ---------------------------------------------------------------------------------------------- full-size properties
 def test_full_size_properties():
     """BASELINE config sizes (oracle too slow to sweep every step here): size-independent properties."""
-    for task, n in (("anymal_c_rough", 4096), ("a1", 16384)):
+    for task, n in (("anymal_c_rough", 4096), ("a1", 16384), ("anymal_c_rough", 65536)):
         case = harness.build_case(task, n, seed=2)
         env, feeder = product_env(case)
         for step in range(3):

@@ -457,7 +457,7 @@ def gpu_arm(args):
     rollout = rollout_phase(dev)
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_arm(N, steps=10, warmup=3)
+        cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores
     dom = dict(roof["torque_lstm"])
     dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, "torque_kernel<1>"))
     roof["post_physics"]["traffic"] = ncu_traffic(N, "post_scalar_kernel", "scan_obs_fast_kernel")
@@ -500,8 +500,8 @@ def reference_arm(args):
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
-        # bounded: the CPU path takes ~0.1 s per 4096-env step
-        a.steps, a.warmup = min(a.steps, 30), min(a.warmup, 5)
+        # bounded: the CPU path takes ~20 ms per 4096-env step -> at most ~10 s of timed work
+        a.steps, a.warmup = min(a.steps, 500), min(a.warmup, 5)
         reference_arm(a)
     else:
         gpu_arm(a)

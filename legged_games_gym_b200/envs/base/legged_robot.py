@@ -318,9 +318,34 @@ class LeggedRobot(BaseTask):
         ini = self.cfg.init_state
         self.base_init_state = torch.tensor(ini.pos + ini.rot + ini.lin_vel + ini.ang_vel, dtype=torch.float, device=dev)
         self._get_env_origins()
+        self._randomize_physical_props()
         if self.gym is None:
             self.gym = StateFeeder(self.num_envs, self.num_bodies + self._extra_bodies_per_env(), self.num_dof, device=dev,
                                    seed=getattr(self.cfg, "seed", 0) or 0, actors_per_env=self._actors_per_env())
+
+    def _randomize_physical_props(self):
+        """Init-time domain randomisation of the reference's creation callbacks: 64 friction buckets drawn once and
+        assigned per env (LR:261-283 _process_rigid_shape_props) and a uniform added base mass per env (LR:316-327
+        _process_rigid_body_props).  PhysX is what consumes them: they are kept as tensors and offered to the sim backend
+        (``set_rigid_shape_friction`` / ``set_base_mass_offsets``); no per-step cost."""
+        dr = self.cfg.domain_rand
+        self.friction_coeffs = None
+        self.added_base_mass = None
+        if dr.randomize_friction:
+            num_buckets = 64
+            bucket_ids = torch.randint(0, num_buckets, (self.num_envs, 1))
+            lo, hi = dr.friction_range
+            friction_buckets = (hi - lo) * torch.rand(num_buckets, 1) + lo          # torch_rand_float on the CPU (LR:279)
+            self.friction_coeffs = friction_buckets[bucket_ids]                      # [N, 1, 1] like the reference
+        if dr.randomize_base_mass:
+            lo, hi = dr.added_mass_range
+            self.added_base_mass = torch.from_numpy(np.random.uniform(lo, hi, self.num_envs).astype(np.float32))
+        gym = self.gym
+        if gym is not None:
+            if self.friction_coeffs is not None and hasattr(gym, "set_rigid_shape_friction"):
+                gym.set_rigid_shape_friction(self.friction_coeffs)
+            if self.added_base_mass is not None and hasattr(gym, "set_base_mass_offsets"):
+                gym.set_base_mass_offsets(self.added_base_mass)
 
     def _actors_per_env(self):
         return 1

@@ -98,6 +98,13 @@ class SimBackend:
     def set_actor_root_state_tensor(self, root_states):
         pass
 
+    # init-time domain randomisation (the reference writes these into PhysX shape / body properties, LR:261-283, 316-327)
+    def set_rigid_shape_friction(self, friction_coeffs):
+        self.friction_coeffs = friction_coeffs
+
+    def set_base_mass_offsets(self, added_mass):
+        self.added_base_mass = added_mass
+
 
 class StateFeeder(SimBackend):
     """Device-resident synthetic state (inputs already in HBM when a step starts)."""

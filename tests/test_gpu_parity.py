@@ -298,6 +298,19 @@ def test_full_size_properties():
         assert torch.equal(env._get_heights().cpu(), orc.get_heights())
 
 
+def test_domain_randomisation_props_reach_the_backend():
+    """a1 (BASELINE configs[2]): friction buckets and added base mass are drawn at construction (LR:261-283, 316-327)."""
+    case = harness.build_case("a1", 256, seed=4, overrides={"domain_rand.randomize_base_mass": True})
+    env, feeder = product_env(case)
+    lo, hi = env.cfg.domain_rand.friction_range
+    assert tuple(env.friction_coeffs.shape) == (256, 1, 1)
+    assert float(env.friction_coeffs.min()) >= lo and float(env.friction_coeffs.max()) <= hi
+    assert env.friction_coeffs.unique().numel() <= 64                 # 64 buckets
+    mlo, mhi = env.cfg.domain_rand.added_mass_range
+    assert tuple(env.added_base_mass.shape) == (256,) and float(env.added_base_mass.min()) >= mlo and float(env.added_base_mass.max()) <= mhi
+    assert feeder.friction_coeffs is env.friction_coeffs and feeder.added_base_mass is env.added_base_mass
+
+
 def feeder_actions(n, step):
     return torch.from_numpy(np.random.default_rng(100 + step).normal(0, 1, (n, 12)).astype(np.float32)).to(DEV)
 

@@ -427,7 +427,7 @@ def gpu_arm(args):
     h2d = sim_h2d + d_actions.numel() * 4
     d2h = sim_d2h + (h_obs.numel() + h_rew.numel()) * 4 + h_reset.numel()
     e2e = dict(value=world * N * e2e_steps / float(e2e_secs.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
-               d2h_bytes_per_step=int(d2h), steps=e2e_steps)
+               d2h_bytes_per_step=int(d2h), steps=e2e_steps, cuda_graph=bool(getattr(env_h, "_graph", None) is not None))
     del env_h, feeder_h
 
     if rank != 0:

@@ -311,6 +311,35 @@ def test_domain_randomisation_props_reach_the_backend():
     assert feeder.friction_coeffs is env.friction_coeffs and feeder.added_base_mass is env.added_base_mass
 
 
+def test_host_sim_state_step_replays_copies_inside_the_graph():
+    """bench.py's e2e leg: sim state in PINNED host memory, the whole step (H2D copies, kernels, D2H copies) replayed as one
+    CUDA graph.  The copies must really run at every replay: change the host state between steps and compare with an
+    env whose state lives on the device."""
+    import bench
+    bench.USE_GRAPH, bench.TILE = True, 0
+    torch.manual_seed(0)                         # initial terrain levels come from torch's generator (LR:762)
+    env_h, fh = bench.make_env(512, DEV, host_sim=True)
+    torch.manual_seed(0)
+    env_d, fd = bench.make_env(512, DEV, host_sim=False)
+    acts = fd.synthetic_actions
+    g = torch.Generator().manual_seed(5)
+    for step in range(5):
+        env_h.step(acts)
+        env_d.step(acts)
+        torch.cuda.synchronize()
+        assert torch.equal(env_h.obs_buf, env_d.obs_buf) and torch.equal(env_h.rew_buf, env_d.rew_buf), step
+        assert torch.equal(env_h.reset_buf, env_d.reset_buf)
+        assert torch.equal(fh.h_torques, env_d.torques.cpu())                       # D2H copy of the last sub-step's torques
+        # the "simulator" moves: new joint velocities on the host side / on the device side
+        dv = torch.randn(fh.h_dof.shape[0], generator=g) * 0.1
+        fh.h_dof[:, 1] += dv
+        fh.refresh_dof_state_tensor()            # a sim step ends with a refresh (LR:96); later refreshes replay in the graph
+        fd.dof_state[:, 1] += dv.to(DEV)
+        # resets were written back into the host copy of the sim state (set_*_indexed hooks)
+        assert torch.equal(fh.h_root, env_d.root_states.cpu())
+    assert env_h._graph is not None and env_d._graph is not None
+
+
 def feeder_actions(n, step):
     return torch.from_numpy(np.random.default_rng(100 + step).normal(0, 1, (n, 12)).astype(np.float32)).to(DEV)
 

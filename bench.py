@@ -430,6 +430,25 @@ def gpu_arm(args):
                d2h_bytes_per_step=int(d2h), steps=e2e_steps, cuda_graph=bool(getattr(env_h, "_graph", None) is not None))
     del env_h, feeder_h
 
+    # ---- the one collective of the job (learning side): the flat PPO gradient bucket, 20 all-reduces per iteration
+    allreduce = None
+    if world > 1:
+        nparam = 2 * (235 * 512 + 512 + 512 * 256 + 256 + 256 * 128 + 128) + 128 * 12 + 12 + 128 + 1 + 12      # actor + critic + std
+        flat = torch.zeros(nparam, device=dev)
+        for _ in range(5):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(100):
+            dist.all_reduce(flat)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / 100 * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item())
+        allreduce = dict(what="PPO gradient bucket all-reduce over NCCL (20 per iteration; not on the env-step path)",
+                         bytes=nparam * 4, us=round(us, 2), bus_gbs=round(2 * (world - 1) / world * nparam * 4 / us / 1e3, 1))
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -475,6 +494,8 @@ def gpu_arm(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if allreduce is not None:
+        line["allreduce"] = allreduce
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

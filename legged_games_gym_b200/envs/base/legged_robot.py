@@ -99,6 +99,13 @@ class LeggedRobot(BaseTask):
             return self._step_graphed(actions)
         return self._step_eager(actions)
 
+    def set_env_id_offset(self, offset):
+        """Global id of this process's env 0 (multi-GPU sharding: rank r passes r * num_envs): keeps the counter-based
+        RNG streams of the shards disjoint and identical to a single-process job over all envs."""
+        self.env_id_offset = int(offset)
+        self._params.env_id_offset = int(offset)
+        self._graph = None                      # parameters are baked into the captured graph
+
     @property
     def action_buffer(self):
         """[num_envs, num_actions] fp32 device buffer the captured step graph reads its actions from.  A policy that

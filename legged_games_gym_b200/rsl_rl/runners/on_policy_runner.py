@@ -5,6 +5,7 @@ import time
 from collections import deque
 
 import torch
+import torch.distributed as dist
 
 from ..algorithms import PPO
 from ..modules import ActorCritic
@@ -51,7 +52,7 @@ class OnPolicyRunner:
                     obs, pobs, rewards, dones, infos = env.step(actions)
                     critic_obs = pobs if pobs is not None else obs
                     alg.process_env_step(rewards, dones, infos)
-                    if self.log_dir is not None:
+                    if self.log_dir is not None or (dist.is_available() and dist.is_initialized()):
                         if "episode" in infos:
                             ep_infos.append(infos["episode"])
                         cur_rew += rewards
@@ -69,9 +70,21 @@ class OnPolicyRunner:
             self.learn_time = time.time() - start
             self.tot_timesteps += self.num_steps_per_env * env.num_envs
             self.tot_time += self.collection_time + self.learn_time
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            self.tot_timesteps += (world - 1) * self.num_steps_per_env * env.num_envs
+            if world > 1:
+                # episode statistics over ALL shards: (sum of finished-episode returns, lengths, count) all-reduced
+                stats = torch.tensor([sum(rewbuffer), sum(lenbuffer), float(len(rewbuffer))], device=self.device,
+                                     dtype=torch.float64)
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+                self.global_episode_stats = dict(mean_reward=(stats[0] / stats[2]).item() if stats[2] > 0 else float("nan"),
+                                                 mean_length=(stats[1] / stats[2]).item() if stats[2] > 0 else float("nan"),
+                                                 episodes=int(stats[2].item()))
             if self.log_dir is not None:
-                fps = int(self.num_steps_per_env * env.num_envs / (self.collection_time + self.learn_time))
+                fps = int(world * self.num_steps_per_env * env.num_envs / (self.collection_time + self.learn_time))
                 mr = statistics.mean(rewbuffer) if len(rewbuffer) else float("nan")
+                if world > 1:
+                    mr = self.global_episode_stats["mean_reward"]
                 print(f"it {it}/{tot_iter} steps/s {fps} collection {self.collection_time:.3f}s learning {self.learn_time:.3f}s "
                       f"value_loss {mean_value_loss:.4f} surrogate {mean_surrogate_loss:.4f} mean_reward {mr:.3f}")
                 if it % self.save_interval == 0:

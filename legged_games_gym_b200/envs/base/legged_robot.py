@@ -21,7 +21,7 @@ import torch
 
 from ... import _native as nat
 from ...sim.asset_model import model_for_asset
-from ...sim.state_feeder import StateFeeder, SimBackend, synth_height_field, synth_terrain_origins
+from ...sim.state_feeder import StateFeeder, synth_height_field, synth_terrain_origins
 from ...utils.helpers import class_to_dict
 from .base_task import BaseTask
 from ...utils.terrain import Terrain

@@ -5,7 +5,7 @@ numbers the hot path needs are tabulated from the URDFs under resources/robots/ 
 Body/DOF ORDER is decided by Isaac Gym's loader and is not derivable from the repo; the tables use
 the depth-first, alphabetical-sibling order Isaac Gym is known to produce and every index set stays a
 runtime tensor exactly as in the reference, so a real sim backend can overwrite them."""
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List
 
 

@@ -15,7 +15,6 @@ Randomness is an explicit input: ``tables[stream]`` are per-env uniform tables f
 Third-party maths (isaacgym.torch_utils) comes from oracle/isaac_torch_utils.py: PARITY UNPINNED
 for those six helpers (no reference test covers them).
 """
-import math
 
 import numpy as np
 import torch

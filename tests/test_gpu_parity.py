@@ -4,7 +4,6 @@ identical seeded inputs, and against the golden fixtures produced by the referen
 Bars (BASELINE.json north_star): bit-exact for reset / time-out masks, height-sample indices, episode counters,
 terrain levels and command resampling under the shared Philox stream; rtol 1e-5 (atol 1e-5 x scale) for fp32
 observations, rewards, torques; 1e-3 for policy outputs and GAE."""
-import ctypes as C
 import os
 
 import numpy as np
@@ -246,7 +245,6 @@ def test_user_reward_term_runs_split_phases():
     """A subclass adds a torch-written _reward_<name>: the step runs PRE, the Python term, POST (LR:199-203 order)."""
     from legged_games_gym_b200.envs import LeggedRobot, task_registry
     from legged_games_gym_b200.envs.a1.a1_config import A1RoughCfg
-    from legged_games_gym_b200.envs.base.base_config import cfg_from_spec
 
     class MyEnv(LeggedRobot):
         def _reward_zz_height_bonus(self):

@@ -58,7 +58,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ------------------------------------------------------------------ K1 shared-memory carve-up (bytes, 16-aligned)
 struct TileLayout {
-  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, frame, sums, ep, rew, flags, misc, total;
+  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, frame, sums, ep, rew, flags, part, misc, total;
 };
 
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
@@ -87,6 +87,7 @@ __host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots)
   L.ep = o;      o += al16(kTile * 8);                                // episode_length_buf (int64)
   L.rew = o;     o += al16(kTile * 4);
   L.flags = o;   o += al16(kTile * 2);                                // reset flags [32] then time_out flags [32]
+  L.part = o;    o += al16(PS_COUNT * 3 * kTile * 4);                 // partial sums of roles 1..3: [slot][role-1][env]
   L.misc = o;    o += 16;   // mbarrier
   L.total = o;
   return L;
@@ -112,7 +113,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int kFrameFloats = 8;
 
 // ------------------------------------------------------------------ K1
-// CTA = 4 warps = one tile of 32 envs; four consecutive lanes (a "quad", roles 0..3) share an env, so a warp covers 8 envs.
+// CTA = 4 warps = one tile of 32 envs, lane = env, warp = role (see lgk_step_device.cuh): phase A every role reduces its
+// joints / foot / bodies to partial sums, phase B role 0 does the once-per-env work, phase C every role finishes its
+// joints (reset, observation columns, histories).  Total work per tile is about a third of running all four lanes of an
+// env through everything, and the chain on the critical path about half of a lane-per-env thread's.
 constexpr int kK1Threads = 4 * kTile;
 __device__ long long* g_k1_timeline = nullptr;     // profiling hook (lgk_step_debug_timeline): stamps of CTA 0
 __device__ __forceinline__ void k1_stamp(int slot) {
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
   long long* s_ep = reinterpret_cast<long long*>(smem + L.ep);
   float* s_rew = reinterpret_cast<float*>(smem + L.rew);
   uint8_t* s_flags = smem + L.flags;
+  float* s_part = reinterpret_cast<float*>(smem + L.part);
   const int K = p.num_reward_slots;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.misc);
 
@@ -219,98 +224,108 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
     if (tid < nval) s_ep[tid] = p.episode_length_buf[env0 + tid];
     __syncthreads();
   }
-
   k1_stamp(2);
-  // ---------------- per-env scalar work: quad (4 lanes) per env
-  const int e = tid >> 2, role = tid & 3, env = env0 + e;
+
+  // ---------------- phase A: every role, its share of the per-joint / per-foot / per-body terms
+  const int e = lane, role = warp, env = env0 + e;
   const bool valid = e < nval;
-  const int envc = valid ? env : env0;        // clamped id for global reads of the (discarded) lanes of a partial tile
   const uint32_t genv = (uint32_t)(p.env_id_offset + env);
-  EnvScalars s;
-  s.reset = false; s.time_out = false; s.rew = 0.f; s.ep_len = 0;
   float* root = s_root + e * 13;
   float* dof = s_dof + e * 24;
   float* cmd = s_cmd + e * 4;
   float* fat = s_fat + e * F;
   uint8_t* lc = s_lc + e * F;
   float* sums = s_sums + e;                 // tile-local episode sums, row stride kTile
-  const bool want_frames = p.measure_heights && !p.terrain_is_plane && p.scan_frames != nullptr;
+  RolePartials mine;
   if (pre) {
-    if (want_frames && role == 3) {     // pre-reset yaw frame for K2 (LR:853-854 uses the pose of THIS step before reset_idx)
-      const YawFrame yf = yaw_frame(root[5], root[6], root[0], root[1]);
-      *reinterpret_cast<float4*>(s_frame + e * kFrameFloats) = make_float4(yf.zn, yf.wn, yf.rx, yf.ry);
-    }
-    float mh = 0.f;
-    if (p.reward_active[LGK_R_BASE_HEIGHT]) {        // mean_p(z - h_p), LR:886 (the scan ran before this kernel)
-      if (p.measure_heights) {
-        for (int j = role; j < P; j += 4) mh += root[2] - p.measured_heights[(size_t)envc * P + j];
-        mh = quad_sum(mh) / (float)P;
-      } else {
-        mh = root[2];                                 // measured_heights is the int 0 (LR:562)
-      }
-    }
-    env_pre_quad(p, do_push, key, genv, lane, root, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12,
-                 s_lact + e * 12, s_ldv + e * 12, cmd, fat, lc, sums, kTile, s_ep[e], mh, s);
-    if (role < 3) {
-      const V3 v = role == 0 ? s.blv : (role == 1 ? s.bav : s.pg);
-      float* dst = (role == 0 ? s_blv : (role == 1 ? s_bav : s_pg)) + 3 * e;
-      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
-    }
-  } else {   // split mode: PRE ran in an earlier launch, pick its results up from global memory
-    s.blv = V3{p.base_lin_vel[3 * envc], p.base_lin_vel[3 * envc + 1], p.base_lin_vel[3 * envc + 2]};
-    s.bav = V3{p.base_ang_vel[3 * envc], p.base_ang_vel[3 * envc + 1], p.base_ang_vel[3 * envc + 2]};
-    s.pg = V3{p.projected_gravity[3 * envc], p.projected_gravity[3 * envc + 1], p.projected_gravity[3 * envc + 2]};
-    s.ep_len = s_ep[e];
-    s.reset = p.reset_buf[envc] != 0;
-    s.time_out = p.time_out_buf[envc] != 0;
-    s.rew = p.rew_buf[envc];
-  }
-  k1_stamp(3);
-  if (post) {
-    if (p.only_positive_rewards) s.rew = fmaxf(s.rew, 0.f);                      // LR:204-205
-    if (p.reward_active[LGK_R_TERMINATION]) {                                    // LR:206-210
-      const float r_ = ((s.reset && !s.time_out) ? 1.f : 0.f) * p.reward_scale[LGK_R_TERMINATION];
-      s.rew += r_;
-      if (role == 0) sums[(size_t)p.reward_slot[LGK_R_TERMINATION] * kTile] += r_;
-    }
-  }
-  // cross-env sums for extras["episode"] use the PRE-reset episode sums of the envs that reset (LR:179-183)
-  const bool resetting = post && valid && s.reset;
-  if (post) {
-    float* stats = p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2);
-    __syncwarp();                                     // role 0's sums[] updates are visible to the quad
-    const uint32_t wmask = __ballot_sync(0xffffffffu, resetting && role == 0);
-    if (wmask != 0) {
-      for (int k = 0; k < p.num_reward_slots; ++k) {
-        float v = 0.f;
-        if (resetting && role == 0) { v = sums[k * kTile]; sums[k * kTile] = 0.f; }
-        v = warp_sum(v);
-        if (lane == 0) atomicAdd(stats + k, v);
-      }
-      if (lane == 0) atomicAdd(stats + p.num_reward_slots, (float)__popc(wmask));
-    }
-    if (resetting) env_reset_quad(p, key, genv, env, role, root, dof, cmd, fat, s.ep_len);
-    if (p.terrain_curriculum) {                       // mean terrain level over ALL envs (LR:186), after the level updates
-      __syncwarp();
-      float lv = (valid && role == 0) ? (float)p.terrain_levels[env] : 0.f;
-      lv = warp_sum(lv);
-      if (lane == 0) atomicAdd(stats + p.num_reward_slots + 1, lv);
-    }
-  }
-  k1_stamp(4);
-  __syncthreads();       // every quad is done with its contact rows (the region now holds the observation head) and resets
-  if (post) {
-    env_obs_head_quad(p, s, role, dof, cmd, s_act + e * 12, s_head + e * 49);
+    const float* hrow = (valid && p.measure_heights && p.reward_active[LGK_R_BASE_HEIGHT])
+                            ? p.measured_heights + (size_t)env * P : nullptr;       // the scan ran before this kernel
+    role_partials(p, role, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12, s_lact + e * 12, s_ldv + e * 12,
+                  fat, lc, root[2], hrow, mine);
+    if (role > 0) {
 #pragma unroll
-    for (int d = 3 * role; d < 3 * role + 3; ++d) s_ldv[e * 12 + d] = dof[2 * d + 1];   // LR:133 (post-reset dof_vel)
-    if (role == 1) { for (int i = 0; i < 6; ++i) s_lrv[e * 6 + i] = root[7 + i]; }      // LR:134 (post push/reset)
-    if (role == 2 && valid && p.scan_frames) p.scan_frames[(size_t)env * kFrameFloats + 4] = root[2] - 0.5f;   // post-reset z (SURVEY A.6)
+      for (int k = 0; k < PS_COUNT; ++k) s_part[(k * 3 + role - 1) * kTile + e] = mine.v[k];
+    }
   }
+  __syncthreads();
+  k1_stamp(3);
+
+  // ---------------- phase B: role 0, everything that exists once per env
+  EnvScalars s;
+  s.reset = false; s.time_out = false; s.rew = 0.f; s.ep_len = 0;
+  const bool want_frames = p.measure_heights && !p.terrain_is_plane && p.scan_frames != nullptr;
   if (role == 0) {
+    if (pre) {
+      uint32_t bits = __float_as_uint(mine.v[PS_BITS]);
+      uint32_t any = bits & 5u, feet_down = (bits >> 1) & 1u;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int k = 0; k < PS_COUNT; ++k) {
+          const float v = s_part[(k * 3 + r) * kTile + e];
+          if (k == PS_BITS) { const uint32_t b = __float_as_uint(v); any |= b & 5u; feet_down += (b >> 1) & 1u; }
+          else mine.v[k] += v;
+        }
+      }
+      mine.v[PS_BITS] = __uint_as_float(any | (feet_down << 8));
+      if (want_frames) {     // pre-reset yaw frame for K2 (LR:853-854 uses the pose of THIS step before reset_idx)
+        const YawFrame yf = yaw_frame(root[5], root[6], root[0], root[1]);
+        *reinterpret_cast<float4*>(s_frame + e * kFrameFloats) = make_float4(yf.zn, yf.wn, yf.rx, yf.ry);
+      }
+      env_finish(p, do_push, key, genv, root, cmd, sums, kTile, s_ep[e], mine, s);
+      s_blv[3 * e] = s.blv.x; s_blv[3 * e + 1] = s.blv.y; s_blv[3 * e + 2] = s.blv.z;
+      s_bav[3 * e] = s.bav.x; s_bav[3 * e + 1] = s.bav.y; s_bav[3 * e + 2] = s.bav.z;
+      s_pg[3 * e] = s.pg.x; s_pg[3 * e + 1] = s.pg.y; s_pg[3 * e + 2] = s.pg.z;
+    } else {   // split mode: PRE ran in an earlier launch, pick its results up from global memory
+      const int envc = valid ? env : env0;
+      s.blv = V3{p.base_lin_vel[3 * envc], p.base_lin_vel[3 * envc + 1], p.base_lin_vel[3 * envc + 2]};
+      s.bav = V3{p.base_ang_vel[3 * envc], p.base_ang_vel[3 * envc + 1], p.base_ang_vel[3 * envc + 2]};
+      s.pg = V3{p.projected_gravity[3 * envc], p.projected_gravity[3 * envc + 1], p.projected_gravity[3 * envc + 2]};
+      s.ep_len = s_ep[e];
+      s.reset = p.reset_buf[envc] != 0;
+      s.time_out = p.time_out_buf[envc] != 0;
+      s.rew = p.rew_buf[envc];
+    }
+    const bool resetting = post && valid && s.reset;
+    if (post) {
+      s.rew = env_finish_reward(p, s.rew, s.reset, s.time_out, sums, kTile);
+      // cross-env sums for extras["episode"] over the envs that reset, using their PRE-reset episode sums (LR:179-183)
+      float* stats = p.reset_stats + (size_t)(step_eff & 1) * (p.num_reward_slots + 2);
+      const uint32_t rmask = __ballot_sync(0xffffffffu, resetting);
+      if (rmask != 0) {
+        for (int k = 0; k < p.num_reward_slots; ++k) {
+          float v = 0.f;
+          if (resetting) { v = sums[k * kTile]; sums[k * kTile] = 0.f; }
+          v = warp_sum(v);
+          if (lane == 0) atomicAdd(stats + k, v);
+        }
+        if (lane == 0) atomicAdd(stats + p.num_reward_slots, (float)__popc(rmask));
+      }
+      if (resetting) { env_reset_base(p, key, genv, env, root, cmd); s.ep_len = 0; }      // LR:176
+      if (p.terrain_curriculum) {                       // mean terrain level over ALL envs (LR:186), after the level updates
+        float lv = valid ? (float)p.terrain_levels[env] : 0.f;
+        lv = warp_sum(lv);
+        if (lane == 0) atomicAdd(stats + p.num_reward_slots + 1, lv);
+      }
+    }
     s_rew[e] = s.rew;
     s_ep[e] = s.ep_len;
     s_flags[e] = s.reset ? 1 : 0;
     s_flags[kTile + e] = s.time_out ? 1 : 0;
+  }
+  __syncthreads();       // contact rows are dead from here on: their region becomes the observation head
+  k1_stamp(4);
+
+  // ---------------- phase C: every role finishes its joints
+  const bool reset_e = post && valid && s_flags[e] != 0;
+  if (post) {
+    if (reset_e) env_reset_joints(p, key, genv, role, dof, fat);
+    env_obs_head_role(p, role, dof, s_act + e * 12, s_head + e * 49);
+    if (role == 0) env_obs_head_base(p, s, cmd, s_head + e * 49);
+#pragma unroll
+    for (int d = 3 * role; d < 3 * role + 3; ++d) s_ldv[e * 12 + d] = dof[2 * d + 1];   // LR:133 (post-reset dof_vel)
+    if (role == 1) { for (int i = 0; i < 6; ++i) s_lrv[e * 6 + i] = root[7 + i]; }      // LR:134 (post push/reset)
+    if (role == 2 && valid && p.scan_frames) p.scan_frames[(size_t)env * kFrameFloats + 4] = root[2] - 0.5f;   // post-reset z (SURVEY A.6)
   }
   fence_async_smem();
   __syncthreads();
@@ -376,18 +391,21 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
     }
   }
   // scan frames (pose part): 4 floats per env, strided rows of 8
-  if (pre && want_frames && valid && role == 3) {
+  if (pre && want_frames && valid && role == 0) {
     *reinterpret_cast<float4*>(p.scan_frames + (size_t)env * kFrameFloats) =
         *reinterpret_cast<const float4*>(s_frame + e * kFrameFloats);
   }
-
   k1_stamp(6);
+
   if (post) {
-    // ---------------- reset rows of this warp's 8 envs: dof_state / root_states write-back + LSTM state zeroing (ANY:56-60)
-    uint32_t rm = __ballot_sync(0xffffffffu, resetting && role == 0);
+    // ---------------- reset rows: dof_state / root_states write-back + LSTM state zeroing (ANY:56-60); every warp sees the
+    // same reset mask (lane = env) and takes every fourth reset env
+    uint32_t rm = __ballot_sync(0xffffffffu, reset_e);
+    int turn = 0;
     while (rm) {
-      const int ee = warp * 8 + ((__ffs(rm) - 1) >> 2);
+      const int ee = __ffs(rm) - 1;
       rm &= rm - 1;
+      if ((turn++ & 3) != warp) continue;
       const int en = env0 + ee;
       if (lane < 24) p.dof_state[(size_t)en * 24 + lane] = s_dof[ee * 24 + lane];
       if (lane < 13)

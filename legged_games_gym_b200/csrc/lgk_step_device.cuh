@@ -182,264 +182,237 @@ LGK_D void env_pre(const LgkStepParams& p, bool do_push, const RngKey& key, uint
   o.rew = rew;
 }
 
-// ------------------------------------------------------------------ quad-cooperative variants (scalar kernel)
-// Four consecutive lanes ("roles" 0..3) share one environment: role r owns joints {3r,3r+1,3r+2}, foot r, the
-// penalised bodies {r, r+4, ...} and the termination bodies {r, r+4}; the three rotations and the heading are computed by
-// one role each and exchanged by shuffles, per-joint reward terms are reduced over the quad with two xor-shuffles.
-// Same reference lines as env_pre / env_reset / env_obs_head above; only the summation order inside a term differs
-// (fp32, within the 1e-5 bar).  All 32 lanes of the warp must call these together.
+// ------------------------------------------------------------------ role-split variants (scalar kernel)
+// The scalar kernel runs a tile of 32 envs on four warps, lane = env.  Warp ("role") r owns joints {3r,3r+1,3r+2}, foot r,
+// the penalised bodies {r, r+4, ...} and the termination bodies {r, r+4}: in a first phase every role reduces its share of
+// the per-joint / per-foot / per-body reward terms to a handful of partial sums (role_partials); after a CTA barrier
+// role 0 alone does everything that exists once per env -- rotations, commands, termination, the reward terms in the
+// reference's alphabetical order (env_finish) -- reading the other roles' partials from shared memory.  Same reference
+// lines as env_pre above; only the summation order inside a term differs (fp32, within the 1e-5 bar).
 #if defined(__CUDACC__)
-__device__ __forceinline__ float quad_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  return v;
-}
-__device__ __forceinline__ float quad_bcast(float v, int lane, int role) { return __shfl_sync(0xffffffffu, v, (lane & ~3) | role); }
-__device__ __forceinline__ uint32_t quad_ballot(bool pred, int lane) {
-  return (__ballot_sync(0xffffffffu, pred) >> (lane & ~3)) & 0xFu;
-}
+enum {   // partial-sum slots, one float per (role, env)
+  PS_ACTION_RATE = 0, PS_DOF_ACC, PS_DOF_POS_LIMITS, PS_DOF_VEL, PS_DOF_VEL_LIMITS, PS_STAND_STILL, PS_TORQUE_LIMITS,
+  PS_TORQUES, PS_COLLISION, PS_FEET_AIR_TIME, PS_FEET_CONTACT_FORCES, PS_HEIGHT_ERR, PS_BITS, PS_COUNT
+};
+// PS_BITS packs the role's boolean facts: bit 0 termination contact, bit 1 foot in the air test of no_fly (contact z > 0.1),
+// bit 2 stumble
+struct RolePartials { float v[PS_COUNT]; };
 
-LGK_D void env_pre_quad(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, int lane, float* root,
-                        const float* dof, const float* contact, const float* act, const float* tq, const float* lact,
-                        const float* ldv, float* cmd, float* fat, uint8_t* lc, float* sums, int sums_stride,
-                        long long ep_in, float mean_height_err, EnvScalars& o) {
-  const int role = lane & 3;
-  o.ep_len = ep_in + 1;
-  const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
-  // roles 0,1,2: one rotation each (LR:119-121); role 3: heading (LR:338-339)
-  V3 mine = V3{0.f, 0.f, 0.f};
-  if (role == 0) mine = quat_rotate_inverse(qx, qy, qz, qw, V3{root[7], root[8], root[9]});
-  else if (role == 1) mine = quat_rotate_inverse(qx, qy, qz, qw, V3{root[10], root[11], root[12]});
-  else if (role == 2) mine = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
-  else if (p.heading_command) mine.x = heading_of(qx, qy, qz, qw);
-  o.blv = V3{quad_bcast(mine.x, lane, 0), quad_bcast(mine.y, lane, 0), quad_bcast(mine.z, lane, 0)};
-  o.bav = V3{quad_bcast(mine.x, lane, 1), quad_bcast(mine.y, lane, 1), quad_bcast(mine.z, lane, 1)};
-  o.pg = V3{quad_bcast(mine.x, lane, 2), quad_bcast(mine.y, lane, 2), quad_bcast(mine.z, lane, 2)};
-  const float heading = quad_bcast(mine.x, lane, 3);
-  // _post_physics_step_callback LR:329-345 (role 0 owns the env's command row and the push)
-  if (role == 0) {
-    if (o.ep_len % (long long)p.resample_period == 0)
-      resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_CMD, 0));
-    if (p.heading_command) cmd[2] = clampf(0.5f * wrap_to_pi(cmd[3] - heading), -1.f, 1.f);
-    if (do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
-      const U4 r = rng_block_cold(key, genv, LGK_STREAM_PUSH, 0);
-      const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
-      root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));
-      root[8] = scale_uniform(range, lo, u32_to_uniform(r.y));
-    }
-  }
-  __syncwarp();
-  const float c0 = cmd[0], c1 = cmd[1], c2 = cmd[2];
-  // check_termination LR:139-145
-  bool term = false;
-  for (int t = role; t < p.num_term; t += 4) {
-    const float* f = contact + 3 * p.term_idx[t];
-    term = term || (norm3(f[0], f[1], f[2]) > 1.0f);
-  }
-  term = quad_ballot(term, lane) != 0;
-  o.time_out = (float)o.ep_len > p.max_episode_length;
-  o.reset = term || o.time_out;
-
-  // compute_reward LR:193-210, terms in alphabetical order; every lane carries the full sum, role 0 books episode_sums
-  float rew = 0.f;
-  const float cmd_norm = norm2(c0, c1);
+// role r's share of LR:139-145 (termination contacts) and of the per-joint / per-foot / per-body terms of LR:872-969.
+// dof/act/tq/lact/ldv/contact/fat/lc are the env's rows inside the staged tile.
+LGK_D void role_partials(const LgkStepParams& p, int role, const float* dof, const float* contact, const float* act,
+                         const float* tq, const float* lact, const float* ldv, float* fat, uint8_t* lc, float root_z,
+                         const float* heights_row, RolePartials& o) {
   const int d0 = 3 * role;
-#undef LGK_TERM
-#define LGK_TERM(ID, EXPR)                                                      \
-  if (p.reward_active[ID]) {                                                    \
-    const float r_ = (EXPR) * p.reward_scale[ID];                               \
-    rew += r_;                                                                  \
-    if (role == 0) sums[(size_t)p.reward_slot[ID] * sums_stride] += r_;         \
+#pragma unroll
+  for (int k = 0; k < PS_COUNT; ++k) o.v[k] = 0.f;
+  uint32_t bits = 0;
+  for (int t = role; t < p.num_term; t += 4) {                        // LR:142
+    const float* f = contact + 3 * p.term_idx[t];
+    if (norm3(f[0], f[1], f[2]) > 1.0f) bits |= 1u;
   }
   if (p.reward_active[LGK_R_ACTION_RATE]) {                           // LR:901-903
-    float s = 0.f;
 #pragma unroll
-    for (int d = d0; d < d0 + 3; ++d) { const float e = lact[d] - act[d]; s += e * e; }
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_ACTION_RATE, s)
-  }
-  LGK_TERM(LGK_R_ANG_VEL_XY, o.bav.x * o.bav.x + o.bav.y * o.bav.y)   // LR:876-878
-  if (p.reward_active[LGK_R_BASE_HEIGHT]) {                           // LR:884-887
-    const float e = mean_height_err - p.base_height_target;
-    LGK_TERM(LGK_R_BASE_HEIGHT, e * e)
+    for (int d = d0; d < d0 + 3; ++d) { const float e = lact[d] - act[d]; o.v[PS_ACTION_RATE] += e * e; }
   }
   if (p.reward_active[LGK_R_COLLISION]) {                             // LR:905-908
-    float s = 0.f;
     for (int b = role; b < p.num_pen; b += 4) {
       const float* f = contact + 3 * p.pen_idx[b];
-      s += norm3(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f;
+      o.v[PS_COLLISION] += norm3(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f;
     }
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_COLLISION, s)
   }
   if (p.reward_active[LGK_R_DOF_ACC]) {                               // LR:897-899
-    float s = 0.f;
 #pragma unroll
-    for (int d = d0; d < d0 + 3; ++d) { const float a = (ldv[d] - dof[2 * d + 1]) / p.dt; s += a * a; }
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_DOF_ACC, s)
+    for (int d = d0; d < d0 + 3; ++d) { const float a = (ldv[d] - dof[2 * d + 1]) / p.dt; o.v[PS_DOF_ACC] += a * a; }
   }
   if (p.reward_active[LGK_R_DOF_POS_LIMITS]) {                        // LR:914-918
-    float s = 0.f;
 #pragma unroll
     for (int d = d0; d < d0 + 3; ++d) {
       const float q = dof[2 * d];
-      s += -fminf(q - p.dof_pos_lo[d], 0.f) + fmaxf(q - p.dof_pos_hi[d], 0.f);
+      o.v[PS_DOF_POS_LIMITS] += -fminf(q - p.dof_pos_lo[d], 0.f) + fmaxf(q - p.dof_pos_hi[d], 0.f);
     }
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_DOF_POS_LIMITS, s)
   }
   if (p.reward_active[LGK_R_DOF_VEL]) {                               // LR:893-895
-    float s = 0.f;
 #pragma unroll
-    for (int d = d0; d < d0 + 3; ++d) { const float v = dof[2 * d + 1]; s += v * v; }
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_DOF_VEL, s)
+    for (int d = d0; d < d0 + 3; ++d) { const float v = dof[2 * d + 1]; o.v[PS_DOF_VEL] += v * v; }
   }
   if (p.reward_active[LGK_R_DOF_VEL_LIMITS]) {                        // LR:920-925
-    float s = 0.f;
 #pragma unroll
     for (int d = d0; d < d0 + 3; ++d)
-      s += clampf(fabsf(dof[2 * d + 1]) - p.dof_vel_limits[d] * p.soft_dof_vel_limit, 0.f, 1.f);
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_DOF_VEL_LIMITS, s)
+      o.v[PS_DOF_VEL_LIMITS] += clampf(fabsf(dof[2 * d + 1]) - p.dof_vel_limits[d] * p.soft_dof_vel_limit, 0.f, 1.f);
   }
-  const bool has_foot = role < p.num_feet;
-  const float* cf = contact + 3 * p.feet_idx[has_foot ? role : 0];    // this role's foot
-  if (p.reward_active[LGK_R_FEET_AIR_TIME]) {                         // LR:942-954 (stateful)
-    float s = 0.f;
-    if (has_foot) {
+  if (role < p.num_feet) {
+    const float* cf = contact + 3 * p.feet_idx[role];                 // this role's foot
+    if (p.reward_active[LGK_R_FEET_AIR_TIME]) {                       // LR:942-954 (stateful)
       const int f = role;
       const bool c = cf[2] > 1.0f;
       const bool filt = c || (lc[f] != 0);
       lc[f] = c ? 1 : 0;
       const bool first = (fat[f] > 0.f) && filt;
       const float air = fat[f] + p.dt;
-      s = (air - 0.5f) * (first ? 1.f : 0.f);
+      o.v[PS_FEET_AIR_TIME] = (air - 0.5f) * (first ? 1.f : 0.f);
       fat[f] = filt ? 0.f * air : air;     // air *= ~filt
     }
-    s = quad_sum(s);
-    s *= cmd_norm > 0.1f ? 1.f : 0.f;
-    LGK_TERM(LGK_R_FEET_AIR_TIME, s)
+    if (p.reward_active[LGK_R_FEET_CONTACT_FORCES])                   // LR:966-969
+      o.v[PS_FEET_CONTACT_FORCES] = fmaxf(norm3(cf[0], cf[1], cf[2]) - p.max_contact_force, 0.f);
+    if (p.reward_active[LGK_R_NO_FLY] && cf[2] > 0.1f) bits |= 2u;    // CAS:43-46
+    if (p.reward_active[LGK_R_STUMBLE] && norm2(cf[0], cf[1]) > 5.f * fabsf(cf[2])) bits |= 4u;   // LR:956-959
   }
-  if (p.reward_active[LGK_R_FEET_CONTACT_FORCES]) {                   // LR:966-969
-    float s = has_foot ? fmaxf(norm3(cf[0], cf[1], cf[2]) - p.max_contact_force, 0.f) : 0.f;
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_FEET_CONTACT_FORCES, s)
-  }
-  LGK_TERM(LGK_R_LIN_VEL_Z, o.blv.z * o.blv.z)                        // LR:872-874
-  if (p.reward_active[LGK_R_NO_FLY]) {                                // CAS:43-46
-    const int n = __popc(quad_ballot(has_foot && cf[2] > 0.1f, lane));
-    LGK_TERM(LGK_R_NO_FLY, n == 1 ? 1.f : 0.f)
-  }
-  LGK_TERM(LGK_R_ORIENTATION, o.pg.x * o.pg.x + o.pg.y * o.pg.y)      // LR:880-882
   if (p.reward_active[LGK_R_STAND_STILL]) {                           // LR:961-964
-    float s = 0.f;
 #pragma unroll
-    for (int d = d0; d < d0 + 3; ++d) s += fabsf(dof[2 * d] - p.default_dof_pos[d]);
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_STAND_STILL, s * (cmd_norm < 0.1f ? 1.f : 0.f))
-  }
-  if (p.reward_active[LGK_R_STUMBLE]) {                               // LR:956-959
-    const bool any = quad_ballot(has_foot && (norm2(cf[0], cf[1]) > 5.f * fabsf(cf[2])), lane) != 0;
-    LGK_TERM(LGK_R_STUMBLE, any ? 1.f : 0.f)
+    for (int d = d0; d < d0 + 3; ++d) o.v[PS_STAND_STILL] += fabsf(dof[2 * d] - p.default_dof_pos[d]);
   }
   if (p.reward_active[LGK_R_TORQUE_LIMITS]) {                         // LR:927-930
-    float s = 0.f;
 #pragma unroll
-    for (int d = d0; d < d0 + 3; ++d) s += fmaxf(fabsf(tq[d]) - p.torque_limits[d] * p.soft_torque_limit, 0.f);
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_TORQUE_LIMITS, s)
+    for (int d = d0; d < d0 + 3; ++d)
+      o.v[PS_TORQUE_LIMITS] += fmaxf(fabsf(tq[d]) - p.torque_limits[d] * p.soft_torque_limit, 0.f);
   }
   if (p.reward_active[LGK_R_TORQUES]) {                               // LR:889-891
-    float s = 0.f;
 #pragma unroll
-    for (int d = d0; d < d0 + 3; ++d) s += tq[d] * tq[d];
-    s = quad_sum(s);
-    LGK_TERM(LGK_R_TORQUES, s)
+    for (int d = d0; d < d0 + 3; ++d) o.v[PS_TORQUES] += tq[d] * tq[d];
   }
+  if (p.reward_active[LGK_R_BASE_HEIGHT] && heights_row != nullptr) { // LR:886: sum_p (z - h_p), points p = role, role+4, ...
+    for (int j = role; j < p.num_height_points; j += 4) o.v[PS_HEIGHT_ERR] += root_z - heights_row[j];
+  }
+  o.v[PS_BITS] = __uint_as_float(bits);
+}
+
+// LR:114-127 for one env on role 0's lane: `sum` holds the four roles' partial sums already added up (PS_BITS or-ed)
+LGK_D void env_finish(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, float* root, float* cmd,
+                      float* sums, int sums_stride, long long ep_in, const RolePartials& sum, EnvScalars& o) {
+  o.ep_len = ep_in + 1;
+  const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+  o.blv = quat_rotate_inverse(qx, qy, qz, qw, V3{root[7], root[8], root[9]});
+  o.bav = quat_rotate_inverse(qx, qy, qz, qw, V3{root[10], root[11], root[12]});
+  o.pg = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
+  // _post_physics_step_callback LR:329-345
+  if (o.ep_len % (long long)p.resample_period == 0)
+    resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_CMD, 0));
+  if (p.heading_command) {
+    const float h = heading_of(qx, qy, qz, qw);
+    cmd[2] = clampf(0.5f * wrap_to_pi(cmd[3] - h), -1.f, 1.f);
+  }
+  if (do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
+    const U4 r = rng_block_cold(key, genv, LGK_STREAM_PUSH, 0);
+    const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
+    root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));
+    root[8] = scale_uniform(range, lo, u32_to_uniform(r.y));
+  }
+  const uint32_t bits = __float_as_uint(sum.v[PS_BITS]);
+  o.time_out = (float)o.ep_len > p.max_episode_length;                // LR:139-145
+  o.reset = ((bits & 1u) != 0) || o.time_out;
+  // compute_reward LR:193-210, terms in alphabetical order
+  float rew = 0.f;
+  const float cmd_norm = norm2(cmd[0], cmd[1]);
+#undef LGK_TERM
+#define LGK_TERM(ID, EXPR)                                            \
+  if (p.reward_active[ID]) {                                          \
+    const float r_ = (EXPR) * p.reward_scale[ID];                     \
+    rew += r_;                                                        \
+    sums[(size_t)p.reward_slot[ID] * sums_stride] += r_;              \
+  }
+  LGK_TERM(LGK_R_ACTION_RATE, sum.v[PS_ACTION_RATE])
+  LGK_TERM(LGK_R_ANG_VEL_XY, o.bav.x * o.bav.x + o.bav.y * o.bav.y)   // LR:876-878
+  if (p.reward_active[LGK_R_BASE_HEIGHT]) {                           // LR:884-887
+    const float mh = p.measure_heights ? sum.v[PS_HEIGHT_ERR] / (float)p.num_height_points : root[2];   // LR:562: heights = 0
+    const float e = mh - p.base_height_target;
+    LGK_TERM(LGK_R_BASE_HEIGHT, e * e)
+  }
+  LGK_TERM(LGK_R_COLLISION, sum.v[PS_COLLISION])
+  LGK_TERM(LGK_R_DOF_ACC, sum.v[PS_DOF_ACC])
+  LGK_TERM(LGK_R_DOF_POS_LIMITS, sum.v[PS_DOF_POS_LIMITS])
+  LGK_TERM(LGK_R_DOF_VEL, sum.v[PS_DOF_VEL])
+  LGK_TERM(LGK_R_DOF_VEL_LIMITS, sum.v[PS_DOF_VEL_LIMITS])
+  LGK_TERM(LGK_R_FEET_AIR_TIME, sum.v[PS_FEET_AIR_TIME] * (cmd_norm > 0.1f ? 1.f : 0.f))
+  LGK_TERM(LGK_R_FEET_CONTACT_FORCES, sum.v[PS_FEET_CONTACT_FORCES])
+  LGK_TERM(LGK_R_LIN_VEL_Z, o.blv.z * o.blv.z)                        // LR:872-874
+  LGK_TERM(LGK_R_NO_FLY, ((bits >> 8) & 0xFFu) == 1u ? 1.f : 0.f)     // exactly one foot on the ground (count in bits 8..15)
+  LGK_TERM(LGK_R_ORIENTATION, o.pg.x * o.pg.x + o.pg.y * o.pg.y)      // LR:880-882
+  LGK_TERM(LGK_R_STAND_STILL, sum.v[PS_STAND_STILL] * (cmd_norm < 0.1f ? 1.f : 0.f))
+  LGK_TERM(LGK_R_STUMBLE, (bits & 4u) ? 1.f : 0.f)
+  LGK_TERM(LGK_R_TORQUE_LIMITS, sum.v[PS_TORQUE_LIMITS])
+  LGK_TERM(LGK_R_TORQUES, sum.v[PS_TORQUES])
   {                                                                   // LR:937-940
-    const float e = c2 - o.bav.z;
+    const float e = cmd[2] - o.bav.z;
     LGK_TERM(LGK_R_TRACKING_ANG_VEL, expf(-(e * e) / p.tracking_sigma))
   }
   {                                                                   // LR:932-935
-    const float ex = c0 - o.blv.x, ey = c1 - o.blv.y;
+    const float ex = cmd[0] - o.blv.x, ey = cmd[1] - o.blv.y;
     LGK_TERM(LGK_R_TRACKING_LIN_VEL, expf(-(ex * ex + ey * ey) / p.tracking_sigma))
   }
 #undef LGK_TERM
   o.rew = rew;
 }
 
-// reset_idx for one env, shared by its quad (LR:147-191): role 0 = terrain curriculum, root state, command resample;
-// roles 1..3 = the three Philox blocks of the joint positions (joints 4b..4b+3, b = role-1); role r clears foot r
-LGK_COLD void env_reset_quad(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, int role, float* root,
-                             float* dof, float* cmd, float* fat, long long& ep_len) {
-  if (role == 0) {
-    float ox = 0.f, oy = 0.f, oz = 0.f;
-    if (p.env_origins) { ox = p.env_origins[3 * env]; oy = p.env_origins[3 * env + 1]; oz = p.env_origins[3 * env + 2]; }
-    if (p.terrain_curriculum) {                                         // LR:446-469
-      const float dist = norm2(root[0] - ox, root[1] - oy);
-      const bool up = dist > p.half_env_length;
-      const bool down = (dist < norm2(cmd[0], cmd[1]) * p.max_episode_length_s * 0.5f) && !up;
-      long long lvl = p.terrain_levels[env] + (up ? 1 : 0) - (down ? 1 : 0);
-      if (lvl >= p.max_terrain_level) {
-        const U4 r = rng_block_cold(key, genv, LGK_STREAM_TERRAIN, 0);
-        lvl = (long long)(r.x % (uint32_t)p.max_terrain_level);
-      } else if (lvl < 0) {
-        lvl = 0;
-      }
-      p.terrain_levels[env] = lvl;
-      const float* o = p.terrain_origins + 3 * ((size_t)lvl * p.terrain_num_cols + (size_t)p.terrain_types[env]);
-      ox = o[0]; oy = o[1]; oz = o[2];
-      p.env_origins[3 * env] = ox; p.env_origins[3 * env + 1] = oy; p.env_origins[3 * env + 2] = oz;
+// reset_idx, role 0's part for one env (LR:147-191): terrain curriculum, root state (in the staged row), predator spawn,
+// command resample
+LGK_COLD void env_reset_base(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, float* root, float* cmd) {
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+  if (p.env_origins) { ox = p.env_origins[3 * env]; oy = p.env_origins[3 * env + 1]; oz = p.env_origins[3 * env + 2]; }
+  if (p.terrain_curriculum) {                                         // LR:446-469
+    const float dist = norm2(root[0] - ox, root[1] - oy);
+    const bool up = dist > p.half_env_length;
+    const bool down = (dist < norm2(cmd[0], cmd[1]) * p.max_episode_length_s * 0.5f) && !up;
+    long long lvl = p.terrain_levels[env] + (up ? 1 : 0) - (down ? 1 : 0);
+    if (lvl >= p.max_terrain_level) {
+      const U4 r = rng_block_cold(key, genv, LGK_STREAM_TERRAIN, 0);
+      lvl = (long long)(r.x % (uint32_t)p.max_terrain_level);
+    } else if (lvl < 0) {
+      lvl = 0;
     }
-    // _reset_root_states LR:414-432
-    const U4 r0 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 0);
-    const U4 r1 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 1);
-    for (int i = 0; i < 13; ++i) root[i] = p.base_init_state[i];
-    root[0] = f_add(root[0], ox); root[1] = f_add(root[1], oy); root[2] = f_add(root[2], oz);
-    if (p.custom_origins) {
-      root[0] = f_add(root[0], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.x)));
-      root[1] = f_add(root[1], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.y)));
-    }
-    root[7] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.z));
-    root[8] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.w));
-    root[9] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.x));
-    root[10] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.y));
-    root[11] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.z));
-    root[12] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.w));
-    if (p.predator_spawn) spawn_predator(p, key, genv, env, root);
-    resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170 (after the curriculum read cmd)
-  } else {
-    // _reset_dofs LR:397-407
-    const int b = role - 1;
-    const U4 r = rng_block_cold(key, genv, LGK_STREAM_RESET_DOF, b);
-    for (int i = 0; i < 4; ++i) {
-      const int d = 4 * b + i;
-      dof[2 * d] = f_mul(p.default_dof_pos[d], scale_uniform(1.0f, 0.5f, u32_to_uniform(pick(r, i))));
-      dof[2 * d + 1] = 0.f;
-    }
+    p.terrain_levels[env] = lvl;
+    const float* o = p.terrain_origins + 3 * ((size_t)lvl * p.terrain_num_cols + (size_t)p.terrain_types[env]);
+    ox = o[0]; oy = o[1]; oz = o[2];
+    p.env_origins[3 * env] = ox; p.env_origins[3 * env + 1] = oy; p.env_origins[3 * env + 2] = oz;
   }
-  if (role < p.num_feet) fat[role] = 0.f;                                         // LR:175
-  ep_len = 0;                                                                     // LR:176
+  // _reset_root_states LR:414-432
+  const U4 r0 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 0);
+  const U4 r1 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 1);
+  for (int i = 0; i < 13; ++i) root[i] = p.base_init_state[i];
+  root[0] = f_add(root[0], ox); root[1] = f_add(root[1], oy); root[2] = f_add(root[2], oz);
+  if (p.custom_origins) {
+    root[0] = f_add(root[0], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.x)));
+    root[1] = f_add(root[1], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.y)));
+  }
+  root[7] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.z));
+  root[8] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.w));
+  root[9] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.x));
+  root[10] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.y));
+  root[11] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.z));
+  root[12] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.w));
+  if (p.predator_spawn) spawn_predator(p, key, genv, env, root);
+  resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170 (after the curriculum read cmd)
 }
 
-// LR:212-222: the 48 proprioceptive columns, before noise -- role r writes the nine columns of its joints, role 0 the
-// twelve base / command columns
-LGK_D void env_obs_head_quad(const LgkStepParams& p, const EnvScalars& s, int role, const float* dof, const float* cmd,
-                             const float* act, float* out48) {
-  if (role == 0) {
-    out48[0] = s.blv.x * p.obs_scale_lin_vel; out48[1] = s.blv.y * p.obs_scale_lin_vel; out48[2] = s.blv.z * p.obs_scale_lin_vel;
-    out48[3] = s.bav.x * p.obs_scale_ang_vel; out48[4] = s.bav.y * p.obs_scale_ang_vel; out48[5] = s.bav.z * p.obs_scale_ang_vel;
-    out48[6] = s.pg.x; out48[7] = s.pg.y; out48[8] = s.pg.z;
-    out48[9] = cmd[0] * p.obs_scale_lin_vel; out48[10] = cmd[1] * p.obs_scale_lin_vel; out48[11] = cmd[2] * p.obs_scale_ang_vel;
+// _reset_dofs LR:397-407 for role r's joints (joint d uses word d%4 of Philox block d/4: at most two blocks per role)
+LGK_COLD void env_reset_joints(const LgkStepParams& p, const RngKey& key, uint32_t genv, int role, float* dof, float* fat) {
+  const int d0 = 3 * role, b_lo = d0 >> 2, b_hi = (d0 + 2) >> 2;
+  const U4 r_lo = rng_block_cold(key, genv, LGK_STREAM_RESET_DOF, b_lo);
+  U4 r_hi = r_lo;
+  if (b_hi != b_lo) r_hi = rng_block_cold(key, genv, LGK_STREAM_RESET_DOF, b_hi);
+  for (int d = d0; d < d0 + 3; ++d) {
+    const uint32_t w = pick((d >> 2) == b_lo ? r_lo : r_hi, d & 3);
+    dof[2 * d] = f_mul(p.default_dof_pos[d], scale_uniform(1.0f, 0.5f, u32_to_uniform(w)));
+    dof[2 * d + 1] = 0.f;
   }
+  if (role < p.num_feet) fat[role] = 0.f;                                         // LR:175
+}
+
+// LR:212-222: the 48 proprioceptive columns, before noise -- role r writes the nine columns of its joints, role 0 also
+// the twelve base / command columns
+LGK_D void env_obs_head_role(const LgkStepParams& p, int role, const float* dof, const float* act, float* out48) {
 #pragma unroll
   for (int d = 3 * role; d < 3 * role + 3; ++d) {
     out48[12 + d] = (dof[2 * d] - p.default_dof_pos[d]) * p.obs_scale_dof_pos;
     out48[24 + d] = dof[2 * d + 1] * p.obs_scale_dof_vel;
     out48[36 + d] = act[d];
   }
+}
+LGK_D void env_obs_head_base(const LgkStepParams& p, const EnvScalars& s, const float* cmd, float* out48) {
+  out48[0] = s.blv.x * p.obs_scale_lin_vel; out48[1] = s.blv.y * p.obs_scale_lin_vel; out48[2] = s.blv.z * p.obs_scale_lin_vel;
+  out48[3] = s.bav.x * p.obs_scale_ang_vel; out48[4] = s.bav.y * p.obs_scale_ang_vel; out48[5] = s.bav.z * p.obs_scale_ang_vel;
+  out48[6] = s.pg.x; out48[7] = s.pg.y; out48[8] = s.pg.z;
+  out48[9] = cmd[0] * p.obs_scale_lin_vel; out48[10] = cmd[1] * p.obs_scale_lin_vel; out48[11] = cmd[2] * p.obs_scale_ang_vel;
 }
 #endif
 

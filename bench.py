@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--tile", type=int, default=0, help="envs per CTA of the fused kernel (0 = auto)")
+    ap.add_argument("--tile", type=int, default=0, help="reserved (the scalar kernel tiles 32 envs per CTA)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="rotate: cycle over env replicas whose buffers exceed L2; flush: write 256 MiB between steps")
     ap.add_argument("--no-graph", action="store_true")

@@ -103,7 +103,7 @@ typedef struct LgkStepParams {
   int32_t actors_per_env;             /* root_states rows per env (1; 2 in low_level_game, LLG:532) */
   int32_t root_actor_offset;          /* row of the robot inside the env's actor group (prey index) */
   int32_t phase_mask;                 /* LGK_PHASE_* */
-  int32_t tile_envs;                  /* reserved (tile size is fixed at 32 envs per warp) */
+  int32_t tile_envs;                  /* reserved (the scalar kernel tiles 32 envs per CTA) */
   int32_t push_interval;              /* used with step_counter_dev: push when step % interval == 0 (0 = never) */
   int32_t step;                       /* common_step_counter AFTER the += 1 of LR:115 (RNG counter) */
   uint64_t seed;

@@ -1,18 +1,20 @@
 // lgk_post_physics.cu -- post-physics step (reference LR:106-230, 329-508, 831-969) for sm_100a, one kernel per phase:
 //
-//  K1  post_scalar_kernel   one WARP per tile of 32 consecutive envs, lane = env.  Every reference tensor is env-major
-//      row-major, so the tile's slice of root_states / dof_state / contact_forces / actions / torques / last_actions /
-//      last_dof_vel / commands / feet_air_time is ONE contiguous chunk per tensor: each arrives by a single TMA bulk copy
-//      (cp.async.bulk.shared::cluster.global, mbarrier completion) and whole-tile results (commands, feet_air_time,
-//      last_*, base_*, scan frames) leave by bulk stores.  The lane does all per-env scalar work: rotations, command
-//      resampling / heading, push, termination, the reward terms in the reference's alphabetical order, reset_idx,
-//      the 48 proprioceptive observation columns (un-noised).  Reset rows + LSTM-state zeroing are written
+//  K1  post_scalar_kernel   one CTA (4 warps) per tile of 32 consecutive envs, lane = env, warp = role.  Every reference
+//      tensor is env-major row-major, so the tile's slice of root_states / dof_state / contact_forces / actions / torques /
+//      last_actions / last_dof_vel / commands / feet_air_time is ONE contiguous chunk per tensor: each arrives by a single
+//      TMA bulk copy (cp.async.bulk.shared::cluster.global, mbarrier completion) and whole-tile results (commands,
+//      feet_air_time, last_*, base_*) leave by bulk stores.  Phase A: every role reduces its three joints, its foot and
+//      its share of the penalised / termination bodies to partial sums.  Phase B: role 0 does the once-per-env work:
+//      rotations, command resampling / heading, push, termination, the reward terms in the reference's alphabetical
+//      order, reset of root / commands / terrain level.  Phase C: every role finishes its joints (reset draw, the 48
+//      proprioceptive observation columns un-noised, histories).  Reset rows + LSTM-state zeroing are written
 //      cooperatively; cross-env sums for extras["episode"] use warp shuffles + one atomicAdd per tile.
-//  K2  scan_obs_kernel      one WARP per env, lanes over columns: the 187-point height scan (packed f32x2 op-exact
-//      index path, all int16 gathers of the env issued back to back from the precomputed min3 field), measured_heights,
-//      and the finished observation row: height columns, in-kernel Philox noise, clip -- lane l owns columns l+32m, so
-//      one Philox block serves four coalesced 128-byte row segments.  Persistent CTAs keep the point grid in shared
-//      memory and the noise scales in registers.
+//  K2  scan_obs_fast_kernel (specialised, branch-free) / scan_obs_kernel (generic)   one WARP per env, lanes over
+//      columns: the 187-point height scan (packed f32x2 op-exact index path, all int16 gathers of the env issued back
+//      to back from the precomputed min3 field), measured_heights, and the finished observation row: height columns,
+//      in-kernel Philox noise, clip -- lane l owns columns l+32m, so one Philox block serves four coalesced 128-byte
+//      row segments.  Persistent CTAs; point grid, noise scales and column masks live in registers.
 //
 // lgk_post_physics orders them (K1 then K2; when the base_height reward is active the scan runs first) and runs the
 // PRE / POST phases of K1 separately when Python code has to run in between.
@@ -68,7 +70,7 @@ __host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots)
   int o = 0;
   L.root = o;    o += al16(kTile * 13 * 4);
   L.dof = o;     o += al16(kTile * 24 * 4);
-  // the 48-column observation head (row stride 49: conflict-free lane-per-env writes) reuses the contact tile, which
+  // the 48-column observation head (row stride 49: conflict-free lane = env writes) reuses the contact tile, which
   // is dead once env_pre has run (a __syncwarp separates the two uses)
   { const int c = al16(kTile * nb * 3 * 4), h = al16(kTile * 49 * 4); L.contact = o; L.head = o; o += c > h ? c : h; }
   L.act = o;     o += al16(kTile * 12 * 4);
@@ -116,7 +118,7 @@ constexpr int kFrameFloats = 8;
 // CTA = 4 warps = one tile of 32 envs, lane = env, warp = role (see lgk_step_device.cuh): phase A every role reduces its
 // joints / foot / bodies to partial sums, phase B role 0 does the once-per-env work, phase C every role finishes its
 // joints (reset, observation columns, histories).  Total work per tile is about a third of running all four lanes of an
-// env through everything, and the chain on the critical path about half of a lane-per-env thread's.
+// env through everything, and the chain on the critical path about half of that of one thread doing a whole env.
 constexpr int kK1Threads = 4 * kTile;
 __device__ long long* g_k1_timeline = nullptr;     // profiling hook (lgk_step_debug_timeline): stamps of CTA 0
 __device__ __forceinline__ void k1_stamp(int slot) {
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(kK2Threads, 5) scan_obs_fast_kernel(const __gr
 __global__ void __launch_bounds__(128) reset_idx_kernel(const __grid_constant__ LgkStepParams p,
                                                        const int64_t* __restrict__ ids, int n) {
   // one warp per listed env: lane 0 performs the per-env reset on a small shared scratch row set, then the
-  // warp writes rows back cooperatively (same write path as the fused kernel).
+  // warp writes rows back cooperatively (same write path as the step kernel).
   __shared__ float s_root[4][13], s_dof[4][24], s_cmd[4][4], s_fat[4][LGK_MAX_FEET];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * 4 + w;

@@ -10,9 +10,9 @@ Same constructor, attributes, tensor layouts and method names; every per-env com
 Python keeps only what is host logic in the reference too: cfg parsing, buffer allocation, the push /
 curriculum step counters and the extension points.  Supported extension points for subclasses (README.md:29-32,
 56-66 of the reference): extra ``_reward_<name>`` terms written in torch (the step then runs PRE, the Python
-terms, POST), ``_compute_torques``, ``compute_observations`` (called after the fused step when overridden),
+terms, POST), ``_compute_torques``, ``compute_observations`` (called after the native step when overridden),
 ``_get_noise_scale_vec``, ``_init_buffers``.  Overriding ``check_termination`` / ``_post_physics_step_callback``
-/ ``compute_reward`` is rejected at construction: those run inside the fused kernel.
+/ ``compute_reward`` is rejected at construction: those run inside the step kernels.
 """
 import ctypes as C
 

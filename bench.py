@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the PPO training-iteration timing")
     ap.add_argument("--tile", type=int, default=0, help="reserved (the scalar kernel tiles 32 envs per CTA)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="rotate: cycle over env replicas whose buffers exceed L2; flush: write 256 MiB between steps")
@@ -358,6 +359,35 @@ def rollout_phase(dev, n_envs=4096, T=24, reps=20):
                                      peak_source="MEASURED_PEAKS.json bf16_tflops / 2"))
 
 
+def train_iteration(dev, num_envs=4096, iters=4):
+    """One PPO iteration of the reference's training flow (scripts/train.py: 24 rollout steps of anymal_c_rough + GAE +
+    PPO.update with 5 epochs x 4 mini-batches) through task_registry / OnPolicyRunner: wall-clock of the last iteration.
+    The update runs as CUDA graphs in fp32 (reference numerics), then once more with TF32 matmuls."""
+    import torch
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.utils import get_args
+    out = {}
+    for label, tf32 in (("fp32", False), ("tf32_matmul", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        a = get_args(["--task", TASK, "--num_envs", str(num_envs), "--headless", "--sim_device", dev, "--rl_device", dev])
+        env, _ = task_registry.make_env(name=TASK, args=a)
+        runner, _ = task_registry.make_alg_runner(env=env, name=TASK, args=a, log_root=None)
+        for it in range(iters):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            runner.learn(num_learning_iterations=1, init_at_random_ep_len=(it == 0))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out[label] = dict(ms_per_iteration=round(dt * 1e3, 2), collection_ms=round(runner.collection_time * 1e3, 2),
+                          learning_ms=round(runner.learn_time * 1e3, 2),
+                          env_steps_per_sec=round(runner.num_steps_per_env * num_envs / dt, 1))
+        del env, runner
+        torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["workload"] = f"{TASK}, {num_envs} envs x 24 steps per iteration, PPO 5 epochs x 4 mini-batches (LeggedRobotCfgPPO)"
+    return out
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -474,6 +504,7 @@ def gpu_arm(args):
             del env2, feeder2, envs2, feeders2
             torch.cuda.empty_cache()
     rollout = rollout_phase(dev)
+    training = None if args.no_train else train_iteration(dev)
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores
@@ -490,7 +521,7 @@ def gpu_arm(args):
                    "timing": "CUDA events on the launch stream around the K steps; barrier+synchronize both sides",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep, "rollout_phase": rollout,
+        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep, "rollout_phase": rollout, "train_iteration": training,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

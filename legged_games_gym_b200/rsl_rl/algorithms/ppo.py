@@ -1,5 +1,7 @@
 """PPO with the rsl_rl v1.0.2 API.  act / process_env_step / compute_returns feed the CUDA hot path; update() is plain
-PyTorch autograd.  Multi-GPU (one process per GPU, envs sharded): gradients are flattened into one bucket and
+PyTorch autograd -- on a single GPU captured once into a CUDA graph (one replay per mini-batch: gathers, forward, losses,
+backward, gradient clipping, Adam, the adaptive-KL learning-rate rule and the loss accumulators all on the device, no
+host synchronisation inside the loop), eager otherwise.  Multi-GPU (one process per GPU, envs sharded): gradients are flattened into one bucket and
 all-reduced over NCCL once per mini-batch; the KL estimate that drives the adaptive learning rate is all-reduced so
 every rank takes the same schedule."""
 import torch
@@ -17,7 +19,7 @@ def _world():
 class PPO:
     def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
                  value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0,
-                 use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device="cpu"):
+                 use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device="cpu", tf32_matmul=None):
         self.device = device
         self.desired_kl, self.schedule, self.learning_rate = desired_kl, schedule, learning_rate
         self.actor_critic = actor_critic.to(device)
@@ -30,6 +32,17 @@ class PPO:
         self.use_clipped_value_loss = use_clipped_value_loss
         self._flat_grad = None
         self.allreduce_calls = 0
+        # fp32 GEMMs like the reference by default; tf32_matmul=True (or LGK_PPO_TF32=1) lets cuBLAS use TF32 tensor cores
+        # for the update's matmuls (the rollout-time policy kernel is TF32 already)
+        import os
+        if tf32_matmul is None:
+            tf32_matmul = os.environ.get("LGK_PPO_TF32", "0") == "1"
+        self.tf32_matmul = bool(tf32_matmul)
+        if self.tf32_matmul:
+            torch.backends.cuda.matmul.allow_tf32 = True
+        # single-GPU fast path of update(): whole mini-batch step as one CUDA graph (set to False for the eager loop)
+        self.use_cuda_graph = True
+        self._graph = None
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
@@ -81,7 +94,119 @@ class PPO:
             off += k
         self.allreduce_calls += 1
 
+    # ------------------------------------------------------------------ graphed update (single process, CUDA)
+    def _minibatch_loss(self, obs, cobs, acts, tvals, adv, rets, old_lp, old_mu, old_sigma, lr_t):
+        """One mini-batch of rsl_rl PPO.update with the learning-rate rule on the device (lr_t: 0-dim tensor)."""
+        ac = self.actor_critic
+        ac.update_distribution(obs)
+        lp = ac.distribution.log_prob(acts).sum(dim=-1)
+        value = ac.critic(cobs)
+        mu, sigma, entropy = ac.distribution.mean, ac.distribution.stddev, ac.entropy
+        if self.desired_kl is not None and self.schedule == "adaptive":
+            with torch.no_grad():
+                kl = torch.sum(torch.log(sigma / old_sigma + 1.e-5) +
+                               (torch.square(old_sigma) + torch.square(old_mu - mu)) / (2.0 * torch.square(sigma)) - 0.5, axis=-1)
+                kl_mean = torch.mean(kl)
+                down = torch.clamp(lr_t / 1.5, min=1e-5)
+                up = torch.clamp(lr_t * 1.5, max=1e-2)
+                new_lr = torch.where(kl_mean > self.desired_kl * 2.0, down,
+                                     torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr_t))
+                lr_t.copy_(new_lr)
+        ratio = torch.exp(lp - torch.squeeze(old_lp))
+        a = torch.squeeze(adv)
+        surrogate_loss = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param)).mean()
+        if self.use_clipped_value_loss:
+            vc = tvals + (value - tvals).clamp(-self.clip_param, self.clip_param)
+            value_loss = torch.max((value - rets).pow(2), (vc - rets).pow(2)).mean()
+        else:
+            value_loss = (rets - value).pow(2).mean()
+        loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy.mean()
+        return loss, value_loss, surrogate_loss
+
+    def _graph_step(self, g):
+        """gather the mini-batch named by g['idx'] from the flat rollout tensors, then one optimisation step"""
+        st = g["flat"]
+        idx = g["idx"]
+        take = lambda t: t.index_select(0, idx)
+        loss, vl, sl = self._minibatch_loss(take(st["obs"]), take(st["cobs"]), take(st["acts"]), take(st["vals"]), take(st["adv"]),
+                                            take(st["rets"]), take(st["olp"]), take(st["mu"]), take(st["sg"]), g["lr"])
+        self.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
+        self.optimizer.step()
+        g["acc"][0] += vl.detach()
+        g["acc"][1] += sl.detach()
+
+    def _build_graph(self):
+        st, dev = self.storage, self.device
+        B = st.num_envs * st.num_transitions_per_env
+        mb = B // self.num_mini_batches
+        obs = st.observations.flatten(0, 1)
+        flat = dict(obs=obs, cobs=st.privileged_observations.flatten(0, 1) if st.privileged_observations is not None else obs,
+                    acts=st.actions.flatten(0, 1), vals=st.values.flatten(0, 1), rets=st.returns.flatten(0, 1),
+                    olp=st.actions_log_prob.flatten(0, 1), adv=st.advantages.flatten(0, 1), mu=st.mu.flatten(0, 1),
+                    sg=st.sigma.flatten(0, 1))
+        # Adam whose step counter and learning rate live on the device (capturable); state carried over from the eager optimizer
+        state = self.optimizer.state_dict()
+        lr_t = torch.tensor(float(self.learning_rate), device=dev)
+        self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=lr_t, capturable=True)
+        if state["state"]:
+            for s_ in state["state"].values():
+                if not torch.is_tensor(s_["step"]) or not s_["step"].is_cuda:
+                    s_["step"] = torch.as_tensor(float(s_["step"]), device=dev)
+            for grp in state["param_groups"]:
+                grp["lr"], grp["capturable"] = lr_t, True
+            self.optimizer.load_state_dict(state)
+        for grp in self.optimizer.param_groups:
+            grp["lr"] = lr_t
+        g = dict(flat=flat, idx=torch.zeros(mb, dtype=torch.long, device=dev), lr=lr_t, mb=mb,
+                 acc=torch.zeros(2, device=dev))
+        # the live weights / optimizer state must not be touched by warm-up and capture: snapshot, run, restore
+        snap_p = [p.detach().clone() for p in self.actor_critic.parameters()]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._graph_step(g)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):      # same stream as the warm-up: the AccumulateGrad nodes stay on it
+            self._graph_step(g)
+        with torch.no_grad():
+            for p, q in zip(self.actor_critic.parameters(), snap_p):
+                p.copy_(q)
+        for s_ in self.optimizer.state.values():      # the warm-up steps must not count: zero moments and step
+            s_["step"].zero_(); s_["exp_avg"].zero_(); s_["exp_avg_sq"].zero_()
+        if state["state"]:
+            self.optimizer.load_state_dict(state)
+            for grp in self.optimizer.param_groups:
+                grp["lr"] = lr_t
+        lr_t.fill_(float(self.learning_rate))
+        g["graph"] = graph
+        self._graph = g
+
+    def _update_graphed(self):
+        if self._graph is None:
+            self._build_graph()
+        g = self._graph
+        g["acc"].zero_()
+        g["lr"].fill_(float(self.learning_rate))
+        B = g["mb"] * self.num_mini_batches
+        perm = torch.randperm(B, requires_grad=False, device=self.device)     # one permutation per update(), like the generator
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                g["idx"].copy_(perm[i * g["mb"]:(i + 1) * g["mb"]])
+                g["graph"].replay()
+        n = self.num_learning_epochs * self.num_mini_batches
+        acc = (g["acc"] / n).tolist()                                       # the only host synchronisation of the update
+        self.learning_rate = float(g["lr"].item())
+        self.storage.clear()
+        return acc[0], acc[1]
+
     def update(self):
+        if (self.use_cuda_graph and _world() == 1 and torch.device(self.device).type == "cuda"
+                and self.storage.observations.is_cuda):
+            return self._update_graphed()
         mean_value_loss = mean_surrogate_loss = 0.0
         ac = self.actor_critic
         gen = self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs)

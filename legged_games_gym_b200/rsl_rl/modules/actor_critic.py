@@ -67,7 +67,8 @@ class ActorCritic(nn.Module):
 
     def update_distribution(self, observations):
         mean = self.actor(observations)
-        self.distribution = Normal(mean, mean * 0. + self.std)
+        # validate_args=False: no host-synchronising range checks (rsl_rl disables validation too), CUDA-graph capturable
+        self.distribution = Normal(mean, mean * 0. + self.std, validate_args=False)
         self._fused = None
 
     def _run_fused(self, obs, critic_obs, sample):

@@ -42,3 +42,44 @@ def test_train_checkpoint_play_export(tmp_path):
     with torch.inference_mode():
         fused = runner.alg.actor_critic.act_inference(obs.to(env.device)).cpu()
     assert torch.allclose(fused, want, rtol=1e-3, atol=1e-3)
+
+
+def test_graphed_ppo_update_matches_eager_update():
+    """PPO.update as one CUDA graph per mini-batch (device-side Adam step counter, learning-rate rule, loss accumulators)
+    must do what the eager rsl_rl loop does: same data, same permutation -> same parameters, losses and learning rate."""
+    from legged_games_gym_b200.rsl_rl.modules import ActorCritic
+    from legged_games_gym_b200.rsl_rl.algorithms import PPO
+    dev = "cuda:0"
+
+    def make(graph):
+        torch.manual_seed(0)
+        ac = ActorCritic(48, 48, 12, [128, 64, 32], [128, 64, 32]).to(dev)
+        alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, schedule="adaptive", desired_kl=0.01, learning_rate=1e-3,
+                  entropy_coef=0.01, device=dev)
+        alg.use_cuda_graph = graph
+        alg.init_storage(256, 8, [48], [None], [12])
+        g = torch.Generator().manual_seed(1)
+        st = alg.storage
+        for name in ("observations", "actions", "values", "returns", "advantages", "actions_log_prob", "mu"):
+            t = getattr(st, name)
+            t.copy_(torch.randn(t.shape, generator=g))
+        st.sigma.copy_(torch.rand(st.sigma.shape, generator=g) + 0.5)
+        st.step = 8
+        return alg
+
+    results = []
+    for graph in (False, True):
+        alg = make(graph)
+        out = []
+        for it in range(3):                         # three updates: the graph is built in the first, replayed in the others
+            alg.storage.step = 8
+            torch.manual_seed(100 + it)             # same mini-batch permutation in both runs
+            out.append(alg.update())
+        results.append((out, [p.detach().clone() for p in alg.actor_critic.parameters()], alg.learning_rate))
+    (l0, p0, lr0), (l1, p1, lr1) = results
+    assert lr0 == pytest.approx(lr1, rel=1e-6)
+    for a, b in zip(l0, l1):
+        assert a[0] == pytest.approx(b[0], rel=1e-4, abs=1e-6) and a[1] == pytest.approx(b[1], rel=1e-4, abs=1e-6)
+    for a, b in zip(p0, p1):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    assert any(not torch.equal(a, torch.zeros_like(a)) for a in p1)

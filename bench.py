@@ -362,13 +362,13 @@ def rollout_phase(dev, n_envs=4096, T=24, reps=20):
 def train_iteration(dev, num_envs=4096, iters=4):
     """One PPO iteration of the reference's training flow (scripts/train.py: 24 rollout steps of anymal_c_rough + GAE +
     PPO.update with 5 epochs x 4 mini-batches) through task_registry / OnPolicyRunner: wall-clock of the last iteration.
-    The update runs as CUDA graphs in fp32 (reference numerics), then once more with TF32 matmuls."""
+    The update runs as CUDA graphs with strict-fp32 cuBLAS, then with TF32 matmuls (the library default, see PPO)."""
     import torch
     from legged_games_gym_b200.envs import task_registry
     from legged_games_gym_b200.utils import get_args
     out = {}
     for label, tf32 in (("fp32", False), ("tf32_matmul", True)):
-        torch.backends.cuda.matmul.allow_tf32 = tf32
+        os.environ["LGK_PPO_TF32"] = "1" if tf32 else "0"
         a = get_args(["--task", TASK, "--num_envs", str(num_envs), "--headless", "--sim_device", dev, "--rl_device", dev])
         env, _ = task_registry.make_env(name=TASK, args=a)
         runner, _ = task_registry.make_alg_runner(env=env, name=TASK, args=a, log_root=None)
@@ -383,6 +383,7 @@ def train_iteration(dev, num_envs=4096, iters=4):
                           env_steps_per_sec=round(runner.num_steps_per_env * num_envs / dt, 1))
         del env, runner
         torch.cuda.empty_cache()
+    os.environ.pop("LGK_PPO_TF32", None)
     torch.backends.cuda.matmul.allow_tf32 = False
     out["workload"] = f"{TASK}, {num_envs} envs x 24 steps per iteration, PPO 5 epochs x 4 mini-batches (LeggedRobotCfgPPO)"
     return out

@@ -32,14 +32,14 @@ class PPO:
         self.use_clipped_value_loss = use_clipped_value_loss
         self._flat_grad = None
         self.allreduce_calls = 0
-        # fp32 GEMMs like the reference by default; tf32_matmul=True (or LGK_PPO_TF32=1) lets cuBLAS use TF32 tensor cores
-        # for the update's matmuls (the rollout-time policy kernel is TF32 already)
+        # The update's matmuls run on TF32 tensor cores by default: that is what the reference's stack did (its README pins
+        # PyTorch 1.10, where torch.backends.cuda.matmul.allow_tf32 defaulted to True; 1.12 flipped the default), and the
+        # rollout-time policy kernel is TF32 as well.  tf32_matmul=False or LGK_PPO_TF32=0 keeps cuBLAS in strict fp32.
         import os
         if tf32_matmul is None:
-            tf32_matmul = os.environ.get("LGK_PPO_TF32", "0") == "1"
+            tf32_matmul = os.environ.get("LGK_PPO_TF32", "1") != "0"
         self.tf32_matmul = bool(tf32_matmul)
-        if self.tf32_matmul:
-            torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32_matmul
         # single-GPU fast path of update(): whole mini-batch step as one CUDA graph (set to False for the eager loop)
         self.use_cuda_graph = True
         self._graph = None
@@ -149,13 +149,13 @@ class PPO:
         # Adam whose step counter and learning rate live on the device (capturable); state carried over from the eager optimizer
         state = self.optimizer.state_dict()
         lr_t = torch.tensor(float(self.learning_rate), device=dev)
-        self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=lr_t, capturable=True)
+        self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=lr_t, capturable=True, fused=True)     # one multi-tensor kernel
         if state["state"]:
             for s_ in state["state"].values():
                 if not torch.is_tensor(s_["step"]) or not s_["step"].is_cuda:
                     s_["step"] = torch.as_tensor(float(s_["step"]), device=dev)
             for grp in state["param_groups"]:
-                grp["lr"], grp["capturable"] = lr_t, True
+                grp["lr"], grp["capturable"], grp["fused"], grp["foreach"] = lr_t, True, True, False
             self.optimizer.load_state_dict(state)
         for grp in self.optimizer.param_groups:
             grp["lr"] = lr_t

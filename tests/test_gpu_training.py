@@ -37,7 +37,7 @@ def test_train_checkpoint_play_export(tmp_path):
     jit = torch.jit.load(os.path.join(exported, "policy_1.pt"))
     obs = env2.get_observations().cpu()
     want = runner.alg.actor_critic.actor(obs.to(env.device)).cpu()
-    assert torch.allclose(jit(obs), want, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(jit(obs), want, rtol=1e-3, atol=1e-3)    # CPU fp32 TorchScript vs the GPU modules (TF32 matmuls)
     # the rollout-time fused kernel agrees with the autograd modules it replaces
     with torch.inference_mode():
         fused = runner.alg.actor_critic.act_inference(obs.to(env.device)).cpu()
@@ -55,7 +55,7 @@ def test_graphed_ppo_update_matches_eager_update():
         torch.manual_seed(0)
         ac = ActorCritic(48, 48, 12, [128, 64, 32], [128, 64, 32]).to(dev)
         alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, schedule="adaptive", desired_kl=0.01, learning_rate=1e-3,
-                  entropy_coef=0.01, device=dev)
+                  entropy_coef=0.01, device=dev, tf32_matmul=False)      # strict fp32: the two paths must agree tightly
         alg.use_cuda_graph = graph
         alg.init_storage(256, 8, [48], [None], [12])
         g = torch.Generator().manual_seed(1)

@@ -18,6 +18,7 @@ Own arm, one JSON line on rank 0:
 """
 import argparse
 import json
+import re
 import os
 import sys
 import threading
@@ -293,7 +294,7 @@ def ncu_traffic(num_envs, *kernels):
     tot, found = 0, 0
     for want in kernels:
         for name, rec in table.items():
-            if want in name:
+            if re.search(want, name):
                 tot += int(rec["dram_bytes"])
                 found += 1
                 break
@@ -499,7 +500,7 @@ def gpu_arm(args):
             s2, _ = time_steps(envs2, [f.synthetic_actions for f in feeders2], 100, 10, flush, lambda: None)
             r2 = kernel_rooflines(envs2, [f.synthetic_actions for f in feeders2], peak_gbs, reps=50)
             r2["torque_lstm"]["traffic"] = ncu_traffic(n2, "torque_kernel<1>")
-            r2["post_physics"]["traffic"] = ncu_traffic(n2, "post_scalar_kernel", "scan_obs_fast_kernel")
+            r2["post_physics"]["traffic"] = ncu_traffic(n2, r"post_(scalar_)?kernel", "scan_obs_fast_kernel")
             sweep[str(n2)] = dict(value=n2 * 100 / s2, ms_per_step=s2 / 100 * 1e3,
                                   roofline_torque_lstm=r2["torque_lstm"], roofline_post_physics=r2["post_physics"])
             del env2, feeder2, envs2, feeders2
@@ -511,7 +512,7 @@ def gpu_arm(args):
         cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores
     dom = dict(roof["torque_lstm"])
     dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, "torque_kernel<1>"))
-    roof["post_physics"]["traffic"] = ncu_traffic(N, "post_scalar_kernel", "scan_obs_fast_kernel")
+    roof["post_physics"]["traffic"] = ncu_traffic(N, r"post_(scalar_)?kernel", "scan_obs_fast_kernel")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -300,6 +300,15 @@ int lgk_abi_version(void);
  * prologue while its predecessor on the stream drains, and waits (griddepcontrol.wait) before touching memory.
  * Returns the previous setting. */
 int lgk_set_pdl(int enable);
+/* Fused post-physics kernel (opt-in, default off; LGK_FUSED=1 in the environment turns it on at load): lgk_post_physics
+ * runs the per-env scalar work (role warps) and the height scan / observation row (scan warps) of LR:106-230 as ONE launch
+ * whenever a height field backs the observation and no reward term needs this step's heights.  Results are identical
+ * bit for bit to the default two-kernel chain (tests/test_gpu_parity.py); on B200 it is 5-8 % slower (both
+ * halves compete for the same register file), so it is kept as a measured variant.  Returns the previous setting. */
+int lgk_set_fused(int enable);
+/* Scan warps per CTA of the fused kernel: 1..8, 0 = automatic (8 when the grid is at most two tiles per SM, else 4).
+ * Returns the previous setting. */
+int lgk_set_fused_scan_warps(int n);
 /* Write `bytes` of a scratch buffer (L2 flush between timed iterations; bench only). */
 int lgk_l2_flush(void* scratch, int64_t bytes, void* stream);
 /* number of kernel launches issued through this library since load (bench's gpu_launches). */

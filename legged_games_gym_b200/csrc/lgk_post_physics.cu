@@ -1,6 +1,6 @@
 // lgk_post_physics.cu -- post-physics step (reference LR:106-230, 329-508, 831-969) for sm_100a, one kernel per phase:
 //
-//  K1  post_scalar_kernel   one CTA (4 warps) per tile of 32 consecutive envs, lane = env, warp = role.  Every reference
+//  K1  post_kernel<0>       one CTA (4 warps) per tile of 32 consecutive envs, lane = env, warp = role.  Every reference
 //      tensor is env-major row-major, so the tile's slice of root_states / dof_state / contact_forces / actions / torques /
 //      last_actions / last_dof_vel / commands / feet_air_time is ONE contiguous chunk per tensor: each arrives by a single
 //      TMA bulk copy (cp.async.bulk.shared::cluster.global, mbarrier completion) and whole-tile results (commands,
@@ -18,6 +18,12 @@
 //
 // lgk_post_physics orders them (K1 then K2; when the base_height reward is active the scan runs first) and runs the
 // PRE / POST phases of K1 separately when Python code has to run in between.
+//
+//  Fused variant (opt-in, lgk_set_fused): post_kernel<G, RECIP> with G > 0 adds 1..8 scan warps to the K1 CTA; they run
+//  K2's arithmetic for the tile's 32 envs concurrently with the role warps (named barriers; speculative height columns with
+//  the pre-reset root z, redone by a role warp for the rare reset env; the 48-column head never leaves shared memory).
+//  Bit-identical to the chain, one launch less, but measured slower on B200.
+#include <stdlib.h>
 #include "lgk_step_device.cuh"
 
 namespace lgk {
@@ -60,12 +66,12 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ------------------------------------------------------------------ K1 shared-memory carve-up (bytes, 16-aligned)
 struct TileLayout {
-  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, frame, sums, ep, rew, flags, part, misc, total;
+  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, frame, sums, ep, rew, flags, part, noise, misc, total;
 };
 
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots) {
+__host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots, bool fused = false) {
   TileLayout L;
   int o = 0;
   L.root = o;    o += al16(kTile * 13 * 4);
@@ -90,6 +96,7 @@ __host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots)
   L.rew = o;     o += al16(kTile * 4);
   L.flags = o;   o += al16(kTile * 2);                                // reset flags [32] then time_out flags [32]
   L.part = o;    o += al16(PS_COUNT * 3 * kTile * 4);                 // partial sums of roles 1..3: [slot][role-1][env]
+  L.noise = o;   o += fused ? al16(kTile * 48 * 4) : 0;             // fused kernel: 2u-1 of the 48 head columns, from the scan warps
   L.misc = o;    o += 16;   // mbarrier
   L.total = o;
   return L;
@@ -111,6 +118,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// observation noise (LR:229-230): obs + (2u - 1) * noise_scale, as ONE fused multiply-add on the individually rounded
+// observation -- written out so that every kernel variant rounds identically
+__device__ __forceinline__ float noise_unit(uint32_t word) { return f_fma(2.0f, u32_to_uniform(word), -1.0f); }
+__device__ __forceinline__ float noisy_obs(float v, uint32_t word, float scale) { return f_fma(noise_unit(word), scale, v); }
+
 // scan frame of one env: [zn, wn, root_x, root_y] (pre-reset yaw frame, LR:853-854) + [root_z_post_reset - 0.5] (LR:225)
 constexpr int kFrameFloats = 8;
 
@@ -129,9 +141,34 @@ __device__ __forceinline__ void k1_stamp(int slot) {
   }
 }
 
-__global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_constant__ LgkStepParams p) {
+__device__ __forceinline__ void scan_stamp(int slot) {      // first scan warp of CTA 0
+  if (g_k1_timeline != nullptr && blockIdx.x == 0 && threadIdx.x == kK1Threads) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_k1_timeline[slot] = (long long)t;
+  }
+}
+
+// named barriers: 1 = the four role warps (what __syncthreads() is to the unfused kernel), 2 = scan warps -> role warps
+// hand-over of the fused kernel (scan warps arrive, role warps wait)
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void role_sync() { named_sync(1, kK1Threads); }
+
+template <int G, bool RECIP>
+__device__ __forceinline__ void scan_tile(const LgkStepParams& p, const RngKey& key, int env0, int nval, int e0, int e1,
+                                          int de, int lane, float* s_noise);
+LGK_COLD void refresh_reset_height_obs(const LgkStepParams& p, const RngKey& key, int env, float rz, int lane);
+
+// G == 0: K1 alone (128 threads).  G > 0: the fused post-physics kernel -- warps 0..3 are the role warps of K1, warps
+// 4.. are scan warps that run K2's work for the same 32 envs concurrently (the role warps' dependent chain leaves the
+// issue slots the scan warps need); the un-noised observation head never leaves shared memory.
+template <int G, bool RECIP>
+__global__ void __launch_bounds__(G > 0 ? kK1Threads + 256 : kK1Threads, G > 0 ? 2 : 7)
+post_kernel(const __grid_constant__ LgkStepParams p) {
+  constexpr bool FUSED = G > 0;
   extern __shared__ __align__(128) uint8_t smem[];
-  const TileLayout L = make_layout(p.num_bodies, p.num_feet, p.num_reward_slots);
+  const TileLayout L = make_layout(p.num_bodies, p.num_feet, p.num_reward_slots, FUSED);
   float* s_root = reinterpret_cast<float*>(smem + L.root);
   float* s_dof = reinterpret_cast<float*>(smem + L.dof);
   float* s_contact = reinterpret_cast<float*>(smem + L.contact);
@@ -172,6 +209,16 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
   }
   __syncthreads();
   pdl_wait();              // everything below reads state written by the previous kernels of the step
+  if constexpr (FUSED) if (warp >= 4) {        // scan warps: heights + height observation columns + the noise of the whole row
+    scan_stamp(9);
+    const int step_s = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
+    scan_tile<G, RECIP>(p, make_key(p.seed, step_s), env0, nval, warp - 4, nval, (int)(blockDim.x >> 5) - 4, lane,
+                        reinterpret_cast<float*>(smem + L.noise));
+    scan_stamp(11);
+    __threadfence_block();
+    named_arrive(2, blockDim.x);
+    return;
+  }
 
   // ---------------- stage the tile
   if (bulk) {
@@ -224,7 +271,7 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
       s_sums[k * kTile + e] = p.episode_sums[(size_t)k * N + env0 + e];
     }
     if (tid < nval) s_ep[tid] = p.episode_length_buf[env0 + tid];
-    __syncthreads();
+    role_sync();
   }
   k1_stamp(2);
 
@@ -249,13 +296,13 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
       for (int k = 0; k < PS_COUNT; ++k) s_part[(k * 3 + role - 1) * kTile + e] = mine.v[k];
     }
   }
-  __syncthreads();
+  role_sync();
   k1_stamp(3);
 
   // ---------------- phase B: role 0, everything that exists once per env
   EnvScalars s;
   s.reset = false; s.time_out = false; s.rew = 0.f; s.ep_len = 0;
-  const bool want_frames = p.measure_heights && !p.terrain_is_plane && p.scan_frames != nullptr;
+  const bool want_frames = !FUSED && p.measure_heights && !p.terrain_is_plane && p.scan_frames != nullptr;
   if (role == 0) {
     if (pre) {
       uint32_t bits = __float_as_uint(mine.v[PS_BITS]);
@@ -315,7 +362,7 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
     s_flags[e] = s.reset ? 1 : 0;
     s_flags[kTile + e] = s.time_out ? 1 : 0;
   }
-  __syncthreads();       // contact rows are dead from here on: their region becomes the observation head
+  role_sync();           // contact rows are dead from here on: their region becomes the observation head
   k1_stamp(4);
 
   // ---------------- phase C: every role finishes its joints
@@ -327,10 +374,10 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
 #pragma unroll
     for (int d = 3 * role; d < 3 * role + 3; ++d) s_ldv[e * 12 + d] = dof[2 * d + 1];   // LR:133 (post-reset dof_vel)
     if (role == 1) { for (int i = 0; i < 6; ++i) s_lrv[e * 6 + i] = root[7 + i]; }      // LR:134 (post push/reset)
-    if (role == 2 && valid && p.scan_frames) p.scan_frames[(size_t)env * kFrameFloats + 4] = root[2] - 0.5f;   // post-reset z
+    if (!FUSED && role == 2 && valid && p.scan_frames) p.scan_frames[(size_t)env * kFrameFloats + 4] = root[2] - 0.5f;   // post-reset z
   }
   fence_async_smem();
-  __syncthreads();
+  role_sync();
   k1_stamp(5);
 
   // ---------------- whole-tile write-backs
@@ -355,7 +402,8 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
         bulk_s2g(p.last_actions + (size_t)env0 * 12, s_act, kTile * 12 * 4);
         bulk_s2g(p.last_dof_vel + (size_t)env0 * 12, s_ldv, kTile * 12 * 4);
         bulk_s2g(p.last_root_vel + (size_t)env0 * 6, s_lrv, kTile * 6 * 4);
-        if (do_push && pre) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
+        // (fused: the scan warps read root poses from global memory, so the pushed tile goes out after their barrier)
+        if (do_push && pre && !FUSED) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
       }
       bulk_commit();
     }
@@ -400,6 +448,12 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
   k1_stamp(6);
 
   if (post) {
+    // fused: from here on the scan warps' speculative height columns (pre-reset z), measured_heights and the head noise
+    // are complete and visible
+    if (FUSED) {
+      named_sync(2, blockDim.x);
+      if (bulk && tid == 0 && do_push) { bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4); bulk_commit(); }
+    }
     // ---------------- reset rows: dof_state / root_states write-back + LSTM state zeroing (ANY:56-60); every warp sees the
     // same reset mask (lane = env) and takes every fourth reset env
     uint32_t rm = __ballot_sync(0xffffffffu, reset_e);
@@ -409,6 +463,8 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
       rm &= rm - 1;
       if ((turn++ & 3) != warp) continue;
       const int en = env0 + ee;
+      // height columns of a reset env use the post-reset root z (LR:225 after LR:160)
+      if (FUSED) refresh_reset_height_obs(p, key, en, s_root[ee * 13 + 2] - 0.5f, lane);
       if (lane < 24) p.dof_state[(size_t)en * 24 + lane] = s_dof[ee * 24 + lane];
       if (lane < 13)
         p.root_states[((size_t)en * p.actors_per_env + p.root_actor_offset) * 13 + lane] = s_root[ee * 13 + lane];
@@ -423,11 +479,29 @@ __global__ void __launch_bounds__(kK1Threads) post_scalar_kernel(const __grid_co
         if (lane < 24) { h0[lane] = z; h1[lane] = z; c0[lane] = z; c1[lane] = z; }
       }
     }
-    // ---------------- the 48 proprioceptive columns, un-noised (K2 adds noise + clip): coalesced row segments
-    for (int ee = warp * 8; ee < min(warp * 8 + 8, nval); ++ee) {
-      float* orow = p.obs_buf + (size_t)(env0 + ee) * O;
-      orow[lane] = s_head[ee * 49 + lane];
-      if (lane < 16) orow[32 + lane] = s_head[ee * 49 + 32 + lane];
+    if (FUSED) {
+      // ---------------- the 48 proprioceptive columns, finished: noise (the scan warps' uniforms) + clip (LR:100-101, 229-230)
+      const float* s_noise = reinterpret_cast<const float*>(smem + L.noise);
+      const bool noisy = p.add_noise != 0;
+      const float nz0 = noisy ? __ldg(p.noise_scale_vec + lane) : 0.f;
+      const float nz1 = (noisy && lane < 16) ? __ldg(p.noise_scale_vec + 32 + lane) : 0.f;
+      const float clip = p.clip_obs;
+      for (int ee = warp * 8; ee < min(warp * 8 + 8, nval); ++ee) {
+        float* orow = p.obs_buf + (size_t)(env0 + ee) * O;
+        const float v0 = f_fma(s_noise[ee * 48 + lane], nz0, s_head[ee * 49 + lane]);
+        orow[lane] = clampf(v0, -clip, clip);
+        if (lane < 16) {
+          const float v1 = f_fma(s_noise[ee * 48 + 32 + lane], nz1, s_head[ee * 49 + 32 + lane]);
+          orow[32 + lane] = clampf(v1, -clip, clip);
+        }
+      }
+    } else {
+      // ---------------- the 48 proprioceptive columns, un-noised (K2 adds noise + clip): coalesced row segments
+      for (int ee = warp * 8; ee < min(warp * 8 + 8, nval); ++ee) {
+        float* orow = p.obs_buf + (size_t)(env0 + ee) * O;
+        orow[lane] = s_head[ee * 49 + lane];
+        if (lane < 16) orow[32 + lane] = s_head[ee * 49 + 32 + lane];
+      }
     }
   }
   k1_stamp(7);
@@ -549,8 +623,8 @@ __global__ void __launch_bounds__(kK2Threads, 8) scan_obs_kernel(const __grid_co
               float v;
               if (g == 0) v = head0;
               else if (g == 1 && lane < 16) v = head1;
-              else v = hcols ? clampf(rz - h[g], -1.f, 1.f) * hsc : 0.f;
-              v = v + (2.0f * u32_to_uniform(pick(r, k)) - 1.0f) * nz[g];
+              else v = hcols ? f_mul(clampf(rz - h[g], -1.f, 1.f), hsc) : 0.f;
+              v = noisy_obs(v, pick(r, k), nz[g]);
               orow[j] = clampf(v, -clip, clip);
             }
           }
@@ -663,13 +737,114 @@ __global__ void __launch_bounds__(kK2Threads, 5) scan_obs_fast_kernel(const __gr
             float v;
             if (g == 0) v = cur.head0;
             else {
-              v = clampf(cur.rz - h[g], -1.f, 1.f) * hsc;
+              v = f_mul(clampf(cur.rz - h[g], -1.f, 1.f), hsc);
               if (g == 1) v = lane < 16 ? cur.head1 : v;
             }
-            v = v + (2.0f * u32_to_uniform(pick(r, k)) - 1.0f) * nz[g];
+            v = noisy_obs(v, pick(r, k), nz[g]);
             if ((omask >> g) & 1u) orow[32 * g + lane] = clampf(v, -clip, clip);
           }
         }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ scan warps of the fused kernel
+// K2's work for the 32 envs of one K1 tile, spread over the CTA's nsw scan warps (warp per env, lane = column, exactly
+// the arithmetic of scan_obs_fast_kernel<G, kScan | kObs, RECIP>).  Nothing here waits for the role warps: the yaw frames
+// come straight from root_states (pre-reset pose, LR:853-854), the height columns are finished with the pre-reset root z
+// (the role warps redo the rare reset env, refresh_reset_height_obs), and of the 48 head columns only the uniforms are
+// produced (2u-1, parked in shared memory for the role warps' final write).
+template <int G, bool RECIP>
+__device__ __forceinline__ void scan_tile(const LgkStepParams& p, const RngKey& key, int env0, int nval, int e0, int e1,
+                                          int de, int lane, float* s_noise) {
+  const int P = p.num_height_points, O = p.num_obs;
+  f2_t Bv[G], Bsv[G];
+  float nz[G];
+  uint32_t pmask = 0, omask = 0;
+  const bool noisy = p.add_noise != 0;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int j = 32 * g + lane, pt = j - 48;
+    const bool isp = pt >= 0 && pt < P;
+    float bx = 0.f, by = 0.f;
+    if (isp) { const float2 b = __ldg(reinterpret_cast<const float2*>(p.height_points_xy) + pt); bx = b.x; by = b.y; }
+    Bv[g] = pack2(bx, by); Bsv[g] = pack2(by, bx);
+    pmask |= (isp ? 1u : 0u) << g;
+    omask |= ((j < O && j >= 48) ? 1u : 0u) << g;
+    nz[g] = (noisy && j < O) ? __ldg(p.noise_scale_vec + j) : 0.f;
+  }
+  const float rt_one = __int_as_float(0x3f800000u | ((uint32_t)p.num_envs >> 31));   // 1.0f the compiler cannot see
+  const float clip = p.clip_obs, vs = p.vertical_scale, hsc = p.obs_scale_height;
+  const float border = p.border_size, hscale = p.horizontal_scale, hrecip = p.horizontal_scale_recip;
+  const int rows = p.hf_rows, cols = p.hf_cols;
+  // lane l holds the frame of env l of the tile; the env loop broadcasts it by shuffle
+  const float* r = p.root_states + ((size_t)(env0 + min(lane, nval - 1)) * p.actors_per_env + p.root_actor_offset) * 13;
+  const YawFrame fl = yaw_frame(r[5], r[6], r[0], r[1]);
+  const float rzl = r[2] - 0.5f;
+  if (rzl == 123456.f) scan_stamp(12);      // (keeps the frame loads ahead of the next stamp)
+  scan_stamp(10);
+#pragma unroll 1
+  for (int e = e0; e < e1; e += de) {
+    const int env = env0 + e;
+    const YawFrame2 yf = yaw_frame2(YawFrame{__shfl_sync(0xffffffffu, fl.zn, e), __shfl_sync(0xffffffffu, fl.wn, e),
+                                             __shfl_sync(0xffffffffu, fl.rx, e), __shfl_sync(0xffffffffu, fl.ry, e)});
+    const float rz = __shfl_sync(0xffffffffu, rzl, e);
+    float* orow = p.obs_buf + (size_t)env * O;
+    float* hrow = p.measured_heights + (size_t)env * P;
+    float h[G];
+    int off[G];
+    h[0] = 0.f;
+#pragma unroll
+    for (int g = 1; g < G; ++g) {
+      int ix, iy;
+      height_index2<RECIP>(yf, Bv[g], Bsv[g], border, hscale, hrecip, rt_one, rows, cols, ix, iy);
+      off[g] = ix * cols + iy;
+    }
+#pragma unroll
+    for (int g = 1; g < G; ++g) h[g] = f_mul((float)__ldg(p.height_min3 + off[g]), vs);      // LR:869
+#pragma unroll
+    for (int g = 1; g < G; ++g) if ((pmask >> g) & 1u) hrow[32 * g + lane - 48] = h[g];
+    const uint32_t genv = (uint32_t)(p.env_id_offset + env);
+#pragma unroll
+    for (int sc = 0; sc < (G + 3) / 4; ++sc) {
+      U4 rr = U4{0, 0, 0, 0};
+      if (noisy) rr = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = sc * 4 + k;
+        if (g < G) {
+          const float t = noise_unit(pick(rr, k));
+          if (g == 0) s_noise[e * 48 + lane] = t;
+          if (g == 1 && lane < 16) s_noise[e * 48 + 32 + lane] = t;
+          if (g >= 1) {
+            const float v = f_fma(t, nz[g], f_mul(clampf(rz - h[g], -1.f, 1.f), hsc));
+            if ((omask >> g) & 1u) orow[32 * g + lane] = clampf(v, -clip, clip);
+          }
+        }
+      }
+    }
+  }
+}
+
+// height columns of an env that reset this step, redone with its post-reset root z (cold: a warp of the role group per env)
+LGK_COLD void refresh_reset_height_obs(const LgkStepParams& p, const RngKey& key, int env, float rz, int lane) {
+  const int P = p.num_height_points, O = p.num_obs;
+  const bool noisy = p.add_noise != 0;
+  const uint32_t genv = (uint32_t)(p.env_id_offset + env);
+  const float* hrow = p.measured_heights + (size_t)env * P;
+  float* orow = p.obs_buf + (size_t)env * O;
+#pragma unroll 1
+  for (int sc = 0; sc * 128 < O; ++sc) {
+    U4 rr = U4{0, 0, 0, 0};
+    if (noisy) rr = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const int j = 128 * sc + 32 * k + lane;
+      if (j >= 48 && j < O) {
+        const float v = f_fma(noise_unit(pick(rr, k)), noisy ? p.noise_scale_vec[j] : 0.f,
+                              f_mul(clampf(rz - hrow[j - 48], -1.f, 1.f), p.obs_scale_height));
+        orow[j] = clampf(v, -p.clip_obs, p.clip_obs);
       }
     }
   }
@@ -858,16 +1033,63 @@ static int launch_k1(const LgkStepParams* p, cudaStream_t st) {
   const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_reward_slots);
   static int smem_set = 0;
   if (L.total > smem_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(post_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
-                            "cudaFuncSetAttribute(post_scalar_kernel)")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(post_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
+                            "cudaFuncSetAttribute(post_kernel)")) return rc;
     smem_set = L.total;
     // one warp per CTA, ~15 KB of staged tiles each: ask for the largest shared-memory carve-out so that a whole
     // 65k-env grid (2048 CTAs) is resident in a single wave
-    cudaFuncSetAttribute(post_scalar_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(post_kernel<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
-  const cudaError_t e = launch_chained(post_scalar_kernel, dim3((p->num_envs + kTile - 1) / kTile), dim3(kK1Threads), (size_t)L.total, st, *p);
+  const cudaError_t e = launch_chained(post_kernel<0, false>, dim3((p->num_envs + kTile - 1) / kTile), dim3(kK1Threads), (size_t)L.total, st, *p);
   count_launch();
-  return check_cuda(e, "post_scalar_kernel launch");
+  return check_cuda(e, "post_kernel launch");
+}
+
+// ---- fused K1 + K2 (one launch): a height field behind the height columns, heights not needed by a reward term.
+// LGK_FUSED=0 / lgk_set_fused(0) keeps the two-kernel path; LGK_FUSED_SCAN_WARPS overrides the scan-warp count.
+static int g_fused = -1, g_fused_sw = 0;
+extern "C" int lgk_set_fused(int enable) { const int prev = g_fused; g_fused = enable ? 1 : 0; return prev < 0 ? 0 : prev; }
+static bool g_fused_sw_set = false;
+extern "C" int lgk_set_fused_scan_warps(int n) { const int prev = g_fused_sw; g_fused_sw = n; g_fused_sw_set = true; return prev; }
+static bool fused_eligible(const LgkStepParams* p) {
+  static bool env_read = false;
+  if (!env_read) {
+    env_read = true;
+    const char* e = getenv("LGK_FUSED");
+    if (g_fused < 0) g_fused = (e && e[0] == '1') ? 1 : 0;
+    const char* w = getenv("LGK_FUSED_SCAN_WARPS");
+    if (!g_fused_sw_set) g_fused_sw = w ? atoi(w) : 0;
+  }
+  const int groups = (48 + p->num_height_points + 31) / 32;
+  return g_fused && p->measure_heights && !p->terrain_is_plane && p->num_height_points > 0 && groups > 2 && groups <= 12 &&
+         !p->reward_active[LGK_R_BASE_HEIGHT];
+}
+
+template <int G, bool RECIP>
+static int launch_fused_t(const LgkStepParams* p, int scan_warps, cudaStream_t st) {
+  const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_reward_slots, true);
+  static int smem_set = 0;
+  if (L.total > smem_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(post_kernel<G, RECIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
+                            "cudaFuncSetAttribute(post_kernel fused)")) return rc;
+    smem_set = L.total;
+    cudaFuncSetAttribute(post_kernel<G, RECIP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
+  const cudaError_t e = launch_chained(post_kernel<G, RECIP>, dim3((p->num_envs + kTile - 1) / kTile), dim3(kK1Threads + 32 * scan_warps),
+                                       (size_t)L.total, st, *p);
+  count_launch();
+  return check_cuda(e, "post_kernel (fused) launch");
+}
+
+static int launch_fused(const LgkStepParams* p, cudaStream_t st) {
+  const int groups = (48 + p->num_height_points + 31) / 32;
+  // few tiles per SM: 8 scan warps keep the scan shorter than the role warps' chain; many tiles: 4, so that three tiles
+  // are resident per SM
+  int sw = g_fused_sw > 0 ? g_fused_sw : ((p->num_envs + kTile - 1) / kTile <= 2 * 148 ? 8 : 4);
+  sw = sw < 1 ? 1 : (sw > 8 ? 8 : sw);
+  const bool rc = p->horizontal_scale_recip != 0.f;
+  if (groups <= 8) return rc ? launch_fused_t<8, true>(p, sw, st) : launch_fused_t<8, false>(p, sw, st);
+  return rc ? launch_fused_t<12, true>(p, sw, st) : launch_fused_t<12, false>(p, sw, st);
 }
 
 static int launch_k2(const LgkStepParams* p, int mode, cudaStream_t st) {
@@ -913,6 +1135,7 @@ extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
   const bool scan_first = heights && p->reward_active[LGK_R_BASE_HEIGHT] != 0;
   if (heights && !p->terrain_is_plane) LGK_REQUIRE(p->scan_frames != nullptr, "scan_frames buffer is null");
   if (pre && post) {              // fused step
+    if (fused_eligible(p)) return launch_fused(p, st);
     if (scan_first)
       if (int rc = launch_k2(p, kScan, st)) return rc;
     if (int rc = launch_k1(p, st)) return rc;

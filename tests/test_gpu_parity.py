@@ -201,6 +201,54 @@ def test_env_step_cuda_graph_and_tiles(task, n, tile):
     assert env._graph is not None
 
 
+@pytest.mark.parametrize("task,n,ov,sw", [
+    ("anymal_c_rough", 4096, {"env.episode_length_s": 0.3, "domain_rand.push_interval_s": 0.04}, 0),
+    ("a1", 1000, {"env.episode_length_s": 0.2, "commands.curriculum": True}, 4),
+    ("anymal_c_rough", 77, {"noise.add_noise": False}, 3),
+    ("cassie", 2080, {"env.episode_length_s": 0.2}, 8),
+    ("low_level_game", 200, {"env.episode_length_s": 0.2}, 0)])
+def test_fused_post_physics_kernel_equals_two_kernel_chain(task, n, ov, sw):
+    """lgk_post_physics as ONE launch (role warps + scan warps, speculative height columns redone for reset envs) gives
+    bit-identical results to the K1 -> K2 chain it replaces: every snapshot tensor, 8 steps with resets (short
+    episodes), pushes, partial tiles and every scan-warp count."""
+    lib = nat().lib
+    case = harness.build_case(task, n, seed=11, overrides=ov)
+    envs = []
+    for fused in (1, 0):
+        lib.lgk_set_fused(fused)
+        env, feeder = product_env(case)
+        envs.append((fused, env, feeder_state(feeder)))
+    before = nat().launch_count()
+    try:
+        lib.lgk_set_fused_scan_warps(sw)
+        n_reset = 0
+        for step in range(1, 9):
+            acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (n, 12)).astype(np.float32)).to(DEV)
+            noise = harness.make_noise(case, step, 5)
+            snaps = []
+            for fused, env, st in envs:
+                lib.lgk_set_fused(fused)
+                c0 = nat().launch_count()
+                env.step(acts.clone())
+                torch.cuda.synchronize()
+                launches = nat().launch_count() - c0
+                snaps.append((harness.snapshot(env), launches))
+                harness.apply_noise(st, noise)
+            (a, la), (b, lb) = snaps
+            assert la == lb - 1, f"the fused path saves one launch per step ({la} vs {lb})"
+            n_reset += int(a["reset_buf"].sum())
+            for k in b:
+                if k.startswith("ex_"):        # cross-tile float atomics: summation order varies from launch to launch
+                    assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), f"step {step}: {k}"
+                    continue
+                assert torch.equal(a[k], b[k]), f"step {step}: {k} differs between the fused kernel and the chain"
+        assert n_reset > 0, "the case must exercise the reset re-do of the speculative height columns"
+    finally:
+        lib.lgk_set_fused(0)
+        lib.lgk_set_fused_scan_warps(0)
+    assert nat().launch_count() > before
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_env_step_matches_reference_fixture(name):
     spec = CASES[name]

@@ -102,7 +102,36 @@ def step_tables(seed, step, num_envs, num_obs, num_dof=12, env_offset=0):
         philox.STREAM_TERRAIN: philox.raw_u32(seed, step, ids, philox.STREAM_TERRAIN, 1),
         philox.STREAM_OBS: philox.obs_uniforms(seed, step, ids, num_obs),
         philox.STREAM_PREDATOR: philox.uniforms(seed, step, ids, philox.STREAM_PREDATOR, 4),
+        philox.STREAM_GAME_ROOT: philox.uniforms(seed, step, ids, philox.STREAM_GAME_ROOT, 8),
+        philox.STREAM_GAME_PREDATOR: philox.uniforms(seed, step, ids, philox.STREAM_GAME_PREDATOR, 4),
+        philox.STREAM_GAME_DOF: philox.uniforms(seed, step, ids, philox.STREAM_GAME_DOF, num_dof),
     }
+
+
+def game_inputs(case, step, variant):
+    """Seeded high-level commands of one game step: prey command [N,4] and predator command [N,2] (scaled so that
+    the clips of HLG:162-169 trigger), plus low-level actions [N,12]."""
+    n = case["cfg"].env.num_envs
+    g = np.random.default_rng(7919 * step + 13)
+    prey = g.normal(0, 1.5, (n, 4)).astype(np.float32)
+    prey[:, 2] *= 3.0                                   # heading beyond +-pi: wrap_to_pi path
+    pred = g.normal(0, 2.5, (n, 2)).astype(np.float32)
+    acts = g.normal(0, 1, (n, 12)).astype(np.float32)
+    return torch.from_numpy(prey), torch.from_numpy(pred), torch.from_numpy(acts)
+
+
+def place_predators(state, seed):
+    """Put the predator sphere of every env near its prey (synthetic states scatter them over the whole terrain): a third
+    within capture distance, the rest 0.5..6 m away at a random bearing, so that captures, visible and occluded
+    predators all occur.  `state` holds torch tensors; mutated in place."""
+    r = state["root_states"]
+    n = r.shape[0] // 2
+    g = np.random.default_rng(seed + 4242)
+    dist = np.where(g.random(n) < 0.33, g.uniform(0.05, 0.45, n), g.uniform(0.5, 6.0, n)).astype(np.float32)
+    ang = g.uniform(-np.pi, np.pi, n).astype(np.float32)
+    r[1::2, 0] = r[0::2, 0] + torch.from_numpy(dist * np.cos(ang)).to(r.device)
+    r[1::2, 1] = r[0::2, 1] + torch.from_numpy(dist * np.sin(ang)).to(r.device)
+    r[1::2, 2] = 0.3
 
 
 def make_noise(case, step, seed):

@@ -28,6 +28,11 @@ STREAM_TERRAIN = 5     # raw uint32 for the terrain-level wrap randint
 STREAM_OBS = 6         # observation noise, one uniform per obs column
 STREAM_ACT = 7         # policy action noise (Box-Muller pairs)
 STREAM_PREDATOR = 8    # low_level_game predator spawn: offset xyz (3) then the sign draw
+# the high-level games reset root / dof state of the SAME low-level env a second time in one step (HLG:326-347,
+# DHLG:270-296): their draws come from streams of their own
+STREAM_GAME_ROOT = 9       # xy offset (2) then base velocity (6)
+STREAM_GAME_PREDATOR = 10  # predator spawn: offset xyz (3) then the sign draw
+STREAM_GAME_DOF = 11       # 12 dof position factors (DecHighLevelGame only)
 
 
 def philox4x32_10(counter, key):

@@ -244,6 +244,7 @@ class RngTap:
         self.stream = None
         self.col = 0
         self.in_reset = False
+        self.game = False         # inside HighLevelGame.reset_idx / DecHighLevelGame.reset_idx: the GAME_* streams
         self._wrap()
 
     def set_tables(self, tables):
@@ -274,14 +275,14 @@ class RngTap:
     # low_level_game's predator spawn (low_level_game.py:421-422): Tensor.uniform_ on a [len(ids), 3] tensor, then
     # torch.rand(len(ids)) -- served from the PREDATOR table, columns 0:3 and 3
     def _uniform_(self, x, a=0.0, b=1.0):
-        u = self.tables[philox.STREAM_PREDATOR][self.ids, 0:x.shape[1]]
+        u = self.tables[philox.STREAM_GAME_PREDATOR if self.game else philox.STREAM_PREDATOR][self.ids, 0:x.shape[1]]
         assert tuple(u.shape) == tuple(x.shape), (u.shape, x.shape)
         x.copy_((b - a) * u + a)
         return x
 
     def _rand(self, n, **k):
         assert n == len(self.ids)
-        return self.tables[philox.STREAM_PREDATOR][self.ids, 3].clone()
+        return self.tables[philox.STREAM_GAME_PREDATOR if self.game else philox.STREAM_PREDATOR][self.ids, 3].clone()
 
     def _wrap(self):
         env, tap = self.env, self
@@ -298,11 +299,11 @@ class RngTap:
             return o_resample(self_, env_ids)
 
         def dofs(self_, env_ids):
-            tap._begin(philox.STREAM_RESET_DOF, env_ids)
+            tap._begin(philox.STREAM_GAME_DOF if tap.game else philox.STREAM_RESET_DOF, env_ids)
             return o_dofs(self_, env_ids)
 
         def roots(self_, env_ids):
-            tap._begin(philox.STREAM_RESET_ROOT, env_ids)
+            tap._begin(philox.STREAM_GAME_ROOT if tap.game else philox.STREAM_RESET_ROOT, env_ids)
             if not self_.custom_origins:
                 tap.col = 2     # the xy draw is skipped on flat ground (legged_robot.py:427-429)
             return o_roots(self_, env_ids)
@@ -353,3 +354,76 @@ def attach_tap(env):
     mod = importlib.import_module(type(env).__module__) if type(env).__name__ == "LowLevelGame" else \
         importlib.import_module("legged_gym.envs.base.legged_robot")
     return RngTap(env, mod)
+
+
+# ---------------------------------------------------------------------------------------------- high-level games
+def make_ref_game(variant, ll_env, tap, cfg_overrides=None):
+    """Build the reference HighLevelGame ("hl") / DecHighLevelGame ("dec") around an already built reference LowLevelGame
+    instance, without its constructor (high_level_game.py:27-144 needs Isaac Gym, the forked rsl_rl LLPolicyRunner and a
+    checkpoint that is not in the tree): object.__new__ + the attributes __init__ would set + the reference's own
+    _parse_cfg / _init_buffers / _prepare_reward_function*.  The low-level policy is ``game.ll_policy`` (the caller sets
+    it to a function returning the low-level actions of the step).  reset_idx is wrapped so that the second reset of the
+    low-level root / dof state inside one step draws from the GAME_* streams of the tap."""
+    import copy
+    load_reference()
+    from legged_gym.utils.task_registry import task_registry
+    name = "high_level_game" if variant == "hl" else "dec_high_level_game"
+    cls = task_registry.get_task_class(name)
+    cfg = copy.deepcopy(task_registry.env_cfgs[name])
+    n = ll_env.num_envs
+    cfg.env.num_envs = n
+    for path, val in (cfg_overrides or {}).items():
+        obj = cfg
+        parts = path.split(".")
+        for p in parts[:-1]:
+            obj = getattr(obj, p)
+        setattr(obj, parts[-1], val)
+    g = object.__new__(cls)
+    g.cfg = cfg
+    g.device = "cpu"
+    g.headless = True
+    g.capture_dist = cfg.env.capture_dist
+    g.MAX_REL_POS = 100.
+    g.ll_env = ll_env
+    g.ll_policy = None
+    g._parse_cfg(cfg)
+    g.num_envs = n
+    g.reset_buf = torch.ones(n, dtype=torch.long)
+    g.episode_length_buf = torch.zeros(n, dtype=torch.long)
+    g.time_out_buf = torch.zeros(n, dtype=torch.bool)
+    g.curr_episode_step = torch.zeros(n, dtype=torch.long)
+    g.extras = {}
+    if variant == "hl":
+        g.num_obs, g.num_privileged_obs, g.num_actions = cfg.env.num_observations, cfg.env.num_privileged_obs, cfg.env.num_actions
+        g.obs_buf = g.MAX_REL_POS * torch.ones(n, g.num_obs, dtype=torch.float)
+        g.rew_buf = torch.zeros(n, dtype=torch.float)
+        g.privileged_obs_buf = None
+        g._init_buffers()
+        g._prepare_reward_function()
+    else:
+        g.num_obs_prey, g.num_obs_pred = cfg.env.num_observations_prey, cfg.env.num_observations_predator
+        g.num_actions_prey, g.num_actions_pred = cfg.env.num_actions_prey, cfg.env.num_actions_predator
+        g.num_privileged_obs_prey = g.num_privileged_obs_pred = None
+        g.obs_buf_prey = g.MAX_REL_POS * torch.ones(n, g.num_obs_prey, dtype=torch.float)
+        g.obs_buf_prey[:, 12:16] = 0
+        g.rew_buf_prey = torch.zeros(n, dtype=torch.float)
+        g.obs_buf_pred = g.MAX_REL_POS * torch.ones(n, g.num_obs_pred, dtype=torch.float)
+        g.rew_buf_pred = torch.zeros(n, dtype=torch.float)
+        g.privileged_obs_buf_pred = g.privileged_obs_buf_prey = None
+        g._init_buffers()
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            g._prepare_reward_function_pred()
+            g._prepare_reward_function_prey()
+    g.init_done = True
+    o_reset = cls.reset_idx
+
+    def reset(self_, env_ids):
+        tap.game = True
+        try:
+            return o_reset(self_, env_ids)
+        finally:
+            tap.game = False
+
+    g.reset_idx = types.MethodType(reset, g)
+    return g

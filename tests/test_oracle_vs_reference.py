@@ -44,6 +44,64 @@ def test_oracle_is_bit_exact_with_reference(task, n, ov):
         harness.perturb_state(st_or, step, 5)
 
 
+GAME_CASES = [("hl", 96, None), ("hl", 64, {"env.env_radius": 40.0, "rewards.scales.termination": -2.0, "rewards.only_positive_rewards": False}),
+              ("dec", 96, {"env.episode_length_s": 0.08}), ("dec", 64, {"rewards_prey.scales.termination": -3.0, "rewards_prey.only_positive_rewards": False})]
+
+
+@pytest.mark.parametrize("variant,n,ov", GAME_CASES)
+def test_game_oracle_is_bit_exact_with_reference(variant, n, ov):
+    """HighLevelGame / DecHighLevelGame (reference classes built around the reference LowLevelGame, low-level policy
+    replaced by fixed actions) against oracle/game_oracle.py: every buffer after each of 6 steps."""
+    import contextlib
+    import io
+    from oracle import game_oracle
+    ll_ov = {"env.episode_length_s": 0.1}
+    case = harness.build_case("low_level_game", n, seed=9, overrides=ll_ov)
+    st_ref, st_or = harness.torch_state(case), harness.torch_state(case)
+    harness.place_predators(st_ref, 9), harness.place_predators(st_or, 9)
+    hs = torch.from_numpy(case["height_samples"].copy())
+    ll_ref = ref_loader.make_ref_env("low_level_game", n, case["consts"], st_ref, height_samples=hs, cfg_overrides=ll_ov,
+                                     init_levels=case["init_levels"])
+    ll_ref.episode_length_buf[:] = torch.from_numpy(case["state"]["episode_length_buf"])
+    tap = ref_loader.attach_tap(ll_ref)
+    ref = ref_loader.make_ref_game(variant, ll_ref, tap, cfg_overrides=ov)
+    ref.predator_pos = st_ref["root_states"][1::2, :3].clone()
+    ll_or = harness.make_oracle(case, st_or)
+    import copy
+    cfg = copy.deepcopy(ref.cfg)
+    orc = game_oracle.GameOracle(cfg, ll_or, variant)
+    saw_reset = 0
+    for step in range(1, 7):
+        tables = harness.step_tables(case["seed"], step, n, ll_ref.num_obs)
+        prey, pred, acts = harness.game_inputs(case, step, variant)
+        tap.set_tables(tables)
+        ref.ll_policy = lambda obs: acts.clone()
+        with tap.active(), contextlib.redirect_stdout(io.StringIO()):
+            if variant == "hl":
+                ref.step(torch.cat((prey, pred), dim=1).clone())
+            else:
+                ref.step(pred.clone(), prey.clone())
+        if variant == "hl":
+            orc.step(torch.cat((prey, pred), dim=1).clone(), acts.clone(), tables)
+        else:
+            orc.step_dec(pred.clone(), prey.clone(), acts.clone(), tables)
+        a, b = game_oracle.snapshot(ref), game_oracle.snapshot(orc)
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), f"{variant} step {step}: {k} differs from the reference"
+        sa, sb = game_oracle.game_sums(ref), game_oracle.game_sums(orc)
+        assert sa.keys() == sb.keys()
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), f"{variant} step {step}: episode sum {k}"
+        la, lb = harness.snapshot(ll_ref), harness.snapshot(ll_or)
+        for k in la:
+            assert torch.equal(la[k], lb[k]), f"{variant} step {step}: low-level {k}"
+        saw_reset += int(a["reset_buf"].sum())
+        harness.perturb_state(st_ref, step, 5)
+        harness.perturb_state(st_or, step, 5)
+    assert saw_reset > 0
+
+
 def test_product_cfgs_equal_reference_cfgs():
     """The cfg mirror (dict-spec built classes) must carry exactly the reference's values."""
     ref_loader.load_reference()

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LGK_ABI_VERSION 2
+#define LGK_ABI_VERSION 3
 #define LGK_NUM_DOF 12          /* every registered task has 12 DOF = 12 actions */
 #define LGK_MAX_FEET 4
 #define LGK_MAX_PEN 16
@@ -48,7 +48,9 @@ enum {
 enum {
   LGK_STREAM_CMD = 0, LGK_STREAM_PUSH = 1, LGK_STREAM_RESET_DOF = 2, LGK_STREAM_RESET_ROOT = 3,
   LGK_STREAM_RESET_CMD = 4, LGK_STREAM_TERRAIN = 5, LGK_STREAM_OBS = 6, LGK_STREAM_ACT = 7,
-  LGK_STREAM_PREDATOR = 8
+  LGK_STREAM_PREDATOR = 8,
+  /* the high-level games reset the low-level root / dof state a second time within one step (HLG:326-347, DHLG:270-296) */
+  LGK_STREAM_GAME_ROOT = 9, LGK_STREAM_GAME_PREDATOR = 10, LGK_STREAM_GAME_DOF = 11
 };
 
 enum { LGK_CTRL_P = 0, LGK_CTRL_V = 1, LGK_CTRL_T = 2 };
@@ -203,6 +205,10 @@ typedef struct LgkStepParams {
    * push_interval), and finalize(advance=1) stores counter+1: a whole env step then has no per-step host-side
    * parameter and can be replayed as one CUDA graph. */
   int32_t* step_counter_dev;
+  /* optional output [N,4]: the root quaternion (xyzw) this step's rotations used, i.e. the pose BEFORE reset_idx.
+   * LowLevelGame keeps exactly this copy as `base_quat` until its next step (LLG:123), and the high-level games read
+   * it after the reset (HLG:432). */
+  float* base_quat;
 } LgkStepParams;
 
 int lgk_post_physics(const LgkStepParams* p, void* stream);
@@ -223,6 +229,66 @@ int lgk_step_debug_timeline(int64_t* device_buf16);
  * of time_out_buf into time_outs_extras; (c) clears the other ping-pong slot of reset_stats. */
 int lgk_finalize_step(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset_count,
                       float* episode_means, uint8_t* time_outs_extras, int32_t advance, void* stream);
+
+/* ------------------------------------------------------------------ hierarchical predator / prey games
+ * HighLevelGame.step after ll_env.step (legged_gym/envs/a1_game/high_level_game.py:178-239 = HLG) and
+ * DecHighLevelGame.step / post_physics_step (dec_high_level_game.py:204-261 = DHLG), one thread per env: predator
+ * single integrator (HLG:265-287), agent states (HLG:510-517), rewards evasion / pursuit / termination on top of the
+ * low-level reward (HLG:357-378, DHLG:321-361), capture / radius / time-out / low-level dones (HLG:190-236,
+ * DHLG:263-268), reset of the low-level root (and, DHLG, dof) state with predator re-spawn (LLG:384-451) and of the
+ * observation history (HLG:341-347), field-of-view sensing and the 4-frame history (HLG:380-482, DHLG:364-472).
+ * variant 0 = HighLevelGame (obs_prey and obs_pred point into one [N,19] buffer, columns 0 and 16; one reward: rew_prey
+ * with BOTH agents' terms in `prey`), 1 = DecHighLevelGame.  Reward terms are indexed LGK_G_EVASION.. in the
+ * reference's alphabetical order. */
+enum { LGK_G_EVASION = 0, LGK_G_PURSUIT = 1, LGK_G_TERMINATION = 2, LGK_G_COUNT = 3 };
+
+typedef struct {
+  int32_t active[LGK_G_COUNT];        /* scale != 0 */
+  float scale[LGK_G_COUNT];           /* cfg scale * low-level dt (HLG:546) */
+  int32_t slot[LGK_G_COUNT];          /* row of `sums` */
+  int32_t only_positive;
+  float* sums;                        /* [num slots, N] episode sums */
+  float* rew;                         /* [N] */
+} LgkGameAgent;
+
+typedef struct {
+  int32_t num_envs, variant, decimation, custom_origins;
+  int32_t step;                       /* RNG counter word (the game's own step count) */
+  int32_t has_env_radius, reset_dofs;
+  int32_t reset_only;                 /* 1: reset_idx on the envs flagged in ll_dones and nothing else (HLG:351-355 reset()) */
+  uint64_t seed;
+  int64_t env_id_offset;
+  float sim_dt, capture_dist, env_radius, max_episode_length, half_fov, max_rel_pos, ll_rew_weight, pad0;
+  float base_init_state[13];
+  float default_dof_pos[LGK_NUM_DOF];
+  float pad1[3];
+  LgkGameAgent prey, pred;            /* variant 0 uses `prey` only (rew = ll_rew_weight * ll_rews + terms) */
+  float* root_states;                 /* [2N,13]: prey row 2i, predator row 2i+1 (LLG:799-812) */
+  float* dof_state;                   /* [N*12,2] (reset_dofs only) */
+  const float* env_origins;           /* [N,3] of the low-level env */
+  const float* base_quat;             /* [N,4] LowLevelGame.base_quat (pre-reset copy, see LgkStepParams.base_quat) */
+  const float* command_pred;          /* predator command rows, 2 used floats */
+  int64_t command_pred_stride;        /* floats between rows (6 for HLG's [N,6] command, 2 for DHLG) */
+  const float* ll_rews;               /* [N] */
+  const uint8_t* ll_dones;            /* [N] bool: the low-level reset_buf */
+  float* predator_pos;                /* [N,3] the game's own copy, carried between steps (HLG:280-286, 517) */
+  float* prey_states;                 /* [N,13] out (HLG:512) */
+  float* obs_prey; int64_t obs_prey_stride;   /* 16 columns used */
+  float* obs_pred; int64_t obs_pred_stride;   /* 3 columns used */
+  uint8_t* reset_buf;                 /* [N] bool in/out (the termination reward reads the PREVIOUS value) */
+  uint8_t* time_out_buf;              /* [N] bool */
+  int64_t* episode_length_buf;        /* [N] */
+  int64_t* curr_episode_step;         /* [N] */
+  float* reset_stats;                 /* [prey slots + pred slots + 1] zeroed by the caller: sums of the episode sums
+                                       * over the envs reset this step, then the reset count (DHLG:298-306) */
+  int32_t num_prey_slots, num_pred_slots;
+  /* 8 int32 of device scratch, zero at allocation and left zero by every launch.  sense_predator flattens a [K,2]
+   * nonzero() result (HLG:456-458), so env 0 is in its "occluded" id list whenever ANY env is occluded and keeps its
+   * previous sensed position then; the last CTA to finish applies that to env 0's row. */
+  int32_t* scratch;
+} LgkGameParams;
+
+int lgk_game_step(const LgkGameParams* p, void* stream);
 
 /* ------------------------------------------------------------------ height field (LR:831-869) */
 /* min3[r,c] = min(hs[r,c], hs[r+1,c], hs[r,c+1]) for r<=rows-2, c<=cols-2 (the three samples LR:863-867
@@ -313,7 +379,7 @@ int lgk_set_fused_scan_warps(int n);
 int lgk_l2_flush(void* scratch, int64_t bytes, void* stream);
 /* number of kernel launches issued through this library since load (bench's gpu_launches). */
 int64_t lgk_launch_count(void);
-/* sizeof() of the parameter structs as compiled (0 Torque, 1 LstmWeights, 2 Step, 3 Policy): lets a foreign-language
+/* sizeof() of the parameter structs as compiled (0 Torque, 1 LstmWeights, 2 Step, 3 Policy, 4 Game): lets a foreign-language
  * binding (ctypes / cgo / JNI) verify its mirror of the layout before the first call. */
 int lgk_struct_size(int which);
 

@@ -69,7 +69,31 @@ class StepParams(C.Structure):
         ("base_lin_vel", vp), ("base_ang_vel", vp), ("projected_gravity", vp), ("measured_heights", vp),
         ("obs_buf", vp), ("rew_buf", vp), ("reset_buf", vp), ("time_out_buf", vp),
         ("height_min3", vp), ("height_points_xy", vp), ("noise_scale_vec", vp), ("reset_stats", vp),
-        ("scan_frames", vp), ("step_counter_dev", vp)]
+        ("scan_frames", vp), ("step_counter_dev", vp), ("base_quat", vp)]
+
+
+GAME_TERMS = ["evasion", "pursuit", "termination"]        # LGK_G_* (alphabetical, like class_to_dict)
+
+
+class GameAgent(C.Structure):
+    _fields_ = [("active", i32 * 3), ("scale", f32 * 3), ("slot", i32 * 3), ("only_positive", i32), ("sums", vp), ("rew", vp)]
+
+
+class GameParams(C.Structure):
+    _fields_ = [
+        ("num_envs", i32), ("variant", i32), ("decimation", i32), ("custom_origins", i32),
+        ("step", i32), ("has_env_radius", i32), ("reset_dofs", i32), ("reset_only", i32),
+        ("seed", u64), ("env_id_offset", i64),
+        ("sim_dt", f32), ("capture_dist", f32), ("env_radius", f32), ("max_episode_length", f32), ("half_fov", f32),
+        ("max_rel_pos", f32), ("ll_rew_weight", f32), ("pad0", f32),
+        ("base_init_state", f32 * 13), ("default_dof_pos", f32 * 12), ("pad1", f32 * 3),
+        ("prey", GameAgent), ("pred", GameAgent),
+        ("root_states", vp), ("dof_state", vp), ("env_origins", vp), ("base_quat", vp),
+        ("command_pred", vp), ("command_pred_stride", i64), ("ll_rews", vp), ("ll_dones", vp),
+        ("predator_pos", vp), ("prey_states", vp), ("obs_prey", vp), ("obs_prey_stride", i64),
+        ("obs_pred", vp), ("obs_pred_stride", i64), ("reset_buf", vp), ("time_out_buf", vp),
+        ("episode_length_buf", vp), ("curr_episode_step", vp), ("reset_stats", vp),
+        ("num_prey_slots", i32), ("num_pred_slots", i32), ("scratch", vp)]
 
 
 class PolicyParams(C.Structure):
@@ -110,14 +134,15 @@ def _load():
     lib.lgk_l2_flush.argtypes = [vp, i64, vp]
     lib.lgk_struct_size.argtypes = [C.c_int]
     lib.lgk_set_pdl.argtypes = [C.c_int]
+    lib.lgk_game_step.argtypes = [C.POINTER(GameParams), vp]
     lib.lgk_set_fused.argtypes = [C.c_int]
     lib.lgk_set_fused_scan_warps.argtypes = [C.c_int]
     lib.lgk_step_debug_timeline.argtypes = [vp]
-    for which, cls in enumerate((TorqueParams, LstmWeights, StepParams, PolicyParams)):
+    for which, cls in enumerate((TorqueParams, LstmWeights, StepParams, PolicyParams, GameParams)):
         n = lib.lgk_struct_size(which)
         if n != C.sizeof(cls):
             raise ImportError(f"liblgk.so struct {cls.__name__} is {n} bytes, ctypes mirror is {C.sizeof(cls)}: rebuild")
-    if lib.lgk_abi_version() != 2:
+    if lib.lgk_abi_version() != 3:
         raise ImportError("liblgk.so ABI version mismatch")
     return lib
 
@@ -125,7 +150,7 @@ def _load():
 lib = _load()
 
 EXPORTS = ["lgk_set_lstm_weights", "lgk_compute_torques", "lgk_post_physics", "lgk_reset_idx", "lgk_finalize_step",
-           "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline", "lgk_set_pdl", "lgk_set_fused", "lgk_set_fused_scan_warps", "lgk_step_debug_timeline",
+           "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline", "lgk_set_pdl", "lgk_game_step", "lgk_set_fused", "lgk_set_fused_scan_warps", "lgk_step_debug_timeline",
            "lgk_gae", "lgk_last_error_string", "lgk_abi_version", "lgk_l2_flush", "lgk_launch_count",
            "lgk_struct_size"]
 

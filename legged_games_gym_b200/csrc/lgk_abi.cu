@@ -69,6 +69,7 @@ extern "C" int lgk_struct_size(int which) {
     case 1: return (int)sizeof(LgkLstmWeights);
     case 2: return (int)sizeof(LgkStepParams);
     case 3: return (int)sizeof(LgkPolicyParams);
+    case 4: return (int)sizeof(LgkGameParams);
     default: return -1;
   }
 }

@@ -321,6 +321,8 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
         const YawFrame yf = yaw_frame(root[5], root[6], root[0], root[1]);
         *reinterpret_cast<float4*>(s_frame + e * kFrameFloats) = make_float4(yf.zn, yf.wn, yf.rx, yf.ry);
       }
+      if (p.base_quat != nullptr && valid)      // LowLevelGame.base_quat: the pose the rotations below use, kept past reset_idx
+        *reinterpret_cast<float4*>(p.base_quat + (size_t)env * 4) = make_float4(root[3], root[4], root[5], root[6]);
       env_finish(p, do_push, key, genv, root, cmd, sums, kTile, s_ep[e], mine, s);
       s_blv[3 * e] = s.blv.x; s_blv[3 * e + 1] = s.blv.y; s_blv[3 * e + 2] = s.blv.z;
       s_bav[3 * e] = s.bav.x; s_bav[3 * e + 1] = s.bav.y; s_bav[3 * e + 2] = s.bav.z;

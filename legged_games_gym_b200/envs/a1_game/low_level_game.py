@@ -36,8 +36,9 @@ class LowLevelGame(LeggedRobot):
     def _init_buffers(self):
         super()._init_buffers()
         n = self.num_envs
-        # a strided VIEW of the prey rows: always current, where the reference re-copies it every step (LLG:123)
-        self.base_quat = self.root_states.view(n, 2, 13)[:, 0, 3:7]
+        # the reference re-copies the prey quaternions at the top of every post_physics_step (LLG:123) and keeps that copy
+        # past reset_idx (the high-level games read it then, HLG:432): the step kernel writes it (LgkStepParams.base_quat)
+        self.base_quat = self.root_states.view(n, 2, 13)[:, 0, 3:7].clone()
         # LLG:538-558 -- initial predator position (init-time draw from torch's global generator, like the reference)
         init_prey_pos = self.root_states[self.prey_indices, :3].detach().clone()
         rand_offset = torch.zeros_like(init_prey_pos).uniform_(1.0, 10.0)
@@ -48,6 +49,7 @@ class LowLevelGame(LeggedRobot):
 
     def _configure_native(self, p):
         p.predator_spawn, p.predator_actor_offset = 1, 1
+        p.base_quat = self.base_quat.data_ptr()
 
     def _push_resets_to_sim(self):
         # LLG:441-451: dof states and root states of the prey actors, then root states of the predator actors

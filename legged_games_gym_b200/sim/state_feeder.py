@@ -98,6 +98,9 @@ class SimBackend:
     def set_actor_root_state_tensor(self, root_states):
         pass
 
+    def set_dof_state_tensor(self, dof_state):
+        pass
+
     # init-time domain randomisation (the reference writes these into PhysX shape / body properties, LR:261-283, 316-327)
     def set_rigid_shape_friction(self, friction_coeffs):
         self.friction_coeffs = friction_coeffs

@@ -108,6 +108,25 @@ def step_tables(seed, step, num_envs, num_obs, num_dof=12, env_offset=0):
     }
 
 
+def game_ll_overrides(game_cfg):
+    """What the games' constructors change in the low-level cfg before building the low-level env (HLG:69-85)."""
+    return {"terrain.num_rows": game_cfg.terrain.num_rows, "terrain.num_cols": game_cfg.terrain.num_cols,
+            "terrain.curriculum": game_cfg.terrain.curriculum, "terrain.mesh_type": game_cfg.terrain.mesh_type,
+            "noise.add_noise": game_cfg.noise.add_noise,
+            "domain_rand.randomize_friction": game_cfg.domain_rand.randomize_friction,
+            "domain_rand.push_robots": game_cfg.domain_rand.push_robots, "rewards.scales.torques": -5.}
+
+
+def product_game_cfg(variant, num_envs, overrides=None):
+    import importlib
+    mod, cls = (("envs.a1_game.high_level_game_flat_config", "HighLevelGameFlatCfg") if variant == "hl"
+                else ("envs.a1_game.dec_high_level_game_config", "DecHighLevelGameCfg"))
+    cfg = getattr(importlib.import_module("legged_games_gym_b200." + mod), cls)()
+    cfg.env.num_envs = num_envs
+    apply_overrides(cfg, overrides)
+    return cfg
+
+
 def game_inputs(case, step, variant):
     """Seeded high-level commands of one game step: prey command [N,4] and predator command [N,2] (scaled so that
     the clips of HLG:162-169 trigger), plus low-level actions [N,12]."""

@@ -11,8 +11,8 @@ import pytest
 import torch
 
 from oracle import harness, philox
-from oracle.make_golden import CASES, GOLDEN_DIR, build
-from tests.util import product_env, feeder_state, assert_snapshots_close
+from oracle.make_golden import CASES, GAME_CASES, GOLDEN_DIR, build, build_game
+from tests.util import product_env, product_game, feeder_state, assert_snapshots_close
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -247,6 +247,90 @@ def test_fused_post_physics_kernel_equals_two_kernel_chain(task, n, ov, sw):
         lib.lgk_set_fused(0)
         lib.lgk_set_fused_scan_warps(0)
     assert nat().launch_count() > before
+
+
+GAME_STEP_CASES = [("hl", 96, None, None), ("hl", 200, {"env.env_radius": 40.0, "rewards.scales.termination": -2.0, "rewards.only_positive_rewards": False}, None),
+              ("dec", 96, {"env.episode_length_s": 0.08}, {"terrain.mesh_type": "plane", "terrain.curriculum": False}),
+              ("dec", 160, {"rewards_prey.scales.termination": -3.0, "rewards_prey.only_positive_rewards": False},
+               {"terrain.mesh_type": "plane", "terrain.curriculum": False})]
+
+
+@pytest.mark.parametrize("variant,n,ov,ll_ov", GAME_STEP_CASES)
+def test_high_level_games_match_oracle(variant, n, ov, ll_ov):
+    """HighLevelGame / DecHighLevelGame (lgk_game_step on top of the LowLevelGame kernels) against oracle/game_oracle.py,
+    which tests/test_oracle_vs_reference.py pins bit-exactly to the reference classes: masks, counters and the sensing
+    bits exact, fp32 within 1e-5, over 6 steps with captures, time-outs, low-level dones and occluded predators."""
+    import copy
+    from oracle import game_oracle
+    ll_over = {"env.episode_length_s": 0.1}
+    ll_over.update(ll_ov or {})
+    case = harness.build_case("low_level_game", n, seed=9, overrides=ll_over)
+    case["state"]["root_states"] = case["state"]["root_states"].copy()
+    st_or = harness.torch_state(case)
+    harness.place_predators(st_or, 9)
+    case["state"]["root_states"] = st_or["root_states"].numpy().copy()
+    acts_box = {}
+    game, feeder = product_game(case, variant, ov, ll_policy=lambda obs: acts_box["a"])
+    st_gpu = feeder_state(feeder)
+    game.predator_pos.copy_(st_gpu["root_states"][1::2, :3])
+    case_or = dict(case, cfg=copy.deepcopy(game.ll_env.cfg))
+    ll_or = harness.make_oracle(case_or, st_or)
+    orc = game_oracle.GameOracle(copy.deepcopy(game.cfg), ll_or, variant)
+    saw_reset = saw_occluded = 0
+    for step in range(1, 7):
+        tables = harness.step_tables(case["seed"], step, n, ll_or.num_obs)
+        prey, pred, acts = harness.game_inputs(case, step, variant)
+        acts_box["a"] = acts.to(DEV)
+        if variant == "hl":
+            orc.step(torch.cat((prey, pred), dim=1).clone(), acts.clone(), tables)
+            game.step(torch.cat((prey, pred), dim=1).to(DEV))
+        else:
+            orc.step_dec(pred.clone(), prey.clone(), acts.clone(), tables)
+            game.step(pred.to(DEV), prey.to(DEV))
+        torch.cuda.synchronize()
+        a, b = game_oracle.snapshot(game), game_oracle.snapshot(orc)
+        a = {k: v for k, v in a.items() if k in b}
+        assert_snapshots_close(a, b, f"{variant}/{step}", exact=("reset_buf", "time_out_buf", "episode_length_buf", "curr_episode_step"))
+        obs_a, obs_b = (a["obs_buf"], b["obs_buf"]) if variant == "hl" else (a["obs_buf_prey"], b["obs_buf_prey"])
+        assert torch.equal(obs_a[:, 12:16], obs_b[:, 12:16]), "field-of-view sensing bits must be exact"
+        sa, sb = game_oracle.game_sums(game), game_oracle.game_sums(orc)
+        assert sa.keys() == sb.keys()
+        assert_snapshots_close(sa, sb, f"{variant}/{step} sums")
+        assert_snapshots_close(harness.snapshot(game.ll_env), harness.snapshot(ll_or), f"{variant}/{step} low-level",
+                               atol_scale={"torques": max(1.0, float(ll_or.torques.abs().max()))})
+        saw_reset += int(b["reset_buf"].sum())
+        saw_occluded += int((obs_b[:, 15] == 0).sum())
+        noise = harness.make_noise(case, step, 5)
+        harness.apply_noise(st_or, noise)
+        harness.apply_noise(st_gpu, noise)
+    assert saw_reset > 0 and saw_occluded > 0
+
+
+@pytest.mark.parametrize("name", sorted(GAME_CASES))
+def test_high_level_games_match_reference_fixture(name):
+    """The product games against tests/golden/*high_level_game*.npz = outputs of the UNMODIFIED reference classes."""
+    from oracle import game_oracle
+    from tests.test_golden import check_game_snapshot
+    spec = GAME_CASES[name]
+    fx = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    case, gcfg, _ = build_game(spec)
+    acts_box = {}
+    game, feeder = product_game(case, spec["variant"], spec["overrides"], ll_policy=lambda obs: acts_box["a"])
+    st_gpu = feeder_state(feeder)
+    game.predator_pos.copy_(st_gpu["root_states"][1::2, :3])
+    for step in range(1, spec["steps"] + 1):
+        prey, pred, acts = (torch.from_numpy(fx[f"s{step}_{k}"].copy()).to(DEV) for k in ("prey", "pred", "actions"))
+        acts_box["a"] = acts
+        if spec["variant"] == "hl":
+            game.step(torch.cat((prey, pred), dim=1))
+        else:
+            game.step(pred, prey)
+        torch.cuda.synchronize()
+        snap = {k: v for k, v in game_oracle.snapshot(game).items() if f"s{step}_{k}" in fx}
+        assert {k for k in fx.files if k.startswith(f"s{step}_ex_")} <= {f"s{step}_{k}" for k in snap}
+        check_game_snapshot(fx, step, snap, game_oracle.game_sums(game), name, 1e-5, 1e-5)
+        assert np.allclose(game.ll_env.obs_buf.cpu().numpy(), fx[f"s{step}_ll_obs_buf"], rtol=1e-5, atol=1e-5 * 100)
+        harness.apply_noise(st_gpu, {k: fx[f"s{step}_noise_{k}"] for k in ("dof_state", "contact_forces", "root_vel", "root_xy")})
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

@@ -118,6 +118,12 @@ def test_product_cfgs_equal_reference_cfgs():
     from legged_games_gym_b200.envs import LowLevelGameCfg, LowLevelGamePPO
     assert class_to_dict(LowLevelGameCfg()) == {k: v for k, v in ref_c2d(ref_reg.env_cfgs["low_level_game"]).items() if k != "seed"}
     assert class_to_dict(LowLevelGamePPO()) == ref_c2d(ref_reg.train_cfgs["low_level_game"])
+    for name in ("high_level_game", "dec_high_level_game"):
+        a, b = class_to_dict(type(task_registry.env_cfgs[name])()), ref_c2d(ref_reg.env_cfgs[name])
+        b.pop("seed", None)
+        assert a == b, f"cfg mismatch for {name}"
+        assert class_to_dict(type(task_registry.train_cfgs[name])()) == ref_c2d(ref_reg.train_cfgs[name])
+    assert sorted(task_registry.task_classes) == sorted(ref_reg.task_classes)        # all eight tasks are registered
 
 
 def test_lstm_plain_restatement_matches_aten_lstm():

@@ -50,6 +50,50 @@ def product_env(case, device="cuda:0", graph=False, tile=0):
     return env, feeder
 
 
+def product_game(case, variant, overrides=None, ll_policy=None, device="cuda:0"):
+    """The PRODUCT HighLevelGame ("hl") / DecHighLevelGame ("dec") around a LowLevelGame fed by the case's state."""
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.sim.state_feeder import SimBackend
+    from legged_games_gym_b200.utils.helpers import SimParams
+
+    class ExplicitFeeder(SimBackend):
+        graph_safe = False
+
+        def __init__(self, st):
+            self.root_states = torch.from_numpy(st["root_states"].copy()).to(device)
+            self.dof_state = torch.from_numpy(st["dof_state"].copy()).to(device)
+            self.contact_forces = torch.from_numpy(st["contact_forces"].copy()).to(device)
+
+        def acquire_actor_root_state_tensor(self):
+            return self.root_states
+
+        def acquire_dof_state_tensor(self):
+            return self.dof_state
+
+        def acquire_net_contact_force_tensor(self):
+            return self.contact_forces
+
+    name = "high_level_game" if variant == "hl" else "dec_high_level_game"
+    cfg = copy.deepcopy(task_registry.env_cfgs[name])
+    cfg.env.num_envs = case["cfg"].env.num_envs
+    harness.apply_overrides(cfg, overrides)
+    ll_cfg = copy.deepcopy(case["cfg"])
+    ll_cfg.seed = case["seed"]
+    terrain = None
+    if case["height_samples"] is not None:
+        hs = case["height_samples"]
+        terrain = types.SimpleNamespace(cfg=ll_cfg.terrain, env_length=ll_cfg.terrain.terrain_length,
+                                        env_width=ll_cfg.terrain.terrain_width, heightsamples=hs, tot_rows=hs.shape[0],
+                                        tot_cols=hs.shape[1], env_origins=case["terrain_origins"])
+    feeder = ExplicitFeeder(case["state"])
+    cls = task_registry.get_task_class(name)
+    game = cls(cfg=cfg, sim_params=SimParams(dt=ll_cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
+               sim_device=device, headless=True, ll_policy=ll_policy, ll_env_cfg=ll_cfg, sim_backend=feeder,
+               terrain=terrain, init_terrain_levels=case["init_levels"])
+    game.ll_env.episode_length_buf[:] = torch.from_numpy(case["state"]["episode_length_buf"]).to(device)
+    return game, feeder
+
+
 def feeder_state(feeder):
     return dict(root_states=feeder.root_states, dof_state=feeder.dof_state, contact_forces=feeder.contact_forces)
 

@@ -91,6 +91,26 @@ def get_load_path(root, load_run=-1, checkpoint=-1):
     return os.path.join(load_run, model)
 
 
+def get_dec_load_path(root, agent_id, load_run=-1, checkpoint=-1):
+    """helpers.py:127-156: checkpoints of the decentralised game, ``pred_model_<n>.pt`` (agent 0) / ``prey_model_<n>.pt``"""
+    try:
+        runs = sorted(os.listdir(root))
+        if "exported" in runs:
+            runs.remove("exported")
+        last_run = os.path.join(root, runs[-1])
+    except Exception:
+        raise ValueError("No runs in this directory: " + root)
+    load_run = last_run if load_run == -1 else os.path.join(root, load_run)
+    agent_name = "pred" if agent_id == 0 else "prey"
+    if checkpoint == -1:
+        models = [f for f in os.listdir(load_run) if agent_name + "_model_" in f]
+        models.sort(key=lambda m: "{0:0>15}".format(m))
+        model = models[-1]
+    else:
+        model = (agent_name + "_model_{}.pt").format(checkpoint)
+    return os.path.join(load_run, model)
+
+
 def update_cfg_from_args(env_cfg, cfg_train, args):
     if env_cfg is not None and getattr(args, "num_envs", None) is not None:
         env_cfg.env.num_envs = args.num_envs

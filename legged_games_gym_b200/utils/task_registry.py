@@ -1,10 +1,10 @@
 """TaskRegistry (mirror of reference legged_gym/utils/task_registry.py:44-224: register / get_task_class / get_cfgs /
-make_env / make_alg_runner, same signatures)."""
+make_env / make_alg_runner / make_dec_alg_runner, same signatures)."""
 import os
 from datetime import datetime
 
 from .. import LEGGED_GYM_ROOT_DIR
-from .helpers import get_args, update_cfg_from_args, class_to_dict, get_load_path, set_seed, parse_sim_params
+from .helpers import get_args, update_cfg_from_args, class_to_dict, get_load_path, get_dec_load_path, set_seed, parse_sim_params
 
 
 class TaskRegistry:
@@ -43,7 +43,14 @@ class TaskRegistry:
         return env, env_cfg
 
     def make_alg_runner(self, env, name=None, args=None, train_cfg=None, log_root="default"):
-        from ..rsl_rl.runners import OnPolicyRunner
+        return self._make_runner(False, env, name, args, train_cfg, log_root)
+
+    def make_dec_alg_runner(self, env, name=None, args=None, train_cfg=None, log_root="default"):
+        """task_registry.py:172-221: the two-agent runner of dec_high_level_game"""
+        return self._make_runner(True, env, name, args, train_cfg, log_root)
+
+    def _make_runner(self, dec, env, name, args, train_cfg, log_root):
+        from ..rsl_rl.runners import OnPolicyRunner, DecGamePolicyRunner
         if args is None:
             args = get_args()
         if train_cfg is None:
@@ -60,6 +67,15 @@ class TaskRegistry:
             log_dir = None
         else:
             log_dir = os.path.join(log_root, datetime.now().strftime("%b%d_%H-%M-%S") + "_" + train_cfg.runner.run_name)
+        if dec:
+            runner = DecGamePolicyRunner(env, class_to_dict(train_cfg), log_dir, device=args.rl_device)
+            if train_cfg.runner.resume:
+                for agent_id, label in ((0, "PREDATOR"), (1, "PREY")):
+                    path = get_dec_load_path(log_root, agent_id=agent_id, load_run=train_cfg.runner.load_run,
+                                             checkpoint=train_cfg.runner.checkpoint)
+                    print(f"Loading {label} model from: {path}")
+                    runner.load(agent_id=agent_id, path=path)
+            return runner, train_cfg
         runner = OnPolicyRunner(env, class_to_dict(train_cfg), log_dir, device=args.rl_device)
         if train_cfg.runner.resume:
             resume_path = get_load_path(log_root, load_run=train_cfg.runner.load_run, checkpoint=train_cfg.runner.checkpoint)

@@ -4,6 +4,7 @@ checkpoints with the reference's model_<it>.pt layout, scripts/play.py (resume, 
 import glob
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -83,3 +84,58 @@ def test_graphed_ppo_update_matches_eager_update():
     for a, b in zip(p0, p1):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
     assert any(not torch.equal(a, torch.zeros_like(a)) for a in p1)
+
+
+def _random_ll_policy(dev, seed=0):
+    """a frozen low-level locomotion policy with the A1 cfg's shape (the reference loads a trained one from a checkpoint
+    that is not in its tree)"""
+    from legged_games_gym_b200.rsl_rl.modules import ActorCritic
+    torch.manual_seed(seed)
+    ac = ActorCritic(235, 235, 12, [512, 256, 128], [512, 256, 128]).to(dev).eval()
+    return ac.act_inference
+
+
+def test_high_level_game_trains_and_plays(tmp_path):
+    """scripts/train.py and scripts/play_game.py flow on high_level_game: OnPolicyRunner on the 19-float observation /
+    6-command action space, checkpoint, reload, TorchScript export, roll-out."""
+    from legged_games_gym_b200.scripts.play_game import play_game
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.utils import get_args
+    dev = "cuda:0"
+    root = str(tmp_path / "logs")
+    a = get_args(["--task", "high_level_game", "--num_envs", "256", "--headless", "--max_iterations", "2", "--sim_device", dev, "--rl_device", dev])
+    env, _ = task_registry.make_env(name=a.task, args=a, ll_policy=_random_ll_policy(dev))
+    runner, train_cfg = task_registry.make_alg_runner(env=env, name=a.task, args=a, log_root=root)
+    v, s_ = runner.learn(num_learning_iterations=2, init_at_random_ep_len=True)
+    assert np.isfinite(v) and np.isfinite(s_)
+    assert env.obs_buf.shape == (256, 19) and torch.isfinite(env.obs_buf).all() and torch.isfinite(env.rew_buf).all()
+    assert int(env.curr_episode_step.max()) > 0
+    env2, exported = play_game(a, num_steps=20, log_root=root, ll_policy=_random_ll_policy(dev))
+    assert os.path.exists(os.path.join(exported, "policy_1.pt"))
+    assert env2.cfg.terrain.mesh_type == "plane"         # play_game's overrides (an explicit --num_envs wins, as in the reference)
+    assert torch.isfinite(env2.obs_buf).all()
+
+
+def test_dec_high_level_game_trains_and_plays(tmp_path):
+    """scripts/train_dec_game.py and scripts/play_dec_game.py flow: two PPO agents in alternating evolutions, per-agent
+    checkpoints (pred_model_*.pt / prey_model_*.pt), reload through make_dec_alg_runner."""
+    from legged_games_gym_b200.scripts.play_dec_game import play_dec_game
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.utils import get_args
+    dev = "cuda:0"
+    root = str(tmp_path / "logs")
+    a = get_args(["--task", "dec_high_level_game", "--num_envs", "256", "--headless", "--sim_device", dev, "--rl_device", dev])
+    env, _ = task_registry.make_env(name=a.task, args=a, ll_policy=_random_ll_policy(dev))
+    runner, train_cfg = task_registry.make_dec_alg_runner(env=env, name=a.task, args=a, log_root=root)
+    before = [p.detach().clone() for alg in runner.algs for p in alg.actor_critic.actor.parameters()]
+    losses = runner.learn(max_num_evolutions=2, num_learning_iterations=1, init_at_random_ep_len=True)
+    assert all(np.isfinite(x) for x in losses)
+    after = [p.detach() for alg in runner.algs for p in alg.actor_critic.actor.parameters()]
+    assert any(not torch.equal(x, y) for x, y in zip(before[:len(before) // 2], after[:len(after) // 2])), "predator did not learn"
+    assert any(not torch.equal(x, y) for x, y in zip(before[len(before) // 2:], after[len(after) // 2:])), "prey did not learn"
+    run = os.path.join(root, sorted(os.listdir(root))[-1])
+    assert {"pred_model_1.pt", "prey_model_1.pt"} <= set(os.listdir(run))
+    assert "rew_prey_evasion" in env.extras["episode"] and "rew_pred_pursuit" in env.extras["episode"]
+    env2 = play_dec_game(a, num_steps=20, log_root=root, ll_policy=_random_ll_policy(dev))
+    assert env2.cfg.noise.add_noise is False
+    assert torch.isfinite(env2.obs_buf_prey).all() and torch.isfinite(env2.obs_buf_pred).all()

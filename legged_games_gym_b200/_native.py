@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblgk.so")
+LIB_PATH = os.environ.get("LGK_LIB_PATH") or os.path.join(_HERE, "liblgk.so")      # override: A/B of kernel builds
 
 NUM_DOF, MAX_FEET, MAX_PEN, MAX_TERM, MAX_BODIES = 12, 4, 16, 8, 32
 PHASE_PRE, PHASE_POST = 1, 2

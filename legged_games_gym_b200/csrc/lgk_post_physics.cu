@@ -134,10 +134,10 @@ constexpr int kFrameFloats = 8;
 constexpr int kK1Threads = 4 * kTile;
 __device__ long long* g_k1_timeline = nullptr;     // profiling hook (lgk_step_debug_timeline): stamps of CTA 0
 __device__ __forceinline__ void k1_stamp(int slot) {
-  if (g_k1_timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (g_k1_timeline != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || (blockIdx.x == gridDim.x - 1 && (slot == 1 || slot == 8)))) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    g_k1_timeline[slot] = (long long)t;
+    g_k1_timeline[blockIdx.x == 0 ? slot : (slot == 1 ? 13 : 14)] = (long long)t;      // 13 / 14: last CTA after the wait / at its end
   }
 }
 
@@ -164,7 +164,10 @@ LGK_COLD void refresh_reset_height_obs(const LgkStepParams& p, const RngKey& key
 // 4.. are scan warps that run K2's work for the same 32 envs concurrently (the role warps' dependent chain leaves the
 // issue slots the scan warps need); the un-noised observation head never leaves shared memory.
 template <int G, bool RECIP>
-__global__ void __launch_bounds__(G > 0 ? kK1Threads + 256 : kK1Threads, G > 0 ? 2 : 7)
+#ifndef LGK_K1_MINBLOCKS
+#define LGK_K1_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(G > 0 ? kK1Threads + 256 : kK1Threads, G > 0 ? 2 : LGK_K1_MINBLOCKS)
 post_kernel(const __grid_constant__ LgkStepParams p) {
   constexpr bool FUSED = G > 0;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -225,10 +228,7 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
     if (tid == 0) {
       uint32_t bytes = kTile * (13 + 24 + 3 * NB + 12 + 12 + 12 + 12 + 4) * 4;
       if (F > 0) bytes += kTile * F * 4 + kTile * F;
-      bytes += K * kTile * 4 + kTile * 8;
       mbar_expect_tx(bar, bytes);
-      for (int k = 0; k < K; ++k) bulk_g2s(s_sums + k * kTile, p.episode_sums + (size_t)k * N + env0, kTile * 4, bar);
-      bulk_g2s(s_ep, p.episode_length_buf + env0, kTile * 8, bar);
       bulk_g2s(s_root, p.root_states + (size_t)env0 * 13, kTile * 13 * 4, bar);
       bulk_g2s(s_dof, p.dof_state + (size_t)env0 * 24, kTile * 24 * 4, bar);
       bulk_g2s(s_contact, p.contact_forces + (size_t)env0 * NB * 3, kTile * NB * 3 * 4, bar);
@@ -242,6 +242,12 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
         bulk_g2s(s_lc, p.last_contacts + (size_t)env0 * F, kTile * F, bar);
       }
     }
+  }
+  // per-env scalars (one 128-byte row segment per tensor and tile) come by plain coalesced loads, lane = env, issued while
+  // the bulk copies are in flight: 20 fewer bulk operations per tile (measured neutral for the kernel time)
+  if (bulk) {
+    for (int k = warp; k < K; k += 4) s_sums[k * kTile + lane] = p.episode_sums[(size_t)k * N + env0 + lane];
+    if (warp == (K & 3)) s_ep[lane] = p.episode_length_buf[env0 + lane];
   }
   // the device step counter is read while the tile loads are in flight
   const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
@@ -392,10 +398,6 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
         if (do_push && !post) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
       }
       bulk_s2g(p.commands + (size_t)env0 * 4, s_cmd, kTile * 4 * 4);
-      for (int k = 0; k < K; ++k) bulk_s2g(p.episode_sums + (size_t)k * N + env0, s_sums + k * kTile, kTile * 4);
-      bulk_s2g(p.episode_length_buf + env0, s_ep, kTile * 8);
-      bulk_s2g(p.rew_buf + env0, s_rew, kTile * 4);
-      if (pre) { bulk_s2g(p.reset_buf + env0, s_flags, kTile); bulk_s2g(p.time_out_buf + env0, s_flags + kTile, kTile); }
       if (fat_active || (post && F > 0)) {
         bulk_s2g(p.feet_air_time + (size_t)env0 * F, s_fat, kTile * F * 4);
         if (pre) bulk_s2g(p.last_contacts + (size_t)env0 * F, s_lc, kTile * F);
@@ -409,6 +411,10 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
       }
       bulk_commit();
     }
+    for (int k = warp; k < K; k += 4) p.episode_sums[(size_t)k * N + env0 + lane] = s_sums[k * kTile + lane];
+    if (warp == (K & 3)) p.episode_length_buf[env0 + lane] = s_ep[lane];
+    if (warp == ((K + 1) & 3)) p.rew_buf[env0 + lane] = s_rew[lane];
+    if (pre && warp == ((K + 2) & 3)) { p.reset_buf[env0 + lane] = s_flags[lane]; p.time_out_buf[env0 + lane] = s_flags[kTile + lane]; }
   } else {
     if (pre) {
       copy_f32(p.base_lin_vel + (size_t)env0 * 3, s_blv, nval * 3, tid);

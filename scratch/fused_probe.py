@@ -21,7 +21,7 @@ for n in sizes:
         fns.append(lambda e=env: nat.lib.lgk_post_physics(C.byref(e._params), st))
     reps = 200 if n <= 16384 else 60
     res = {}
-    for label, fused, sw in (("chain", 0, 0), ("fused roles", 1, -1), ("fused sw=4", 1, 4), ("fused sw=8", 1, 8)):
+    for label, fused, sw in ((os.environ.get("LABEL", "chain"), 0, 0),):
         nat.lib.lgk_set_fused(fused)
         nat.lib.lgk_set_fused_scan_warps(sw)
         mean_s, best_s = bench.time_kernel(fns, reps)

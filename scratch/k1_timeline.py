@@ -12,5 +12,5 @@ for rep in range(3):
         e.step(f.synthetic_actions)
     torch.cuda.synchronize()
     t = tl.cpu().tolist()
-    print(N, "K1 stamps (ns from entry):", [t[i] - t[0] for i in range(9)], "scan warp 0 (start, frames, end):", [t[i] - t[0] for i in (9, 10, 11)], flush=True)
+    print(N, "K1 stamps (ns from entry):", [t[i] - t[0] for i in range(9)], "last CTA (after wait, end) rel. to CTA 0 after wait:", [t[i] - t[1] for i in (13, 14)], flush=True)
 nat.lib.lgk_step_debug_timeline(None)

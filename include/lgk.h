@@ -376,6 +376,11 @@ int lgk_set_fused(int enable);
 /* Scan warps per CTA of the fused kernel: 1..8, 0 = automatic (8 when the grid is at most two tiles per SM, else 4).
  * Returns the previous setting. */
 int lgk_set_fused_scan_warps(int n);
+/* Host-sim pipeline (the reference's sim_device=cpu: PhysX results are host tensors, LR:515-530 hand back host memory):
+ * stream-ordered, graph-capturable copies between PINNED (cudaHostAlloc / torch pin_memory) host memory and device
+ * memory done by a kernel over the unified address space instead of a memcpy node.  bytes % 16 == 0, 16-byte aligned. */
+int lgk_copy_from_pinned(void* dst_device, const void* src_pinned_host, int64_t bytes, void* stream);
+int lgk_copy_to_pinned(void* dst_pinned_host, const void* src_device, int64_t bytes, void* stream);
 /* Write `bytes` of a scratch buffer (L2 flush between timed iterations; bench only). */
 int lgk_l2_flush(void* scratch, int64_t bytes, void* stream);
 /* number of kernel launches issued through this library since load (bench's gpu_launches). */

@@ -8,6 +8,8 @@ device and fills them with the seeded synthetic distributions of SURVEY.md secti
 ``HostStateFeeder`` keeps the sim state in pinned HOST memory and copies across PCIe at the same API
 points where a CPU-pipeline PhysX would (the e2e leg of bench.py).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -151,13 +153,28 @@ class HostStateFeeder(StateFeeder):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    # tensors up to this size cross PCIe through a kernel over the unified address space (lgk_copy_*_pinned): inside a
+    # captured graph that is 1.2-2x faster than a memcpy node for the 4 KB - 1 MB transfers of an env step
+    # (scratch/pcie_probe.py); larger ones (the observation matrix) keep the copy engine
+    KERNEL_COPY_MAX_BYTES = int(os.environ.get("LGK_KERNEL_COPY_MAX", 1 << 20))
+
+    def _copy(self, dst, src, from_host):
+        nbytes = src.numel() * src.element_size()
+        if (nbytes <= self.KERNEL_COPY_MAX_BYTES and nbytes % 16 == 0 and dst.is_contiguous() and src.is_contiguous()
+                and dst.data_ptr() % 16 == 0 and src.data_ptr() % 16 == 0):
+            from .. import _native as nat
+            st = torch.cuda.current_stream().cuda_stream
+            fn = nat.lib.lgk_copy_from_pinned if from_host else nat.lib.lgk_copy_to_pinned
+            nat.check(fn(dst.data_ptr(), src.data_ptr(), nbytes, st), "lgk_copy_pinned")
+        else:
+            dst.copy_(src, non_blocking=True)
+        return nbytes
+
     def _h2d(self, dst, src):
-        dst.copy_(src, non_blocking=True)
-        self.h2d_bytes += src.numel() * src.element_size()
+        self.h2d_bytes += self._copy(dst, src, True)
 
     def _d2h(self, dst, src):
-        dst.copy_(src, non_blocking=True)
-        self.d2h_bytes += src.numel() * src.element_size()
+        self.d2h_bytes += self._copy(dst, src, False)
 
     def refresh_dof_state_tensor(self):
         self._h2d(self.dof_state, self.h_dof)

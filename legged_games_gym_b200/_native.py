@@ -5,6 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+ABI_VERSION = 3          # include/lgk.h LGK_ABI_VERSION
 LIB_PATH = os.environ.get("LGK_LIB_PATH") or os.path.join(_HERE, "liblgk.so")      # override: A/B of kernel builds
 
 NUM_DOF, MAX_FEET, MAX_PEN, MAX_TERM, MAX_BODIES = 12, 4, 16, 8, 32
@@ -144,7 +145,7 @@ def _load():
         n = lib.lgk_struct_size(which)
         if n != C.sizeof(cls):
             raise ImportError(f"liblgk.so struct {cls.__name__} is {n} bytes, ctypes mirror is {C.sizeof(cls)}: rebuild")
-    if lib.lgk_abi_version() != 3:
+    if lib.lgk_abi_version() != ABI_VERSION:
         raise ImportError("liblgk.so ABI version mismatch")
     return lib
 

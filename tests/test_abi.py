@@ -26,7 +26,7 @@ def test_struct_mirrors_match():
     from legged_games_gym_b200 import _native as nat
     for which, cls in enumerate((nat.TorqueParams, nat.LstmWeights, nat.StepParams, nat.PolicyParams, nat.GameParams)):
         assert nat.lib.lgk_struct_size(which) == ctypes.sizeof(cls)
-    assert nat.lib.lgk_abi_version() == 3
+    assert nat.lib.lgk_abi_version() == nat.ABI_VERSION == 3
 
 
 def test_argument_errors_are_codes_not_crashes():

@@ -360,6 +360,45 @@ def rollout_phase(dev, n_envs=4096, T=24, reps=20):
                                      peak_source="MEASURED_PEAKS.json bf16_tflops / 2"))
 
 
+def game_phase(dev, num_envs=2000, steps=200):
+    """high_level_game at the reference's own num_envs (high_level_game_flat_config.py:10): one high-level step = frozen
+    low-level policy act() + LowLevelGame step (graph) + lgk_game_step; reported beside the game kernel alone."""
+    import ctypes as C
+    import torch
+    from legged_games_gym_b200 import _native as nat
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.rsl_rl.modules import ActorCritic
+    from legged_games_gym_b200.utils import get_args
+    torch.manual_seed(0)
+    ll = ActorCritic(235, 235, 12, [512, 256, 128], [512, 256, 128]).to(dev).eval()
+    a = get_args(["--task", "high_level_game", "--num_envs", str(num_envs), "--headless", "--sim_device", dev, "--rl_device", dev])
+    with torch.inference_mode():
+        env, _ = task_registry.make_env(name="high_level_game", args=a, ll_policy=ll.act_inference)
+        cmd = torch.randn(num_envs, 6, device=dev)
+        for _ in range(10):
+            env.step(cmd.clone())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            env.step(cmd)
+        e1.record()
+        torch.cuda.synchronize()
+        step_s = e0.elapsed_time(e1) / 1e3 / steps
+        st = torch.cuda.current_stream().cuda_stream
+        e0.record()
+        for _ in range(steps):
+            nat.lib.lgk_game_step(C.byref(env._params), st)
+        e1.record()
+        torch.cuda.synchronize()
+        k_s = e0.elapsed_time(e1) / 1e3 / steps
+    del env
+    torch.cuda.empty_cache()
+    return dict(workload=f"high_level_game, {num_envs} envs: low-level act() + LowLevelGame step + lgk_game_step per high-level step",
+                us_per_step=round(step_s * 1e6, 2), env_steps_per_sec=round(num_envs / step_s, 1),
+                game_kernel_us=round(k_s * 1e6, 2))
+
+
 def train_iteration(dev, num_envs=4096, iters=4):
     """One PPO iteration of the reference's training flow (scripts/train.py: 24 rollout steps of anymal_c_rough + GAE +
     PPO.update with 5 epochs x 4 mini-batches) through task_registry / OnPolicyRunner: wall-clock of the last iteration.
@@ -507,6 +546,7 @@ def gpu_arm(args):
             torch.cuda.empty_cache()
     rollout = rollout_phase(dev)
     training = None if args.no_train else train_iteration(dev)
+    game = None if args.no_train else game_phase(dev)
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores
@@ -523,7 +563,7 @@ def gpu_arm(args):
                    "timing": "CUDA events on the launch stream around the K steps; barrier+synchronize both sides",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep, "rollout_phase": rollout, "train_iteration": training,
+        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep, "rollout_phase": rollout, "train_iteration": training, "game_phase": game,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -94,7 +94,9 @@ __device__ __forceinline__ YawFrame2 yaw_frame2(const YawFrame& f) {
 }
 
 // B = (bx, by), Bs = (by, bx)
-template <bool kRecipDiv>
+// kInRange: the caller has checked that the env's root position is below 1e17 m, so no quotient can reach 2^63 and the
+// saturating conversion alone reproduces .long() + clip (NaN -> 0 either way, negative overflow clips to 0 either way).
+template <bool kRecipDiv, bool kInRange = false>
 __device__ __forceinline__ void height_index2(const YawFrame2& f, f2_t B, f2_t Bs, float border, float hscale,
                                               float hrecip, float one, int rows, int cols, int& ix, int& iy) {
   const f2_t T = mul2(f.T, Bs);                 // (t0, t1) = (-(2zn*by), 2zn*bx)
@@ -118,8 +120,13 @@ __device__ __forceinline__ void height_index2(const YawFrame2& f, f2_t B, f2_t B
     qx = f_div(px, hscale); qy = f_div(py, hscale);
   }
   // .long(): truncation; x86 turns NaN / inf / |q| >= 2^63 into INT64_MIN, which the clip maps to 0
-  ix = qx < 9.2233720368547758e18f ? __float2int_rz(qx) : 0;
-  iy = qy < 9.2233720368547758e18f ? __float2int_rz(qy) : 0;
+  if (kInRange) {
+    ix = __float2int_rz(qx);
+    iy = __float2int_rz(qy);
+  } else {
+    ix = qx < 9.2233720368547758e18f ? __float2int_rz(qx) : 0;
+    iy = qy < 9.2233720368547758e18f ? __float2int_rz(qy) : 0;
+  }
   ix = min(max(ix, 0), rows - 2);
   iy = min(max(iy, 0), cols - 2);
 }

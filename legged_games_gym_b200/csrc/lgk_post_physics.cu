@@ -24,6 +24,7 @@
 //  the pre-reset root z, redone by a role warp for the rare reset env; the 48-column head never leaves shared memory).
 //  Bit-identical to the chain, one launch less, but measured slower on B200.
 #include <stdlib.h>
+#include <type_traits>
 #include "lgk_step_device.cuh"
 
 namespace lgk {
@@ -675,6 +676,12 @@ __global__ void __launch_bounds__(kK2Threads, 5) scan_obs_fast_kernel(const __gr
   const float border = p.border_size, hscale = p.horizontal_scale, hrecip = p.horizontal_scale_recip;
   const int rows = p.hf_rows, cols = p.hf_cols;
   const bool k1_frames = OBS && p.scan_frames != nullptr;     // K1 ran before this pass: use its pre-reset yaw frame
+  // a height column is clamp(.,-1,1) * scale + noise: when scale + noise_scale <= clip_obs the final clip (LR:100-101) cannot
+  // act on it (the inner clamp also removes NaN), so groups >= 2 (height columns only) skip it
+  bool hclip = false;
+#pragma unroll
+  for (int g = 2; g < G; ++g) hclip = hclip || !(fabsf(hsc) + fabsf(nz[g]) <= clip);
+  hclip = __any_sync(0xffffffffu, hclip);
   pdl_wait();
   const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
   const RngKey key = make_key(p.seed, step_eff);
@@ -717,11 +724,20 @@ __global__ void __launch_bounds__(kK2Threads, 5) scan_obs_fast_kernel(const __gr
         const YawFrame2 yf = k1_frames ? yaw_frame2(YawFrame{cur.f.x, cur.f.y, cur.f.z, cur.f.w})
                                        : yaw_frame2(yaw_frame(cur.f.x, cur.f.y, cur.f.z, cur.f.w));
         int off[G];
+        if (cur.f.z < 1e17f && cur.f.w < 1e17f) {      // (warp-uniform) no quotient can reach 2^63: skip the per-point guard
 #pragma unroll
-        for (int g = 1; g < G; ++g) {
-          int ix, iy;
-          height_index2<RECIP>(yf, Bv[g], Bsv[g], border, hscale, hrecip, rt_one, rows, cols, ix, iy);
-          off[g] = ix * cols + iy;
+          for (int g = 1; g < G; ++g) {
+            int ix, iy;
+            height_index2<RECIP, true>(yf, Bv[g], Bsv[g], border, hscale, hrecip, rt_one, rows, cols, ix, iy);
+            off[g] = ix * cols + iy;
+          }
+        } else {
+#pragma unroll
+          for (int g = 1; g < G; ++g) {
+            int ix, iy;
+            height_index2<RECIP>(yf, Bv[g], Bsv[g], border, hscale, hrecip, rt_one, rows, cols, ix, iy);
+            off[g] = ix * cols + iy;
+          }
         }
 #pragma unroll
         for (int g = 1; g < G; ++g) h[g] = f_mul((float)__ldg(p.height_min3 + off[g]), vs);      // LR:869
@@ -734,25 +750,30 @@ __global__ void __launch_bounds__(kK2Threads, 5) scan_obs_fast_kernel(const __gr
     }
     if (OBS) {
       const uint32_t genv = (uint32_t)(p.env_id_offset + env);
+      auto finish_row = [&](auto clip_heights) {
+        constexpr bool kClipHeights = decltype(clip_heights)::value;
 #pragma unroll
-      for (int sc = 0; sc < (G + 3) / 4; ++sc) {
-        U4 r = U4{0, 0, 0, 0};
-        if (noisy) r = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
+        for (int sc = 0; sc < (G + 3) / 4; ++sc) {
+          U4 r = U4{0, 0, 0, 0};
+          if (noisy) r = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int g = sc * 4 + k;
-          if (g < G) {
-            float v;
-            if (g == 0) v = cur.head0;
-            else {
-              v = f_mul(clampf(cur.rz - h[g], -1.f, 1.f), hsc);
-              if (g == 1) v = lane < 16 ? cur.head1 : v;
+          for (int k = 0; k < 4; ++k) {
+            const int g = sc * 4 + k;
+            if (g < G) {
+              float v;
+              if (g == 0) v = cur.head0;
+              else {
+                v = f_mul(clampf(cur.rz - h[g], -1.f, 1.f), hsc);
+                if (g == 1) v = lane < 16 ? cur.head1 : v;
+              }
+              v = noisy_obs(v, pick(r, k), nz[g]);
+              if (g < 2 || kClipHeights) v = clampf(v, -clip, clip);
+              if ((omask >> g) & 1u) orow[32 * g + lane] = v;
             }
-            v = noisy_obs(v, pick(r, k), nz[g]);
-            if ((omask >> g) & 1u) orow[32 * g + lane] = clampf(v, -clip, clip);
           }
         }
-      }
+      };
+      if (hclip) finish_row(std::true_type{}); else finish_row(std::false_type{});
     }
   }
 }

@@ -53,3 +53,9 @@ def test_env_fails_loudly_without_gpu():
     import copy
     with pytest.raises(RuntimeError):
         task_registry.make_env("a1", get_args([]), env_cfg=copy.deepcopy(task_registry.env_cfgs["a1"]))
+
+
+def test_graft_entry_build_runs_on_cpu():
+    """the driver's "does it build" check: compiles (or finds up to date) liblgk.so, loads it, imports the checker"""
+    import __graft_entry__ as g
+    g.build()

@@ -81,6 +81,10 @@ typedef struct LgkTorqueParams {
   float* torques;                     /* [N,12] out */
   float* sea_hidden_state;            /* [2,N*12,8] r/w (ANY:65-69) */
   float* sea_cell_state;              /* [2,N*12,8] r/w */
+  /* Host-sim pipelines: `dof_state` may point at PINNED host memory (the kernel pulls it over PCIe with uncached loads),
+   * and `torques_mirror` (optional, e.g. pinned host memory) receives a second copy of the torques, so that a sub-step
+   * of LR:88-96 is one launch instead of copy-in, kernel, copy-out. */
+  float* torques_mirror;
 } LgkTorqueParams;
 
 /* LSTM actuator weights (resources/actuator_nets/anydrive_v3_lstm.pt: LSTM(2,8,layers=2) + Linear(8,1),

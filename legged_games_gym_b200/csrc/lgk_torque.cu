@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_
   float a = p.actions_in[idx];
   a = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);                       // LR:86-87
   if (p.actions_clipped) p.actions_clipped[idx] = a;
-  const float2 qs = *reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx);   // (pos, vel)
+  const float2 qs = __ldcv(reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx));   // (pos, vel); never from a cache: may be pinned host memory
   const float a_s = f_mul(a, p.action_scale);
   if (LSTM) {
     // ANY:75-76 sea_input, then x * in_scale inside the TorchScript module
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_
 #pragma unroll
     for (int k = 0; k < 8; ++k) y = fmaf(c_lstm.lin_w[k], h1[k], y);
     p.torques[idx] = y;                                                        // out_scale folded; no clip (ANY:77-78)
+    if (p.torques_mirror) p.torques_mirror[idx] = y;
     store8(H, h0); store8(C, c0); store8(H + layer, h1); store8(C + layer, c1);
   } else {
     // PD law, op-for-op as torch evaluates it on fp32 tensors (each op rounded; LR:383-395)
@@ -119,7 +120,9 @@ __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_
     } else {
       tq = a_s;
     }
-    p.torques[idx] = fminf(fmaxf(tq, -p.torque_limits[d]), p.torque_limits[d]);
+    const float tc = fminf(fmaxf(tq, -p.torque_limits[d]), p.torque_limits[d]);
+    p.torques[idx] = tc;
+    if (p.torques_mirror) p.torques_mirror[idx] = tc;
   }
 }
 
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(128) torque_lstm_split_kernel(const __grid_con
     float a = p.actions_in[idx];
     a = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);                     // LR:86-87
     if (p.actions_clipped && w == 0) p.actions_clipped[idx] = a;
-    const float2 qs = *reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx);
+    const float2 qs = __ldcv(reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx));
     x[0] = f_sub(f_add(f_mul(a, p.action_scale), p.default_dof_pos[d]), qs.x);   // ANY:75 (in_scale folded into w_ih0)
     x[1] = qs.y;                                                                 // ANY:76
   }
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(128) torque_lstm_split_kernel(const __grid_con
 #pragma unroll
     for (int k = 0; k < 8; ++k) y = fmaf(c_lstm.lin_w[k], s_hnew[1][lane][k], y);
     p.torques[idx] = y;                                   // out_scale folded; no clip on this path (ANY:77-78)
+    if (p.torques_mirror) p.torques_mirror[idx] = y;
   }
   for (int i = tid; i < 4 * 64; i += 128) {
     const int arr = i >> 6, q = i & 63;

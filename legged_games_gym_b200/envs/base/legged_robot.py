@@ -139,6 +139,7 @@ class LeggedRobot(BaseTask):
         clip_actions = self.cfg.normalization.clip_actions
         gym = self.gym
         native_tq = self._native_torques
+        zc_src = zc_sink = None
         if native_tq:
             tp = self._tq_params
             tp.actions_in = actions.data_ptr()
@@ -146,6 +147,10 @@ class LeggedRobot(BaseTask):
                 actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
                 tp.actions_in = actions.data_ptr()
             tp.actions_clipped = self.actions.data_ptr()
+            # a host-resident sim may hand the kernels its pinned buffers (zero-copy sub-steps, SimBackend.dof_state_source)
+            zc_src, zc_sink = gym.dof_state_source(), gym.actuation_force_sink()
+            tp.dof_state = (zc_src if zc_src is not None else self.dof_state).data_ptr()
+            tp.torques_mirror = zc_sink.data_ptr() if zc_sink is not None else None
         else:
             torch.clamp(actions.to(self.device), -clip_actions, clip_actions, out=self.actions)
         self.render()
@@ -159,7 +164,10 @@ class LeggedRobot(BaseTask):
                 self.torques[:] = self._compute_torques(self.actions).view(self.torques.shape)
             gym.set_dof_actuation_force_tensor(self.torques)
             gym.simulate()
-            gym.refresh_dof_state_tensor()
+            if not (native_tq and zc_src is not None) or k == self.cfg.control.decimation - 1:
+                gym.refresh_dof_state_tensor()       # zero-copy source: the device copy is needed by post-physics only
+            elif k + 1 < self.cfg.control.decimation:
+                gym.dof_state_source(), gym.actuation_force_sink()      # (byte accounting of the next launch)
         self.post_physics_step()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 

@@ -84,6 +84,15 @@ class SimBackend:
     def set_dof_actuation_force_tensor(self, torques):
         pass
 
+    # optional zero-copy endpoints of a sim that lives in PINNED host memory: when they return a tensor, the torque kernel
+    # reads the dof state from / mirrors its torques into that memory directly during the decimation loop, and the env
+    # refreshes its device copy of the dof state once per step (after the last sub-step) instead of once per sub-step
+    def dof_state_source(self):
+        return None
+
+    def actuation_force_sink(self):
+        return None
+
     def simulate(self):
         pass
 
@@ -119,6 +128,7 @@ class StateFeeder(SimBackend):
                  actors_per_env=1, p_contact_body0=None):
         s = synth_state(num_envs, num_bodies, num_dof, seed, p_contact, actors_per_env, p_contact_body0=p_contact_body0)
         self.device = torch.device(device)
+        self.num_envs, self.num_dof = num_envs, num_dof
         self.root_states = torch.from_numpy(s["root_states"]).to(self.device)
         self.dof_state = torch.from_numpy(s["dof_state"]).to(self.device)
         self.contact_forces = torch.from_numpy(s["contact_forces"]).to(self.device)
@@ -150,6 +160,7 @@ class HostStateFeeder(StateFeeder):
         self.h_dof = self.dof_state.cpu().pin_memory()
         self.h_contact = self.contact_forces.cpu().pin_memory()
         self.h_torques = None
+        self.zero_copy = os.environ.get("LGK_HOST_ZERO_COPY", "1") != "0"
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -186,9 +197,25 @@ class HostStateFeeder(StateFeeder):
         self._h2d(self.contact_forces, self.h_contact)
 
     def set_dof_actuation_force_tensor(self, torques):
+        if self.zero_copy:
+            return                      # the torque kernel has already written h_torques (actuation_force_sink)
         if self.h_torques is None:
             self.h_torques = torch.empty(torques.shape, dtype=torques.dtype).pin_memory()
         self._d2h(self.h_torques, torques)
+
+    def dof_state_source(self):
+        if not self.zero_copy:
+            return None
+        self.h2d_bytes += self.h_dof.numel() * 4           # one pull of the tensor per torque launch
+        return self.h_dof
+
+    def actuation_force_sink(self):
+        if not self.zero_copy:
+            return None
+        if self.h_torques is None:
+            self.h_torques = torch.empty(self.num_envs, self.num_dof, dtype=torch.float).pin_memory()
+        self.d2h_bytes += self.h_torques.numel() * 4
+        return self.h_torques
 
     def set_dof_state_tensor_indexed(self, dof_state, env_ids_int32, count):
         self._d2h(self.h_dof, dof_state)

@@ -545,8 +545,9 @@ def gpu_arm(args):
             del env2, feeder2, envs2, feeders2
             torch.cuda.empty_cache()
     rollout = rollout_phase(dev)
-    training = None if args.no_train else train_iteration(dev)
-    game = None if args.no_train else game_phase(dev)
+    # single-process legs only: a PPO update on rank 0 alone would all-reduce against ranks that are waiting in the barrier
+    training = None if (args.no_train or world > 1) else train_iteration(dev)
+    game = None if (args.no_train or world > 1) else game_phase(dev)
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores

@@ -549,7 +549,9 @@ def gpu_arm(args):
     training = None if (args.no_train or world > 1) else train_iteration(dev)
     game = None if (args.no_train or world > 1) else game_phase(dev)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
+        # N=1 only: with other ranks spinning in the closing barrier the OpenMP team of the CPU arm is oversubscribed and
+        # collapses (the N=2 run sat here for > 10 minutes)
         cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores
     dom = dict(roof["torque_lstm"])
     dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, "torque_kernel<1>"))
@@ -593,6 +595,9 @@ def reference_arm(args):
 
 
 if __name__ == "__main__":
+    if os.environ.get("LGK_BENCH_WATCHDOG"):       # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["LGK_BENCH_WATCHDOG"]), exit=True)
     a = parse()
     if a.impl == "reference":
         # bounded: the CPU path takes ~20 ms per 4096-env step -> at most ~10 s of timed work

@@ -294,6 +294,12 @@ typedef struct {
 } LgkGameParams;
 
 int lgk_game_step(const LgkGameParams* p, void* stream);
+/* HLG:161-174 / DHLG:181-195 before ll_env.step: clip the prey command (x, y) and the predator command (x, y) in place to
+ * ranges8 = {lin_vel_x lo, hi, lin_vel_y lo, hi, predator_lin_vel_x lo, hi, predator_lin_vel_y lo, hi} (host array),
+ * wrap the prey's heading command to (-pi, pi] when heading_command, and copy the prey's four commands into the
+ * low-level env's command buffer [N,4].  Strides in floats. */
+int lgk_game_prepare(float* command_prey, int64_t prey_stride, float* command_pred, int64_t pred_stride,
+                     float* ll_commands, int32_t num_envs, const float* ranges8, int32_t heading_command, void* stream);
 
 /* ------------------------------------------------------------------ height field (LR:831-869) */
 /* min3[r,c] = min(hs[r,c], hs[r+1,c], hs[r,c+1]) for r<=rows-2, c<=cols-2 (the three samples LR:863-867

@@ -138,6 +138,7 @@ def _load():
     lib.lgk_struct_size.argtypes = [C.c_int]
     lib.lgk_set_pdl.argtypes = [C.c_int]
     lib.lgk_game_step.argtypes = [C.POINTER(GameParams), vp]
+    lib.lgk_game_prepare.argtypes = [vp, i64, vp, i64, vp, i32, C.POINTER(f32 * 8), i32, vp]
     lib.lgk_set_fused.argtypes = [C.c_int]
     lib.lgk_set_fused_scan_warps.argtypes = [C.c_int]
     lib.lgk_step_debug_timeline.argtypes = [vp]
@@ -153,7 +154,7 @@ def _load():
 lib = _load()
 
 EXPORTS = ["lgk_set_lstm_weights", "lgk_compute_torques", "lgk_post_physics", "lgk_reset_idx", "lgk_finalize_step",
-           "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline", "lgk_set_pdl", "lgk_game_step", "lgk_set_fused", "lgk_set_fused_scan_warps", "lgk_step_debug_timeline",
+           "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline", "lgk_set_pdl", "lgk_game_step", "lgk_game_prepare", "lgk_set_fused", "lgk_set_fused_scan_warps", "lgk_step_debug_timeline",
            "lgk_gae", "lgk_last_error_string", "lgk_abi_version", "lgk_l2_flush", "lgk_copy_from_pinned", "lgk_copy_to_pinned", "lgk_launch_count",
            "lgk_struct_size"]
 

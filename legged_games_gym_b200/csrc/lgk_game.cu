@@ -241,9 +241,40 @@ __device__ __forceinline__ void game_observe_and_store(const LgkGameParams& p, i
   p.curr_episode_step[e] = ces;
 }
 
+// HLG:161-174 / DHLG:181-195: clip the prey's and the predator's high-level commands in place (torch.clip semantics: NaN
+// stays NaN), wrap the prey's heading command, and hand the prey command to the low-level env's command buffer.
+__device__ __forceinline__ float clip_keep_nan(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+__global__ void game_prepare_kernel(float* prey, long long prey_stride, float* pred, long long pred_stride, float* ll_commands,
+                                    int n, float x0, float x1, float y0, float y1, float px0, float px1, float py0, float py1,
+                                    int heading_command) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float* a = prey + (size_t)e * prey_stride;
+  float* b = pred + (size_t)e * pred_stride;
+  const float c0 = clip_keep_nan(a[0], x0, x1), c1 = clip_keep_nan(a[1], y0, y1);
+  const float c2 = heading_command ? wrap_to_pi(a[2]) : a[2];
+  a[0] = c0; a[1] = c1; a[2] = c2;
+  b[0] = clip_keep_nan(b[0], px0, px1);
+  b[1] = clip_keep_nan(b[1], py0, py1);
+  *reinterpret_cast<float4*>(ll_commands + 4 * (size_t)e) = make_float4(c0, c1, c2, a[3]);
+}
+
 }  // namespace lgk
 
 using namespace lgk;
+
+extern "C" int lgk_game_prepare(float* command_prey, int64_t prey_stride, float* command_pred, int64_t pred_stride,
+                                float* ll_commands, int32_t num_envs, const float* ranges8, int32_t heading_command, void* stream) {
+  LGK_REQUIRE(command_prey && command_pred && ll_commands && ranges8 && num_envs > 0, "game_prepare: bad arguments");
+  LGK_REQUIRE(prey_stride >= 4 && pred_stride >= 2, "game_prepare: bad row stride");
+  LGK_ALIGNED16(ll_commands, "ll_commands");
+  game_prepare_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      command_prey, prey_stride, command_pred, pred_stride, ll_commands, num_envs, ranges8[0], ranges8[1], ranges8[2], ranges8[3],
+      ranges8[4], ranges8[5], ranges8[6], ranges8[7], heading_command);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "game_prepare_kernel launch");
+}
 
 extern "C" int lgk_game_step(const LgkGameParams* p, void* stream) {
   LGK_REQUIRE(p != nullptr, "game params is null");

@@ -45,8 +45,7 @@ class DecHighLevelGame(_GameBase):
 
     # ------------------------------------------------------------------ DHLG:169-261
     def step(self, command_pred, command_prey):
-        self._clip_commands(command_prey, command_pred)
-        self._ll_step(command_prey)
+        self._ll_step(command_prey, command_pred)
         self.common_step_counter += 1
         self._stats.zero_()
         self._launch(command_pred)

@@ -19,7 +19,6 @@ import torch
 from ... import LEGGED_GYM_ROOT_DIR
 from ... import _native as nat
 from ...utils.helpers import class_to_dict, get_load_path
-from ...utils.math import wrap_to_pi
 from .low_level_game import LowLevelGame
 
 
@@ -171,6 +170,9 @@ class _GameBase:
         p.episode_length_buf, p.curr_episode_step = self.episode_length_buf.data_ptr(), self.curr_episode_step.data_ptr()
         p.reset_stats = self._stats.data_ptr()
         p.scratch = self._scratch.data_ptr()
+        r = self.command_ranges
+        self._ranges8 = (C.c_float * 8)(*[float(v) for k in ("lin_vel_x", "lin_vel_y", "predator_lin_vel_x", "predator_lin_vel_y")
+                                          for v in r[k]])
 
     def _launch(self, command_pred, reset_only=False, dones=None):
         p = self._params
@@ -184,19 +186,18 @@ class _GameBase:
         p.env_id_offset = int(getattr(self.ll_env, "env_id_offset", 0))
         nat.check(nat.lib.lgk_game_step(C.byref(p), _stream_ptr()), "lgk_game_step")
 
-    def _clip_commands(self, prey, pred):
-        """HLG:161-169 (in place, like the reference)"""
-        r = self.command_ranges
-        prey[:, 0].clamp_(r["lin_vel_x"][0], r["lin_vel_x"][1])
-        prey[:, 1].clamp_(r["lin_vel_y"][0], r["lin_vel_y"][1])
-        if self.cfg.commands.heading_command:
-            prey[:, 2] = wrap_to_pi(prey[:, 2])
-        pred[:, 0].clamp_(r["predator_lin_vel_x"][0], r["predator_lin_vel_x"][1])
-        pred[:, 1].clamp_(r["predator_lin_vel_y"][0], r["predator_lin_vel_y"][1])
-
-    def _ll_step(self, command_prey):
+    def _ll_step(self, command_prey, command_pred):
+        """HLG:161-181: clip / wrap the commands in place and hand the prey's to the low-level env (one kernel), then the
+        frozen low-level policy and the low-level step.  The reference aliases ``ll_env.commands`` to the command tensor
+        (HLG:174); the kernels own a persistent buffer, so the values are copied."""
         ll = self.ll_env
-        ll.commands[:, :4] = command_prey[:, :4]          # the reference aliases the tensor (HLG:174); the kernels own theirs
+        for t in (command_prey, command_pred):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1):
+                raise TypeError("high-level commands must be fp32 CUDA tensors with unit column stride")
+        nat.check(nat.lib.lgk_game_prepare(command_prey.data_ptr(), command_prey.stride(0), command_pred.data_ptr(),
+                                           command_pred.stride(0), ll.commands.data_ptr(), self.num_envs,
+                                           C.byref(self._ranges8), int(bool(self.cfg.commands.heading_command)),
+                                           _stream_ptr()), "lgk_game_prepare")
         ll_obs = ll.get_observations()
         actions = self.ll_policy(ll_obs.detach())
         return ll.step(actions.detach())
@@ -252,8 +253,7 @@ class HighLevelGame(_GameBase):
 
     # ------------------------------------------------------------------ HLG:146-241
     def step(self, command):
-        self._clip_commands(command[:, 0:4], command[:, 4:6])
-        self._ll_step(command)
+        self._ll_step(command[:, 0:4], command[:, 4:6])
         self.common_step_counter += 1
         self._launch(command[:, 4:6])
         self._push_game_state_to_sim()

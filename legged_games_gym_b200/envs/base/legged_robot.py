@@ -139,7 +139,6 @@ class LeggedRobot(BaseTask):
         clip_actions = self.cfg.normalization.clip_actions
         gym = self.gym
         native_tq = self._native_torques
-        zc_src = zc_sink = None
         if native_tq:
             tp = self._tq_params
             tp.actions_in = actions.data_ptr()
@@ -147,15 +146,19 @@ class LeggedRobot(BaseTask):
                 actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
                 tp.actions_in = actions.data_ptr()
             tp.actions_clipped = self.actions.data_ptr()
-            # a host-resident sim may hand the kernels its pinned buffers (zero-copy sub-steps, SimBackend.dof_state_source)
-            zc_src, zc_sink = gym.dof_state_source(), gym.actuation_force_sink()
-            tp.dof_state = (zc_src if zc_src is not None else self.dof_state).data_ptr()
-            tp.torques_mirror = zc_sink.data_ptr() if zc_sink is not None else None
         else:
             torch.clamp(actions.to(self.device), -clip_actions, clip_actions, out=self.actions)
         self.render()
-        for k in range(self.cfg.control.decimation):
+        decimation = self.cfg.control.decimation
+        for k in range(decimation):
+            zero_copy = False
             if native_tq:
+                # a host-resident sim may hand the kernel its pinned buffers for this sub-step (SimBackend.dof_state_source /
+                # actuation_force_sink): the launch then pulls the dof state and pushes the torques over PCIe itself
+                src, sink = gym.dof_state_source(), gym.actuation_force_sink()
+                zero_copy = src is not None
+                tp.dof_state = (src if zero_copy else self.dof_state).data_ptr()
+                tp.torques_mirror = sink.data_ptr() if sink is not None else None
                 nat.check(nat.lib.lgk_compute_torques(C.byref(tp), _stream_ptr()), "lgk_compute_torques")
                 if k == 0:      # later sub-steps read the clipped copy (clip is idempotent)
                     tp.actions_in = self.actions.data_ptr()
@@ -164,10 +167,8 @@ class LeggedRobot(BaseTask):
                 self.torques[:] = self._compute_torques(self.actions).view(self.torques.shape)
             gym.set_dof_actuation_force_tensor(self.torques)
             gym.simulate()
-            if not (native_tq and zc_src is not None) or k == self.cfg.control.decimation - 1:
-                gym.refresh_dof_state_tensor()       # zero-copy source: the device copy is needed by post-physics only
-            elif k + 1 < self.cfg.control.decimation:
-                gym.dof_state_source(), gym.actuation_force_sink()      # (byte accounting of the next launch)
+            if not zero_copy or k == decimation - 1:
+                gym.refresh_dof_state_tensor()       # zero-copy source: only post-physics needs the device copy
         self.post_physics_step()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 

@@ -391,6 +391,11 @@ int lgk_set_fused_scan_warps(int n);
  * memory done by a kernel over the unified address space instead of a memcpy node.  bytes % 16 == 0, 16-byte aligned. */
 int lgk_copy_from_pinned(void* dst_device, const void* src_pinned_host, int64_t bytes, void* stream);
 int lgk_copy_to_pinned(void* dst_pinned_host, const void* src_device, int64_t bytes, void* stream);
+/* The indexed variant (gym.set_dof_state_tensor_indexed / set_actor_root_state_tensor_indexed, LR:409-412, 433-436) for a
+ * host-resident sim: rows `ids[i] * row_stride + row_offset`, i < min(*count, max_ids), of a [rows, row_floats] fp32
+ * tensor go from device to the same rows of its pinned host twin.  ids / count: device int32 (lgk_finalize_step). */
+int lgk_copy_rows_to_pinned(void* dst_pinned_host, const void* src_device, int32_t row_floats, const int32_t* ids,
+                            const int32_t* count, int32_t row_stride, int32_t row_offset, int32_t max_ids, void* stream);
 /* Write `bytes` of a scratch buffer (L2 flush between timed iterations; bench only). */
 int lgk_l2_flush(void* scratch, int64_t bytes, void* stream);
 /* number of kernel launches issued through this library since load (bench's gpu_launches). */

@@ -73,9 +73,37 @@ __global__ void __launch_bounds__(256) pinned_copy_kernel(uint4* __restrict__ ds
   for (; i < n16; i += stride) dst[i] = from_host ? __ldcv(src + i) : src[i];
 }
 
+// set_*_tensor_indexed of a host-resident sim (LR:409-412, 433-436): only the rows of the envs reset this step go back
+// over PCIe.  ids / count are the device-side outputs of lgk_finalize_step; one warp per listed env.
+__global__ void __launch_bounds__(128) pinned_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int row_floats,
+                                                          const int32_t* __restrict__ ids, const int32_t* __restrict__ count,
+                                                          int row_stride, int row_offset, int max_ids) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = min(*count, max_ids);
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 4 + (threadIdx.x >> 5); i < n; i += gridDim.x * 4) {
+    const size_t row = ((size_t)ids[i] * row_stride + row_offset) * row_floats;
+    for (int c = lane; c < row_floats; c += 32) dst[row + c] = src[row + c];
+  }
+}
+
 }  // namespace lgk
 
 using namespace lgk;
+
+extern "C" int lgk_copy_rows_to_pinned(void* dst_pinned_host, const void* src_device, int32_t row_floats, const int32_t* ids,
+                                       const int32_t* count, int32_t row_stride, int32_t row_offset, int32_t max_ids, void* stream) {
+  LGK_REQUIRE(dst_pinned_host && src_device && ids && count && row_floats > 0 && row_stride > 0 && row_offset >= 0 && max_ids > 0,
+              "copy_rows_to_pinned: bad arguments");
+  int blocks = (max_ids + 3) / 4;
+  blocks = blocks > 148 * 4 ? 148 * 4 : blocks;
+  const cudaError_t e = launch_chained(pinned_rows_kernel, dim3(blocks), dim3(128), 0, (cudaStream_t)stream,
+                                       reinterpret_cast<float*>(dst_pinned_host), reinterpret_cast<const float*>(src_device),
+                                       (int)row_floats, ids, count, (int)row_stride, (int)row_offset, (int)max_ids);
+  count_launch();
+  return check_cuda(e, "pinned_rows_kernel launch");
+}
 
 static int pinned_copy(void* dst, const void* src, int64_t bytes, int from_host, void* stream) {
   LGK_REQUIRE(dst != nullptr && src != nullptr && bytes > 0 && bytes % 16 == 0, "pinned copy: bad arguments (bytes must be a multiple of 16)");

@@ -161,6 +161,9 @@ class HostStateFeeder(StateFeeder):
         self.h_contact = self.contact_forces.cpu().pin_memory()
         self.h_torques = None
         self.zero_copy = os.environ.get("LGK_HOST_ZERO_COPY", "1") != "0"
+        # reset rows only (lgk_copy_rows_to_pinned) instead of whole tensors: 0.6 MB less D2H per step, measured neutral
+        # for the step time at 4096 envs (two tiny launches against two 5-8 us copies), so off unless asked for
+        self.indexed_rows = os.environ.get("LGK_HOST_INDEXED_ROWS", "0") == "1"
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -217,11 +220,27 @@ class HostStateFeeder(StateFeeder):
         self.d2h_bytes += self.h_torques.numel() * 4
         return self.h_torques
 
+    def _d2h_rows(self, dst, src, row_floats, env_ids_int32, count, stride, offset):
+        """rows of the reset envs only (lgk_copy_rows_to_pinned); the byte counter takes the count of the step being run
+        eagerly (the first one: bench.py reads the counters after it), a replayed graph moves what its step resets"""
+        from .. import _native as nat
+        st = torch.cuda.current_stream().cuda_stream
+        nat.check(nat.lib.lgk_copy_rows_to_pinned(dst.data_ptr(), src.data_ptr(), row_floats, env_ids_int32.data_ptr(),
+                                                  count.data_ptr(), stride, offset, env_ids_int32.numel(), st),
+                  "lgk_copy_rows_to_pinned")
+        if not torch.cuda.is_current_stream_capturing():
+            self.d2h_bytes += int(count.item()) * row_floats * 4
+
     def set_dof_state_tensor_indexed(self, dof_state, env_ids_int32, count):
-        self._d2h(self.h_dof, dof_state)
+        if self.indexed_rows and torch.is_tensor(count):
+            self._d2h_rows(self.h_dof, dof_state, 2 * self.num_dof, env_ids_int32, count, 1, 0)
+        else:
+            self._d2h(self.h_dof, dof_state)
 
     def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count, actor_stride=1, actor_offset=0):
-        if actor_offset == 0:          # one copy of the whole tensor covers every actor of the env
+        if self.indexed_rows and torch.is_tensor(count):
+            self._d2h_rows(self.h_root, root_states, 13, env_ids_int32, count, actor_stride, actor_offset)
+        elif actor_offset == 0:          # one copy of the whole tensor covers every actor of the env
             self._d2h(self.h_root, root_states)
 
     def set_actor_root_state_tensor(self, root_states):

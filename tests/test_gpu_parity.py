@@ -441,7 +441,8 @@ def test_domain_randomisation_props_reach_the_backend():
     assert feeder.friction_coeffs is env.friction_coeffs and feeder.added_base_mass is env.added_base_mass
 
 
-def test_host_sim_state_step_replays_copies_inside_the_graph():
+@pytest.mark.parametrize("indexed_rows", [False, True])
+def test_host_sim_state_step_replays_copies_inside_the_graph(indexed_rows):
     """bench.py's e2e leg: sim state in PINNED host memory, the whole step (H2D copies, kernels, D2H copies) replayed as one
     CUDA graph.  The copies must really run at every replay: change the host state between steps and compare with an
     env whose state lives on the device."""
@@ -449,6 +450,8 @@ def test_host_sim_state_step_replays_copies_inside_the_graph():
     bench.USE_GRAPH, bench.TILE = True, 0
     torch.manual_seed(0)                         # initial terrain levels come from torch's generator (LR:762)
     env_h, fh = bench.make_env(512, DEV, host_sim=True)
+    fh.indexed_rows = indexed_rows               # reset rows only (lgk_copy_rows_to_pinned) / whole tensors
+    assert fh.zero_copy                          # torque sub-steps read / write the pinned buffers directly
     torch.manual_seed(0)
     env_d, fd = bench.make_env(512, DEV, host_sim=False)
     acts = fd.synthetic_actions

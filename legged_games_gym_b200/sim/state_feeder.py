@@ -145,14 +145,30 @@ class StateFeeder(SimBackend):
         return self.contact_forces
 
 
-class HostStateFeeder(StateFeeder):
-    # every hook is a stream-ordered cudaMemcpyAsync between PINNED host memory and the device: capturable, so the whole
-    # step (copies + kernels) still replays as one CUDA graph
-    graph_safe = True
+class _PinnedAlias:
+    """__cuda_array_interface__ view of a pinned host tensor: with unified addressing the device reaches the allocation
+    through the same pointer, so torch can wrap it as a CUDA tensor and every kernel works on it unchanged."""
 
-    """Sim state lives in pinned host memory (the reference's ``sim_device=cpu`` pipeline: PhysX
-    results are host tensors).  refresh_* = H2D copy; set_* = D2H copy.  Byte counters feed bench.py's
-    ``e2e.h2d_bytes_per_step`` / ``d2h_bytes_per_step``."""
+    def __init__(self, t):
+        self.__cuda_array_interface__ = {"shape": tuple(t.shape), "typestr": "<f4", "data": (t.data_ptr(), False),
+                                         "version": 2, "strides": None}
+
+
+class HostStateFeeder(StateFeeder):
+    """Sim state lives in PINNED host memory (the reference's ``sim_device=cpu`` pipeline: PhysX results are host tensors).
+    Three levels, each an A/B switch of the one above (bench.py's e2e leg; byte counters feed ``e2e.h2d_bytes_per_step`` /
+    ``d2h_bytes_per_step``):
+
+    * unified (default, ``LGK_HOST_UNIFIED=0`` turns it off): the tensors the env acquires ARE the pinned buffers, wrapped
+      as CUDA tensors over the unified address space.  The step kernels pull what they read over PCIe themselves (K1's TMA
+      bulk copies included) and write reset rows / pushed velocities straight back; refresh_* / set_* have nothing to do
+      and a step has no copy at all.  Measured at 4096 envs: 110 us per step against 147 us with explicit transfers.
+    * explicit transfers: device-resident twins, refresh_* = H2D, set_* = D2H, done by kernels over the unified address
+      space for tensors up to 1 MB (``LGK_KERNEL_COPY_MAX``) and with zero-copy torque sub-steps (``LGK_HOST_ZERO_COPY``).
+    * plain: cudaMemcpyAsync for everything (both switches off).
+
+    Every hook is stream-ordered and capturable, so the whole step still replays as one CUDA graph."""
+    graph_safe = True
 
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
@@ -160,10 +176,19 @@ class HostStateFeeder(StateFeeder):
         self.h_dof = self.dof_state.cpu().pin_memory()
         self.h_contact = self.contact_forces.cpu().pin_memory()
         self.h_torques = None
+        self.unified = os.environ.get("LGK_HOST_UNIFIED", "1") != "0"
         self.zero_copy = os.environ.get("LGK_HOST_ZERO_COPY", "1") != "0"
         # reset rows only (lgk_copy_rows_to_pinned) instead of whole tensors: 0.6 MB less D2H per step, measured neutral
         # for the step time at 4096 envs (two tiny launches against two 5-8 us copies), so off unless asked for
         self.indexed_rows = os.environ.get("LGK_HOST_INDEXED_ROWS", "0") == "1"
+        if self.unified:
+            dev = self.root_states.device
+            self.root_states = torch.as_tensor(_PinnedAlias(self.h_root), device=dev)
+            self.dof_state = torch.as_tensor(_PinnedAlias(self.h_dof), device=dev)
+            self.contact_forces = torch.as_tensor(_PinnedAlias(self.h_contact), device=dev)
+            for d, h in ((self.root_states, self.h_root), (self.dof_state, self.h_dof), (self.contact_forces, self.h_contact)):
+                if not (d.is_cuda and d.data_ptr() == h.data_ptr()):
+                    raise RuntimeError("pinned host memory is not reachable through the unified address space on this system")
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -172,8 +197,12 @@ class HostStateFeeder(StateFeeder):
     # (scratch/pcie_probe.py); larger ones (the observation matrix) keep the copy engine
     KERNEL_COPY_MAX_BYTES = int(os.environ.get("LGK_KERNEL_COPY_MAX", 1 << 20))
 
+    @staticmethod
+    def _nbytes(t):
+        return t.numel() * t.element_size()
+
     def _copy(self, dst, src, from_host):
-        nbytes = src.numel() * src.element_size()
+        nbytes = self._nbytes(src)
         if (nbytes <= self.KERNEL_COPY_MAX_BYTES and nbytes % 16 == 0 and dst.is_contiguous() and src.is_contiguous()
                 and dst.data_ptr() % 16 == 0 and src.data_ptr() % 16 == 0):
             from .. import _native as nat
@@ -190,58 +219,74 @@ class HostStateFeeder(StateFeeder):
     def _d2h(self, dst, src):
         self.d2h_bytes += self._copy(dst, src, False)
 
+    # unified mode: nothing to copy; the counters take what the kernels of the step pull / push over PCIe instead --
+    # dof state: one pull per torque launch (counted at the refresh that follows it) plus K1's; root state: K1's tile loads
+    # plus K2's pose reads; contact forces: K1's; torques: the mirror; reset rows: K1's direct writes
     def refresh_dof_state_tensor(self):
-        self._h2d(self.dof_state, self.h_dof)
+        if self.unified:
+            self.h2d_bytes += self._nbytes(self.h_dof)
+        else:
+            self._h2d(self.dof_state, self.h_dof)
 
     def refresh_actor_root_state_tensor(self):
-        self._h2d(self.root_states, self.h_root)
+        if self.unified:
+            self.h2d_bytes += 2 * self._nbytes(self.h_root) + self._nbytes(self.h_dof)
+        else:
+            self._h2d(self.root_states, self.h_root)
 
     def refresh_net_contact_force_tensor(self):
-        self._h2d(self.contact_forces, self.h_contact)
+        if self.unified:
+            self.h2d_bytes += self._nbytes(self.h_contact)
+        else:
+            self._h2d(self.contact_forces, self.h_contact)
 
     def set_dof_actuation_force_tensor(self, torques):
-        if self.zero_copy:
+        if self.zero_copy or self.unified:
             return                      # the torque kernel has already written h_torques (actuation_force_sink)
         if self.h_torques is None:
             self.h_torques = torch.empty(torques.shape, dtype=torques.dtype).pin_memory()
         self._d2h(self.h_torques, torques)
 
     def dof_state_source(self):
-        if not self.zero_copy:
-            return None
-        self.h2d_bytes += self.h_dof.numel() * 4           # one pull of the tensor per torque launch
+        if self.unified or not self.zero_copy:
+            return None                 # unified: the env's own dof_state tensor already is the pinned buffer
+        self.h2d_bytes += self._nbytes(self.h_dof)           # one pull of the tensor per torque launch
         return self.h_dof
 
     def actuation_force_sink(self):
-        if not self.zero_copy:
+        if not (self.zero_copy or self.unified):
             return None
         if self.h_torques is None:
             self.h_torques = torch.empty(self.num_envs, self.num_dof, dtype=torch.float).pin_memory()
-        self.d2h_bytes += self.h_torques.numel() * 4
+        self.d2h_bytes += self._nbytes(self.h_torques)
         return self.h_torques
 
     def _d2h_rows(self, dst, src, row_floats, env_ids_int32, count, stride, offset):
         """rows of the reset envs only (lgk_copy_rows_to_pinned); the byte counter takes the count of the step being run
         eagerly (the first one: bench.py reads the counters after it), a replayed graph moves what its step resets"""
-        from .. import _native as nat
-        st = torch.cuda.current_stream().cuda_stream
-        nat.check(nat.lib.lgk_copy_rows_to_pinned(dst.data_ptr(), src.data_ptr(), row_floats, env_ids_int32.data_ptr(),
-                                                  count.data_ptr(), stride, offset, env_ids_int32.numel(), st),
-                  "lgk_copy_rows_to_pinned")
+        if not self.unified:
+            from .. import _native as nat
+            st = torch.cuda.current_stream().cuda_stream
+            nat.check(nat.lib.lgk_copy_rows_to_pinned(dst.data_ptr(), src.data_ptr(), row_floats, env_ids_int32.data_ptr(),
+                                                      count.data_ptr(), stride, offset, env_ids_int32.numel(), st),
+                      "lgk_copy_rows_to_pinned")
         if not torch.cuda.is_current_stream_capturing():
             self.d2h_bytes += int(count.item()) * row_floats * 4
 
     def set_dof_state_tensor_indexed(self, dof_state, env_ids_int32, count):
-        if self.indexed_rows and torch.is_tensor(count):
+        if (self.unified or self.indexed_rows) and torch.is_tensor(count):
             self._d2h_rows(self.h_dof, dof_state, 2 * self.num_dof, env_ids_int32, count, 1, 0)
-        else:
+        elif not self.unified:
             self._d2h(self.h_dof, dof_state)
 
     def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count, actor_stride=1, actor_offset=0):
-        if self.indexed_rows and torch.is_tensor(count):
+        if (self.unified or self.indexed_rows) and torch.is_tensor(count):
             self._d2h_rows(self.h_root, root_states, 13, env_ids_int32, count, actor_stride, actor_offset)
-        elif actor_offset == 0:          # one copy of the whole tensor covers every actor of the env
+        elif actor_offset == 0 and not self.unified:          # one copy of the whole tensor covers every actor of the env
             self._d2h(self.h_root, root_states)
 
     def set_actor_root_state_tensor(self, root_states):
-        self._d2h(self.h_root, root_states)
+        if self.unified:
+            self.d2h_bytes += self._nbytes(self.h_root)       # the pushed tile rows were written by K1
+        else:
+            self._d2h(self.h_root, root_states)

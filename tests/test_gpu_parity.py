@@ -441,19 +441,30 @@ def test_domain_randomisation_props_reach_the_backend():
     assert feeder.friction_coeffs is env.friction_coeffs and feeder.added_base_mass is env.added_base_mass
 
 
-@pytest.mark.parametrize("indexed_rows", [False, True])
-def test_host_sim_state_step_replays_copies_inside_the_graph(indexed_rows):
-    """bench.py's e2e leg: sim state in PINNED host memory, the whole step (H2D copies, kernels, D2H copies) replayed as one
-    CUDA graph.  The copies must really run at every replay: change the host state between steps and compare with an
-    env whose state lives on the device."""
+@pytest.mark.parametrize("mode", ["unified", "explicit", "explicit_indexed_rows", "memcpy"])
+def test_host_sim_state_step_replays_inside_the_graph(mode, monkeypatch):
+    """bench.py's e2e leg: sim state in PINNED host memory, the whole step replayed as one CUDA graph.  `unified`: the
+    kernels (K1's TMA bulk copies included) work directly on the pinned buffers over the unified address space;
+    `explicit*`: device twins refreshed / written back by copy kernels, zero-copy torque sub-steps; `memcpy`: plain
+    cudaMemcpyAsync nodes.  The host state changes between steps, pushes happen every second step, and everything must
+    equal an env whose state lives on the device."""
     import bench
     bench.USE_GRAPH, bench.TILE = True, 0
+    monkeypatch.setenv("LGK_HOST_UNIFIED", "1" if mode == "unified" else "0")
+    monkeypatch.setenv("LGK_HOST_ZERO_COPY", "0" if mode == "memcpy" else "1")
     torch.manual_seed(0)                         # initial terrain levels come from torch's generator (LR:762)
     env_h, fh = bench.make_env(512, DEV, host_sim=True)
-    fh.indexed_rows = indexed_rows               # reset rows only (lgk_copy_rows_to_pinned) / whole tensors
-    assert fh.zero_copy                          # torque sub-steps read / write the pinned buffers directly
     torch.manual_seed(0)
     env_d, fd = bench.make_env(512, DEV, host_sim=False)
+    assert fh.unified == (mode == "unified") and fh.zero_copy == (mode != "memcpy")
+    fh.indexed_rows = mode == "explicit_indexed_rows"
+    if mode == "memcpy":
+        fh.KERNEL_COPY_MAX_BYTES = 0
+    if mode == "unified":
+        assert env_h.root_states.is_cuda and env_h.root_states.data_ptr() == fh.h_root.data_ptr()
+    for e in (env_h, env_d):                     # pushes at steps 2 and 4 (whole-tile root write-back of K1)
+        e.cfg.domain_rand.push_interval = 2
+        e._params.push_interval = 2
     acts = fd.synthetic_actions
     g = torch.Generator().manual_seed(5)
     for step in range(5):
@@ -462,15 +473,16 @@ def test_host_sim_state_step_replays_copies_inside_the_graph(indexed_rows):
         torch.cuda.synchronize()
         assert torch.equal(env_h.obs_buf, env_d.obs_buf) and torch.equal(env_h.rew_buf, env_d.rew_buf), step
         assert torch.equal(env_h.reset_buf, env_d.reset_buf)
-        assert torch.equal(fh.h_torques, env_d.torques.cpu())                       # D2H copy of the last sub-step's torques
+        assert torch.equal(fh.h_torques, env_d.torques.cpu())                       # the host's copy of the last sub-step's torques
         # the "simulator" moves: new joint velocities on the host side / on the device side
         dv = torch.randn(fh.h_dof.shape[0], generator=g) * 0.1
         fh.h_dof[:, 1] += dv
         fh.refresh_dof_state_tensor()            # a sim step ends with a refresh (LR:96); later refreshes replay in the graph
         fd.dof_state[:, 1] += dv.to(DEV)
-        # resets were written back into the host copy of the sim state (set_*_indexed hooks)
+        # resets and pushes were written back into the host copy of the sim state
         assert torch.equal(fh.h_root, env_d.root_states.cpu())
     assert env_h._graph is not None and env_d._graph is not None
+    assert fh.h2d_bytes > 0 and fh.d2h_bytes > 0
 
 
 def feeder_actions(n, step):

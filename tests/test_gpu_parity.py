@@ -252,7 +252,9 @@ def test_fused_post_physics_kernel_equals_two_kernel_chain(task, n, ov, sw):
 GAME_STEP_CASES = [("hl", 96, None, None), ("hl", 200, {"env.env_radius": 40.0, "rewards.scales.termination": -2.0, "rewards.only_positive_rewards": False}, None),
               ("dec", 96, {"env.episode_length_s": 0.08}, {"terrain.mesh_type": "plane", "terrain.curriculum": False}),
               ("dec", 160, {"rewards_prey.scales.termination": -3.0, "rewards_prey.only_positive_rewards": False},
-               {"terrain.mesh_type": "plane", "terrain.curriculum": False})]
+               {"terrain.mesh_type": "plane", "terrain.curriculum": False}),
+              # the reference's own num_envs (high_level_game_flat_config.py:10) and a single partial warp
+              ("hl", 2000, None, None), ("dec", 33, None, {"terrain.mesh_type": "plane", "terrain.curriculum": False}), ("hl", 1, None, None)]
 
 
 @pytest.mark.parametrize("variant,n,ov,ll_ov", GAME_STEP_CASES)

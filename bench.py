@@ -90,6 +90,33 @@ def cpu_arm(num_envs, steps, warmup):
                 sample=f"{steps} timed + {warmup} warm-up steps of {TASK} at {num_envs} envs (median), torch CPU {cores} threads")
 
 
+def eager_gpu_arm(num_envs, device, steps=30, warmup=5):
+    """The reference algorithm as it runs on a GPU today (SURVEY 8(d) "the real incumbent"): the same torch code as the
+    CPU arm with every tensor on the device, ~1300 eager dispatches per step.  A baseline beside cpu_baseline, not a
+    product path."""
+    import torch
+    from oracle import harness
+    case = harness.build_case(TASK, num_envs, seed=0)
+    with torch.device(device):
+        orc = harness.make_oracle(case, device=device)
+        acts = torch.from_numpy(case["state"]["actions"].copy()).to(device)
+        import numpy as np
+        tables = {k: torch.from_numpy(v.astype(np.int64) if v.dtype == np.uint32 else v).to(device)     # (no uint32 indexing on CUDA)
+                  for k, v in harness.step_tables(0, 1, num_envs, orc.num_obs).items()}
+        for _ in range(warmup):
+            orc.step(acts, tables)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            orc.step(acts, tables)
+        b.record()
+        torch.cuda.synchronize()
+    sec = a.elapsed_time(b) / 1e3 / steps
+    return dict(value=num_envs / sec, unit=UNIT, ms_per_step=sec * 1e3,
+                what=f"reference algorithm (oracle port) as eager torch on the same GPU, {steps} steps of {TASK} at {num_envs} envs")
+
+
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     def __init__(self, index):
@@ -553,6 +580,10 @@ def gpu_arm(args):
         # N=1 only: with other ranks spinning in the closing barrier the OpenMP team of the CPU arm is oversubscribed and
         # collapses (the N=2 run sat here for > 10 minutes)
         cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores
+        try:
+            cpu["eager_torch_gpu"] = eager_gpu_arm(N, dev)
+        except Exception as e:                       # a baseline, never a reason to lose the bench line
+            cpu["eager_torch_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     dom = dict(roof["torque_lstm"])
     dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, "torque_kernel<1>"))
     roof["post_physics"]["traffic"] = ncu_traffic(N, r"post_(scalar_)?kernel", "scan_obs_fast_kernel")

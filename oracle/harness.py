@@ -81,13 +81,17 @@ def torch_state(case):
     return {k: torch.from_numpy(case["state"][k].copy()) for k in ("root_states", "dof_state", "contact_forces")}
 
 
-def make_oracle(case, state=None):
+def make_oracle(case, state=None, device="cpu"):
+    """device != "cpu": the same torch code with every tensor on that device (the caller must also step it under
+    ``with torch.device(device)``): bench.py's "reference algorithm as eager torch on the GPU" figure."""
     state = state if state is not None else torch_state(case)
-    hs = None if case["height_samples"] is None else torch.from_numpy(case["height_samples"].copy())
+    state = {k: v.to(device) for k, v in state.items()} if str(device) != "cpu" else state
+    hs = None if case["height_samples"] is None else torch.from_numpy(case["height_samples"].copy()).to(device)
     w = lstm_weights() if case["kind"] == "anymal" else None
-    env = OracleEnv(copy.deepcopy(case["cfg"]), case["consts"], state, kind=case["kind"], height_samples=hs,
-                    terrain_origins=case["terrain_origins"], init_levels=case["init_levels"], lstm_weights=w)
-    env.episode_length_buf[:] = torch.from_numpy(case["state"]["episode_length_buf"])
+    with torch.device(device):
+        env = OracleEnv(copy.deepcopy(case["cfg"]), case["consts"], state, kind=case["kind"], height_samples=hs,
+                        terrain_origins=case["terrain_origins"], init_levels=case["init_levels"], lstm_weights=w)
+    env.episode_length_buf[:] = torch.from_numpy(case["state"]["episode_length_buf"]).to(device)
     return env
 
 

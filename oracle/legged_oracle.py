@@ -57,10 +57,10 @@ class ActuatorLSTM:
     ``forward`` runs aten::lstm (what the TorchScript module dispatches to) so CPU numerics equal
     the reference's; ``forward_plain`` is the gate-by-gate restatement used to document the math."""
 
-    def __init__(self, weights):
-        w = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32) for k, v in weights.items()}
+    def __init__(self, weights, device="cpu"):
+        w = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32).to(device) for k, v in weights.items()}
         self.w = w
-        self.lstm = torch.nn.LSTM(input_size=2, hidden_size=8, num_layers=2, batch_first=True)
+        self.lstm = torch.nn.LSTM(input_size=2, hidden_size=8, num_layers=2, batch_first=True).to(device)
         with torch.no_grad():
             for l in (0, 1):
                 getattr(self.lstm, f"weight_ih_l{l}").copy_(w[f"weight_ih_l{l}"])
@@ -107,6 +107,9 @@ class OracleEnv:
                  init_levels=None, lstm_weights=None):
         self.cfg = cfg
         self.kind = kind
+        # the tensors live where the caller's state lives (CPU for every parity use; bench.py's "eager torch on the GPU" leg
+        # builds the same object under ``with torch.device("cuda")``)
+        self.device = state["root_states"].device
         N = cfg.env.num_envs
         self.N = N
         # ---- _parse_cfg (LR:781-791)
@@ -152,10 +155,10 @@ class OracleEnv:
         self.custom_origins = cfg.terrain.mesh_type in ("heightfield", "trimesh")
         self.env_origins = torch.zeros(N, 3)
         if self.custom_origins:
-            self.terrain_levels = torch.as_tensor(init_levels, dtype=torch.long).clone()
+            self.terrain_levels = torch.as_tensor(init_levels, dtype=torch.long).clone().to(self.device)
             self.terrain_types = torch.div(torch.arange(N), (N / cfg.terrain.num_cols), rounding_mode="floor").to(torch.long)
             self.max_terrain_level = cfg.terrain.num_rows
-            self.terrain_origins = torch.from_numpy(np.asarray(terrain_origins)).to(torch.float)
+            self.terrain_origins = torch.from_numpy(np.asarray(terrain_origins)).to(torch.float).to(self.device)
             self.env_origins[:] = self.terrain_origins[self.terrain_levels, self.terrain_types]
         else:
             ncol = np.floor(np.sqrt(N))
@@ -227,7 +230,7 @@ class OracleEnv:
         # ---- Anymal (ANY:62-69)
         self.use_actuator_net = kind == "anymal" and getattr(cfg.control, "use_actuator_network", False)
         if self.use_actuator_net:
-            self.actuator = ActuatorLSTM(lstm_weights)
+            self.actuator = ActuatorLSTM(lstm_weights, self.device)
             self.sea_input = torch.zeros(N * self.num_actions, 1, 2)
             self.sea_hidden_state = torch.zeros(2, N * self.num_actions, 8)
             self.sea_cell_state = torch.zeros(2, N * self.num_actions, 8)
@@ -287,7 +290,8 @@ class OracleEnv:
 
     # ------------------------------------------------------------------ LR:106-137
     def post_physics_step(self, tables):
-        self.tables = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in tables.items()}
+        self.tables = {k: (v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))).to(self.device)
+                       for k, v in tables.items()}
         self.episode_length_buf += 1
         self.common_step_counter += 1
         if self.llg:

@@ -548,3 +548,64 @@ def test_policy_act_matches_restated_rsl_rl(n, nobs, hidden, variant):
         again = ac.act(o)
     assert torch.equal(again, got_a)
     nat().lib.lgk_policy_set_variant(0)
+
+
+def test_pinned_copy_kernels():
+    """lgk_copy_from_pinned / lgk_copy_to_pinned / lgk_copy_rows_to_pinned: exact copies over the unified address space,
+    argument errors as codes."""
+    lib = nat().lib
+    g = torch.Generator().manual_seed(3)
+    for n in (4, 1000, 98304, 262144 + 4):
+        h = torch.randn(n, generator=g).pin_memory()
+        d = torch.zeros(n, device=DEV)
+        assert lib.lgk_copy_from_pinned(d.data_ptr(), h.data_ptr(), n * 4, stream()) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(d.cpu(), h)
+        h2 = torch.zeros(n).pin_memory()
+        assert lib.lgk_copy_to_pinned(h2.data_ptr(), d.data_ptr(), n * 4, stream()) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(h2, h)
+    assert lib.lgk_copy_from_pinned(d.data_ptr(), h.data_ptr(), 24, stream()) == 1          # not a multiple of 16
+    assert lib.lgk_copy_from_pinned(d.data_ptr() + 4, h.data_ptr(), 16, stream()) == 2      # LGK_ERR_ALIGN
+    # indexed rows: actor rows 2 * id + 1 of a [2N, 13] tensor, first `count` ids only
+    N = 300
+    src = torch.randn(2 * N, 13, generator=g).to(DEV)
+    dst = torch.zeros(2 * N, 13).pin_memory()
+    ids = torch.tensor([5, 17, 299, 0, 42], dtype=torch.int32, device=DEV)
+    count = torch.tensor([3], dtype=torch.int32, device=DEV)
+    assert lib.lgk_copy_rows_to_pinned(dst.data_ptr(), src.data_ptr(), 13, ids.data_ptr(), count.data_ptr(), 2, 1, 5, stream()) == 0
+    torch.cuda.synchronize()
+    want = torch.zeros(2 * N, 13)
+    for i in (5, 17, 299):
+        want[2 * i + 1] = src[2 * i + 1].cpu()
+    assert torch.equal(dst, want)
+
+
+def test_game_prepare_clips_like_torch():
+    """lgk_game_prepare = HLG:161-174: torch.clip semantics (NaN stays NaN), wrap_to_pi on the heading command, prey
+    command handed to the low-level command buffer."""
+    import ctypes as C
+    from oracle.legged_oracle import wrap_pi
+    lib = nat().lib
+    n = 257
+    g = torch.Generator().manual_seed(4)
+    cmd = torch.randn(n, 6, generator=g) * 3.0
+    cmd[3, 0] = float("nan")
+    cmd[4, 2] = 9.5
+    cmd[5, 2] = -7.0
+    want = cmd.clone()
+    want[:, 0] = torch.clip(want[:, 0], min=-1.0, max=1.0)
+    want[:, 1] = torch.clip(want[:, 1], min=-0.5, max=0.75)
+    want[:, 2] = wrap_pi(want[:, 2].clone())
+    want[:, 4] = torch.clip(want[:, 4], min=-2.0, max=2.0)
+    want[:, 5] = torch.clip(want[:, 5], min=-1.5, max=2.5)
+    d = cmd.to(DEV)
+    ll = torch.zeros(n, 4, device=DEV)
+    ranges = (C.c_float * 8)(-1.0, 1.0, -0.5, 0.75, -2.0, 2.0, -1.5, 2.5)
+    rc = lib.lgk_game_prepare(d.data_ptr(), 6, d[:, 4:].data_ptr(), 6, ll.data_ptr(), n, C.byref(ranges), 1, stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = d.cpu()
+    assert torch.allclose(got, want, rtol=0, atol=1e-6, equal_nan=True)
+    assert torch.equal(got[:, [0, 1, 3, 4, 5]].nan_to_num(7.0), want[:, [0, 1, 3, 4, 5]].nan_to_num(7.0))      # clips are exact
+    assert torch.equal(ll.cpu().nan_to_num(7.0), got[:, :4].nan_to_num(7.0))

@@ -565,7 +565,7 @@ def gpu_arm(args):
             env2, feeder2 = envs2[0], feeders2[0]
             s2, _ = time_steps(envs2, [f.synthetic_actions for f in feeders2], 100, 10, flush, lambda: None)
             r2 = kernel_rooflines(envs2, [f.synthetic_actions for f in feeders2], peak_gbs, reps=50)
-            r2["torque_lstm"]["traffic"] = ncu_traffic(n2, "torque_kernel<1>")
+            r2["torque_lstm"]["traffic"] = ncu_traffic(n2, r"torque_kernel<1(, 0)?>")
             r2["post_physics"]["traffic"] = ncu_traffic(n2, r"post_(scalar_)?kernel", "scan_obs_fast_kernel")
             sweep[str(n2)] = dict(value=n2 * 100 / s2, ms_per_step=s2 / 100 * 1e3,
                                   roofline_torque_lstm=r2["torque_lstm"], roofline_post_physics=r2["post_physics"])
@@ -585,7 +585,7 @@ def gpu_arm(args):
         except Exception as e:                       # a baseline, never a reason to lose the bench line
             cpu["eager_torch_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     dom = dict(roof["torque_lstm"])
-    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, "torque_kernel<1>"))
+    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, r"torque_kernel<1(, 0)?>"))
     roof["post_physics"]["traffic"] = ncu_traffic(N, r"post_(scalar_)?kernel", "scan_obs_fast_kernel")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -85,6 +85,8 @@ typedef struct LgkTorqueParams {
    * and `torques_mirror` (optional, e.g. pinned host memory) receives a second copy of the torques, so that a sub-step
    * of LR:88-96 is one launch instead of copy-in, kernel, copy-out. */
   float* torques_mirror;
+  int32_t host_io;                    /* 1: dof_state is (or may be) host memory / torques_mirror is used; 0: device-resident fast path */
+  int32_t pad_;
 } LgkTorqueParams;
 
 /* LSTM actuator weights (resources/actuator_nets/anydrive_v3_lstm.pt: LSTM(2,8,layers=2) + Linear(8,1),

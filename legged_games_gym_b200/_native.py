@@ -29,7 +29,8 @@ class TorqueParams(C.Structure):
                 ("p_gains", f32 * NUM_DOF), ("d_gains", f32 * NUM_DOF), ("torque_limits", f32 * NUM_DOF),
                 ("default_dof_pos", f32 * NUM_DOF),
                 ("actions_in", vp), ("actions_clipped", vp), ("dof_state", vp), ("last_dof_vel", vp),
-                ("torques", vp), ("sea_hidden_state", vp), ("sea_cell_state", vp), ("torques_mirror", vp)]
+                ("torques", vp), ("sea_hidden_state", vp), ("sea_cell_state", vp), ("torques_mirror", vp),
+                ("host_io", i32), ("pad_", i32)]
 
 
 class LstmWeights(C.Structure):

@@ -78,7 +78,9 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-template <bool LSTM>
+// HOSTIO: dof_state may be pinned host memory (uncached loads) and the torques are mirrored into torques_mirror; the
+// device-resident instantiation carries neither (the uncached load alone cost 3 % at 65 536 envs).
+template <bool LSTM, bool HOSTIO = false>
 __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_constant__ LgkTorqueParams p) {
   pdl_launch_dependents();
   const int idx = blockIdx.x * 128 + threadIdx.x;
@@ -89,7 +91,8 @@ __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_
   float a = p.actions_in[idx];
   a = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);                       // LR:86-87
   if (p.actions_clipped) p.actions_clipped[idx] = a;
-  const float2 qs = __ldcv(reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx));   // (pos, vel); never from a cache: may be pinned host memory
+  const float2* qsp = reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx);   // (pos, vel)
+  const float2 qs = HOSTIO ? __ldcv(qsp) : *qsp;
   const float a_s = f_mul(a, p.action_scale);
   if (LSTM) {
     // ANY:75-76 sea_input, then x * in_scale inside the TorchScript module
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_
 #pragma unroll
     for (int k = 0; k < 8; ++k) y = fmaf(c_lstm.lin_w[k], h1[k], y);
     p.torques[idx] = y;                                                        // out_scale folded; no clip (ANY:77-78)
-    if (p.torques_mirror) p.torques_mirror[idx] = y;
+    if (HOSTIO && p.torques_mirror) p.torques_mirror[idx] = y;
     store8(H, h0); store8(C, c0); store8(H + layer, h1); store8(C + layer, c1);
   } else {
     // PD law, op-for-op as torch evaluates it on fp32 tensors (each op rounded; LR:383-395)
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_
     }
     const float tc = fminf(fmaxf(tq, -p.torque_limits[d]), p.torque_limits[d]);
     p.torques[idx] = tc;
-    if (p.torques_mirror) p.torques_mirror[idx] = tc;
+    if (HOSTIO && p.torques_mirror) p.torques_mirror[idx] = tc;
   }
 }
 
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(128) torque_lstm_split_kernel(const __grid_con
     float a = p.actions_in[idx];
     a = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);                     // LR:86-87
     if (p.actions_clipped && w == 0) p.actions_clipped[idx] = a;
-    const float2 qs = __ldcv(reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx));
+    const float2 qs = *reinterpret_cast<const float2*>(p.dof_state + 2 * (size_t)idx);
     x[0] = f_sub(f_add(f_mul(a, p.action_scale), p.default_dof_pos[d]), qs.x);   // ANY:75 (in_scale folded into w_ih0)
     x[1] = qs.y;                                                                 // ANY:76
   }
@@ -244,7 +247,6 @@ __global__ void __launch_bounds__(128) torque_lstm_split_kernel(const __grid_con
 #pragma unroll
     for (int k = 0; k < 8; ++k) y = fmaf(c_lstm.lin_w[k], s_hnew[1][lane][k], y);
     p.torques[idx] = y;                                   // out_scale folded; no clip on this path (ANY:77-78)
-    if (p.torques_mirror) p.torques_mirror[idx] = y;
   }
   for (int i = tid; i < 4 * 64; i += 128) {
     const int arr = i >> 6, q = i & 63;
@@ -309,13 +311,17 @@ extern "C" int lgk_compute_torques(const LgkTorqueParams* p, void* stream) {
   if ((reinterpret_cast<uintptr_t>(p->dof_state) & 7u) != 0) return set_error(LGK_ERR_ALIGN, "dof_state must be 8-byte aligned");
   const int blocks = (p->num_envs * kDof + 127) / 128;
   LGK_REQUIRE(p->lstm_variant >= 0 && p->lstm_variant <= 2, "lstm_variant must be 0, 1 or 2");
+  LGK_REQUIRE(p->host_io || p->torques_mirror == nullptr, "torques_mirror needs host_io = 1");
+  LGK_REQUIRE(!(p->host_io && p->use_lstm && p->lstm_variant == 2), "the role-split LSTM kernel has no host_io path");
   // auto = one thread per sequence: measured faster at 4096, 16384 and 65536 envs (bench.py --lstm-variant 2 to compare)
   const bool split = p->lstm_variant == 2;
   cudaError_t e;
   if (p->use_lstm && split)
     e = launch_chained(torque_lstm_split_kernel, dim3((p->num_envs * kDof + kSeqPerCta - 1) / kSeqPerCta), dim3(128), 0, (cudaStream_t)stream, *p);
-  else if (p->use_lstm) e = launch_chained(torque_kernel<true>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p);
-  else e = launch_chained(torque_kernel<false>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p);
+  else if (p->use_lstm) e = p->host_io ? launch_chained(torque_kernel<true, true>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p)
+                                       : launch_chained(torque_kernel<true, false>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p);
+  else e = p->host_io ? launch_chained(torque_kernel<false, true>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p)
+                      : launch_chained(torque_kernel<false, false>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p);
   count_launch();
   return check_cuda(e, "torque_kernel launch");
 }

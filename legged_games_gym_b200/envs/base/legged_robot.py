@@ -159,6 +159,7 @@ class LeggedRobot(BaseTask):
                 zero_copy = src is not None
                 tp.dof_state = (src if zero_copy else self.dof_state).data_ptr()
                 tp.torques_mirror = sink.data_ptr() if sink is not None else None
+                tp.host_io = int(zero_copy or sink is not None or bool(getattr(gym, "state_in_host_memory", False)))
                 nat.check(nat.lib.lgk_compute_torques(C.byref(tp), _stream_ptr()), "lgk_compute_torques")
                 if k == 0:      # later sub-steps read the clipped copy (clip is idempotent)
                     tp.actions_in = self.actions.data_ptr()

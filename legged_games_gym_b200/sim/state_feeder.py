@@ -181,6 +181,7 @@ class HostStateFeeder(StateFeeder):
         # reset rows only (lgk_copy_rows_to_pinned) instead of whole tensors: 0.6 MB less D2H per step, measured neutral
         # for the step time at 4096 envs (two tiny launches against two 5-8 us copies), so off unless asked for
         self.indexed_rows = os.environ.get("LGK_HOST_INDEXED_ROWS", "0") == "1"
+        self.state_in_host_memory = self.unified          # the env then launches the uncached-load (host_io) torque kernel
         if self.unified:
             dev = self.root_states.device
             self.root_states = torch.as_tensor(_PinnedAlias(self.h_root), device=dev)

@@ -504,6 +504,20 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
           orow[32 + lane] = clampf(v1, -clip, clip);
         }
       }
+    } else if (!p.measure_heights) {
+      // ---------------- no height columns (flat tasks): the row is finished here -- noise (one Philox block per env and
+      // lane, the words K2 would use) + clip -- and lgk_post_physics launches no K2
+      const bool noisy = p.add_noise != 0;
+      const float nz0 = noisy ? __ldg(p.noise_scale_vec + lane) : 0.f;
+      const float nz1 = (noisy && lane < 16) ? __ldg(p.noise_scale_vec + 32 + lane) : 0.f;
+      const float clip = p.clip_obs;
+      for (int ee = warp * 8; ee < min(warp * 8 + 8, nval); ++ee) {
+        float* orow = p.obs_buf + (size_t)(env0 + ee) * O;
+        U4 r = U4{0, 0, 0, 0};
+        if (noisy) r = rng_block(key, (uint32_t)(p.env_id_offset + env0 + ee), LGK_STREAM_OBS, (uint32_t)lane);
+        orow[lane] = clampf(noisy_obs(s_head[ee * 49 + lane], r.x, nz0), -clip, clip);
+        if (lane < 16) orow[32 + lane] = clampf(noisy_obs(s_head[ee * 49 + 32 + lane], r.y, nz1), -clip, clip);
+      }
     } else {
       // ---------------- the 48 proprioceptive columns, un-noised (K2 adds noise + clip): coalesced row segments
       for (int ee = warp * 8; ee < min(warp * 8 + 8, nval); ++ee) {
@@ -1168,6 +1182,7 @@ extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
     if (scan_first)
       if (int rc = launch_k2(p, kScan, st)) return rc;
     if (int rc = launch_k1(p, st)) return rc;
+    if (!heights) return LGK_OK;                    // flat tasks: K1 finished the 48-column rows itself
     return launch_k2(p, scan_first ? kObs : (kScan | kObs), st);
   }
   if (pre) {                      // Python code follows (user reward terms may read measured_heights): scan now
@@ -1176,7 +1191,7 @@ extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
     return launch_k1(p, st);
   }
   if (int rc = launch_k1(p, st)) return rc;      // POST only
-  return launch_k2(p, kObs, st);
+  return heights ? launch_k2(p, kObs, st) : LGK_OK;
 }
 
 extern "C" int lgk_step_debug_timeline(int64_t* device_buf16) {

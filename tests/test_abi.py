@@ -59,3 +59,14 @@ def test_graft_entry_build_runs_on_cpu():
     """the driver's "does it build" check: compiles (or finds up to date) liblgk.so, loads it, imports the checker"""
     import __graft_entry__ as g
     g.build()
+
+
+def test_unknown_task_raises_value_error():
+    """task_registry.make_env on an unregistered name: ValueError like the reference (task_registry.py:87)"""
+    import pytest
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.utils.helpers import get_args
+    with pytest.raises(ValueError, match="was not registered"):
+        task_registry.make_env("no_such_task", get_args([]))
+    with pytest.raises(ValueError, match="Either 'name' or 'train_cfg'"):
+        task_registry.make_alg_runner(env=None, name=None, args=get_args([]), train_cfg=None)

@@ -609,3 +609,26 @@ def test_game_prepare_clips_like_torch():
     assert torch.allclose(got, want, rtol=0, atol=1e-6, equal_nan=True)
     assert torch.equal(got[:, [0, 1, 3, 4, 5]].nan_to_num(7.0), want[:, [0, 1, 3, 4, 5]].nan_to_num(7.0))      # clips are exact
     assert torch.equal(ll.cpu().nan_to_num(7.0), got[:, :4].nan_to_num(7.0))
+
+
+def test_reference_error_behaviour():
+    """The Python layer raises what the reference raises: NameError for an unknown control type (LR:394),
+    ValueError for an unknown terrain mesh type (LR:250); the games:
+    AttributeError for a predator termination scale (DHLG:358-359), ValueError when the low-level checkpoint directory is
+    missing (helpers.py:109, reached from HLG:100)."""
+    from legged_games_gym_b200.envs import task_registry
+    from legged_games_gym_b200.utils import get_args
+    # (the string 'none' never reaches the NameError of LR:847 in the reference either: create_sim rejects it first, LR:250)
+    for ov, exc in (({"control.control_type": "X"}, NameError), ({"terrain.mesh_type": "none"}, ValueError),
+                    ({"terrain.mesh_type": "blob"}, ValueError)):
+        case = harness.build_case("a1", 32, seed=1)
+        harness.apply_overrides(case["cfg"], ov)
+        with pytest.raises(exc):
+            env, _ = product_env(case)
+            env.step(torch.zeros(32, 12, device=DEV))
+    case = harness.build_case("low_level_game", 32, seed=1, overrides={"terrain.mesh_type": "plane", "terrain.curriculum": False})
+    with pytest.raises(AttributeError, match="reward_scales"):
+        product_game(case, "dec", {"rewards_predator.scales.termination": 1.0}, ll_policy=lambda o: o)
+    a = get_args(["--task", "high_level_game", "--num_envs", "32", "--headless"])
+    with pytest.raises(ValueError, match="No runs in this directory"):
+        task_registry.make_env(name="high_level_game", args=a)

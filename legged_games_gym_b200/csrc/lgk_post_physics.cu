@@ -825,7 +825,6 @@ __device__ __forceinline__ void scan_tile(const LgkStepParams& p, const RngKey& 
   const float* r = p.root_states + ((size_t)(env0 + min(lane, nval - 1)) * p.actors_per_env + p.root_actor_offset) * 13;
   const YawFrame fl = yaw_frame(r[5], r[6], r[0], r[1]);
   const float rzl = r[2] - 0.5f;
-  if (rzl == 123456.f) scan_stamp(12);      // (keeps the frame loads ahead of the next stamp)
   scan_stamp(10);
 #pragma unroll 1
   for (int e = e0; e < e1; e += de) {

@@ -225,9 +225,9 @@ int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int32_t num_id
 
 /* Profiling hook: when non-NULL, CTA 0 of the scalar post-physics kernel writes %globaltimer stamps (ns) into
  * device_buf16[0..8]: entry, step counter read, tile staged, rewards done, reset done, outputs staged, bulk stores issued,
- * rows written, bulk stores drained; [13], [14]: the LAST CTA after its dependency wait and at its end (the kernel's
- * in-situ span = [14] - [1]); [9..11]: first scan warp of the fused variant (start, frames loaded, end). */
-int lgk_step_debug_timeline(int64_t* device_buf16);
+ * rows written, bulk stores drained; [16..24]: the same nine stamps of the LAST CTA (the kernel's in-situ span =
+ * [24] - [1]); [9..11]: first scan warp of the fused variant (start, frames loaded, end).  The buffer holds 32 int64. */
+int lgk_step_debug_timeline(int64_t* device_buf32);
 
 /* After lgk_post_physics / lgk_reset_idx: single-CTA pass that (a) compacts reset_buf into an ascending
  * int32 id list + count (what set_*_tensor_indexed needs, LR:409-412, 433-436), (b) if count > 0 writes the

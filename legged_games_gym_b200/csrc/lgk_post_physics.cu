@@ -135,10 +135,10 @@ constexpr int kFrameFloats = 8;
 constexpr int kK1Threads = 4 * kTile;
 __device__ long long* g_k1_timeline = nullptr;     // profiling hook (lgk_step_debug_timeline): stamps of CTA 0
 __device__ __forceinline__ void k1_stamp(int slot) {
-  if (g_k1_timeline != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || (blockIdx.x == gridDim.x - 1 && (slot == 1 || slot == 8)))) {
+  if (g_k1_timeline != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    g_k1_timeline[blockIdx.x == 0 ? slot : (slot == 1 ? 13 : 14)] = (long long)t;      // 13 / 14: last CTA after the wait / at its end
+    g_k1_timeline[blockIdx.x == 0 ? slot : 16 + slot] = (long long)t;      // [16..24]: the same stamps of the LAST CTA
   }
 }
 

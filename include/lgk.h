@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LGK_ABI_VERSION 3
+#define LGK_ABI_VERSION 4
 #define LGK_NUM_DOF 12          /* every registered task has 12 DOF = 12 actions */
 #define LGK_MAX_FEET 4
 #define LGK_MAX_PEN 16
@@ -352,6 +352,9 @@ typedef struct LgkPolicyParams {
    * version of the weight tensors; the packed image in `workspace` is reused while version, workspace and shapes
    * are unchanged (the Python ActorCritic passes the sum of the parameters' torch version counters + 1). */
   int64_t weights_version;
+  /* which networks run: 0 or 3 = actor and critic (PPO.act), 1 = actor only (act / act_inference: critic_obs, values may be
+   * NULL and num_critic_obs columns are never read), 2 = critic only (evaluate: obs and the action outputs may be NULL) */
+  int32_t nets; int32_t pad_;
 } LgkPolicyParams;
 
 int64_t lgk_policy_workspace_bytes(const LgkPolicyParams* p);

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 3          # include/lgk.h LGK_ABI_VERSION
+ABI_VERSION = 4          # include/lgk.h LGK_ABI_VERSION
 LIB_PATH = os.environ.get("LGK_LIB_PATH") or os.path.join(_HERE, "liblgk.so")      # override: A/B of kernel builds
 
 NUM_DOF, MAX_FEET, MAX_PEN, MAX_TERM, MAX_BODIES = 12, 4, 16, 8, 32
@@ -104,7 +104,8 @@ class PolicyParams(C.Structure):
                 ("actor_w", vp * 4), ("actor_b", vp * 4), ("critic_w", vp * 4), ("critic_b", vp * 4),
                 ("std", vp), ("seed", u64), ("step", i32), ("env_id_offset", i64), ("sample", i32),
                 ("actions", vp), ("action_mean", vp), ("action_sigma", vp), ("values", vp),
-                ("actions_log_prob", vp), ("workspace", vp), ("workspace_bytes", i64), ("weights_version", i64)]
+                ("actions_log_prob", vp), ("workspace", vp), ("workspace_bytes", i64), ("weights_version", i64),
+                ("nets", i32), ("pad_", i32)]
 
 
 class LgkError(RuntimeError):

@@ -3,6 +3,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace lgk {
 
@@ -22,6 +25,22 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// cudaFuncSetAttribute is per (device, function): remember the largest dynamic shared-memory size set for every pair so that
+// a process driving several GPUs (or switching devices) configures each of them
+int ensure_func_attr(const void* func, int smem_bytes, const char* name, bool max_carveout) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> done;
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  std::lock_guard<std::mutex> lk(mu);
+  int& have = done[std::make_pair(dev, func)];
+  if (smem_bytes <= have) return LGK_OK;
+  if (int rc = check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), name)) return rc;
+  if (max_carveout) cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  have = smem_bytes;
+  return LGK_OK;
+}
 
 // kind 0: uniforms, 1: raw words, 2: Box-Muller normals on pairs (ACT stream convention)
 __global__ void rng_dump_kernel(uint64_t seed, int step, long long env_off, int n, int stream_id, int count, int kind,

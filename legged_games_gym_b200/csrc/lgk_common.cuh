@@ -54,6 +54,7 @@ constexpr int kDof = LGK_NUM_DOF;
 int set_error(int code, const char* msg);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+int ensure_func_attr(const void* func, int smem_bytes, const char* name, bool max_carveout = false);   // per device
 
 // ---- programmatic dependent launch (PDL): the kernels of one env step form a chain on one stream; launched with
 // programmatic stream serialization each may start (prologue, barrier init, constant staging) while its predecessor

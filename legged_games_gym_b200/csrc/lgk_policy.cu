@@ -130,8 +130,11 @@ static void launch_gemm(const float* X, const float* W, const float* b, float* Y
 
 extern "C" int lgk_policy_act(const LgkPolicyParams* p, void* stream) {
   LGK_REQUIRE(p != nullptr && p->num_envs > 0, "policy: bad params");
-  LGK_REQUIRE(p->obs && p->critic_obs && p->std && p->actions && p->action_mean && p->action_sigma && p->values &&
-              p->actions_log_prob && p->workspace, "policy: null buffer");
+  LGK_REQUIRE(p->nets >= 0 && p->nets <= 3, "policy: nets must be 0..3");
+  const bool run_actor = p->nets != 2, run_critic = p->nets != 1;
+  LGK_REQUIRE(p->workspace != nullptr, "policy: null buffer");
+  if (run_actor) LGK_REQUIRE(p->obs && p->std && p->actions && p->action_mean && p->action_sigma && p->actions_log_prob, "policy: null buffer");
+  if (run_critic) LGK_REQUIRE(p->critic_obs && p->values, "policy: null buffer");
   for (int i = 0; i < 4; ++i) LGK_REQUIRE(p->actor_w[i] && p->actor_b[i] && p->critic_w[i] && p->critic_b[i], "policy: null weights");
   LGK_REQUIRE(p->workspace_bytes >= lgk_policy_workspace_bytes(p), "policy: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -146,6 +149,7 @@ extern "C" int lgk_policy_act(const LgkPolicyParams* p, void* stream) {
   float* w0 = reinterpret_cast<float*>(p->workspace);
   float* w1 = w0 + (size_t)N * hmax;
   for (int net = 0; net < 2; ++net) {
+    if (net == 0 ? !run_actor : !run_critic) continue;
     const float* const* W = net ? p->critic_w : p->actor_w;
     const float* const* B = net ? p->critic_b : p->actor_b;
     const float* x = net ? p->critic_obs : p->obs;
@@ -155,7 +159,9 @@ extern "C" int lgk_policy_act(const LgkPolicyParams* p, void* stream) {
     launch_gemm<true>(w1, W[2], B[2], w0, N, p->hidden[1], p->hidden[2], st);
     launch_gemm<false>(w0, W[3], B[3], net ? p->values : p->action_mean, N, p->hidden[2], net ? 1 : p->num_actions, st);
   }
-  sample_kernel<<<(N + 127) / 128, 128, 0, st>>>(*p);
-  count_launch();
+  if (run_actor) {
+    sample_kernel<<<(N + 127) / 128, 128, 0, st>>>(*p);
+    count_launch();
+  }
   return check_cuda(cudaGetLastError(), "policy kernels launch");
 }

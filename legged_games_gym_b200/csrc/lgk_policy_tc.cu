@@ -27,6 +27,8 @@
 // in FP32: within the north_star's 1e-3 for policy outputs (tests/test_gpu_parity.py).
 #include "lgk_policy_common.cuh"
 #include "lgk_policy_tc_plan.h"
+#include <mutex>
+#include <unordered_map>
 
 namespace lgk {
 
@@ -192,6 +194,7 @@ struct TcArgs {
   const uint8_t* packed;      // workspace base (1024-byte aligned)
   long long* timeline;        // optional [16] globaltimer stamps of CTA (0,0) (lgk_policy_debug_timeline)
   int dbg_flags;              // bit 0: skip the weight copies, bit 1: skip the MMAs (profiling experiments only)
+  int net0;                   // first network of the grid's y dimension (0 actor, 1 critic): LgkPolicyParams.nets
 };
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   const LgkPolicyParams& p = a.p;
   const TcPlan& pl = a.pl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int net = blockIdx.y;                     // 0 actor, 1 critic
+  const int net = a.net0 + blockIdx.y;            // 0 actor, 1 critic
   const int m0 = blockIdx.x * kTileM;
   const int N = p.num_envs;
   const int O = pl.o[net], kc1 = pl.kc1[net];
@@ -485,19 +488,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------ host side
-struct PackCache { const void* ws; long long version; int shape[8]; const void* w[8]; };
-static PackCache g_pack = {nullptr, 0, {0}, {nullptr}};
+// Packed-weight cache: one record PER WORKSPACE (a process may alternate several ActorCritic instances -- the games run a
+// low-level policy plus one or two high-level agents -- and each owns its workspace), keyed by the workspace pointer and
+// validated against the caller's weights_version, the shapes and the weight pointers.
+struct PackCache { long long version; int shape[8]; const void* w[8]; };
+static std::mutex g_pack_mu;
+static std::unordered_map<const void*, PackCache> g_pack;
 static long long* g_timeline = nullptr;
 static int g_dbg_flags = 0;
 void policy_tc_set_timeline(long long* dev, int flags) { g_timeline = dev; g_dbg_flags = flags; }
 
 int policy_tc_launch(const LgkPolicyParams* p, const TcPlan& pl, cudaStream_t st) {
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)p->workspace + 1023) & ~(uintptr_t)1023);
+  PackCache want;
+  want.version = p->weights_version;
   const int shape[8] = {pl.o[0], pl.o[1], pl.h0, pl.h1, pl.h2, pl.nact, 0, 0};
-  const void* wptr[8];
-  for (int i = 0; i < 4; ++i) { wptr[i] = p->actor_w[i]; wptr[4 + i] = p->critic_w[i]; }
-  const bool cached = p->weights_version != 0 && g_pack.ws == p->workspace && g_pack.version == p->weights_version &&
-                      memcmp(shape, g_pack.shape, sizeof(shape)) == 0 && memcmp(wptr, g_pack.w, sizeof(wptr)) == 0;
+  memcpy(want.shape, shape, sizeof(shape));
+  for (int i = 0; i < 4; ++i) { want.w[i] = p->actor_w[i]; want.w[4 + i] = p->critic_w[i]; }
+  bool cached = false;
+  if (p->weights_version != 0) {
+    std::lock_guard<std::mutex> lk(g_pack_mu);
+    auto it = g_pack.find(p->workspace);
+    cached = it != g_pack.end() && it->second.version == want.version &&
+             memcmp(want.shape, it->second.shape, sizeof(shape)) == 0 && memcmp(want.w, it->second.w, sizeof(want.w)) == 0;
+  }
   if (!cached) {
     PackJobs jobs;
     for (int net = 0; net < 2; ++net) {
@@ -518,19 +532,18 @@ int policy_tc_launch(const LgkPolicyParams* p, const TcPlan& pl, cudaStream_t st
     policy_pack_kernel<<<dim3(74, 6), 256, 0, st>>>(jobs);
     count_launch();
     if (int rc = check_cuda(cudaGetLastError(), "policy_pack_kernel launch")) return rc;
-    g_pack.ws = p->workspace; g_pack.version = p->weights_version;
-    memcpy(g_pack.shape, shape, sizeof(shape));
-    memcpy(g_pack.w, wptr, sizeof(wptr));
+    if (p->weights_version != 0) {
+      std::lock_guard<std::mutex> lk(g_pack_mu);
+      if (g_pack.size() > 256) g_pack.clear();        // workspaces come and go with their modules: bound the table
+      g_pack[p->workspace] = want;
+    }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
-                            "cudaFuncSetAttribute(policy_tc_kernel)")) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_func_attr(reinterpret_cast<const void*>(policy_tc_kernel), kSmemBytes, "policy_tc_kernel")) return rc;
   TcArgs args;
   args.p = *p; args.pl = pl; args.packed = base; args.timeline = g_timeline; args.dbg_flags = g_dbg_flags;
-  policy_tc_kernel<<<dim3((p->num_envs + kTileM - 1) / kTileM, 2), kTcThreads, kSmemBytes, st>>>(args);
+  args.net0 = p->nets == 2 ? 1 : 0;
+  const int nets = (p->nets == 1 || p->nets == 2) ? 1 : 2;
+  policy_tc_kernel<<<dim3((p->num_envs + kTileM - 1) / kTileM, nets), kTcThreads, kSmemBytes, st>>>(args);
   count_launch();
   return check_cuda(cudaGetLastError(), "policy_tc_kernel launch");
 }

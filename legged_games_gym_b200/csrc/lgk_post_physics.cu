@@ -1073,15 +1073,8 @@ static int validate_step(const LgkStepParams* p) {
 
 static int launch_k1(const LgkStepParams* p, cudaStream_t st) {
   const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_reward_slots);
-  static int smem_set = 0;
-  if (L.total > smem_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(post_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
-                            "cudaFuncSetAttribute(post_kernel)")) return rc;
-    smem_set = L.total;
-    // one warp per CTA, ~15 KB of staged tiles each: ask for the largest shared-memory carve-out so that a whole
-    // 65k-env grid (2048 CTAs) is resident in a single wave
-    cudaFuncSetAttribute(post_kernel<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  }
+  // ~25 KB of staged tiles per CTA: ask for the largest shared-memory carve-out so that 7 CTAs are resident per SM
+  if (int rc = ensure_func_attr(reinterpret_cast<const void*>(post_kernel<0, false>), L.total, "cudaFuncSetAttribute(post_kernel)", true)) return rc;
   const cudaError_t e = launch_chained(post_kernel<0, false>, dim3((p->num_envs + kTile - 1) / kTile), dim3(kK1Threads), (size_t)L.total, st, *p);
   count_launch();
   return check_cuda(e, "post_kernel launch");
@@ -1110,13 +1103,7 @@ static bool fused_eligible(const LgkStepParams* p) {
 template <int G, bool RECIP>
 static int launch_fused_t(const LgkStepParams* p, int scan_warps, cudaStream_t st) {
   const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_reward_slots, true);
-  static int smem_set = 0;
-  if (L.total > smem_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(post_kernel<G, RECIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total),
-                            "cudaFuncSetAttribute(post_kernel fused)")) return rc;
-    smem_set = L.total;
-    cudaFuncSetAttribute(post_kernel<G, RECIP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  }
+  if (int rc = ensure_func_attr(reinterpret_cast<const void*>(post_kernel<G, RECIP>), L.total, "cudaFuncSetAttribute(post_kernel fused)", true)) return rc;
   const cudaError_t e = launch_chained(post_kernel<G, RECIP>, dim3((p->num_envs + kTile - 1) / kTile), dim3(kK1Threads + 32 * scan_warps),
                                        (size_t)L.total, st, *p);
   count_launch();

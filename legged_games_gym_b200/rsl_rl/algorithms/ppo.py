@@ -4,6 +4,8 @@ backward, gradient clipping, Adam, the adaptive-KL learning-rate rule and the lo
 host synchronisation inside the loop), eager otherwise.  Multi-GPU (one process per GPU, envs sharded): gradients are flattened into one bucket and
 all-reduced over NCCL once per mini-batch; the KL estimate that drives the adaptive learning rate is all-reduced so
 every rank takes the same schedule."""
+import copy
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -58,7 +60,20 @@ class PPO:
         t = self.transition
         t.actions, t.values, t.actions_log_prob = out["actions"], out["values"], out["logp"]
         t.action_mean, t.action_sigma = out["mean"], out["sigma"]
-        t.observations, t.critic_observations = obs, critic_obs
+        # Snapshot NOW: `obs` is usually the env's persistent obs_buf, which env.step() rewrites in place before
+        # process_env_step() stores the transition (the reference's env rebinds obs_buf to a fresh tensor every step, so
+        # rsl_rl can keep the reference there).  The copy lands in its final place, the rollout storage slot.
+        st = self.storage
+        if st is not None and st.step < st.num_transitions_per_env:
+            t.observations = st.observations[st.step]
+            t.observations.copy_(obs)
+            if st.privileged_observations is not None:
+                t.critic_observations = st.privileged_observations[st.step]
+                t.critic_observations.copy_(critic_obs)
+            else:
+                t.critic_observations = t.observations
+        else:
+            t.observations, t.critic_observations = obs.clone(), critic_obs.clone()
         return t.actions
 
     def process_env_step(self, rewards, dones, infos):
@@ -147,7 +162,9 @@ class PPO:
                     olp=st.actions_log_prob.flatten(0, 1), adv=st.advantages.flatten(0, 1), mu=st.mu.flatten(0, 1),
                     sg=st.sigma.flatten(0, 1))
         # Adam whose step counter and learning rate live on the device (capturable); state carried over from the eager optimizer
-        state = self.optimizer.state_dict()
+        # deep copy: state_dict() hands out references, and load_state_dict() of same-device tensors aliases them, so the
+        # warm-up steps and the zero_() below would otherwise wipe the moments that are restored afterwards (--resume)
+        state = copy.deepcopy(self.optimizer.state_dict())
         lr_t = torch.tensor(float(self.learning_rate), device=dev)
         self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=lr_t, capturable=True, fused=True)     # one multi-tensor kernel
         if state["state"]:
@@ -204,6 +221,59 @@ class PPO:
         return acc[0], acc[1]
 
     def update(self):
+        out = self._update()
+        # the parameters changed (a graph replay moves no torch version counter): the rollout kernel re-packs its weights
+        self.actor_critic.weights_changed()
+        return out
+
+    # ------------------------------------------------------------------ optimizer state in the reference's format
+    def optimizer_state_dict(self):
+        """Adam state as stock rsl_rl / torch.optim.Adam writes it (plain-float lr, CPU `step`, no capturable / fused
+        flags), whichever optimizer flavour is live: checkpoints stay interchangeable with the reference's."""
+        sd = copy.deepcopy(self.optimizer.state_dict())
+        for s_ in sd["state"].values():
+            if torch.is_tensor(s_.get("step")):
+                s_["step"] = s_["step"].detach().float().cpu()
+        for grp in sd["param_groups"]:
+            grp["lr"] = float(grp["lr"])
+            grp["capturable"], grp["fused"], grp["foreach"] = False, None, None
+        return sd
+
+    def load_optimizer_state_dict(self, sd):
+        """Accepts the reference's format (and this class's own): values are converted to the live optimizer's flavour.
+        Once the update graph is captured the state tensors' addresses are baked into it, so values are copied IN PLACE."""
+        lr = float(sd["param_groups"][0]["lr"])
+        if self._graph is not None and len(self.optimizer.state) > 0:
+            params = [p for g in self.optimizer.param_groups for p in g["params"]]
+            for i, p in enumerate(params):
+                src = sd["state"].get(i)
+                if src is None:
+                    continue
+                dst = self.optimizer.state[p]
+                dst["exp_avg"].copy_(src["exp_avg"])
+                dst["exp_avg_sq"].copy_(src["exp_avg_sq"])
+                dst["step"].fill_(float(src["step"]))
+            self._graph["lr"].fill_(lr)
+        else:
+            sd = copy.deepcopy(sd)
+            live = self.optimizer.param_groups[0]
+            capt = bool(live.get("capturable", False))
+            for s_ in sd["state"].values():
+                if "step" in s_:
+                    s_["step"] = torch.as_tensor(float(s_["step"]), dtype=torch.float32, device=self.device if capt else "cpu")
+            for grp, lg in zip(sd["param_groups"], self.optimizer.param_groups):
+                for k in ("capturable", "fused", "foreach"):
+                    if k in lg:
+                        grp[k] = lg[k]
+                grp["lr"] = lg["lr"]
+                if torch.is_tensor(lg["lr"]):
+                    lg["lr"].fill_(lr)
+                else:
+                    grp["lr"] = lr
+            self.optimizer.load_state_dict(sd)
+        self.learning_rate = lr
+
+    def _update(self):
         if (self.use_cuda_graph and _world() == 1 and torch.device(self.device).type == "cuda"
                 and self.storage.observations.is_cuda):
             return self._update_graphed()

@@ -2,12 +2,16 @@
 Rollout-time calls (no autograd) run the fused lgk_policy_act kernel; calls that need gradients (PPO.update) go through
 the nn.Sequential modules so autograd sees ordinary Linear/ELU ops."""
 import ctypes as C
+import itertools
 
 import torch
 import torch.nn as nn
 from torch.distributions import Normal
 
 from ... import _native as nat
+
+
+_INSTANCE_IDS = itertools.count(1)      # process-wide: no two modules ever present the same weights_version
 
 
 def _mlp(n_in, hidden, n_out, act):
@@ -42,6 +46,29 @@ class ActorCritic(nn.Module):
         self._seed, self._step, self._env_offset = 0, 0, 0
         self._fused = None            # outputs of the last fused call
         self._ws = None
+        # generation of the weight VALUES: the packed TF32 image the kernel keeps in the workspace is rebuilt when it moves.
+        # torch's per-tensor version counters see eager in-place updates (optimizer.step, load_state_dict, .to()) but NOT the
+        # replay of a captured update graph, so whoever changes the parameters out of torch's sight calls weights_changed().
+        self._weights_gen = 0
+        self._instance_id = next(_INSTANCE_IDS)
+
+    def weights_changed(self):
+        """Tell the rollout kernel that the parameter values changed (PPO calls this after every update())."""
+        self._weights_gen += 1
+
+    def _apply(self, fn, *a, **kw):
+        self._weights_gen += 1
+        self._ws = None
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._weights_gen += 1
+        return super().load_state_dict(*a, **kw)
+
+    def _weights_version(self):
+        # instance id (bits 40..62) | generation (bits 20..39) | sum of the tensors' version counters (bits 0..19)
+        tv = sum(int(q._version) for q in self.parameters())
+        return (self._instance_id << 40) | ((self._weights_gen & 0xFFFFF) << 20) | (tv & 0xFFFFF)
 
     # -- RNG of the sampling epilogue (Philox ACT stream); the runner bumps `step` once per env step
     def set_rng(self, seed, step, env_id_offset=0):
@@ -72,14 +99,23 @@ class ActorCritic(nn.Module):
         self._fused = None
 
     def _run_fused(self, obs, critic_obs, sample):
+        """critic_obs=None runs the actor alone (act / act_inference): nothing is read through the critic pointer."""
         n = obs.shape[0]
         dev = obs.device
         p = nat.PolicyParams()
         p.num_envs, p.num_obs, p.num_critic_obs, p.num_actions = n, self.num_actor_obs, self.num_critic_obs, self.num_actions
         p.hidden[:] = self.hidden
         obs = obs.contiguous()
-        critic_obs = critic_obs.contiguous()
-        p.obs, p.critic_obs = obs.data_ptr(), critic_obs.data_ptr()
+        if obs.shape[1] != self.num_actor_obs:
+            raise ValueError(f"observations have {obs.shape[1]} columns, the actor takes {self.num_actor_obs}")
+        p.obs = obs.data_ptr()
+        if critic_obs is not None:
+            critic_obs = critic_obs.contiguous()
+            if critic_obs.shape[1] != self.num_critic_obs or critic_obs.shape[0] != n:
+                raise ValueError(f"critic observations are {tuple(critic_obs.shape)}, the critic takes [{n}, {self.num_critic_obs}]")
+            p.critic_obs, p.nets = critic_obs.data_ptr(), 3
+        else:
+            p.critic_obs, p.nets = None, 1
         for i, li in enumerate((0, 2, 4, 6)):
             p.actor_w[i], p.actor_b[i] = self.actor[li].weight.data_ptr(), self.actor[li].bias.data_ptr()
             p.critic_w[i], p.critic_b[i] = self.critic[li].weight.data_ptr(), self.critic[li].bias.data_ptr()
@@ -87,16 +123,14 @@ class ActorCritic(nn.Module):
         p.seed, p.step, p.env_id_offset, p.sample = self._seed, self._step, self._env_offset, int(sample)
         out = dict(actions=torch.empty(n, self.num_actions, device=dev), mean=torch.empty(n, self.num_actions, device=dev),
                    sigma=torch.empty(n, self.num_actions, device=dev), values=torch.empty(n, 1, device=dev),
-                   logp=torch.empty(n, device=dev), obs_ptr=critic_obs.data_ptr())
+                   logp=torch.empty(n, device=dev))
         p.actions, p.action_mean, p.action_sigma = out["actions"].data_ptr(), out["mean"].data_ptr(), out["sigma"].data_ptr()
         p.values, p.actions_log_prob = out["values"].data_ptr(), out["logp"].data_ptr()
         need = int(nat.lib.lgk_policy_workspace_bytes(C.byref(p)))
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         p.workspace, p.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
-        # torch bumps a tensor's version counter on every in-place update (optimizer.step, load_state_dict): the packed
-        # TF32 weight image inside the workspace is rebuilt only when this sum moves
-        p.weights_version = 1 + sum(int(q._version) for q in self.parameters())
+        p.weights_version = self._weights_version()
         nat.check(nat.lib.lgk_policy_act(C.byref(p), torch.cuda.current_stream().cuda_stream), "lgk_policy_act")
         self._last_params, self._last_inputs = p, (obs, critic_obs)      # keeps the launch's buffers alive
         self._fused = out
@@ -111,7 +145,7 @@ class ActorCritic(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not torch.is_inference_mode_enabled():
             self.update_distribution(observations)
             return self.distribution.sample()
-        return self._run_fused(observations, observations, sample=True)["actions"]
+        return self._run_fused(observations, None, sample=True)["actions"]
 
     def get_actions_log_prob(self, actions):
         if self._fused is not None:
@@ -120,9 +154,9 @@ class ActorCritic(nn.Module):
 
     def act_inference(self, observations):
         with torch.no_grad():
-            return self._run_fused(observations, observations, sample=False)["mean"]
+            return self._run_fused(observations, None, sample=False)["mean"]
 
     def evaluate(self, critic_observations, **kwargs):
-        if self._fused is not None and not torch.is_grad_enabled() and self._fused["obs_ptr"] == critic_observations.data_ptr():
-            return self._fused["values"]
+        # always evaluated: env observation buffers are persistent and rewritten in place, so a cache keyed by the tensor's
+        # address would hand back the values of the PREVIOUS observation
         return self.critic(critic_observations)

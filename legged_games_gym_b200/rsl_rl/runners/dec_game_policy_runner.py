@@ -85,7 +85,7 @@ class DecGamePolicyRunner:
     def save(self, agent_id, path, infos=None):
         os.makedirs(os.path.dirname(path), exist_ok=True)
         alg = self.algs[agent_id]
-        torch.save({"model_state_dict": alg.actor_critic.state_dict(), "optimizer_state_dict": alg.optimizer.state_dict(),
+        torch.save({"model_state_dict": alg.actor_critic.state_dict(), "optimizer_state_dict": alg.optimizer_state_dict(),
                     "iter": self.current_learning_iteration[agent_id], "infos": infos}, path)
 
     def load(self, agent_id, path, load_optimizer=True):
@@ -93,7 +93,7 @@ class DecGamePolicyRunner:
         alg = self.algs[agent_id]
         alg.actor_critic.load_state_dict(d["model_state_dict"])
         if load_optimizer:
-            alg.optimizer.load_state_dict(d["optimizer_state_dict"])
+            alg.load_optimizer_state_dict(d["optimizer_state_dict"])
         self.current_learning_iteration[agent_id] = d["iter"]
         return d["infos"]
 

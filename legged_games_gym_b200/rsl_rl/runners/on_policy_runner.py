@@ -29,9 +29,8 @@ class OnPolicyRunner:
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         env, alg = self.env, self.alg
         if init_at_random_ep_len:
-            env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
-            if hasattr(env, "_params"):
-                env._params.episode_length_buf = env.episode_length_buf.data_ptr()
+            # in place: the env's kernels (and a step graph that may already be captured) hold this buffer's address
+            env.episode_length_buf.copy_(torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length)))
         obs = env.get_observations()
         pobs = env.get_privileged_observations()
         critic_obs = pobs if pobs is not None else obs
@@ -98,14 +97,14 @@ class OnPolicyRunner:
     def save(self, path, infos=None):
         os.makedirs(os.path.dirname(path), exist_ok=True)
         torch.save({"model_state_dict": self.alg.actor_critic.state_dict(),
-                    "optimizer_state_dict": self.alg.optimizer.state_dict(),
+                    "optimizer_state_dict": self.alg.optimizer_state_dict(),
                     "iter": self.current_learning_iteration, "infos": infos}, path)
 
     def load(self, path, load_optimizer=True):
         d = torch.load(path, map_location=self.device)
         self.alg.actor_critic.load_state_dict(d["model_state_dict"])
         if load_optimizer:
-            self.alg.optimizer.load_state_dict(d["optimizer_state_dict"])
+            self.alg.load_optimizer_state_dict(d["optimizer_state_dict"])
         self.current_learning_iteration = d["iter"]
         return d["infos"]
 

@@ -33,8 +33,9 @@ class RolloutStorage:
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
         s = self.step
-        self.observations[s].copy_(t.observations)
-        if self.privileged_observations is not None:
+        if t.observations.data_ptr() != self.observations[s].data_ptr():        # PPO.act already snapshots into the slot
+            self.observations[s].copy_(t.observations)
+        if self.privileged_observations is not None and t.critic_observations.data_ptr() != self.privileged_observations[s].data_ptr():
             self.privileged_observations[s].copy_(t.critic_observations)
         self.actions[s].copy_(t.actions)
         self.rewards[s].copy_(t.rewards.view(-1, 1))

@@ -36,7 +36,7 @@ def train(args, log_root="default"):
     if world > 1:
         env.set_env_id_offset(rank * env.num_envs)
     ppo_runner, train_cfg = task_registry.make_alg_runner(env=env, name=args.task, args=args,
-                                                          log_root=log_root if rank == 0 else None)
+                                                          log_root=log_root)
     ppo_runner.learn(num_learning_iterations=train_cfg.runner.max_iterations, init_at_random_ep_len=True)
     return ppo_runner
 

@@ -67,6 +67,10 @@ class TaskRegistry:
             log_dir = None
         else:
             log_dir = os.path.join(log_root, datetime.now().strftime("%b%d_%H-%M-%S") + "_" + train_cfg.runner.run_name)
+        # multi-GPU: every rank resolves the resume path from the real log root, rank 0 alone writes logs / checkpoints
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+            log_dir = None
         if dec:
             runner = DecGamePolicyRunner(env, class_to_dict(train_cfg), log_dir, device=args.rl_device)
             if train_cfg.runner.resume:

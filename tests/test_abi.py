@@ -26,7 +26,10 @@ def test_struct_mirrors_match():
     from legged_games_gym_b200 import _native as nat
     for which, cls in enumerate((nat.TorqueParams, nat.LstmWeights, nat.StepParams, nat.PolicyParams, nat.GameParams)):
         assert nat.lib.lgk_struct_size(which) == ctypes.sizeof(cls)
-    assert nat.lib.lgk_abi_version() == nat.ABI_VERSION == 3
+    import re
+    header = open(os.path.join(ROOT, "include", "lgk.h")).read()
+    declared = int(re.search(r"#define LGK_ABI_VERSION (\d+)", header).group(1))
+    assert nat.lib.lgk_abi_version() == nat.ABI_VERSION == declared
 
 
 def test_argument_errors_are_codes_not_crashes():

@@ -65,6 +65,27 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 16-byte asynchronous copies global -> shared (LDGSTS): every thread of the CTA moves pieces of the tile's contiguous
+// chunks, no register staging, completion by cp.async.wait_group
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void stage_in16(void* dst_smem, const void* src, int bytes, int tid, int nthreads) {
+  const int n16 = bytes >> 4;
+  for (int i = tid; i < n16; i += nthreads)
+    cp_async16(reinterpret_cast<uint8_t*>(dst_smem) + 16 * i, reinterpret_cast<const uint8_t*>(src) + 16 * i);
+}
+__device__ __forceinline__ void stage_out16(void* dst, const void* src_smem, int bytes, int tid, int nthreads) {
+  const int n16 = bytes >> 4;
+  for (int i = tid; i < n16; i += nthreads)
+    reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src_smem)[i];
+}
+#ifndef LGK_K1_STAGE
+#define LGK_K1_STAGE 0     // 0: TMA bulk copies in and out; 1: cp.async in, bulk out; 2: cp.async in, vector stores out
+#endif
+
 // ------------------------------------------------------------------ K1 shared-memory carve-up (bytes, 16-aligned)
 struct TileLayout {
   int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, frame, sums, ep, rew, flags, part, noise, misc, total;
@@ -142,6 +163,18 @@ __device__ __forceinline__ void k1_stamp(int slot) {
   }
 }
 
+// experiments (-DLGK_EXP_CTA_STAMPS): every CTA records stamps 0..6 and its SM (slot 7) in buf[32 + 8 * blockIdx.x + slot]
+__device__ __forceinline__ void cta_stamp(int which) {
+#ifdef LGK_EXP_CTA_STAMPS
+  if (g_k1_timeline != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_k1_timeline[32 + 8 * blockIdx.x + which] = (long long)t;
+    if (which == 0) { uint32_t sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); g_k1_timeline[32 + 8 * blockIdx.x + 7] = sm; }
+  }
+#endif
+}
+
 __device__ __forceinline__ void scan_stamp(int slot) {      // first scan warp of CTA 0
   if (g_k1_timeline != nullptr && blockIdx.x == 0 && threadIdx.x == kK1Threads) {
     unsigned long long t;
@@ -207,12 +240,14 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
   const bool bulk = (nval == kTile) && (p.actors_per_env == 1) && (p.num_envs % 4 == 0);   // 16-B aligned rows
   pdl_launch_dependents();
   k1_stamp(0);
+  cta_stamp(0);
   if (bulk && tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   pdl_wait();              // everything below reads state written by the previous kernels of the step
+  cta_stamp(2);
   if constexpr (FUSED) if (warp >= 4) {        // scan warps: heights + height observation columns + the noise of the whole row
     scan_stamp(9);
     const int step_s = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
@@ -225,6 +260,27 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
   }
 
   // ---------------- stage the tile
+#if LGK_K1_STAGE >= 1
+#ifdef LGK_EXP_NO_LOADS
+  if (bulk && p.num_envs < 0) {
+#else
+  if (bulk) {
+#endif
+    stage_in16(s_root, p.root_states + (size_t)env0 * 13, kTile * 13 * 4, tid, kK1Threads);
+    stage_in16(s_dof, p.dof_state + (size_t)env0 * 24, kTile * 24 * 4, tid, kK1Threads);
+    stage_in16(s_contact, p.contact_forces + (size_t)env0 * NB * 3, kTile * NB * 3 * 4, tid, kK1Threads);
+    stage_in16(s_act, p.actions + (size_t)env0 * 12, kTile * 12 * 4, tid, kK1Threads);
+    stage_in16(s_tq, p.torques + (size_t)env0 * 12, kTile * 12 * 4, tid, kK1Threads);
+    stage_in16(s_lact, p.last_actions + (size_t)env0 * 12, kTile * 12 * 4, tid, kK1Threads);
+    stage_in16(s_ldv, p.last_dof_vel + (size_t)env0 * 12, kTile * 12 * 4, tid, kK1Threads);
+    stage_in16(s_cmd, p.commands + (size_t)env0 * 4, kTile * 4 * 4, tid, kK1Threads);
+    if (F > 0) {
+      stage_in16(s_fat, p.feet_air_time + (size_t)env0 * F, kTile * F * 4, tid, kK1Threads);
+      stage_in16(s_lc, p.last_contacts + (size_t)env0 * F, kTile * F, tid, kK1Threads);
+    }
+    cp_async_commit();
+  }
+#else
   if (bulk) {
     if (tid == 0) {
       uint32_t bytes = kTile * (13 + 24 + 3 * NB + 12 + 12 + 12 + 12 + 4) * 4;
@@ -244,6 +300,7 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
       }
     }
   }
+#endif
   // per-env scalars (one 128-byte row segment per tensor and tile) come by plain coalesced loads, lane = env, issued while
   // the bulk copies are in flight: 20 fewer bulk operations per tile (measured neutral for the kernel time)
   if (bulk) {
@@ -256,7 +313,12 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
   const RngKey key = make_key(p.seed, step_eff);
   k1_stamp(1);
   if (bulk) {
+#if LGK_K1_STAGE >= 1
+    cp_async_wait0();
+    role_sync();
+#else
     mbar_wait(bar, 0);
+#endif
   } else {
     for (int i = tid; i < nval * 13; i += kK1Threads) {
       const int e = i / 13, c = i - e * 13;
@@ -281,6 +343,7 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
     role_sync();
   }
   k1_stamp(2);
+  cta_stamp(3);
 
   // ---------------- phase A: every role, its share of the per-joint / per-foot / per-body terms
   const int e = lane, role = warp, env = env0 + e;
@@ -293,7 +356,13 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
   uint8_t* lc = s_lc + e * F;
   float* sums = s_sums + e;                 // tile-local episode sums, row stride kTile
   RolePartials mine;
+#ifdef LGK_EXP_SKIP_A
+#pragma unroll
+  for (int k = 0; k < PS_COUNT; ++k) mine.v[k] = 0.f;
+  if (false) {
+#else
   if (pre) {
+#endif
     const float* hrow = (valid && p.measure_heights && p.reward_active[LGK_R_BASE_HEIGHT])
                             ? p.measured_heights + (size_t)env * P : nullptr;       // the scan ran before this kernel
     role_partials(p, role, dof, s_contact + e * NB * 3, s_act + e * 12, s_tq + e * 12, s_lact + e * 12, s_ldv + e * 12,
@@ -310,7 +379,11 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
   EnvScalars s;
   s.reset = false; s.time_out = false; s.rew = 0.f; s.ep_len = 0;
   const bool want_frames = !FUSED && p.measure_heights && !p.terrain_is_plane && p.scan_frames != nullptr;
+#ifdef LGK_EXP_SKIP_B
+  if (false) {
+#else
   if (role == 0) {
+#endif
     if (pre) {
       uint32_t bits = __float_as_uint(mine.v[PS_BITS]);
       uint32_t any = bits & 5u, feet_down = (bits >> 1) & 1u;
@@ -376,7 +449,11 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
 
   // ---------------- phase C: every role finishes its joints
   const bool reset_e = post && valid && s_flags[e] != 0;
+#ifdef LGK_EXP_SKIP_C
+  if (false) {
+#else
   if (post) {
+#endif
     if (reset_e) env_reset_joints(p, key, genv, role, dof, fat);
     env_obs_head_role(p, role, dof, s_act + e * 12, s_head + e * 49);
     if (role == 0) env_obs_head_base(p, s, cmd, s_head + e * 49);
@@ -388,9 +465,43 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
   fence_async_smem();
   role_sync();
   k1_stamp(5);
+  cta_stamp(4);
+#ifdef LGK_EXP_NO_STORES
+  if (p.num_envs > 0) { cta_stamp(1); return; }
+#endif
 
   // ---------------- whole-tile write-backs
+#ifndef LGK_EXP_STORE_MASK
+#define LGK_EXP_STORE_MASK 15      // experiments: 1 tile vectors, 2 per-env scalar rows, 4 scan frames, 8 obs head
+#endif
+#if LGK_K1_STAGE >= 2
   if (bulk) {
+    if (pre && (LGK_EXP_STORE_MASK & 1)) {
+      stage_out16(p.base_lin_vel + (size_t)env0 * 3, s_blv, kTile * 3 * 4, tid, kK1Threads);
+      stage_out16(p.base_ang_vel + (size_t)env0 * 3, s_bav, kTile * 3 * 4, tid, kK1Threads);
+      stage_out16(p.projected_gravity + (size_t)env0 * 3, s_pg, kTile * 3 * 4, tid, kK1Threads);
+      if (do_push && (!post || !FUSED)) stage_out16(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4, tid, kK1Threads);
+    }
+    if (LGK_EXP_STORE_MASK & 1) stage_out16(p.commands + (size_t)env0 * 4, s_cmd, kTile * 4 * 4, tid, kK1Threads);
+    if ((LGK_EXP_STORE_MASK & 1) && (fat_active || (post && F > 0))) {
+      stage_out16(p.feet_air_time + (size_t)env0 * F, s_fat, kTile * F * 4, tid, kK1Threads);
+      if (pre) stage_out16(p.last_contacts + (size_t)env0 * F, s_lc, kTile * F, tid, kK1Threads);
+    }
+    if (post && (LGK_EXP_STORE_MASK & 1)) {
+      stage_out16(p.last_actions + (size_t)env0 * 12, s_act, kTile * 12 * 4, tid, kK1Threads);
+      stage_out16(p.last_dof_vel + (size_t)env0 * 12, s_ldv, kTile * 12 * 4, tid, kK1Threads);
+      stage_out16(p.last_root_vel + (size_t)env0 * 6, s_lrv, kTile * 6 * 4, tid, kK1Threads);
+    }
+    if (LGK_EXP_STORE_MASK & 2) {
+    for (int k = warp; k < K; k += 4) p.episode_sums[(size_t)k * N + env0 + lane] = s_sums[k * kTile + lane];
+    if (warp == (K & 3)) p.episode_length_buf[env0 + lane] = s_ep[lane];
+    if (warp == ((K + 1) & 3)) p.rew_buf[env0 + lane] = s_rew[lane];
+    if (pre && warp == ((K + 2) & 3)) { p.reset_buf[env0 + lane] = s_flags[lane]; p.time_out_buf[env0 + lane] = s_flags[kTile + lane]; }
+    }
+  } else if (false) {
+#else
+  if (bulk) {
+#endif
     if (tid == 0) {
       if (pre) {
         bulk_s2g(p.base_lin_vel + (size_t)env0 * 3, s_blv, kTile * 3 * 4);
@@ -450,7 +561,7 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
     }
   }
   // scan frames (pose part): 4 floats per env, strided rows of 8
-  if (pre && want_frames && valid && role == 0) {
+  if (pre && want_frames && valid && role == 0 && (LGK_EXP_STORE_MASK & 4)) {
     *reinterpret_cast<float4*>(p.scan_frames + (size_t)env * kFrameFloats) =
         *reinterpret_cast<const float4*>(s_frame + e * kFrameFloats);
   }
@@ -518,7 +629,7 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
         orow[lane] = clampf(noisy_obs(s_head[ee * 49 + lane], r.x, nz0), -clip, clip);
         if (lane < 16) orow[32 + lane] = clampf(noisy_obs(s_head[ee * 49 + 32 + lane], r.y, nz1), -clip, clip);
       }
-    } else {
+    } else if (LGK_EXP_STORE_MASK & 8) {
       // ---------------- the 48 proprioceptive columns, un-noised (K2 adds noise + clip): coalesced row segments
       for (int ee = warp * 8; ee < min(warp * 8 + 8, nval); ++ee) {
         float* orow = p.obs_buf + (size_t)(env0 + ee) * O;
@@ -528,8 +639,11 @@ post_kernel(const __grid_constant__ LgkStepParams p) {
     }
   }
   k1_stamp(7);
+#if LGK_K1_STAGE < 2
   if (bulk && tid == 0) bulk_wait_read0();
+#endif
   k1_stamp(8);
+  cta_stamp(1);
 }
 
 // ------------------------------------------------------------------ K2
@@ -663,8 +777,11 @@ __global__ void __launch_bounds__(kK2Threads, 8) scan_obs_kernel(const __grid_co
 // variant are template parameters; every lane computes an in-range sample index for each of its G columns whether or not
 // the column is a height point (the clip of LR:860-861 makes any input a valid index), so the only predication left is on
 // the stores.  Per-lane constants (grid points, noise scales, column masks) live in registers across the env loop.
+#ifndef LGK_K2_MINBLOCKS
+#define LGK_K2_MINBLOCKS 5
+#endif
 template <int G, int MODE, bool RECIP>
-__global__ void __launch_bounds__(kK2Threads, 5) scan_obs_fast_kernel(const __grid_constant__ LgkStepParams p) {
+__global__ void __launch_bounds__(kK2Threads, LGK_K2_MINBLOCKS) scan_obs_fast_kernel(const __grid_constant__ LgkStepParams p) {
   constexpr bool SCAN = (MODE & kScan) != 0, OBS = (MODE & kObs) != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = p.num_envs, P = p.num_height_points, O = p.num_obs;
@@ -1075,7 +1192,10 @@ static int launch_k1(const LgkStepParams* p, cudaStream_t st) {
   const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_reward_slots);
   // ~25 KB of staged tiles per CTA: ask for the largest shared-memory carve-out so that 7 CTAs are resident per SM
   if (int rc = ensure_func_attr(reinterpret_cast<const void*>(post_kernel<0, false>), L.total, "cudaFuncSetAttribute(post_kernel)", true)) return rc;
-  const cudaError_t e = launch_chained(post_kernel<0, false>, dim3((p->num_envs + kTile - 1) / kTile), dim3(kK1Threads), (size_t)L.total, st, *p);
+  static const int extra_smem = getenv("LGK_K1_EXTRA_SMEM") ? atoi(getenv("LGK_K1_EXTRA_SMEM")) : 0;    // occupancy experiments
+  if (extra_smem)
+    if (int rc = ensure_func_attr(reinterpret_cast<const void*>(post_kernel<0, false>), L.total + extra_smem, "cudaFuncSetAttribute(post_kernel)", true)) return rc;
+  const cudaError_t e = launch_chained(post_kernel<0, false>, dim3((p->num_envs + kTile - 1) / kTile), dim3(kK1Threads), (size_t)(L.total + extra_smem), st, *p);
   count_launch();
   return check_cuda(e, "post_kernel launch");
 }
@@ -1134,7 +1254,7 @@ static int launch_k2(const LgkStepParams* p, int mode, cudaStream_t st) {
   const bool field = p->measure_heights && !p->terrain_is_plane && p->num_height_points > 0;
   const bool flat = !p->measure_heights;
   if (field || (flat && mode == kObs)) {
-    const int fblocks = blocks < 148 * 10 ? blocks : 148 * 10;
+    const int fblocks = blocks < 148 * 2 * LGK_K2_MINBLOCKS ? blocks : 148 * 2 * LGK_K2_MINBLOCKS;
     const bool rc = p->horizontal_scale_recip != 0.f;
     const dim3 gd(fblocks), bd(kK2Threads);
 #define LGK_K2(GG, MM) (rc ? launch_chained(scan_obs_fast_kernel<GG, MM, true>, gd, bd, 0, st, *p) \
@@ -1165,6 +1285,9 @@ extern "C" int lgk_post_physics(const LgkStepParams* p, void* stream) {
   if (heights && !p->terrain_is_plane) LGK_REQUIRE(p->scan_frames != nullptr, "scan_frames buffer is null");
   if (pre && post) {              // fused step
     if (fused_eligible(p)) return launch_fused(p, st);
+    static const int only = getenv("LGK_PP_ONLY") ? atoi(getenv("LGK_PP_ONLY")) : 0;     // timing aid (profiles/pp_probe.py)
+    if (only == 1) return launch_k1(p, st);
+    if (only == 2) return launch_k2(p, kScan | kObs, st);
     if (scan_first)
       if (int rc = launch_k2(p, kScan, st)) return rc;
     if (int rc = launch_k1(p, st)) return rc;

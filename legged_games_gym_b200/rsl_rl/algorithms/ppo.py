@@ -167,17 +167,22 @@ class PPO:
         state = copy.deepcopy(self.optimizer.state_dict())
         lr_t = torch.tensor(float(self.learning_rate), device=dev)
         self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=lr_t, capturable=True, fused=True)     # one multi-tensor kernel
-        if state["state"]:
+        carried = bool(state["state"])
+        if carried:
             for s_ in state["state"].values():
-                if not torch.is_tensor(s_["step"]) or not s_["step"].is_cuda:
-                    s_["step"] = torch.as_tensor(float(s_["step"]), device=dev)
+                s_["step"] = torch.as_tensor(float(s_["step"]), dtype=torch.float32, device=dev)
             for grp in state["param_groups"]:
                 grp["lr"], grp["capturable"], grp["fused"], grp["foreach"] = lr_t, True, True, False
-            self.optimizer.load_state_dict(state)
+            self.optimizer.load_state_dict(copy.deepcopy(state))       # `state` itself stays pristine for the restore below
         for grp in self.optimizer.param_groups:
             grp["lr"] = lr_t
         g = dict(flat=flat, idx=torch.zeros(mb, dtype=torch.long, device=dev), lr=lr_t, mb=mb,
                  acc=torch.zeros(2, device=dev))
+        # an autograd graph left over from an eager update (ActorCritic.distribution holds the actor's output) would keep
+        # the parameters' AccumulateGrad nodes alive on the stream they were created on: drop it before warm-up / capture
+        self.actor_critic.distribution = None
+        for p_ in self.actor_critic.parameters():
+            p_.grad = None
         # the live weights / optimizer state must not be touched by warm-up and capture: snapshot, run, restore
         snap_p = [p.detach().clone() for p in self.actor_critic.parameters()]
         side = torch.cuda.Stream()
@@ -192,12 +197,17 @@ class PPO:
         with torch.no_grad():
             for p, q in zip(self.actor_critic.parameters(), snap_p):
                 p.copy_(q)
-        for s_ in self.optimizer.state.values():      # the warm-up steps must not count: zero moments and step
-            s_["step"].zero_(); s_["exp_avg"].zero_(); s_["exp_avg_sq"].zero_()
-        if state["state"]:
-            self.optimizer.load_state_dict(state)
-            for grp in self.optimizer.param_groups:
-                grp["lr"] = lr_t
+        # the warm-up steps must not count: restore moments and step IN PLACE (the graph holds these tensors' addresses)
+        params = [p_ for grp in self.optimizer.param_groups for p_ in grp["params"]]
+        for i, p_ in enumerate(params):
+            live, src = self.optimizer.state[p_], state["state"].get(i) if carried else None
+            for k in ("step", "exp_avg", "exp_avg_sq"):
+                if src is not None:
+                    live[k].copy_(src[k])
+                else:
+                    live[k].zero_()
+        for grp in self.optimizer.param_groups:
+            grp["lr"] = lr_t
         lr_t.fill_(float(self.learning_rate))
         g["graph"] = graph
         self._graph = g

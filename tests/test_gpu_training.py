@@ -150,7 +150,10 @@ def test_rollout_storage_holds_the_observation_the_policy_saw():
     from legged_games_gym_b200.utils import get_args
     args = get_args(["--task", "anymal_c_flat", "--num_envs", "128", "--headless", "--seed", "5"])
     env, _ = task_registry.make_env(name=args.task, args=args)
-    runner, _ = task_registry.make_alg_runner(env=env, name=args.task, args=args, log_root=None)
+    import copy
+    train_cfg = copy.deepcopy(task_registry.train_cfgs[args.task])
+    train_cfg.runner.resume = False            # (play() of an earlier test flips the registry's shared cfg object)
+    runner, _ = task_registry.make_alg_runner(env=env, args=args, train_cfg=train_cfg, log_root=None)
     alg = runner.alg
     obs = env.get_observations()
     fed, acted = [], []

@@ -194,7 +194,7 @@ def make_env(num_envs, device, host_sim=False, env_id_offset=0):
                         p_contact_body0=P_TERMINATE)
     base = task_registry.get_task_class(TASK)
     from legged_games_gym_b200.envs.base.legged_robot import SyntheticTerrain
-    cls = type(base.__name__ + "Bench", (base,), {"tile_envs": TILE, "use_cuda_graph": USE_GRAPH})
+    cls = type(base.__name__ + "Bench", (base,), {"use_cuda_graph": USE_GRAPH})
     # height field = SURVEY 8(d)'s synthetic input (uniform int16 heights): every sample differs from its neighbours,
     # the worst case for the gather; the generated terrain (utils/terrain.py) is the library default
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LGK_ABI_VERSION 4
+#define LGK_ABI_VERSION 5
 #define LGK_NUM_DOF 12          /* every registered task has 12 DOF = 12 actions */
 #define LGK_MAX_FEET 4
 #define LGK_MAX_PEN 16
@@ -57,9 +57,12 @@ enum { LGK_CTRL_P = 0, LGK_CTRL_V = 1, LGK_CTRL_T = 2 };
 
 /* phases of lgk_post_physics (bit mask).  PRE = LR:114-127 up to the per-term reward sum;
  * POST = positive clip + termination term (LR:204-210), reset_idx (LR:147-191), observations
- * (LR:212-230) and the history copies (LR:132-134).  PRE|POST runs fused in one launch; the host
- * splits them only when Python code must run in between (user reward terms, command curriculum). */
-enum { LGK_PHASE_PRE = 1, LGK_PHASE_POST = 2 };
+ * (LR:212-230) and the history copies (LR:132-134).  PRE|POST runs in one pass; the host splits them only when
+ * Python code must run in between (user reward terms, command curriculum).  When a subclass overrides reset_idx
+ * (LR:128-129 calls it every step; ANY:56-60 is such an override) POST is split once more so that the Python
+ * method runs exactly where the reference calls it: POST_REWARD = the reward-finishing part of POST alone,
+ * POST_OBS = observations + histories alone (no in-kernel reset: the caller has run lgk_reset_idx in between). */
+enum { LGK_PHASE_PRE = 1, LGK_PHASE_POST = 2, LGK_PHASE_POST_REWARD = 4, LGK_PHASE_POST_OBS = 8 };
 
 /* ------------------------------------------------------------------ torques (LR:371-395, ANY:71-81) */
 typedef struct LgkTorqueParams {
@@ -215,6 +218,10 @@ typedef struct LgkStepParams {
    * LowLevelGame keeps exactly this copy as `base_quat` until its next step (LLG:123), and the high-level games read
    * it after the reset (HLG:432). */
   float* base_quat;
+  /* [N,48] fp32 hand-over buffer between the two step kernels: K1 leaves the 48 proprioceptive observation columns
+   * (LR:212-222, before noise) here as one contiguous block per 32-env tile and K2 finishes them into obs_buf.
+   * NULL: the columns go through obs_buf itself (192-byte fragments at the row stride). */
+  float* obs_head;
 } LgkStepParams;
 
 int lgk_post_physics(const LgkStepParams* p, void* stream);
@@ -225,8 +232,8 @@ int lgk_reset_idx(const LgkStepParams* p, const int64_t* env_ids, int32_t num_id
 
 /* Profiling hook: when non-NULL, CTA 0 of the scalar post-physics kernel writes %globaltimer stamps (ns) into
  * device_buf16[0..8]: entry, step counter read, tile staged, rewards done, reset done, outputs staged, bulk stores issued,
- * rows written, bulk stores drained; [16..24]: the same nine stamps of the LAST CTA (the kernel's in-situ span =
- * [24] - [1]); [9..11]: first scan warp of the fused variant (start, frames loaded, end).  The buffer holds 32 int64. */
+ * rows written, tile done (first tile of the persistent CTA); [16..24]: the same nine stamps of the LAST CTA.  The
+ * buffer holds 32 int64. */
 int lgk_step_debug_timeline(int64_t* device_buf32);
 
 /* After lgk_post_physics / lgk_reset_idx: single-CTA pass that (a) compacts reset_buf into an ascending
@@ -382,15 +389,6 @@ int lgk_abi_version(void);
  * prologue while its predecessor on the stream drains, and waits (griddepcontrol.wait) before touching memory.
  * Returns the previous setting. */
 int lgk_set_pdl(int enable);
-/* Fused post-physics kernel (opt-in, default off; LGK_FUSED=1 in the environment turns it on at load): lgk_post_physics
- * runs the per-env scalar work (role warps) and the height scan / observation row (scan warps) of LR:106-230 as ONE launch
- * whenever a height field backs the observation and no reward term needs this step's heights.  Results are identical
- * bit for bit to the default two-kernel chain (tests/test_gpu_parity.py); on B200 it is 5-8 % slower (both
- * halves compete for the same register file), so it is kept as a measured variant.  Returns the previous setting. */
-int lgk_set_fused(int enable);
-/* Scan warps per CTA of the fused kernel: 1..8, 0 = automatic (8 when the grid is at most two tiles per SM, else 4).
- * Returns the previous setting. */
-int lgk_set_fused_scan_warps(int n);
 /* Host-sim pipeline (the reference's sim_device=cpu: PhysX results are host tensors, LR:515-530 hand back host memory):
  * stream-ordered, graph-capturable copies between PINNED (cudaHostAlloc / torch pin_memory) host memory and device
  * memory done by a kernel over the unified address space instead of a memcpy node.  bytes % 16 == 0, 16-byte aligned. */

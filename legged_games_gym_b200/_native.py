@@ -5,11 +5,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 4          # include/lgk.h LGK_ABI_VERSION
+ABI_VERSION = 5          # include/lgk.h LGK_ABI_VERSION
 LIB_PATH = os.environ.get("LGK_LIB_PATH") or os.path.join(_HERE, "liblgk.so")      # override: A/B of kernel builds
 
 NUM_DOF, MAX_FEET, MAX_PEN, MAX_TERM, MAX_BODIES = 12, 4, 16, 8, 32
-PHASE_PRE, PHASE_POST = 1, 2
+PHASE_PRE, PHASE_POST, PHASE_POST_REWARD, PHASE_POST_OBS = 1, 2, 4, 8
 CTRL = {"P": 0, "V": 1, "T": 2}
 STREAM_CMD, STREAM_PUSH, STREAM_RESET_DOF, STREAM_RESET_ROOT, STREAM_RESET_CMD, STREAM_TERRAIN, STREAM_OBS, STREAM_ACT = range(8)
 
@@ -71,7 +71,7 @@ class StepParams(C.Structure):
         ("base_lin_vel", vp), ("base_ang_vel", vp), ("projected_gravity", vp), ("measured_heights", vp),
         ("obs_buf", vp), ("rew_buf", vp), ("reset_buf", vp), ("time_out_buf", vp),
         ("height_min3", vp), ("height_points_xy", vp), ("noise_scale_vec", vp), ("reset_stats", vp),
-        ("scan_frames", vp), ("step_counter_dev", vp), ("base_quat", vp)]
+        ("scan_frames", vp), ("step_counter_dev", vp), ("base_quat", vp), ("obs_head", vp)]
 
 
 GAME_TERMS = ["evasion", "pursuit", "termination"]        # LGK_G_* (alphabetical, like class_to_dict)
@@ -142,8 +142,6 @@ def _load():
     lib.lgk_set_pdl.argtypes = [C.c_int]
     lib.lgk_game_step.argtypes = [C.POINTER(GameParams), vp]
     lib.lgk_game_prepare.argtypes = [vp, i64, vp, i64, vp, i32, C.POINTER(f32 * 8), i32, vp]
-    lib.lgk_set_fused.argtypes = [C.c_int]
-    lib.lgk_set_fused_scan_warps.argtypes = [C.c_int]
     lib.lgk_step_debug_timeline.argtypes = [vp]
     for which, cls in enumerate((TorqueParams, LstmWeights, StepParams, PolicyParams, GameParams)):
         n = lib.lgk_struct_size(which)
@@ -157,7 +155,7 @@ def _load():
 lib = _load()
 
 EXPORTS = ["lgk_set_lstm_weights", "lgk_compute_torques", "lgk_post_physics", "lgk_reset_idx", "lgk_finalize_step",
-           "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline", "lgk_set_pdl", "lgk_game_step", "lgk_game_prepare", "lgk_set_fused", "lgk_set_fused_scan_warps", "lgk_step_debug_timeline",
+           "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline", "lgk_set_pdl", "lgk_game_step", "lgk_game_prepare", "lgk_step_debug_timeline",
            "lgk_gae", "lgk_last_error_string", "lgk_abi_version", "lgk_l2_flush", "lgk_copy_from_pinned", "lgk_copy_to_pinned", "lgk_copy_rows_to_pinned", "lgk_launch_count",
            "lgk_struct_size"]
 

@@ -10,8 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "liblgk.so")
-SOURCES = ["lgk_abi.cu", "lgk_heights.cu", "lgk_torque.cu", "lgk_post_physics.cu", "lgk_gae.cu", "lgk_policy.cu", "lgk_policy_tc.cu", "lgk_game.cu"]
-HEADERS = ["lgk_common.cuh", "lgk_rng.cuh", "lgk_math.cuh", "lgk_step_device.cuh", "lgk_policy_common.cuh",
+SOURCES = ["lgk_abi.cu", "lgk_heights.cu", "lgk_torque.cu", "lgk_post_k1.cu", "lgk_post_physics.cu", "lgk_gae.cu", "lgk_policy.cu", "lgk_policy_tc.cu", "lgk_game.cu"]
+HEADERS = ["lgk_common.cuh", "lgk_rng.cuh", "lgk_math.cuh", "lgk_step_device.cuh", "lgk_tile.cuh", "lgk_policy_common.cuh",
            "lgk_policy_tc_plan.h", "../../include/lgk.h"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

@@ -33,155 +33,6 @@ struct EnvScalars {
   float rew;             // rew_buf (LR:193-210)
 };
 
-// ---- LR:114-127 for one env: rotate velocities, resample/heading commands, push, termination and the
-// reward sum.  root/dof/contact/... are the env's rows inside the staged tile (read+write).
-// `sums` points at episode_sums[0*N + env]; row stride = num_envs.
-// `mean_height_err` = mean_p(z - h_p) when the base_height term is active, else unused.
-LGK_D void env_pre(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, float* root, const float* dof,
-                    const float* contact, const float* act, const float* tq, const float* lact,
-                    const float* ldv, float* cmd, float* fat, uint8_t* lc, float* sums, int sums_stride,
-                    long long ep_in, float mean_height_err, EnvScalars& o) {
-  o.ep_len = ep_in + 1;
-  const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
-  o.blv = quat_rotate_inverse(qx, qy, qz, qw, V3{root[7], root[8], root[9]});
-  o.bav = quat_rotate_inverse(qx, qy, qz, qw, V3{root[10], root[11], root[12]});
-  o.pg = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
-  // _post_physics_step_callback LR:329-345
-  if (o.ep_len % (long long)p.resample_period == 0)
-    resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_CMD, 0));
-  if (p.heading_command) {
-    const float h = heading_of(qx, qy, qz, qw);
-    cmd[2] = clampf(0.5f * wrap_to_pi(cmd[3] - h), -1.f, 1.f);
-  }
-  if (do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
-    const U4 r = rng_block_cold(key, genv, LGK_STREAM_PUSH, 0);
-    const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
-    root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));
-    root[8] = scale_uniform(range, lo, u32_to_uniform(r.y));
-  }
-  // check_termination LR:139-145
-  bool term = false;
-  for (int t = 0; t < p.num_term; ++t) {
-    const float* f = contact + 3 * p.term_idx[t];
-    term = term || (norm3(f[0], f[1], f[2]) > 1.0f);
-  }
-  o.time_out = (float)o.ep_len > p.max_episode_length;
-  o.reset = term || o.time_out;
-
-  // compute_reward LR:193-210, terms in alphabetical order
-  float rew = 0.f;
-  const float cmd_norm = norm2(cmd[0], cmd[1]);
-#define LGK_TERM(ID, EXPR)                                            \
-  if (p.reward_active[ID]) {                                          \
-    const float r_ = (EXPR) * p.reward_scale[ID];                     \
-    rew += r_;                                                        \
-    sums[(size_t)p.reward_slot[ID] * sums_stride] += r_;              \
-  }
-  if (p.reward_active[LGK_R_ACTION_RATE]) {                           // LR:901-903
-    float s = 0.f;
-    for (int d = 0; d < kDof; ++d) { const float e = lact[d] - act[d]; s += e * e; }
-    LGK_TERM(LGK_R_ACTION_RATE, s)
-  }
-  LGK_TERM(LGK_R_ANG_VEL_XY, o.bav.x * o.bav.x + o.bav.y * o.bav.y)   // LR:876-878
-  if (p.reward_active[LGK_R_BASE_HEIGHT]) {                           // LR:884-887
-    const float e = mean_height_err - p.base_height_target;
-    LGK_TERM(LGK_R_BASE_HEIGHT, e * e)
-  }
-  if (p.reward_active[LGK_R_COLLISION]) {                             // LR:905-908
-    float s = 0.f;
-    for (int b = 0; b < p.num_pen; ++b) {
-      const float* f = contact + 3 * p.pen_idx[b];
-      s += norm3(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f;
-    }
-    LGK_TERM(LGK_R_COLLISION, s)
-  }
-  if (p.reward_active[LGK_R_DOF_ACC]) {                               // LR:897-899
-    float s = 0.f;
-    for (int d = 0; d < kDof; ++d) { const float a = (ldv[d] - dof[2 * d + 1]) / p.dt; s += a * a; }
-    LGK_TERM(LGK_R_DOF_ACC, s)
-  }
-  if (p.reward_active[LGK_R_DOF_POS_LIMITS]) {                        // LR:914-918
-    float s = 0.f;
-    for (int d = 0; d < kDof; ++d) {
-      const float q = dof[2 * d];
-      s += -fminf(q - p.dof_pos_lo[d], 0.f) + fmaxf(q - p.dof_pos_hi[d], 0.f);
-    }
-    LGK_TERM(LGK_R_DOF_POS_LIMITS, s)
-  }
-  if (p.reward_active[LGK_R_DOF_VEL]) {                               // LR:893-895
-    float s = 0.f;
-    for (int d = 0; d < kDof; ++d) { const float v = dof[2 * d + 1]; s += v * v; }
-    LGK_TERM(LGK_R_DOF_VEL, s)
-  }
-  if (p.reward_active[LGK_R_DOF_VEL_LIMITS]) {                        // LR:920-925
-    float s = 0.f;
-    for (int d = 0; d < kDof; ++d)
-      s += clampf(fabsf(dof[2 * d + 1]) - p.dof_vel_limits[d] * p.soft_dof_vel_limit, 0.f, 1.f);
-    LGK_TERM(LGK_R_DOF_VEL_LIMITS, s)
-  }
-  if (p.reward_active[LGK_R_FEET_AIR_TIME]) {                         // LR:942-954 (stateful)
-    float s = 0.f;
-    for (int f = 0; f < p.num_feet; ++f) {
-      const bool c = contact[3 * p.feet_idx[f] + 2] > 1.0f;
-      const bool filt = c || (lc[f] != 0);
-      lc[f] = c ? 1 : 0;
-      const bool first = (fat[f] > 0.f) && filt;
-      const float air = fat[f] + p.dt;
-      s += (air - 0.5f) * (first ? 1.f : 0.f);
-      fat[f] = filt ? 0.f * air : air;     // air *= ~filt
-    }
-    s *= cmd_norm > 0.1f ? 1.f : 0.f;
-    LGK_TERM(LGK_R_FEET_AIR_TIME, s)
-  }
-  if (p.reward_active[LGK_R_FEET_CONTACT_FORCES]) {                   // LR:966-969
-    float s = 0.f;
-    for (int f = 0; f < p.num_feet; ++f) {
-      const float* c = contact + 3 * p.feet_idx[f];
-      s += fmaxf(norm3(c[0], c[1], c[2]) - p.max_contact_force, 0.f);
-    }
-    LGK_TERM(LGK_R_FEET_CONTACT_FORCES, s)
-  }
-  LGK_TERM(LGK_R_LIN_VEL_Z, o.blv.z * o.blv.z)                        // LR:872-874
-  if (p.reward_active[LGK_R_NO_FLY]) {                                // CAS:43-46
-    int n = 0;
-    for (int f = 0; f < p.num_feet; ++f) n += contact[3 * p.feet_idx[f] + 2] > 0.1f ? 1 : 0;
-    LGK_TERM(LGK_R_NO_FLY, n == 1 ? 1.f : 0.f)
-  }
-  LGK_TERM(LGK_R_ORIENTATION, o.pg.x * o.pg.x + o.pg.y * o.pg.y)      // LR:880-882
-  if (p.reward_active[LGK_R_STAND_STILL]) {                           // LR:961-964
-    float s = 0.f;
-    for (int d = 0; d < kDof; ++d) s += fabsf(dof[2 * d] - p.default_dof_pos[d]);
-    LGK_TERM(LGK_R_STAND_STILL, s * (cmd_norm < 0.1f ? 1.f : 0.f))
-  }
-  if (p.reward_active[LGK_R_STUMBLE]) {                               // LR:956-959
-    bool any = false;
-    for (int f = 0; f < p.num_feet; ++f) {
-      const float* c = contact + 3 * p.feet_idx[f];
-      any = any || (norm2(c[0], c[1]) > 5.f * fabsf(c[2]));
-    }
-    LGK_TERM(LGK_R_STUMBLE, any ? 1.f : 0.f)
-  }
-  if (p.reward_active[LGK_R_TORQUE_LIMITS]) {                         // LR:927-930
-    float s = 0.f;
-    for (int d = 0; d < kDof; ++d) s += fmaxf(fabsf(tq[d]) - p.torque_limits[d] * p.soft_torque_limit, 0.f);
-    LGK_TERM(LGK_R_TORQUE_LIMITS, s)
-  }
-  if (p.reward_active[LGK_R_TORQUES]) {                               // LR:889-891
-    float s = 0.f;
-    for (int d = 0; d < kDof; ++d) s += tq[d] * tq[d];
-    LGK_TERM(LGK_R_TORQUES, s)
-  }
-  {                                                                   // LR:937-940
-    const float e = cmd[2] - o.bav.z;
-    LGK_TERM(LGK_R_TRACKING_ANG_VEL, expf(-(e * e) / p.tracking_sigma))
-  }
-  {                                                                   // LR:932-935
-    const float ex = cmd[0] - o.blv.x, ey = cmd[1] - o.blv.y;
-    LGK_TERM(LGK_R_TRACKING_LIN_VEL, expf(-(ex * ex + ey * ey) / p.tracking_sigma))
-  }
-  o.rew = rew;
-}
-
 // ------------------------------------------------------------------ role-split variants (scalar kernel)
 // The scalar kernel runs a tile of 32 envs on four warps, lane = env.  Warp ("role") r owns joints {3r,3r+1,3r+2}, foot r,
 // the penalised bodies {r, r+4, ...} and the termination bodies {r, r+4}: in a first phase every role reduces its share of
@@ -277,90 +128,140 @@ LGK_D void role_partials(const LgkStepParams& p, int role, const float* dof, con
   o.v[PS_BITS] = __uint_as_float(bits);
 }
 
-// LR:114-127 for one env on role 0's lane: `sum` holds the four roles' partial sums already added up (PS_BITS or-ed)
-LGK_D void env_finish(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, float* root, float* cmd,
-                      float* sums, int sums_stride, long long ep_in, const RolePartials& sum, EnvScalars& o) {
-  o.ep_len = ep_in + 1;
-  const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
-  o.blv = quat_rotate_inverse(qx, qy, qz, qw, V3{root[7], root[8], root[9]});
-  o.bav = quat_rotate_inverse(qx, qy, qz, qw, V3{root[10], root[11], root[12]});
-  o.pg = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
-  // _post_physics_step_callback LR:329-345
-  if (o.ep_len % (long long)p.resample_period == 0)
-    resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_CMD, 0));
-  if (p.heading_command) {
-    const float h = heading_of(qx, qy, qz, qw);
-    cmd[2] = clampf(0.5f * wrap_to_pi(cmd[3] - h), -1.f, 1.f);
-  }
-  if (do_push) {   // LR:438-444; rewards/obs of this step keep the pre-push base_lin_vel
-    const U4 r = rng_block_cold(key, genv, LGK_STREAM_PUSH, 0);
-    const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
-    root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));
-    root[8] = scale_uniform(range, lo, u32_to_uniform(r.y));
-  }
-  const uint32_t bits = __float_as_uint(sum.v[PS_BITS]);
-  o.time_out = (float)o.ep_len > p.max_episode_length;                // LR:139-145
-  o.reset = ((bits & 1u) != 0) || o.time_out;
-  // compute_reward LR:193-210, terms in alphabetical order
-  float rew = 0.f;
-  const float cmd_norm = norm2(cmd[0], cmd[1]);
-#undef LGK_TERM
+// ---- phase B, split over the four role warps (lane = env).  Every role reads the partial sums of ALL four roles from
+// shared memory (`part`: slot k of role r at part[(k * 4 + r) * tile]) for the terms it owns, evaluates its share of
+// LR:114-127 / 193-203 and returns its partial of the reward sum; the per-term episode sums are disjoint rows, so no two
+// roles touch the same one.  Summation order: terms are added role by role instead of alphabetically (fp32, inside the
+// 1e-5 bar).
+//   role 0 "lin":  base_lin_vel (LR:119), push (LR:438-444), lin_vel_z, tracking_lin_vel, feet_air_time, stand_still
+//   role 1 "ang":  base_ang_vel (LR:120), heading -> yaw command (LR:337-340), ang_vel_xy, tracking_ang_vel; owns `cmd`
+//   role 2 "grav": projected_gravity (LR:121), orientation, action_rate, collision, dof_acc, dof_pos_limits, dof_vel,
+//                  dof_vel_limits
+//   role 3 "flag": episode length, time-out / termination / reset flags (LR:139-145), base_height, feet_contact_forces,
+//                  no_fly, stumble, torque_limits, torques
+// Command resampling (LR:347-369, rare) is evaluated by every role on its own register copy of the command so that no
+// role waits for another; role 1 writes the row back.
+struct CmdRegs { float c0, c1, c2, c3; };
+
+LGK_D float part_sum(const float* part, int slot, int tile) {
+  const float* q = part + slot * 4 * tile;
+  return (q[0] + q[tile]) + (q[2 * tile] + q[3 * tile]);
+}
+LGK_D uint32_t part_bits(const float* part, int r, int tile) { return __float_as_uint(part[(PS_BITS * 4 + r) * tile]); }
+
+LGK_COLD void resample_cmd_regs(const LgkStepParams& p, const RngKey& key, uint32_t genv, CmdRegs& c) {
+  float tmp[4] = {c.c0, c.c1, c.c2, c.c3};
+  resample_commands(p, tmp, rng_block(key, genv, LGK_STREAM_CMD, 0));
+  c.c0 = tmp[0]; c.c1 = tmp[1]; c.c2 = tmp[2]; c.c3 = tmp[3];
+}
+
 #define LGK_TERM(ID, EXPR)                                            \
   if (p.reward_active[ID]) {                                          \
     const float r_ = (EXPR) * p.reward_scale[ID];                     \
     rew += r_;                                                        \
     sums[(size_t)p.reward_slot[ID] * sums_stride] += r_;              \
   }
-  LGK_TERM(LGK_R_ACTION_RATE, sum.v[PS_ACTION_RATE])
-  LGK_TERM(LGK_R_ANG_VEL_XY, o.bav.x * o.bav.x + o.bav.y * o.bav.y)   // LR:876-878
+
+// role 0.  root: the env's staged row (read 3..9, push writes 7..8).  Returns the reward partial.
+LGK_D float phase_b_lin(const LgkStepParams& p, bool do_push, const RngKey& key, uint32_t genv, float* root,
+                        const CmdRegs& c, const float* part, int tile, float* sums, int sums_stride, V3& blv) {
+  const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+  blv = quat_rotate_inverse(qx, qy, qz, qw, V3{root[7], root[8], root[9]});
+  if (do_push) {   // LR:438-444; rewards / obs of this step keep the pre-push base_lin_vel
+    const U4 r = rng_block_cold(key, genv, LGK_STREAM_PUSH, 0);
+    const float range = 2.0f * p.max_push_vel, lo = -p.max_push_vel;
+    root[7] = scale_uniform(range, lo, u32_to_uniform(r.x));
+    root[8] = scale_uniform(range, lo, u32_to_uniform(r.y));
+  }
+  float rew = 0.f;
+  const float cmd_norm = norm2(c.c0, c.c1);
+  LGK_TERM(LGK_R_FEET_AIR_TIME, part_sum(part, PS_FEET_AIR_TIME, tile) * (cmd_norm > 0.1f ? 1.f : 0.f))   // LR:942-954
+  LGK_TERM(LGK_R_LIN_VEL_Z, blv.z * blv.z)                            // LR:872-874
+  LGK_TERM(LGK_R_STAND_STILL, part_sum(part, PS_STAND_STILL, tile) * (cmd_norm < 0.1f ? 1.f : 0.f))       // LR:961-964
+  {                                                                   // LR:932-935
+    const float ex = c.c0 - blv.x, ey = c.c1 - blv.y;
+    LGK_TERM(LGK_R_TRACKING_LIN_VEL, expf(-(ex * ex + ey * ey) / p.tracking_sigma))
+  }
+  return rew;
+}
+
+// role 1.  Updates c.c2 (heading controller) and writes the command row.
+LGK_D float phase_b_ang(const LgkStepParams& p, const float* root, CmdRegs& c, float* cmd_row, float* sums, int sums_stride,
+                        V3& bav) {
+  const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+  bav = quat_rotate_inverse(qx, qy, qz, qw, V3{root[10], root[11], root[12]});
+  if (p.heading_command) {                                            // LR:337-340
+    const float h = heading_of(qx, qy, qz, qw);
+    c.c2 = clampf(0.5f * wrap_to_pi(c.c3 - h), -1.f, 1.f);
+  }
+  cmd_row[0] = c.c0; cmd_row[1] = c.c1; cmd_row[2] = c.c2; cmd_row[3] = c.c3;
+  float rew = 0.f;
+  LGK_TERM(LGK_R_ANG_VEL_XY, bav.x * bav.x + bav.y * bav.y)           // LR:876-878
+  {                                                                   // LR:937-940
+    const float e = c.c2 - bav.z;
+    LGK_TERM(LGK_R_TRACKING_ANG_VEL, expf(-(e * e) / p.tracking_sigma))
+  }
+  return rew;
+}
+
+// role 2
+LGK_D float phase_b_grav(const LgkStepParams& p, const float* root, const float* part, int tile, float* sums,
+                         int sums_stride, V3& pg) {
+  pg = quat_rotate_inverse(root[3], root[4], root[5], root[6], V3{0.f, 0.f, -1.f});
+  float rew = 0.f;
+  LGK_TERM(LGK_R_ACTION_RATE, part_sum(part, PS_ACTION_RATE, tile))
+  LGK_TERM(LGK_R_COLLISION, part_sum(part, PS_COLLISION, tile))
+  LGK_TERM(LGK_R_DOF_ACC, part_sum(part, PS_DOF_ACC, tile))
+  LGK_TERM(LGK_R_DOF_POS_LIMITS, part_sum(part, PS_DOF_POS_LIMITS, tile))
+  LGK_TERM(LGK_R_DOF_VEL, part_sum(part, PS_DOF_VEL, tile))
+  LGK_TERM(LGK_R_DOF_VEL_LIMITS, part_sum(part, PS_DOF_VEL_LIMITS, tile))
+  LGK_TERM(LGK_R_ORIENTATION, pg.x * pg.x + pg.y * pg.y)              // LR:880-882
+  return rew;
+}
+
+// role 3.  ep_len: episode_length_buf after += 1 (LR:114).
+LGK_D float phase_b_flag(const LgkStepParams& p, const float* root, const float* part, int tile, float* sums,
+                         int sums_stride, long long ep_len, bool& reset, bool& time_out) {
+  const uint32_t b0 = part_bits(part, 0, tile), b1 = part_bits(part, 1, tile), b2 = part_bits(part, 2, tile),
+                 b3 = part_bits(part, 3, tile);
+  const uint32_t any = b0 | b1 | b2 | b3;
+  const uint32_t feet_down = ((b0 >> 1) & 1u) + ((b1 >> 1) & 1u) + ((b2 >> 1) & 1u) + ((b3 >> 1) & 1u);
+  time_out = (float)ep_len > p.max_episode_length;                    // LR:139-145
+  reset = ((any & 1u) != 0) || time_out;
+  float rew = 0.f;
   if (p.reward_active[LGK_R_BASE_HEIGHT]) {                           // LR:884-887
-    const float mh = p.measure_heights ? sum.v[PS_HEIGHT_ERR] / (float)p.num_height_points : root[2];   // LR:562: heights = 0
+    const float mh = p.measure_heights ? part_sum(part, PS_HEIGHT_ERR, tile) / (float)p.num_height_points : root[2];   // LR:562: heights = 0
     const float e = mh - p.base_height_target;
     LGK_TERM(LGK_R_BASE_HEIGHT, e * e)
   }
-  LGK_TERM(LGK_R_COLLISION, sum.v[PS_COLLISION])
-  LGK_TERM(LGK_R_DOF_ACC, sum.v[PS_DOF_ACC])
-  LGK_TERM(LGK_R_DOF_POS_LIMITS, sum.v[PS_DOF_POS_LIMITS])
-  LGK_TERM(LGK_R_DOF_VEL, sum.v[PS_DOF_VEL])
-  LGK_TERM(LGK_R_DOF_VEL_LIMITS, sum.v[PS_DOF_VEL_LIMITS])
-  LGK_TERM(LGK_R_FEET_AIR_TIME, sum.v[PS_FEET_AIR_TIME] * (cmd_norm > 0.1f ? 1.f : 0.f))
-  LGK_TERM(LGK_R_FEET_CONTACT_FORCES, sum.v[PS_FEET_CONTACT_FORCES])
-  LGK_TERM(LGK_R_LIN_VEL_Z, o.blv.z * o.blv.z)                        // LR:872-874
-  LGK_TERM(LGK_R_NO_FLY, ((bits >> 8) & 0xFFu) == 1u ? 1.f : 0.f)     // exactly one foot on the ground (count in bits 8..15)
-  LGK_TERM(LGK_R_ORIENTATION, o.pg.x * o.pg.x + o.pg.y * o.pg.y)      // LR:880-882
-  LGK_TERM(LGK_R_STAND_STILL, sum.v[PS_STAND_STILL] * (cmd_norm < 0.1f ? 1.f : 0.f))
-  LGK_TERM(LGK_R_STUMBLE, (bits & 4u) ? 1.f : 0.f)
-  LGK_TERM(LGK_R_TORQUE_LIMITS, sum.v[PS_TORQUE_LIMITS])
-  LGK_TERM(LGK_R_TORQUES, sum.v[PS_TORQUES])
-  {                                                                   // LR:937-940
-    const float e = cmd[2] - o.bav.z;
-    LGK_TERM(LGK_R_TRACKING_ANG_VEL, expf(-(e * e) / p.tracking_sigma))
-  }
-  {                                                                   // LR:932-935
-    const float ex = cmd[0] - o.blv.x, ey = cmd[1] - o.blv.y;
-    LGK_TERM(LGK_R_TRACKING_LIN_VEL, expf(-(ex * ex + ey * ey) / p.tracking_sigma))
-  }
-#undef LGK_TERM
-  o.rew = rew;
+  LGK_TERM(LGK_R_FEET_CONTACT_FORCES, part_sum(part, PS_FEET_CONTACT_FORCES, tile))
+  LGK_TERM(LGK_R_NO_FLY, feet_down == 1u ? 1.f : 0.f)                 // CAS:43-46: exactly one foot on the ground
+  LGK_TERM(LGK_R_STUMBLE, (any & 4u) ? 1.f : 0.f)                     // LR:956-959
+  LGK_TERM(LGK_R_TORQUE_LIMITS, part_sum(part, PS_TORQUE_LIMITS, tile))
+  LGK_TERM(LGK_R_TORQUES, part_sum(part, PS_TORQUES, tile))
+  return rew;
 }
+#undef LGK_TERM
 
 // reset_idx, role 0's part for one env (LR:147-191): terrain curriculum, root state (in the staged row), predator spawn,
 // command resample
-LGK_COLD void env_reset_base(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, float* root, float* cmd) {
+// `level`: the env's terrain level (staged in shared memory by the step kernel, written back with the tile)
+LGK_COLD void env_reset_base(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, float* root, float* cmd,
+                             long long* level) {
   float ox = 0.f, oy = 0.f, oz = 0.f;
   if (p.env_origins) { ox = p.env_origins[3 * env]; oy = p.env_origins[3 * env + 1]; oz = p.env_origins[3 * env + 2]; }
   if (p.terrain_curriculum) {                                         // LR:446-469
     const float dist = norm2(root[0] - ox, root[1] - oy);
     const bool up = dist > p.half_env_length;
     const bool down = (dist < norm2(cmd[0], cmd[1]) * p.max_episode_length_s * 0.5f) && !up;
-    long long lvl = p.terrain_levels[env] + (up ? 1 : 0) - (down ? 1 : 0);
+    long long lvl = *level + (up ? 1 : 0) - (down ? 1 : 0);
     if (lvl >= p.max_terrain_level) {
       const U4 r = rng_block_cold(key, genv, LGK_STREAM_TERRAIN, 0);
       lvl = (long long)(r.x % (uint32_t)p.max_terrain_level);
     } else if (lvl < 0) {
       lvl = 0;
     }
-    p.terrain_levels[env] = lvl;
+    *level = lvl;
     const float* o = p.terrain_origins + 3 * ((size_t)lvl * p.terrain_num_cols + (size_t)p.terrain_types[env]);
     ox = o[0]; oy = o[1]; oz = o[2];
     p.env_origins[3 * env] = ox; p.env_origins[3 * env + 1] = oy; p.env_origins[3 * env + 2] = oz;
@@ -408,10 +309,9 @@ LGK_D void env_obs_head_role(const LgkStepParams& p, int role, const float* dof,
     out48[36 + d] = act[d];
   }
 }
-LGK_D void env_obs_head_base(const LgkStepParams& p, const EnvScalars& s, const float* cmd, float* out48) {
-  out48[0] = s.blv.x * p.obs_scale_lin_vel; out48[1] = s.blv.y * p.obs_scale_lin_vel; out48[2] = s.blv.z * p.obs_scale_lin_vel;
-  out48[3] = s.bav.x * p.obs_scale_ang_vel; out48[4] = s.bav.y * p.obs_scale_ang_vel; out48[5] = s.bav.z * p.obs_scale_ang_vel;
-  out48[6] = s.pg.x; out48[7] = s.pg.y; out48[8] = s.pg.z;
+// the twelve base / command columns: role 0 lin vel (0..2), role 1 ang vel (3..5), role 2 gravity (6..8) right after their
+// rotations; the command columns (9..11) once the command row is final (after a possible reset)
+LGK_D void obs_head_cmd(const LgkStepParams& p, const float* cmd, float* out48) {
   out48[9] = cmd[0] * p.obs_scale_lin_vel; out48[10] = cmd[1] * p.obs_scale_lin_vel; out48[11] = cmd[2] * p.obs_scale_ang_vel;
 }
 #endif

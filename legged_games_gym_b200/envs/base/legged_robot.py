@@ -11,8 +11,9 @@ Python keeps only what is host logic in the reference too: cfg parsing, buffer a
 curriculum step counters and the extension points.  Supported extension points for subclasses (README.md:29-32,
 56-66 of the reference): extra ``_reward_<name>`` terms written in torch (the step then runs PRE, the Python
 terms, POST), ``_compute_torques``, ``compute_observations`` (called after the native step when overridden),
-``_get_noise_scale_vec``, ``_init_buffers``.  Overriding ``check_termination`` / ``_post_physics_step_callback``
-/ ``compute_reward`` is rejected at construction: those run inside the step kernels.
+``_get_noise_scale_vec``, ``_init_buffers`` and ``reset_idx`` (the step is then split around the Python method, which runs
+where LR:128-129 calls it).  Overriding ``check_termination`` / ``_post_physics_step_callback`` / ``compute_reward`` is
+rejected at construction: those run inside the step kernels.
 """
 import ctypes as C
 
@@ -186,19 +187,34 @@ class LeggedRobot(BaseTask):
             self.reset_buf = self._reset_bool
         st = _stream_ptr()
         cmd_curr = self.cfg.commands.curriculum and (self.common_step_counter % self.max_episode_length == 0)
-        if self._python_reward_names or cmd_curr:
+        if self._python_reward_names or cmd_curr or self._reset_overridden:
             p.phase_mask = nat.PHASE_PRE
             nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics(PRE)")
             for name in self._python_reward_names:             # user terms, LR:199-203
                 rew = getattr(self, "_reward_" + name)() * self.reward_scales[name]
                 self.rew_buf += rew
                 self.episode_sums[name] += rew
-            if cmd_curr:
-                ids = self.reset_buf.nonzero(as_tuple=False).flatten()
-                if len(ids) > 0:
-                    self.update_command_curriculum(ids)
-            p.phase_mask = nat.PHASE_POST
-            nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics(POST)")
+            if self._reset_overridden:
+                # a subclass's reset_idx runs exactly where the reference calls it (LR:126-130): after compute_reward
+                # (positive clip + termination term), before compute_observations.  The in-kernel reset is off for this
+                # step; the override reaches the kernels through LeggedRobot.reset_idx -> lgk_reset_idx.
+                p.phase_mask = nat.PHASE_POST_REWARD
+                nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics(POST_REWARD)")
+                env_ids = self.reset_buf.nonzero(as_tuple=False).flatten()          # LR:128
+                self._in_step_reset = True
+                try:
+                    self.reset_idx(env_ids)
+                finally:
+                    self._in_step_reset = False
+                p.phase_mask = nat.PHASE_POST_OBS
+                nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics(POST_OBS)")
+            else:
+                if cmd_curr:
+                    ids = self.reset_buf.nonzero(as_tuple=False).flatten()
+                    if len(ids) > 0:
+                        self.update_command_curriculum(ids)
+                p.phase_mask = nat.PHASE_POST
+                nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics(POST)")
         else:
             p.phase_mask = nat.PHASE_PRE | nat.PHASE_POST
             nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics")
@@ -268,13 +284,20 @@ class LeggedRobot(BaseTask):
             self.reset_buf = self._reset_bool
             self.reset_buf.fill_(True)
         st = _stream_ptr()
-        saved = p.terrain_curriculum
+        saved = p.terrain_curriculum, p.step_counter_dev, p.step
         if not self.init_done:
             p.terrain_curriculum = 0            # "don't change on initial reset" (LR:453-455)
+        in_step = getattr(self, "_in_step_reset", False)
+        if in_step:
+            # called from post_physics_step on behalf of a subclass override: the reset belongs to THIS step (same RNG
+            # counter and extras slot as the in-kernel reset), and the step's own finalize / sim push follow
+            p.step_counter_dev, p.step = None, int(self.common_step_counter)
         nat.check(nat.lib.lgk_reset_idx(C.byref(p), env_ids.data_ptr(), int(env_ids.numel()), st), "lgk_reset_idx")
-        p.terrain_curriculum = saved
-        self._finalize(st, advance=0)
-        self._push_resets_to_sim()
+        p.terrain_curriculum, p.step_counter_dev, p.step = saved
+        if not in_step:
+            self._finalize(st, advance=0)
+            self._push_resets_to_sim()
+    reset_idx._lgk_native = True
 
     # ------------------------------------------------------------------ LR:212-230 (torch version for overriders)
     def compute_observations(self):
@@ -534,9 +557,14 @@ class LeggedRobot(BaseTask):
         cls = type(self)
         self._native_torques = getattr(cls._compute_torques, "_lgk_native", False)
         self._obs_overridden = cls.compute_observations is not LeggedRobot.compute_observations
+        # reset_idx is an extension point of the reference (README.md:56-66; its own Anymal overrides it, ANY:56-60): an
+        # override is honoured by splitting the step around it (see post_physics_step)
+        self._reset_overridden = not getattr(cls.reset_idx, "_lgk_native", False)
+        self._in_step_reset = False
         # whole-step CUDA graph: needs the native torque path, no torch-written reward terms, the built-in
         # observations and a sim backend whose hooks enqueue nothing between the kernels
         self._graph_ok = (self._native_torques and not self._python_reward_names and not self._obs_overridden
+                          and not self._reset_overridden
                           and getattr(self.gym, "graph_safe", False) and getattr(self, "use_cuda_graph", True))
         f = lambda t: [float(x) for x in t.detach().flatten().cpu().tolist()]
         # ---- torques (LR:371-395)
@@ -637,9 +665,11 @@ class LeggedRobot(BaseTask):
         p.step_counter_dev = ptr(self._step_counter_dev)
         self._scan_frames = torch.zeros(N, 8, dtype=torch.float, device=self.device)
         p.scan_frames = ptr(self._scan_frames)
+        if mh:         # hand-over buffer of the 48 proprioceptive columns between the two step kernels
+            self._obs_head = torch.zeros(N, 48, dtype=torch.float, device=self.device)
+            p.obs_head = ptr(self._obs_head)
         dr = cfg.domain_rand
         p.push_interval = int(dr.push_interval) if dr.push_robots else 0
-        p.tile_envs = int(getattr(self, "tile_envs", 0))
         if mh:
             p.measured_heights = ptr(self.measured_heights)
             if not p.terrain_is_plane:

@@ -175,16 +175,17 @@ def test_env_step_matches_oracle(task, n, ov):
         harness.apply_noise(st_gpu, noise)
 
 
-@pytest.mark.parametrize("task,n,tile", [("anymal_c_rough", 300, 8), ("anymal_c_rough", 300, 16), ("anymal_c_rough", 300, 32),
-                                         ("cassie", 77, 32), ("a1", 1000, 16)])
-def test_env_step_cuda_graph_and_tiles(task, n, tile):
-    """Same parity bar with the whole step replayed as one CUDA graph (device-side step counter) and for every
-    tile size of the fused kernel; pushes every 2nd step so the device-derived push flag is exercised."""
+@pytest.mark.parametrize("task,n", [("anymal_c_rough", 300), ("anymal_c_rough", 8000), ("cassie", 77), ("a1", 1000),
+                                    ("anymal_c_flat", 2100)])
+def test_env_step_cuda_graph(task, n):
+    """Same parity bar with the whole step replayed as one CUDA graph (device-side step counter); pushes every 2nd step so
+    the device-derived push flag is exercised; 8000 envs = 250 tiles, more than one tile per persistent K1 CTA on a
+    148-SM part only when few CTAs are resident -- LGK_K1_CTAS_PER_SM=1 in test_k1_persistent_loop covers that."""
     ov = {"domain_rand.push_interval_s": 0.04}
     case = harness.build_case(task, n, seed=6, overrides=ov)
     st_or = harness.torch_state(case)
     orc = harness.make_oracle(case, st_or)
-    env, feeder = product_env(case, graph=True, tile=tile)
+    env, feeder = product_env(case, graph=True)
     assert env._graph_ok
     st_gpu = feeder_state(feeder)
     for step in range(1, 8):
@@ -201,54 +202,6 @@ def test_env_step_cuda_graph_and_tiles(task, n, tile):
         harness.apply_noise(st_or, noise)
         harness.apply_noise(st_gpu, noise)
     assert env._graph is not None
-
-
-@pytest.mark.parametrize("task,n,ov,sw", [
-    ("anymal_c_rough", 4096, {"env.episode_length_s": 0.3, "domain_rand.push_interval_s": 0.04}, 0),
-    ("a1", 1000, {"env.episode_length_s": 0.2, "commands.curriculum": True}, 4),
-    ("anymal_c_rough", 77, {"noise.add_noise": False}, 3),
-    ("cassie", 2080, {"env.episode_length_s": 0.2}, 8),
-    ("low_level_game", 200, {"env.episode_length_s": 0.2}, 0)])
-def test_fused_post_physics_kernel_equals_two_kernel_chain(task, n, ov, sw):
-    """lgk_post_physics as ONE launch (role warps + scan warps, speculative height columns redone for reset envs) gives
-    bit-identical results to the K1 -> K2 chain it replaces: every snapshot tensor, 8 steps with resets (short
-    episodes), pushes, partial tiles and every scan-warp count."""
-    lib = nat().lib
-    case = harness.build_case(task, n, seed=11, overrides=ov)
-    envs = []
-    for fused in (1, 0):
-        lib.lgk_set_fused(fused)
-        env, feeder = product_env(case)
-        envs.append((fused, env, feeder_state(feeder)))
-    before = nat().launch_count()
-    try:
-        lib.lgk_set_fused_scan_warps(sw)
-        n_reset = 0
-        for step in range(1, 9):
-            acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (n, 12)).astype(np.float32)).to(DEV)
-            noise = harness.make_noise(case, step, 5)
-            snaps = []
-            for fused, env, st in envs:
-                lib.lgk_set_fused(fused)
-                c0 = nat().launch_count()
-                env.step(acts.clone())
-                torch.cuda.synchronize()
-                launches = nat().launch_count() - c0
-                snaps.append((harness.snapshot(env), launches))
-                harness.apply_noise(st, noise)
-            (a, la), (b, lb) = snaps
-            assert la == lb - 1, f"the fused path saves one launch per step ({la} vs {lb})"
-            n_reset += int(a["reset_buf"].sum())
-            for k in b:
-                if k.startswith("ex_"):        # cross-tile float atomics: summation order varies from launch to launch
-                    assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), f"step {step}: {k}"
-                    continue
-                assert torch.equal(a[k], b[k]), f"step {step}: {k} differs between the fused kernel and the chain"
-        assert n_reset > 0, "the case must exercise the reset re-do of the speculative height columns"
-    finally:
-        lib.lgk_set_fused(0)
-        lib.lgk_set_fused_scan_warps(0)
-    assert nat().launch_count() > before
 
 
 GAME_STEP_CASES = [("hl", 96, None, None), ("hl", 200, {"env.env_radius": 40.0, "rewards.scales.termination": -2.0, "rewards.only_positive_rewards": False}, None),
@@ -404,6 +357,96 @@ def test_user_reward_term_runs_split_phases():
         assert_snapshots_close(harness.snapshot(env), harness.snapshot(orc), step,
                                atol_scale={"torques": max(1.0, float(orc.torques.abs().max()))},
                                heading_command=bool(env.cfg.commands.heading_command))
+
+
+def test_reset_idx_override_runs_where_the_reference_calls_it():
+    """reset_idx is an extension point of the reference (README.md:56-66; its own Anymal overrides it, ANY:56-60) and
+    LR:128-129 calls it every step between compute_reward and compute_observations.  A subclass that zeroes an extra
+    buffer there must see exactly the reference's env_ids at exactly that point, and the step must still equal the oracle."""
+    from legged_games_gym_b200.envs import LeggedRobot, task_registry
+    from legged_games_gym_b200.envs.a1.a1_config import A1RoughCfg
+    seen = []
+
+    class MyEnv(LeggedRobot):
+        def _init_buffers(self):
+            super()._init_buffers()
+            self.steps_since_reset = torch.zeros(self.num_envs, device=self.device)
+
+        def reset_idx(self, env_ids):
+            if self.init_done and len(env_ids) > 0:
+                # the reference's ordering: rewards of this step are final, observations are not yet rebuilt
+                seen.append((env_ids.clone(), self.rew_buf.clone(), self.episode_length_buf[env_ids].clone()))
+            super().reset_idx(env_ids)
+            self.steps_since_reset[env_ids] = 0.
+
+    ov = {"env.episode_length_s": 0.1, "domain_rand.push_interval_s": 0.04, "commands.curriculum": True,
+          "rewards.scales.termination": -2.0}
+    case = harness.build_case("a1", 200, seed=12, overrides=ov)
+    task_registry.register("a1_reset_override", MyEnv, A1RoughCfg(), None)
+    case["task"] = "a1_reset_override"
+    st_or = harness.torch_state(case)
+    orc = harness.make_oracle(case, st_or)
+    env, feeder = product_env(case, graph=True)
+    assert env._reset_overridden and not env._graph_ok          # the split step is not graph-replayed
+    st_gpu = feeder_state(feeder)
+    want_since = torch.zeros(200)
+    n_reset = 0
+    for step in range(1, 9):
+        tables = harness.step_tables(case["seed"], step, 200, orc.num_obs)
+        acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (200, 12)).astype(np.float32))
+        orc.step(acts.clone(), tables)
+        env.steps_since_reset += 1
+        want_since += 1
+        before = len(seen)
+        env.step(acts.to(DEV))
+        torch.cuda.synchronize()
+        ids = orc.reset_buf.nonzero().flatten()
+        want_since[ids] = 0
+        assert_snapshots_close(harness.snapshot(env), harness.snapshot(orc), step,
+                               atol_scale={"torques": max(1.0, float(orc.torques.abs().max()))},
+                               heading_command=bool(env.cfg.commands.heading_command))
+        assert torch.equal(env.steps_since_reset.cpu(), want_since)
+        if len(ids) > 0:
+            assert len(seen) == before + 1, "the override must be called once per step with resets"
+            got_ids, rew_at_call, ep_at_call = seen[-1]
+            assert torch.equal(got_ids.cpu(), ids)                                  # LR:128 nonzero() order
+            assert torch.allclose(rew_at_call.cpu(), orc.rew_buf, rtol=1e-5, atol=1e-5)   # final (clip + termination term)
+            assert bool((ep_at_call > 0).all())                                    # not yet zeroed when the override starts
+            n_reset += len(ids)
+        noise = harness.make_noise(case, step, 5)
+        harness.apply_noise(st_or, noise)
+        harness.apply_noise(st_gpu, noise)
+    assert n_reset > 20
+
+
+def test_k1_persistent_loop_many_tiles_per_cta():
+    """K1's CTAs are persistent: with one resident CTA per SM (tuning knob of the launcher) 20 000 envs are 625 tiles on at
+    most 148 CTAs, i.e. up to five tiles per CTA incl. a partial last tile -- shared-memory reuse, mbarrier phases and the
+    L2 prefetch of the next tile must not change a bit against the default launch."""
+    import subprocess, sys, json
+    code = (
+        "import sys, torch, numpy as np; sys.path.insert(0, %r)\n"
+        "from oracle import harness\n"
+        "from tests.util import product_env\n"
+        "case = harness.build_case('anymal_c_rough', 20004, seed=5, overrides={'env.episode_length_s': 0.1})\n"
+        "env, feeder = product_env(case)\n"
+        "for step in range(1, 4):\n"
+        "    a = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (20004, 12)).astype(np.float32)).cuda()\n"
+        "    env.step(a)\n"
+        "torch.cuda.synchronize()\n"
+        "snap = harness.snapshot(env)\n"
+        "torch.save({k: v for k, v in snap.items() if not k.startswith('ex_')}, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for per_sm in ("1", "7"):
+        path = f"/tmp/lgk_k1_persist_{per_sm}.pt"
+        env = dict(os.environ, LGK_K1_CTAS_PER_SM=per_sm)
+        r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(path))
+    a, b = outs
+    assert a.keys() == b.keys() and int(a["reset_buf"].sum()) > 100
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"{k} differs between 1 and 7 resident K1 CTAs per SM"
 
 
 # ---------------------------------------------------------------------------------------------- full size

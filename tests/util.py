@@ -41,8 +41,6 @@ def product_env(case, device="cuda:0", graph=False, tile=0):
                                         tot_cols=hs.shape[1], env_origins=case["terrain_origins"])
     cls = task_registry.get_task_class(case["task"])
     feeder = ExplicitFeeder(case["state"])
-    if tile:
-        cls = type(cls.__name__ + f"Tile{tile}", (cls,), {"tile_envs": tile})
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
               sim_device=device, headless=True, sim_backend=feeder, terrain=terrain,
               init_terrain_levels=case["init_levels"])

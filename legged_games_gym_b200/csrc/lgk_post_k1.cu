@@ -25,8 +25,8 @@ namespace lgk {
 
 // ------------------------------------------------------------------ shared-memory carve-up (bytes, 16-aligned)
 struct TileLayout {
-  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, frame, sums, ep, epo, lvl, rew, rewp,
-      flags, part, misc, total;
+  int root, dof, contact, act, tq, lact, ldv, cmd, fat, lc, head, blv, bav, pg, lrv, frame, sums, ep, epo, lvl, typ, org, rew,
+      rewp, flags, part, misc, total;
 };
 
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
@@ -55,6 +55,8 @@ __host__ __device__ inline TileLayout make_layout(int nb, int nfeet, int nslots)
   L.ep = o;      o += al16(kTile * 8);                                // episode_length_buf as loaded (int64)
   L.epo = o;     o += al16(kTile * 8);                                // ... as it leaves
   L.lvl = o;     o += al16(kTile * 8);                                // terrain_levels (int64)
+  L.typ = o;     o += al16(kTile * 8);                                // terrain_types (int64)
+  L.org = o;     o += al16(kTile * 3 * 4);                            // env_origins
   L.rew = o;     o += al16(kTile * 4);
   L.rewp = o;    o += al16(4 * kTile * 4);                            // reward partials of the four roles
   L.flags = o;   o += al16(kTile * 2);                                // reset flags [32] then time_out flags [32]
@@ -77,11 +79,13 @@ __device__ __noinline__ void copy_u8(uint8_t* dst, const uint8_t* src, int n, in
 __device__ long long* g_k1_timeline = nullptr;     // profiling hook (lgk_step_debug_timeline)
 // stamps of the first tile of CTA 0 ([0..8]) and of the last CTA ([16..24])
 __device__ __forceinline__ void k1_stamp(int slot, bool first_tile) {
+#ifdef LGK_K1_TIMELINE          // (the stamps cost a global load each: compiled in only for timeline builds)
   if (g_k1_timeline != nullptr && first_tile && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     g_k1_timeline[blockIdx.x == 0 ? slot : 16 + slot] = (long long)t;
   }
+#endif
 }
 
 __device__ __forceinline__ void role_sync() { named_sync(1, kK1Threads); }
@@ -99,10 +103,14 @@ __device__ __forceinline__ bool divisible(long long ep_len, int period) {
 #define LGK_K1_PREFETCH 1
 #endif
 
+constexpr int kMaxRowsPerWarp = 5;      // episode_sums rows per role warp: ceil(LGK_R_COUNT / 4)
+
+// FAST: the whole step in one pass (PRE | POST) over full, 16-byte aligned tiles -- the phase flags and the partial-tile
+// fallback are compiled out (half the code size: the kernel is instruction-fetch sensitive).  !FAST: every other case.
+template <bool FAST>
 __global__ void __launch_bounds__(kK1Threads, LGK_K1_MINBLOCKS)
-post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
+post_kernel(const __grid_constant__ LgkStepParams p, const __grid_constant__ TileLayout L, int ntiles) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const TileLayout L = make_layout(p.num_bodies, p.num_feet, p.num_reward_slots);
   float* s_root = reinterpret_cast<float*>(smem + L.root);
   float* s_dof = reinterpret_cast<float*>(smem + L.dof);
   float* s_contact = reinterpret_cast<float*>(smem + L.contact);
@@ -123,6 +131,8 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
   long long* s_ep = reinterpret_cast<long long*>(smem + L.ep);
   long long* s_epo = reinterpret_cast<long long*>(smem + L.epo);
   long long* s_lvl = reinterpret_cast<long long*>(smem + L.lvl);
+  long long* s_typ = reinterpret_cast<long long*>(smem + L.typ);
+  float* s_org = reinterpret_cast<float*>(smem + L.org);
   float* s_rew = reinterpret_cast<float*>(smem + L.rew);
   float* s_rewp = reinterpret_cast<float*>(smem + L.rewp);
   uint8_t* s_flags = smem + L.flags;
@@ -133,16 +143,17 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
   const int NB = p.num_bodies, F = p.num_feet, P = p.num_height_points, O = p.num_obs, N = p.num_envs;
   const int K = p.num_reward_slots;
   const int mask = p.phase_mask;
-  const bool pre = (mask & LGK_PHASE_PRE) != 0;
-  const bool fin = (mask & (LGK_PHASE_POST | LGK_PHASE_POST_REWARD)) != 0;      // positive clip + termination term
-  const bool rst = (mask & LGK_PHASE_POST) != 0;                                // in-kernel reset_idx
-  const bool obsph = (mask & (LGK_PHASE_POST | LGK_PHASE_POST_OBS)) != 0;       // observations + histories
+  const bool pre = FAST || (mask & LGK_PHASE_PRE) != 0;
+  const bool fin = FAST || (mask & (LGK_PHASE_POST | LGK_PHASE_POST_REWARD)) != 0;      // positive clip + termination term
+  const bool rst = FAST || (mask & LGK_PHASE_POST) != 0;                                // in-kernel reset_idx
+  const bool obsph = FAST || (mask & (LGK_PHASE_POST | LGK_PHASE_POST_OBS)) != 0;       // observations + histories
   const bool fat_active = p.reward_active[LGK_R_FEET_AIR_TIME] != 0 && F > 0;
   const bool curriculum = p.terrain_curriculum != 0;
   const bool want_frames = p.measure_heights && p.scan_frames != nullptr;      // K2 takes the yaw frame and the post-reset z from here
   const bool head_to_k2 = p.measure_heights != 0;      // K2 finishes the rows (noise + clip); flat tasks finish them here
   // whole-tile paths need unit root stride and 16-byte aligned tile chunks
-  const bool bulk_ok = (p.actors_per_env == 1) && (N % 4 == 0);
+  const bool bulk_ok = FAST || ((p.actors_per_env == 1) && (N % 4 == 0));
+  const bool has_org = p.env_origins != nullptr;
   pdl_launch_dependents();
   k1_stamp(0, true);
   if (tid == 0) {
@@ -156,18 +167,37 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
   const RngKey key = make_key(p.seed, step_eff);
   float* stats = p.reset_stats + (size_t)(step_eff & 1) * (K + 2);
 
+  // per-env scalar rows (one 128-byte row segment per tensor and tile; lane = env) travel through registers, loaded one
+  // tile AHEAD: the loads of tile i+1 are in flight while tile i is processed
+  float pf_sum[kMaxRowsPerWarp];
+  long long pf_ep = 0, pf_lvl = 0, pf_typ = 0;
+  auto fetch_rows = [&](int t) {
+    const int e0 = t * kTile;
+    if (t < ntiles && e0 + lane < N) {
+#pragma unroll
+      for (int j = 0; j < kMaxRowsPerWarp; ++j) {
+        const int k = warp + 4 * j;
+        if (k < K) pf_sum[j] = p.episode_sums[(size_t)k * N + e0 + lane];
+      }
+      if (warp == (K & 3)) pf_ep = p.episode_length_buf[e0 + lane];
+      if (curriculum && warp == ((K + 1) & 3)) pf_lvl = p.terrain_levels[e0 + lane];
+      if (curriculum && warp == ((K + 2) & 3)) pf_typ = p.terrain_types[e0 + lane];
+    }
+  };
+  fetch_rows(blockIdx.x);
+
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const bool first = it == 0;
     const int env0 = tile * kTile;
-    const int nval = min(kTile, N - env0);
-    const bool bulk = bulk_ok && nval == kTile;
+    const int nval = FAST ? kTile : min(kTile, N - env0);
+    const bool bulk = FAST || (bulk_ok && nval == kTile);
 
     // ---------------- stage the tile
-    if (!first && tid == 0) bulk_wait_read0();   // the previous tile's bulk stores have read their shared-memory sources
     if (bulk && tid == 0) {
       uint32_t bytes = kTile * (13 + 24 + 3 * NB + 12 + 12 + 12 + 12 + 4) * 4;
       if (F > 0) bytes += kTile * F * 4 + kTile * F;
+      if (has_org) bytes += kTile * 3 * 4;
       mbar_expect_tx(bar, bytes);
       bulk_g2s(s_root, p.root_states + (size_t)env0 * 13, kTile * 13 * 4, bar);
       bulk_g2s(s_dof, p.dof_state + (size_t)env0 * 24, kTile * 24 * 4, bar);
@@ -181,6 +211,7 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
         bulk_g2s(s_fat, p.feet_air_time + (size_t)env0 * F, kTile * F * 4, bar);
         bulk_g2s(s_lc, p.last_contacts + (size_t)env0 * F, kTile * F, bar);
       }
+      if (has_org) bulk_g2s(s_org, p.env_origins + (size_t)env0 * 3, kTile * 3 * 4, bar);
 #if LGK_K1_PREFETCH
       // the CTA's next tile: pull its chunks into L2 now, a whole tile's processing time ahead of their use
       const int nt = tile + gridDim.x;
@@ -198,18 +229,20 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
       }
 #endif
     }
-    // per-env scalar rows (one 128-byte row segment per tensor and tile): plain coalesced loads, lane = env, issued while
-    // the bulk copies are in flight
-    if (lane < nval) {
-      for (int k = warp; k < K; k += 4) s_sums[k * kTile + lane] = p.episode_sums[(size_t)k * N + env0 + lane];
-      if (warp == (K & 3)) s_ep[lane] = p.episode_length_buf[env0 + lane];
-      if (curriculum && warp == ((K + 1) & 3)) s_lvl[lane] = p.terrain_levels[env0 + lane];
+    // the scalar rows of THIS tile are in registers (fetched one tile ago); park them and start the next tile's loads
+#pragma unroll
+    for (int j = 0; j < kMaxRowsPerWarp; ++j) {
+      const int k = warp + 4 * j;
+      if (k < K) s_sums[k * kTile + lane] = pf_sum[j];
     }
+    if (warp == (K & 3)) s_ep[lane] = pf_ep;
+    if (curriculum && warp == ((K + 1) & 3)) s_lvl[lane] = pf_lvl;
+    if (curriculum && warp == ((K + 2) & 3)) s_typ[lane] = pf_typ;
+    fetch_rows(tile + gridDim.x);
     k1_stamp(1, first);
     if (bulk) {
       mbar_wait(bar, it & 1);
-    } else {
-      if (!first) role_sync();                // (thread 0 has waited for the previous tile's bulk stores)
+    } else if (!FAST) {
       for (int i = tid; i < nval * 13; i += kK1Threads) {
         const int e = i / 13, c = i - e * 13;
         s_root[i] = p.root_states[((size_t)(env0 + e) * p.actors_per_env + p.root_actor_offset) * 13 + c];
@@ -225,6 +258,7 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
         copy_f32(s_fat, p.feet_air_time + (size_t)env0 * F, nval * F, tid);
         copy_u8(s_lc, p.last_contacts + (size_t)env0 * F, nval * F, tid);
       }
+      if (has_org) copy_f32(s_org, p.env_origins + (size_t)env0 * 3, nval * 3, tid);
       role_sync();
     }
     k1_stamp(2, first);
@@ -314,12 +348,6 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
           }
           if (lane == 0) atomicAdd(stats + K, (float)__popc(rmask));
         }
-        if (resetting) { env_reset_base(p, key, genv, env, root, cmd, s_lvl + e); ep_len = 0; }      // LR:176
-        if (curriculum) {                       // mean terrain level over ALL envs (LR:186), after the level updates
-          float lv = valid ? (float)s_lvl[e] : 0.f;
-          lv = warp_sum(lv);
-          if (lane == 0) atomicAdd(stats + K + 1, lv);
-        }
       }
       s_rew[e] = rew;
       s_epo[e] = ep_len;
@@ -338,41 +366,70 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
       }
     }
     if (obsph) {
-      if (resetting) env_reset_joints(p, key, genv, role, dof, fat);
       env_obs_head_role(p, role, dof, s_act + e * 12, head);
 #pragma unroll
       for (int d = 3 * role; d < 3 * role + 3; ++d) s_ldv[e * 12 + d] = dof[2 * d + 1];   // LR:133 (post-reset dof_vel)
     }
     fence_async_smem();
     role_sync();
+    // ---------------- reset tail (LR:147-191): every warp sees the same reset mask (lane = env) and takes every fourth reset
+    // env; the env's rows inside the tile are redrawn warp-cooperatively, so the phases above carry no reset branch
+    bool tile_reset = false;
+    if (rst) {
+      uint32_t rm = __ballot_sync(0xffffffffu, resetting);
+      tile_reset = rm != 0;                // (CTA-uniform)
+      if (tile_reset) {
+        int turn = 0;
+        while (rm) {
+          const int ee = __ffs(rm) - 1;
+          rm &= rm - 1;
+          if ((turn++ & 3) != warp) continue;
+          TileRows t{s_root + ee * 13, s_dof + ee * 24, s_cmd + ee * 4, s_fat + ee * F, s_head + ee * 49, s_ldv + ee * 12,
+                     s_lrv + ee * 6, s_frame + ee * kFrameFloats, has_org ? s_org + ee * 3 : nullptr, s_lvl + ee, s_typ + ee,
+                     s_epo + ee};
+          tile_reset_env(p, key, (uint32_t)(p.env_id_offset + env0 + ee), env0 + ee, lane, t, kFrameFloats);
+        }
+        fence_async_smem();
+        role_sync();
+      }
+      if (curriculum && role == 1) {             // mean terrain level over ALL envs (LR:186), after the level updates
+        float lv = valid ? (float)s_lvl[e] : 0.f;
+        lv = warp_sum(lv);
+        if (lane == 0) atomicAdd(stats + K + 1, lv);
+      }
+    }
     k1_stamp(5, first);
 
-    // ---------------- whole-tile write-backs
+    // ---------------- whole-tile write-backs: lane 0 of every warp issues its share of the bulk stores
     const bool frames_tile = bulk && want_frames && pre && obsph;      // both halves of the frame rows are fresh
     if (bulk) {
-      if (tid == 0) {
-        if (pre) {
-          bulk_s2g(p.base_lin_vel + (size_t)env0 * 3, s_blv, kTile * 3 * 4);
-          bulk_s2g(p.base_ang_vel + (size_t)env0 * 3, s_bav, kTile * 3 * 4);
-          bulk_s2g(p.projected_gravity + (size_t)env0 * 3, s_pg, kTile * 3 * 4);
-          bulk_s2g(p.commands + (size_t)env0 * 4, s_cmd, kTile * 4 * 4);
+      if (lane == 0) {
+        if (warp == 0) {
+          if (pre) {
+            bulk_s2g(p.base_lin_vel + (size_t)env0 * 3, s_blv, kTile * 3 * 4);
+            bulk_s2g(p.base_ang_vel + (size_t)env0 * 3, s_bav, kTile * 3 * 4);
+            bulk_s2g(p.projected_gravity + (size_t)env0 * 3, s_pg, kTile * 3 * 4);
+          }
+        } else if (warp == 1) {
+          if (pre || rst) bulk_s2g(p.commands + (size_t)env0 * 4, s_cmd, kTile * 4 * 4);
+          if (F > 0 && ((pre && fat_active) || (rst && obsph))) {
+            bulk_s2g(p.feet_air_time + (size_t)env0 * F, s_fat, kTile * F * 4);
+            if (pre && fat_active) bulk_s2g(p.last_contacts + (size_t)env0 * F, s_lc, kTile * F);
+          }
           if (do_push) bulk_s2g(p.root_states + (size_t)env0 * 13, s_root, kTile * 13 * 4);
-        } else if (rst) {
-          bulk_s2g(p.commands + (size_t)env0 * 4, s_cmd, kTile * 4 * 4);
+        } else if (warp == 2) {
+          if (obsph) {
+            bulk_s2g(p.last_actions + (size_t)env0 * 12, s_act, kTile * 12 * 4);
+            bulk_s2g(p.last_dof_vel + (size_t)env0 * 12, s_ldv, kTile * 12 * 4);
+          }
+        } else {
+          if (obsph) bulk_s2g(p.last_root_vel + (size_t)env0 * 6, s_lrv, kTile * 6 * 4);
+          if (frames_tile) bulk_s2g(p.scan_frames + (size_t)env0 * kFrameFloats, s_frame, kTile * kFrameFloats * 4);
+          if (tile_reset && curriculum && has_org) bulk_s2g(p.env_origins + (size_t)env0 * 3, s_org, kTile * 3 * 4);
         }
-        if (F > 0 && ((pre && fat_active) || (rst && obsph))) {
-          bulk_s2g(p.feet_air_time + (size_t)env0 * F, s_fat, kTile * F * 4);
-          if (pre && fat_active) bulk_s2g(p.last_contacts + (size_t)env0 * F, s_lc, kTile * F);
-        }
-        if (obsph) {
-          bulk_s2g(p.last_actions + (size_t)env0 * 12, s_act, kTile * 12 * 4);
-          bulk_s2g(p.last_dof_vel + (size_t)env0 * 12, s_ldv, kTile * 12 * 4);
-          bulk_s2g(p.last_root_vel + (size_t)env0 * 6, s_lrv, kTile * 6 * 4);
-        }
-        if (frames_tile) bulk_s2g(p.scan_frames + (size_t)env0 * kFrameFloats, s_frame, kTile * kFrameFloats * 4);
         bulk_commit();
       }
-    } else {
+    } else if (!FAST) {
       if (pre) {
         copy_f32(p.base_lin_vel + (size_t)env0 * 3, s_blv, nval * 3, tid);
         copy_f32(p.base_ang_vel + (size_t)env0 * 3, s_bav, nval * 3, tid);
@@ -388,6 +445,7 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
         copy_f32(p.last_dof_vel + (size_t)env0 * 12, s_ldv, nval * 12, tid);
         copy_f32(p.last_root_vel + (size_t)env0 * 6, s_lrv, nval * 6, tid);
       }
+      if (tile_reset && curriculum && has_org) copy_f32(p.env_origins + (size_t)env0 * 3, s_org, nval * 3, tid);
       if (do_push) {
         for (int i = tid; i < nval * 13; i += kK1Threads) {
           const int ee = i / 13, cc = i - ee * 13;
@@ -412,7 +470,7 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
     }
     k1_stamp(6, first);
 
-    if (rst) {
+    if (tile_reset) {
       // ---------------- reset rows: dof_state / root_states write-back + LSTM state zeroing (ANY:56-60); every warp sees
       // the same reset mask (lane = env) and takes every fourth reset env
       uint32_t rm = __ballot_sync(0xffffffffu, resetting);
@@ -455,10 +513,10 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
       } else if (p.obs_head != nullptr) {
         // ---------------- the 48 proprioceptive columns, un-noised, into the compact [N,48] hand-over buffer of K2: the
         // tile is ONE contiguous 6 KB block (K2 adds noise + clip and writes the final row)
-        float* dst = p.obs_head + (size_t)env0 * kHeadCols;
-        for (int i = tid; i < nval * kHeadCols; i += kK1Threads) {
-          const int r = i / kHeadCols, cc = i - r * kHeadCols;
-          dst[i] = s_head[r * 49 + cc];
+        for (int ee = warp * 8; ee < min(warp * 8 + 8, nval); ++ee) {
+          float* dst = p.obs_head + (size_t)(env0 + ee) * kHeadCols;
+          dst[lane] = s_head[ee * 49 + lane];
+          if (lane < 16) dst[32 + lane] = s_head[ee * 49 + 32 + lane];
         }
       } else {
         // (callers without a hand-over buffer: un-noised head columns go through obs_buf)
@@ -470,23 +528,26 @@ post_kernel(const __grid_constant__ LgkStepParams p, int ntiles) {
       }
     }
     k1_stamp(7, first);
+    if (bulk && lane == 0) bulk_wait_read0();      // this lane's bulk stores have read their shared-memory sources
     role_sync();           // every warp is done with the tile's shared memory: the next tile may be staged
     k1_stamp(8, first);
   }
-  if (tid == 0) bulk_wait_read0();
 }
 
 int launch_k1(const LgkStepParams* p, cudaStream_t st) {
   const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_reward_slots);
-  // ~30 KB of staged tiles per CTA: ask for the largest shared-memory carve-out so that LGK_K1_MINBLOCKS CTAs are resident per SM
-  if (int rc = ensure_func_attr(reinterpret_cast<const void*>(post_kernel), L.total, "cudaFuncSetAttribute(post_kernel)", true)) return rc;
+  const bool fast = p->phase_mask == (LGK_PHASE_PRE | LGK_PHASE_POST) && p->actors_per_env == 1 && p->num_envs % kTile == 0;
+  const void* fn = fast ? reinterpret_cast<const void*>(post_kernel<true>) : reinterpret_cast<const void*>(post_kernel<false>);
+  // ~31 KB of staged tiles per CTA: ask for the largest shared-memory carve-out so that LGK_K1_MINBLOCKS CTAs are resident per SM
+  if (int rc = ensure_func_attr(fn, L.total, "cudaFuncSetAttribute(post_kernel)", true)) return rc;
   const int ntiles = (p->num_envs + kTile - 1) / kTile;
   static const int per_sm = getenv("LGK_K1_CTAS_PER_SM") ? atoi(getenv("LGK_K1_CTAS_PER_SM")) : LGK_K1_MINBLOCKS;   // tuning aid
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = sms * (per_sm > 0 ? per_sm : 1);
   if (grid > ntiles) grid = ntiles;
-  const cudaError_t e = launch_chained(post_kernel, dim3(grid), dim3(kK1Threads), (size_t)L.total, st, *p, ntiles);
+  const cudaError_t e = fast ? launch_chained(post_kernel<true>, dim3(grid), dim3(kK1Threads), (size_t)L.total, st, *p, L, ntiles)
+                             : launch_chained(post_kernel<false>, dim3(grid), dim3(kK1Threads), (size_t)L.total, st, *p, L, ntiles);
   count_launch();
   return check_cuda(e, "post_kernel launch");
 }
@@ -495,5 +556,8 @@ int launch_k1(const LgkStepParams* p, cudaStream_t st) {
 
 extern "C" int lgk_step_debug_timeline(int64_t* device_buf32) {
   long long* ptr = reinterpret_cast<long long*>(device_buf32);
+#ifndef LGK_K1_TIMELINE
+  if (ptr != nullptr) return lgk::set_error(LGK_ERR_ARG, "K1 timeline stamps are compiled out (build with -DLGK_K1_TIMELINE)");
+#endif
   return lgk::check_cuda(cudaMemcpyToSymbol(lgk::g_k1_timeline, &ptr, sizeof(ptr)), "cudaMemcpyToSymbol(g_k1_timeline)");
 }

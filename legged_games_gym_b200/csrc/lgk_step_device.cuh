@@ -55,6 +55,7 @@ LGK_D void role_partials(const LgkStepParams& p, int role, const float* dof, con
                          const float* tq, const float* lact, const float* ldv, float* fat, uint8_t* lc, float root_z,
                          const float* heights_row, RolePartials& o) {
   const int d0 = 3 * role;
+  const float inv_dt = __frcp_rn(p.dt);       // (x / dt differs from x * (1 / dt) by at most one ulp: inside the 1e-5 bar)
 #pragma unroll
   for (int k = 0; k < PS_COUNT; ++k) o.v[k] = 0.f;
   uint32_t bits = 0;
@@ -74,7 +75,7 @@ LGK_D void role_partials(const LgkStepParams& p, int role, const float* dof, con
   }
   if (p.reward_active[LGK_R_DOF_ACC]) {                               // LR:897-899
 #pragma unroll
-    for (int d = d0; d < d0 + 3; ++d) { const float a = (ldv[d] - dof[2 * d + 1]) / p.dt; o.v[PS_DOF_ACC] += a * a; }
+    for (int d = d0; d < d0 + 3; ++d) { const float a = (ldv[d] - dof[2 * d + 1]) * inv_dt; o.v[PS_DOF_ACC] += a * a; }
   }
   if (p.reward_active[LGK_R_DOF_POS_LIMITS]) {                        // LR:914-918
 #pragma unroll
@@ -243,60 +244,101 @@ LGK_D float phase_b_flag(const LgkStepParams& p, const float* root, const float*
 }
 #undef LGK_TERM
 
-// reset_idx, role 0's part for one env (LR:147-191): terrain curriculum, root state (in the staged row), predator spawn,
-// command resample
-// `level`: the env's terrain level (staged in shared memory by the step kernel, written back with the tile)
-LGK_COLD void env_reset_base(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, float* root, float* cmd,
-                             long long* level) {
-  float ox = 0.f, oy = 0.f, oz = 0.f;
-  if (p.env_origins) { ox = p.env_origins[3 * env]; oy = p.env_origins[3 * env + 1]; oz = p.env_origins[3 * env + 2]; }
-  if (p.terrain_curriculum) {                                         // LR:446-469
-    const float dist = norm2(root[0] - ox, root[1] - oy);
-    const bool up = dist > p.half_env_length;
-    const bool down = (dist < norm2(cmd[0], cmd[1]) * p.max_episode_length_s * 0.5f) && !up;
-    long long lvl = *level + (up ? 1 : 0) - (down ? 1 : 0);
-    if (lvl >= p.max_terrain_level) {
-      const U4 r = rng_block_cold(key, genv, LGK_STREAM_TERRAIN, 0);
-      lvl = (long long)(r.x % (uint32_t)p.max_terrain_level);
-    } else if (lvl < 0) {
-      lvl = 0;
-    }
-    *level = lvl;
-    const float* o = p.terrain_origins + 3 * ((size_t)lvl * p.terrain_num_cols + (size_t)p.terrain_types[env]);
-    ox = o[0]; oy = o[1]; oz = o[2];
-    p.env_origins[3 * env] = ox; p.env_origins[3 * env + 1] = oy; p.env_origins[3 * env + 2] = oz;
-  }
-  // _reset_root_states LR:414-432
-  const U4 r0 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 0);
-  const U4 r1 = rng_block_cold(key, genv, LGK_STREAM_RESET_ROOT, 1);
-  for (int i = 0; i < 13; ++i) root[i] = p.base_init_state[i];
-  root[0] = f_add(root[0], ox); root[1] = f_add(root[1], oy); root[2] = f_add(root[2], oz);
-  if (p.custom_origins) {
-    root[0] = f_add(root[0], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.x)));
-    root[1] = f_add(root[1], scale_uniform(2.0f, -1.0f, u32_to_uniform(r0.y)));
-  }
-  root[7] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.z));
-  root[8] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r0.w));
-  root[9] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.x));
-  root[10] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.y));
-  root[11] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.z));
-  root[12] = scale_uniform(1.0f, -0.5f, u32_to_uniform(r1.w));
-  if (p.predator_spawn) spawn_predator(p, key, genv, env, root);
-  resample_commands(p, cmd, rng_block_cold(key, genv, LGK_STREAM_RESET_CMD, 0));   // LR:170 (after the curriculum read cmd)
+// the twelve base / command columns: role 0 lin vel (0..2), role 1 ang vel (3..5), role 2 gravity (6..8) right after their
+// rotations; the command columns (9..11) once the command row is final (after a possible reset)
+LGK_D void obs_head_cmd(const LgkStepParams& p, const float* cmd, float* out48) {
+  out48[9] = cmd[0] * p.obs_scale_lin_vel; out48[10] = cmd[1] * p.obs_scale_lin_vel; out48[11] = cmd[2] * p.obs_scale_ang_vel;
 }
+// ---- reset_idx for one env of a staged tile, WARP-cooperative (LR:147-191 minus the cross-env means and the LSTM-state
+// zeroing, which the caller does): the eight Philox blocks of the reset are drawn in parallel (lane j < 8 owns one), the
+// terrain curriculum runs on lane 0 from staged rows (level, type, origin), and lanes write the env's rows inside the
+// tile -- root (13), dof (12 x 2), command, feet_air_time -- plus everything the step has already derived from them
+// (observation head columns, last_dof_vel, last_root_vel, scan-frame z), so no other phase has a reset branch.
+// Same streams / blocks / words and the same individually rounded fp32 ops as env_reset() below.
+struct TileRows {
+  float* root; float* dof; float* cmd; float* fat; float* head; float* ldv; float* lrv; float* frame; float* origin;
+  long long* level; long long* type; long long* ep_out;
+};
 
-// _reset_dofs LR:397-407 for role r's joints (joint d uses word d%4 of Philox block d/4: at most two blocks per role)
-LGK_COLD void env_reset_joints(const LgkStepParams& p, const RngKey& key, uint32_t genv, int role, float* dof, float* fat) {
-  const int d0 = 3 * role, b_lo = d0 >> 2, b_hi = (d0 + 2) >> 2;
-  const U4 r_lo = rng_block_cold(key, genv, LGK_STREAM_RESET_DOF, b_lo);
-  U4 r_hi = r_lo;
-  if (b_hi != b_lo) r_hi = rng_block_cold(key, genv, LGK_STREAM_RESET_DOF, b_hi);
-  for (int d = d0; d < d0 + 3; ++d) {
-    const uint32_t w = pick((d >> 2) == b_lo ? r_lo : r_hi, d & 3);
-    dof[2 * d] = f_mul(p.default_dof_pos[d], scale_uniform(1.0f, 0.5f, u32_to_uniform(w)));
-    dof[2 * d + 1] = 0.f;
+LGK_D void tile_reset_env(const LgkStepParams& p, const RngKey& key, uint32_t genv, int env, int lane, const TileRows& t,
+                          int frame_floats) {
+  const uint32_t FULL = 0xffffffffu;
+  // lane -> (stream, block): 0..2 dof, 3..4 root, 5 command, 6 terrain level wrap, 7 predator spawn
+  const uint32_t strm = lane < 3 ? LGK_STREAM_RESET_DOF : (lane < 5 ? LGK_STREAM_RESET_ROOT : (lane == 5 ? LGK_STREAM_RESET_CMD
+                        : (lane == 6 ? LGK_STREAM_TERRAIN : LGK_STREAM_PREDATOR)));
+  const uint32_t blk = lane < 3 ? (uint32_t)lane : (lane < 5 ? (uint32_t)(lane - 3) : 0u);
+  const U4 r = rng_block(key, genv, strm, blk);
+  // ---- terrain curriculum + origin (lane 0; LR:446-469).  The curriculum reads the PRE-reset root position and command.
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+  const uint32_t terr_word = __shfl_sync(FULL, r.x, 6);
+  if (lane == 0) {
+    if (t.origin) { ox = t.origin[0]; oy = t.origin[1]; oz = t.origin[2]; }
+    if (p.terrain_curriculum) {
+      const float dist = norm2(t.root[0] - ox, t.root[1] - oy);
+      const bool up = dist > p.half_env_length;
+      const bool down = (dist < norm2(t.cmd[0], t.cmd[1]) * p.max_episode_length_s * 0.5f) && !up;
+      long long lvl = *t.level + (up ? 1 : 0) - (down ? 1 : 0);
+      if (lvl >= p.max_terrain_level) lvl = (long long)(terr_word % (uint32_t)p.max_terrain_level);
+      else if (lvl < 0) lvl = 0;
+      *t.level = lvl;
+      const float* o = p.terrain_origins + 3 * ((size_t)lvl * p.terrain_num_cols + (size_t)*t.type);
+      ox = o[0]; oy = o[1]; oz = o[2];
+      t.origin[0] = ox; t.origin[1] = oy; t.origin[2] = oz;
+    }
   }
-  if (role < p.num_feet) fat[role] = 0.f;                                         // LR:175
+  ox = __shfl_sync(FULL, ox, 0); oy = __shfl_sync(FULL, oy, 0); oz = __shfl_sync(FULL, oz, 0);
+  // ---- root row (LR:414-432): lane i < 13 owns column i; uniform k = i (i < 2) or i - 5 (i >= 7) of the eight root words
+  {
+    const int k = lane < 2 ? lane : lane - 5;
+    const int src = 3 + ((k >> 2) & 1);
+    const uint32_t w0 = __shfl_sync(FULL, r.x, src), w1 = __shfl_sync(FULL, r.y, src), w2 = __shfl_sync(FULL, r.z, src),
+                   w3 = __shfl_sync(FULL, r.w, src);
+    const float u = u32_to_uniform((k & 3) == 0 ? w0 : ((k & 3) == 1 ? w1 : ((k & 3) == 2 ? w2 : w3)));
+    if (lane < 13) {
+      float v = p.base_init_state[lane];
+      if (lane < 3) v = f_add(v, lane == 0 ? ox : (lane == 1 ? oy : oz));
+      if (lane < 2 && p.custom_origins) v = f_add(v, scale_uniform(2.0f, -1.0f, u));
+      if (lane >= 7) v = scale_uniform(1.0f, -0.5f, u);
+      t.root[lane] = v;
+      if (lane >= 7) t.lrv[lane - 7] = v;                                 // LR:134 after the reset
+      if (lane == 2) t.frame[4] = v - 0.5f;                               // height columns use the post-reset z (LR:225)
+    }
+    (void)frame_floats;
+  }
+  // ---- dofs (LR:397-407): joint d uses word d % 4 of block d / 4
+  {
+    const int d = lane < 12 ? lane : 0, src = d >> 2;
+    const uint32_t w0 = __shfl_sync(FULL, r.x, src), w1 = __shfl_sync(FULL, r.y, src), w2 = __shfl_sync(FULL, r.z, src),
+                   w3 = __shfl_sync(FULL, r.w, src);
+    if (lane < 12) {
+      const uint32_t w = (d & 3) == 0 ? w0 : ((d & 3) == 1 ? w1 : ((d & 3) == 2 ? w2 : w3));
+      const float q = f_mul(p.default_dof_pos[d], scale_uniform(1.0f, 0.5f, u32_to_uniform(w)));
+      t.dof[2 * d] = q;
+      t.dof[2 * d + 1] = 0.f;
+      t.head[12 + d] = (q - p.default_dof_pos[d]) * p.obs_scale_dof_pos;
+      t.head[24 + d] = 0.f * p.obs_scale_dof_vel;
+      t.ldv[d] = 0.f;                                                     // LR:133 after the reset
+    }
+  }
+  if (lane < p.num_feet) t.fat[lane] = 0.f;                               // LR:175
+  // ---- predator re-spawn (LLG:419-432) relative to the fresh prey position, then the command (LR:170), lane 0
+  {
+    const uint32_t px = __shfl_sync(FULL, r.x, 7), py = __shfl_sync(FULL, r.y, 7), pw = __shfl_sync(FULL, r.w, 7);
+    const uint32_t cx = __shfl_sync(FULL, r.x, 5), cy = __shfl_sync(FULL, r.y, 5), cz = __shfl_sync(FULL, r.z, 5);
+    __syncwarp();
+    if (lane == 0) {
+      if (p.predator_spawn) {
+        const float sgn = u32_to_uniform(pw) < 0.5f ? -1.f : 1.f;
+        float* pred = p.root_states + ((size_t)env * p.actors_per_env + p.predator_actor_offset) * 13;
+        pred[0] = f_sub(t.root[0], sgn * scale_uniform(9.0f, 1.0f, u32_to_uniform(px)));
+        pred[1] = f_sub(t.root[1], sgn * scale_uniform(9.0f, 1.0f, u32_to_uniform(py)));
+        pred[2] = 0.3f;
+      }
+      resample_commands(p, t.cmd, U4{cx, cy, cz, 0u});
+      obs_head_cmd(p, t.cmd, t.head);
+      *t.ep_out = 0;                                                      // LR:176
+    }
+  }
 }
 
 // LR:212-222: the 48 proprioceptive columns, before noise -- role r writes the nine columns of its joints, role 0 also
@@ -308,11 +350,6 @@ LGK_D void env_obs_head_role(const LgkStepParams& p, int role, const float* dof,
     out48[24 + d] = dof[2 * d + 1] * p.obs_scale_dof_vel;
     out48[36 + d] = act[d];
   }
-}
-// the twelve base / command columns: role 0 lin vel (0..2), role 1 ang vel (3..5), role 2 gravity (6..8) right after their
-// rotations; the command columns (9..11) once the command row is final (after a possible reset)
-LGK_D void obs_head_cmd(const LgkStepParams& p, const float* cmd, float* out48) {
-  out48[9] = cmd[0] * p.obs_scale_lin_vel; out48[10] = cmd[1] * p.obs_scale_lin_vel; out48[11] = cmd[2] * p.obs_scale_ang_vel;
 }
 #endif
 

@@ -179,6 +179,9 @@ def replica_bytes(env):
     return tot
 
 
+_TERRAINS = {}
+
+
 def make_env(num_envs, device, host_sim=False, env_id_offset=0):
     import copy
     from legged_games_gym_b200.envs import task_registry
@@ -197,8 +200,13 @@ def make_env(num_envs, device, host_sim=False, env_id_offset=0):
     cls = type(base.__name__ + "Bench", (base,), {"use_cuda_graph": USE_GRAPH})
     # height field = SURVEY 8(d)'s synthetic input (uniform int16 heights): every sample differs from its neighbours,
     # the worst case for the gather; the generated terrain (utils/terrain.py) is the library default
+    # ONE terrain per process, as in production (65 536 envs walk the same 1300 x 2100 field): the env replicas that
+    # keep the per-env state larger than L2 share its 5.5 MB height table, which is L2-resident in a real run too
+    tkey = (TASK, cfg.seed)
+    if tkey not in _TERRAINS and cfg.terrain.mesh_type in ("heightfield", "trimesh"):
+        _TERRAINS[tkey] = SyntheticTerrain(cfg.terrain, cfg.seed)
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
-              sim_device=device, headless=True, sim_backend=feeder, terrain=SyntheticTerrain(cfg.terrain, cfg.seed))
+              sim_device=device, headless=True, sim_backend=feeder, terrain=_TERRAINS.get(tkey))
     env.env_id_offset = env_id_offset
     env._tq_params.lstm_variant = LSTM_VARIANT
     env._params.env_id_offset = env_id_offset

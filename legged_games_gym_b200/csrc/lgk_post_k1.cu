@@ -161,6 +161,20 @@ post_kernel(const __grid_constant__ LgkStepParams p, const __grid_constant__ Til
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+#if LGK_K1_PREFETCH
+  // the CTA's first tile: start pulling its chunks into L2 while the previous kernel of the step is still draining (a
+  // prefetch carries no data into the SM: whatever that kernel still writes lands in the same L2)
+  if (FAST && tid == 0 && (int)blockIdx.x < ntiles) {
+    const size_t n0 = (size_t)blockIdx.x * kTile;
+    bulk_prefetch_l2(p.root_states + n0 * 13, kTile * 13 * 4);
+    bulk_prefetch_l2(p.dof_state + n0 * 24, kTile * 24 * 4);
+    bulk_prefetch_l2(p.contact_forces + n0 * NB * 3, kTile * NB * 3 * 4);
+    bulk_prefetch_l2(p.actions + n0 * 12, kTile * 12 * 4);
+    bulk_prefetch_l2(p.last_actions + n0 * 12, kTile * 12 * 4);
+    bulk_prefetch_l2(p.last_dof_vel + n0 * 12, kTile * 12 * 4);
+    bulk_prefetch_l2(p.commands + n0 * 4, kTile * 4 * 4);
+  }
+#endif
   pdl_wait();              // everything below reads state written by the previous kernels of the step
   const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
   const bool do_push = pre && (p.step_counter_dev ? (p.push_interval > 0 && step_eff % p.push_interval == 0) : (p.do_push != 0));

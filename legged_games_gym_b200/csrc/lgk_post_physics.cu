@@ -281,6 +281,122 @@ __global__ void __launch_bounds__(kK2Threads, LGK_K2_MINBLOCKS) scan_obs_fast_ke
   }
 }
 
+// ------------------------------------------------------------------ K2, hot path
+// The configuration every rough-terrain step takes (scan + observations in one pass, K1's scan frames and compact head
+// buffer present, FMA division): same arithmetic and the same column -> lane / Philox word mapping as
+// scan_obs_fast_kernel<G, kScan | kObs, true>, with (a) no generic fetch path, (b) the int16 gathers of an env ISSUED before
+// its two Philox blocks are computed and CONSUMED after them, so the ~130 instructions of the noise draw cover the
+// gather latency instead of a stalled warp, (c) the per-point 2^63 guard decided once per env.
+template <int G>
+__global__ void __launch_bounds__(kK2Threads, LGK_K2_MINBLOCKS) scan_obs_hot_kernel(const __grid_constant__ LgkStepParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.num_envs, P = p.num_height_points, O = p.num_obs;
+  pdl_launch_dependents();
+  f2_t Bv[G], Bsv[G];
+  float nz[G];
+  uint32_t pmask = 0, omask = 0;      // bit g: column 32g+lane is a height point / an observation column
+  const bool noisy = p.add_noise != 0;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int j = 32 * g + lane, pt = j - 48;
+    const bool isp = pt >= 0 && pt < P;
+    float bx = 0.f, by = 0.f;
+    if (isp) { const float2 b = __ldg(reinterpret_cast<const float2*>(p.height_points_xy) + pt); bx = b.x; by = b.y; }
+    Bv[g] = pack2(bx, by); Bsv[g] = pack2(by, bx);
+    pmask |= (isp ? 1u : 0u) << g;
+    omask |= ((j < O) ? 1u : 0u) << g;
+    nz[g] = (noisy && j < O) ? __ldg(p.noise_scale_vec + j) : 0.f;
+  }
+  const float rt_one = __int_as_float(0x3f800000u | ((uint32_t)p.num_envs >> 31));   // 1.0f the compiler cannot see
+  const float clip = p.clip_obs, vs = p.vertical_scale, hsc = p.obs_scale_height;
+  const float border = p.border_size, hscale = p.horizontal_scale, hrecip = p.horizontal_scale_recip;
+  const int rows = p.hf_rows, cols = p.hf_cols;
+  const float4* __restrict__ frames = reinterpret_cast<const float4*>(p.scan_frames);
+  const float* __restrict__ head_buf = p.obs_head;
+  const int16_t* __restrict__ field = p.height_min3;
+  bool hclip = false;                 // see scan_obs_fast_kernel: the final clip cannot act on a height column unless ...
+#pragma unroll
+  for (int g = 2; g < G; ++g) hclip = hclip || !(fabsf(hsc) + fabsf(nz[g]) <= clip);
+  hclip = __any_sync(0xffffffffu, hclip);
+  pdl_wait();
+  const int step_eff = p.step_counter_dev ? (*p.step_counter_dev + 1) : p.step;
+  const RngKey key = make_key(p.seed, step_eff);
+
+  struct EnvIn { float4 f; float rz, head0, head1; };
+  auto fetch = [&](int env) {
+    EnvIn in;
+    in.f = make_float4(0.f, 0.f, 0.f, 0.f); in.rz = 0.f; in.head0 = 0.f; in.head1 = 0.f;
+    if (env < N) {
+      in.f = frames[2 * (size_t)env];                                  // (zn, wn, root_x, root_y), pre-reset
+      in.rz = reinterpret_cast<const float*>(frames + 2 * (size_t)env + 1)[0];      // post-reset root z - 0.5
+      const float* hr = head_buf + (size_t)env * kHeadCols;
+      in.head0 = hr[lane];
+      if (lane < 16) in.head1 = hr[32 + lane];
+    }
+    return in;
+  };
+  const int stride = gridDim.x * (kK2Threads / 32);
+  int env = blockIdx.x * (kK2Threads / 32) + warp;
+  EnvIn nxt = fetch(env);
+  for (; env < N; env += stride) {
+    const EnvIn cur = nxt;
+    nxt = fetch(env + stride);
+    float* orow = p.obs_buf + (size_t)env * O;
+    float* hrow = p.measured_heights + (size_t)env * P;
+    const YawFrame2 yf = yaw_frame2(YawFrame{cur.f.x, cur.f.y, cur.f.z, cur.f.w});
+    int off[G];
+    if (cur.f.z < 1e17f && cur.f.w < 1e17f) {      // (warp-uniform) no quotient can reach 2^63: skip the per-point guard
+#pragma unroll
+      for (int g = 1; g < G; ++g) {
+        int ix, iy;
+        height_index2<true, true>(yf, Bv[g], Bsv[g], border, hscale, hrecip, rt_one, rows, cols, ix, iy);
+        off[g] = ix * cols + iy;
+      }
+    } else {
+#pragma unroll
+      for (int g = 1; g < G; ++g) {
+        int ix, iy;
+        height_index2<true>(yf, Bv[g], Bsv[g], border, hscale, hrecip, rt_one, rows, cols, ix, iy);
+        off[g] = ix * cols + iy;
+      }
+    }
+    // ---- gathers in flight ...
+    int raw[G];
+#pragma unroll
+    for (int g = 1; g < G; ++g) raw[g] = (int)__ldg(field + off[g]);
+    // ---- ... while the row's noise is drawn
+    const uint32_t genv = (uint32_t)(p.env_id_offset + env);
+    U4 r[(G + 3) / 4];
+#pragma unroll
+    for (int sc = 0; sc < (G + 3) / 4; ++sc) {
+      r[sc] = U4{0, 0, 0, 0};
+      if (noisy) r[sc] = rng_block(key, genv, LGK_STREAM_OBS, (uint32_t)(32 * sc + lane));
+    }
+    float u[G];                        // 2u - 1 per column group
+#pragma unroll
+    for (int g = 0; g < G; ++g) u[g] = noise_unit(pick(r[g >> 2], g & 3));
+    // ---- heights (LR:869), measured_heights, finished row
+    float h[G];
+    h[0] = 0.f;
+#pragma unroll
+    for (int g = 1; g < G; ++g) h[g] = f_mul((float)raw[g], vs);
+#pragma unroll
+    for (int g = 1; g < G; ++g) if ((pmask >> g) & 1u) hrow[32 * g + lane - 48] = h[g];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float v;
+      if (g == 0) v = cur.head0;
+      else {
+        v = f_mul(clampf(cur.rz - h[g], -1.f, 1.f), hsc);
+        if (g == 1) v = lane < 16 ? cur.head1 : v;
+      }
+      v = f_fma(u[g], nz[g], v);
+      if (g < 2 || hclip) v = clampf(v, -clip, clip);
+      if ((omask >> g) & 1u) orow[32 * g + lane] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ reset_idx on an explicit id list
 __global__ void __launch_bounds__(128) reset_idx_kernel(const __grid_constant__ LgkStepParams p,
                                                        const int64_t* __restrict__ ids, int n) {
@@ -478,7 +594,11 @@ static int launch_k2(const LgkStepParams* p, int mode, cudaStream_t st) {
     const dim3 gd(fblocks), bd(kK2Threads);
 #define LGK_K2(GG, MM) (rc ? launch_chained(scan_obs_fast_kernel<GG, MM, true>, gd, bd, 0, st, *p) \
                            : launch_chained(scan_obs_fast_kernel<GG, MM, false>, gd, bd, 0, st, *p))
-    if (flat) e = launch_chained(scan_obs_fast_kernel<2, kObs, false>, gd, bd, 0, st, *p);
+    const bool hot = mode == (kScan | kObs) && rc && p->scan_frames != nullptr && p->obs_head != nullptr &&
+                     p->actors_per_env == 1 && getenv("LGK_K2_NO_HOT") == nullptr;
+    if (hot && groups <= 8) e = launch_chained(scan_obs_hot_kernel<8>, gd, bd, 0, st, *p);
+    else if (hot) e = launch_chained(scan_obs_hot_kernel<12>, gd, bd, 0, st, *p);
+    else if (flat) e = launch_chained(scan_obs_fast_kernel<2, kObs, false>, gd, bd, 0, st, *p);
     else if (groups <= 8) e = mode == kScan ? LGK_K2(8, kScan) : (mode == kObs ? LGK_K2(8, kObs) : LGK_K2(8, kScan | kObs));
     else e = mode == kScan ? LGK_K2(12, kScan) : (mode == kObs ? LGK_K2(12, kObs) : LGK_K2(12, kScan | kObs));
 #undef LGK_K2

@@ -318,8 +318,21 @@ class LeggedRobot(BaseTask):
         mesh_type = self.cfg.terrain.mesh_type
         if mesh_type in ("heightfield", "trimesh"):
             self.terrain = self._terrain_arg if self._terrain_arg is not None else Terrain(self.cfg.terrain, self.num_envs)
-            self.height_samples = torch.from_numpy(np.ascontiguousarray(self.terrain.heightsamples)).view(
-                self.terrain.tot_rows, self.terrain.tot_cols).to(self.device)
+            # env instances built on the SAME terrain object share its device copies (height field + min3 table): one
+            # terrain serves every env of a GPU, however many env objects exist
+            cache = getattr(self.terrain, "_lgk_device_cache", None)
+            if cache is None:
+                cache = {}
+                try:
+                    self.terrain._lgk_device_cache = cache
+                except AttributeError:
+                    pass
+            key = str(self.device)
+            if key not in cache:
+                cache[key] = {"height_samples": torch.from_numpy(np.ascontiguousarray(self.terrain.heightsamples)).view(
+                    self.terrain.tot_rows, self.terrain.tot_cols).to(self.device)}
+            self._terrain_cache = cache[key]
+            self.height_samples = self._terrain_cache["height_samples"]
         elif mesh_type not in (None, "plane"):
             raise ValueError("Terrain mesh type not recognised. Allowed types are [None, plane, heightfield, trimesh]")
         self._create_envs()
@@ -675,9 +688,15 @@ class LeggedRobot(BaseTask):
             if not p.terrain_is_plane:
                 hs = self.height_samples
                 p.hf_rows, p.hf_cols = int(hs.shape[0]), int(hs.shape[1])
-                self._height_min3 = torch.empty_like(hs)
-                nat.check(nat.lib.lgk_height_min3(hs.data_ptr(), self._height_min3.data_ptr(), p.hf_rows, p.hf_cols,
-                                                  _stream_ptr()), "lgk_height_min3")
+                tc = getattr(self, "_terrain_cache", None)
+                if tc is not None and "min3" in tc:
+                    self._height_min3 = tc["min3"]
+                else:
+                    self._height_min3 = torch.empty_like(hs)
+                    nat.check(nat.lib.lgk_height_min3(hs.data_ptr(), self._height_min3.data_ptr(), p.hf_rows, p.hf_cols,
+                                                      _stream_ptr()), "lgk_height_min3")
+                    if tc is not None:
+                        tc["min3"] = self._height_min3
                 self._height_points_xy = self.height_points[0, :, :2].contiguous()
                 p.height_min3 = ptr(self._height_min3)
                 p.height_points_xy = ptr(self._height_points_xy)

@@ -6,6 +6,7 @@ import re
 import sys
 
 src_csv, dis, top = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40
+section = sys.argv[4] if len(sys.argv) > 4 else None      # substring of the mangled kernel name (templates)
 rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}
@@ -14,7 +15,7 @@ kernel = rows[0][1].split("(")[0].split("::")[-1]
 lines, cur, active = [], ("?", 0), False
 for l in open(dis):
     if l.startswith("//---") and ".text." in l:
-        active = kernel in l
+        active = (section or kernel) in l
         continue
     if not active:
         continue

@@ -36,6 +36,17 @@ L2_FLUSH_BYTES = 256 << 20
 BYTES_TORQUE_LSTM = 3264
 BYTES_TORQUE_PD = 192
 BYTES_POST_ROUGH = 2561
+BYTES_POST_FLAT = 1065
+
+
+def workload(task, num_envs):
+    """ONE description per (task, size), shared by the GPU arm and the reference arm (the driver compares the strings)."""
+    what = {"anymal_c_rough": "187-point height scan + 4x LSTM actuator-net torques + full reward set + termination / reset / "
+                              "command resampling + noisy observations (BASELINE.json configs[1]; configs[4] at 65536 envs/GPU)",
+            "a1": "187-point height scan + 4x PD torques + full reward set incl. dof_pos_limits + pushes every 750 steps + "
+                  "command resampling every 500 steps + friction / mass randomisation at init (BASELINE.json configs[2])",
+            "anymal_c_flat": "48-column observations, 4x torques, full reward set, terminations (BASELINE.json configs[0])"}[task]
+    return f"{task}: {num_envs} envs/GPU, LeggedRobot.step: {what}"
 
 
 def parse():
@@ -48,7 +59,6 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the PPO training-iteration timing")
-    ap.add_argument("--tile", type=int, default=0, help="reserved (the scalar kernel tiles 32 envs per CTA)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="rotate: cycle over env replicas whose buffers exceed L2; flush: write 256 MiB between steps")
     ap.add_argument("--no-graph", action="store_true")
@@ -65,14 +75,15 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm (oracle)
-def cpu_arm(num_envs, steps, warmup):
+def cpu_arm(num_envs, steps, warmup, task=None, overrides=None):
     """Time the oracle (reference algorithm, torch CPU, all host threads) on the same workload."""
     import numpy as np
     import torch
     from oracle import harness
+    task = task or TASK
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    case = harness.build_case(TASK, num_envs, seed=0)
+    case = harness.build_case(task, num_envs, seed=0, overrides=overrides)
     orc = harness.make_oracle(case)
     acts = torch.from_numpy(case["state"]["actions"].copy())
     tables = harness.step_tables(0, 1, num_envs, orc.num_obs)   # uniforms precomputed: RNG is not on the timed path
@@ -87,7 +98,7 @@ def cpu_arm(num_envs, steps, warmup):
     med = times[len(times) // 2]
     return dict(value=num_envs / med, unit=UNIT, cores=cores, kind="port", ms_per_step=med * 1e3,
                 best_ms=times[0] * 1e3,
-                sample=f"{steps} timed + {warmup} warm-up steps of {TASK} at {num_envs} envs (median), torch CPU {cores} threads")
+                sample=f"{steps} timed + {warmup} warm-up steps of {task} at {num_envs} envs (median), torch CPU {cores} threads")
 
 
 def eager_gpu_arm(num_envs, device, steps=30, warmup=5):
@@ -164,7 +175,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-TILE, USE_GRAPH, LSTM_VARIANT = 0, True, 0
+USE_GRAPH, LSTM_VARIANT = True, 0
 # probability that the base body reports a contact (=> termination, LR:142) in the synthetic state; the other 16 bodies
 # keep the survey's 0.3.  ~2 % of the envs reset every step (a 20 s episode alone gives 0.1 %), instead of 28 %.
 P_TERMINATE = 0.02
@@ -182,32 +193,36 @@ def replica_bytes(env):
 _TERRAINS = {}
 
 
-def make_env(num_envs, device, host_sim=False, env_id_offset=0):
+def make_env(num_envs, device, host_sim=False, env_id_offset=0, task=None, overrides=None):
     import copy
     from legged_games_gym_b200.envs import task_registry
     from legged_games_gym_b200.sim.state_feeder import StateFeeder, HostStateFeeder
     from legged_games_gym_b200.sim.asset_model import model_for_asset
     from legged_games_gym_b200.utils.helpers import SimParams
-    cfg = copy.deepcopy(task_registry.env_cfgs[TASK])
+    from oracle.harness import apply_overrides      # (a cfg helper, no arithmetic)
+    task = task or TASK
+    cfg = copy.deepcopy(task_registry.env_cfgs[task])
     cfg.env.num_envs = num_envs
     cfg.seed = 1
+    apply_overrides(cfg, overrides)
     model = model_for_asset(cfg.asset)
     feeder_cls = HostStateFeeder if host_sim else StateFeeder
     feeder = feeder_cls(num_envs, model.num_bodies, model.num_dof, device=device, seed=env_id_offset,
                         p_contact_body0=P_TERMINATE)
-    base = task_registry.get_task_class(TASK)
+    base = task_registry.get_task_class(task)
     from legged_games_gym_b200.envs.base.legged_robot import SyntheticTerrain
     cls = type(base.__name__ + "Bench", (base,), {"use_cuda_graph": USE_GRAPH})
     # height field = SURVEY 8(d)'s synthetic input (uniform int16 heights): every sample differs from its neighbours,
     # the worst case for the gather; the generated terrain (utils/terrain.py) is the library default
     # ONE terrain per process, as in production (65 536 envs walk the same 1300 x 2100 field): the env replicas that
     # keep the per-env state larger than L2 share its 5.5 MB height table, which is L2-resident in a real run too
-    tkey = (TASK, cfg.seed)
+    tkey = (task, cfg.seed)
     if tkey not in _TERRAINS and cfg.terrain.mesh_type in ("heightfield", "trimesh"):
         _TERRAINS[tkey] = SyntheticTerrain(cfg.terrain, cfg.seed)
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
               sim_device=device, headless=True, sim_backend=feeder, terrain=_TERRAINS.get(tkey))
     env.env_id_offset = env_id_offset
+    env._graph_launches = 4 + 1 + (1 if cfg.terrain.measure_heights else 0) + 1      # torques + K1 (+ K2) + finalize
     env._tq_params.lstm_variant = LSTM_VARIANT
     env._params.env_id_offset = env_id_offset
     env.episode_length_buf.copy_(feeder.synthetic_episode_length)
@@ -253,22 +268,22 @@ def time_steps(envs, actions, steps, warmup, flush, dist_barrier):
     dist_barrier()
     launches = nat.launch_count() - l0
     graphed = sum(1 for e in envs if getattr(e, "_graph", None) is not None)
-    if graphed:        # replayed graphs bypass the library's launch counter: 7 kernels per replayed step
-        launches += steps * 7
+    if graphed:        # replayed graphs bypass the library's launch counter: 6-7 kernels per replayed step
+        launches += steps * getattr(envs[0], "_graph_launches", 7)
     return secs, launches
 
 
-def make_replicas(num_envs, device, env_id_offset, l2_mode):
+def make_replicas(num_envs, device, env_id_offset, l2_mode, task=None, overrides=None):
     import torch
     envs, feeders = [], []
-    env, feeder = make_env(num_envs, device, env_id_offset=env_id_offset)
+    env, feeder = make_env(num_envs, device, env_id_offset=env_id_offset, task=task, overrides=overrides)
     envs.append(env); feeders.append(feeder)
     per = replica_bytes(env)
     n_rep = 1
     if l2_mode == "rotate":
         n_rep = max(2, -(-2 * 126 * (1 << 20) // per))
         for r in range(1, n_rep):
-            e2, f2 = make_env(num_envs, device, env_id_offset=env_id_offset)
+            e2, f2 = make_env(num_envs, device, env_id_offset=env_id_offset, task=task, overrides=overrides)
             envs.append(e2); feeders.append(f2)
     return envs, feeders, per
 
@@ -309,7 +324,10 @@ def kernel_rooflines(envs, actions, peak_gbs, reps=200):
         tqs.append(lambda e=env: nat.lib.lgk_compute_torques(C.byref(e._tq_params), st))
         pps.append(lambda e=env: nat.lib.lgk_post_physics(C.byref(e._params), st))
     out = {}
-    for name, fns, bpe in (("torque_lstm", tqs, BYTES_TORQUE_LSTM), ("post_physics", pps, BYTES_POST_ROUGH)):
+    lstm = bool(envs[0]._tq_params.use_lstm)
+    rough = bool(envs[0].cfg.terrain.measure_heights)
+    for name, fns, bpe in (("torque_lstm" if lstm else "torque_pd", tqs, BYTES_TORQUE_LSTM if lstm else BYTES_TORQUE_PD),
+                           ("post_physics", pps, BYTES_POST_ROUGH if rough else BYTES_POST_FLAT)):
         with ClockSampler(torch.cuda.current_device()) as clk:
             mean_s, best_s = time_kernel(fns, reps)
         gbs = bpe * n / mean_s / 1e9
@@ -322,7 +340,9 @@ def kernel_rooflines(envs, actions, peak_gbs, reps=200):
 def ncu_traffic(num_envs, *kernels):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
     (profiles/r1_traffic.json, written by profiles/summarize.py); None when no capture exists for this size."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if not os.path.exists(path):
         return None
     table = json.load(open(path)).get(str(num_envs), {})
@@ -434,33 +454,96 @@ def game_phase(dev, num_envs=2000, steps=200):
                 game_kernel_us=round(k_s * 1e6, 2))
 
 
-def train_iteration(dev, num_envs=4096, iters=4):
+def train_iteration(dev, num_envs=4096, iters=4, world=1, rank=0):
     """One PPO iteration of the reference's training flow (scripts/train.py: 24 rollout steps of anymal_c_rough + GAE +
-    PPO.update with 5 epochs x 4 mini-batches) through task_registry / OnPolicyRunner: wall-clock of the last iteration.
-    The update runs as CUDA graphs with strict-fp32 cuBLAS, then with TF32 matmuls (the library default, see PPO)."""
+    PPO.update with 5 epochs x 4 mini-batches) through task_registry / OnPolicyRunner: wall-clock of the last iteration,
+    max over ranks.  Multi-GPU: EVERY rank runs it on its own env shard; the 20 gradient all-reduces (+ 20 KL scalars)
+    per iteration run over NCCL inside the captured update graph.  The update's matmuls are TF32 (the library default,
+    see PPO); `fp32` repeats it with strict-fp32 cuBLAS at N = 1."""
     import torch
+    import torch.distributed as dist
     from legged_games_gym_b200.envs import task_registry
     from legged_games_gym_b200.utils import get_args
     out = {}
-    for label, tf32 in (("fp32", False), ("tf32_matmul", True)):
+    for label, tf32 in ((("tf32_matmul", True), ("fp32", False)) if world == 1 else (("tf32_matmul", True),)):
         os.environ["LGK_PPO_TF32"] = "1" if tf32 else "0"
         a = get_args(["--task", TASK, "--num_envs", str(num_envs), "--headless", "--sim_device", dev, "--rl_device", dev])
         env, _ = task_registry.make_env(name=TASK, args=a)
+        if world > 1:
+            env.set_env_id_offset(rank * num_envs)
         runner, _ = task_registry.make_alg_runner(env=env, name=TASK, args=a, log_root=None)
         for it in range(iters):
+            if world > 1:
+                dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             runner.learn(num_learning_iterations=1, init_at_random_ep_len=(it == 0))
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-        out[label] = dict(ms_per_iteration=round(dt * 1e3, 2), collection_ms=round(runner.collection_time * 1e3, 2),
-                          learning_ms=round(runner.learn_time * 1e3, 2),
-                          env_steps_per_sec=round(runner.num_steps_per_env * num_envs / dt, 1))
+        t = torch.tensor([dt, runner.collection_time, runner.learn_time], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, coll, learn = (float(x) for x in t.tolist())
+        out[label] = dict(ms_per_iteration=round(dt * 1e3, 2), collection_ms=round(coll * 1e3, 2), learning_ms=round(learn * 1e3, 2),
+                          env_steps_per_sec=round(world * runner.num_steps_per_env * num_envs / dt, 1),
+                          graphed_update=bool(runner.alg._graph is not None), allreduces_per_iteration=(
+                              runner.alg.num_learning_epochs * runner.alg.num_mini_batches if world > 1 else 0))
         del env, runner
         torch.cuda.empty_cache()
     os.environ.pop("LGK_PPO_TF32", None)
     torch.backends.cuda.matmul.allow_tf32 = False
-    out["workload"] = f"{TASK}, {num_envs} envs x 24 steps per iteration, PPO 5 epochs x 4 mini-batches (LeggedRobotCfgPPO)"
+    out["workload"] = (f"{TASK}, {num_envs} envs/GPU x 24 steps per iteration on {world} GPU(s), PPO 5 epochs x 4 mini-batches "
+                       "(LeggedRobotCfgPPO); gradients all-reduced over NCCL inside the update graph when N > 1")
+    return out
+
+
+def size_leg(n, dev, rank, world, peak_gbs, l2_mode, flush, steps=100, task=None, overrides=None, barrier=lambda: None):
+    """whole-step throughput + per-kernel rooflines for one (task, envs-per-GPU) size; value aggregated over ranks"""
+    import torch
+    import torch.distributed as dist
+    envs2, feeders2, _ = make_replicas(n, dev, rank * n, l2_mode, task=task, overrides=overrides)
+    s2, _ = time_steps(envs2, [f.synthetic_actions for f in feeders2], steps, 10, flush, barrier)
+    t = torch.tensor([s2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s2 = float(t.item())
+    rec = dict(value=world * n * steps / s2, ms_per_step=s2 / steps * 1e3, n_gpus=world, steps=steps,
+               workload=workload(task or TASK, n), resets_per_step=float(envs2[0].reset_buf.float().mean()),
+               cuda_graph=bool(getattr(envs2[0], "_graph", None) is not None))
+    if rank == 0:
+        r2 = kernel_rooflines(envs2, [f.synthetic_actions for f in feeders2], peak_gbs, reps=50)
+        for k, v in r2.items():
+            rec["roofline_" + k] = v
+    del envs2, feeders2
+    torch.cuda.empty_cache()
+    return rec
+
+
+def flat64_leg(dev, peak_gbs):
+    """BASELINE.json configs[0]: anymal_c_flat, 64 envs, the reference's own CPU-runnable case -- GPU step (graph
+    replay) with LSTM and with PD torques next to the reference algorithm on the host cores."""
+    import torch
+    out = {}
+    for label, ov in (("lstm", None), ("pd", {"control.use_actuator_network": False})):
+        env, feeder = make_env(64, dev, task="anymal_c_flat", overrides=ov)
+        acts = feeder.synthetic_actions
+        env.action_buffer.copy_(acts)
+        for _ in range(10):
+            env.step(env.action_buffer)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(500):
+            env.step(env.action_buffer)
+        b.record()
+        torch.cuda.synchronize()
+        sec = a.elapsed_time(b) / 1e3 / 500
+        cpu = cpu_arm(64, steps=200, warmup=5, task="anymal_c_flat", overrides=ov)
+        out[label] = dict(gpu_us_per_step=round(sec * 1e6, 2), gpu_env_steps_per_sec=round(64 / sec, 1),
+                          cpu_ms_per_step=round(cpu["ms_per_step"], 3), cpu_env_steps_per_sec=round(cpu["value"], 1),
+                          cpu_cores=cpu["cores"], note="64 envs = 2 K1 tiles: a launch-latency measurement (6 kernels per graph-replayed step)")
+        del env, feeder
+    out["workload"] = workload("anymal_c_flat", 64)
     return out
 
 
@@ -480,30 +563,120 @@ def gpu_arm(args):
     peak_gbs, peak_src = peaks()
     if args.no_pdl:
         nat.lib.lgk_set_pdl(0)
-    global TILE, USE_GRAPH, LSTM_VARIANT
-    TILE, USE_GRAPH, LSTM_VARIANT = args.tile, not args.no_graph, args.lstm_variant
+    global USE_GRAPH, LSTM_VARIANT
+    USE_GRAPH, LSTM_VARIANT = not args.no_graph, args.lstm_variant
     envs, feeders, per_bytes = make_replicas(N, dev, rank * N, args.l2)
     env, feeder = envs[0], feeders[0]
-    actions = feeder.synthetic_actions
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     with ClockSampler(local) as clk:
         secs, launches = time_steps(envs, [f.synthetic_actions for f in feeders], args.steps, args.warmup, flush, barrier)
-    l2_note = (f"inputs larger than L2: {len(envs)} env replicas x {per_bytes / 2**20:.0f} MiB stepped round-robin"
+    l2_note = (f"inputs larger than L2: {len(envs)} env replicas x {per_bytes / 2**20:.0f} MiB of per-env state stepped round-robin "
+               "(they share the one 5.5 MB terrain height table, as every env of a real run does)"
                if len(envs) > 1 else f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)")
     t = torch.tensor([secs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs = float(t.item())
     value = world * N * args.steps / secs
+    resets = float(env.reset_buf.float().mean())
+    graphed = bool(getattr(env, "_graph", None) is not None)
+    roof = kernel_rooflines(envs, [f.synthetic_actions for f in feeders], peak_gbs) if rank == 0 else None
+    del envs, feeders, env, feeder
+    torch.cuda.empty_cache()
 
     # ---- e2e: sim state in pinned host memory, actions from host, results read back (rank-local, max over ranks)
+    e2e = e2e_leg(N, dev, rank, world, args, barrier)
+
+    # ---- BASELINE configs[4]: 65 536 envs / GPU on EVERY N (weak scaling of the sharded step); 16 384 at N = 1 as well
+    sweep = {}
+    if not args.no_sweep:
+        for n2 in ((16384, 65536) if world == 1 else (65536,)):
+            if n2 != N:
+                sweep[str(n2)] = size_leg(n2, dev, rank, world, peak_gbs, args.l2, flush, barrier=barrier)
+                if rank == 0:
+                    sweep[str(n2)]["roofline_torque_lstm"]["traffic"] = ncu_traffic(n2, r"torque_kernel<1(, 0)?>")
+                    sweep[str(n2)]["roofline_post_physics"]["traffic"] = ncu_traffic(n2, r"post_kernel", "scan_obs")
+
+    # ---- one PPO iteration on all ranks, NCCL gradient all-reduce inside (the learning side of configs[4])
+    training = None if args.no_train else train_iteration(dev, world=world, rank=rank)
+
+    # ---- the one collective of the job measured alone: the flat PPO gradient bucket
+    allreduce = None
+    if world > 1:
+        nparam = 2 * (235 * 512 + 512 + 512 * 256 + 256 + 256 * 128 + 128) + 128 * 12 + 12 + 128 + 1 + 12      # actor + critic + std
+        flat = torch.zeros(nparam, device=dev)
+        for _ in range(5):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(100):
+            dist.all_reduce(flat)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / 100 * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item())
+        allreduce = dict(what="PPO gradient bucket all-reduce over NCCL alone (20 per iteration; not on the env-step path)",
+                         bytes=nparam * 4, us=round(us, 2), bus_gbs=round(2 * (world - 1) / world * nparam * 4 / us / 1e3, 1))
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---- rank 0 extras (the other ranks wait in the closing barrier): other BASELINE configs, rollout phase, CPU baseline
+    configs = {}
+    rollout = rollout_phase(dev)
+    game = None
+    cpu = None
+    if world == 1:
+        if not args.no_sweep:
+            # configs[2]: a1, 16 384 envs, PD torques; 1500 timed steps = two push steps (every 750) inside the timed region
+            configs["a1_16384"] = size_leg(16384, dev, 0, 1, peak_gbs, args.l2, flush, steps=1500, task="a1")
+            configs["anymal_c_flat_64"] = flat64_leg(dev, peak_gbs)
+        if not args.no_train:
+            game = game_phase(dev)
+        if not args.no_cpu_baseline:
+            # N=1 only: with other ranks spinning in the closing barrier the OpenMP team of the CPU arm is oversubscribed
+            cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores
+            try:
+                cpu["eager_torch_gpu"] = eager_gpu_arm(N, dev)
+            except Exception as e:                       # a baseline, never a reason to lose the bench line
+                cpu["eager_torch_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    dom = dict(roof["torque_lstm"])
+    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, r"torque_kernel<1(, 0)?>"))
+    roof["post_physics"]["traffic"] = ncu_traffic(N, r"post_kernel", "scan_obs")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload(TASK, N), "num_envs_per_gpu": N, "resets_per_step": resets, "l2": l2_note,
+                   "cuda_graph": graphed, "pdl": not args.no_pdl,
+                   "timing": "CUDA events on the launch stream around the K steps; barrier+synchronize both sides",
+                   "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep, "configs": configs,
+        "rollout_phase": rollout, "train_iteration": training, "game_phase": game,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if allreduce is not None:
+        line["allreduce"] = allreduce
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e2e_leg(N, dev, rank, world, args, barrier):
+    import torch
+    import torch.distributed as dist
     env_h, feeder_h = make_env(N, dev, host_sim=True, env_id_offset=rank * N)
     h_actions = feeder_h.synthetic_actions.cpu().pin_memory()
     h_obs = torch.empty(env_h.obs_buf.shape).pin_memory()
     h_rew = torch.empty(N).pin_memory()
     h_reset = torch.empty(N, dtype=torch.bool).pin_memory()
     e2e_steps = max(10, min(args.steps, 200))
-
     d_actions = env_h.action_buffer
 
     def e2e_step():
@@ -532,89 +705,12 @@ def gpu_arm(args):
         dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
     h2d = sim_h2d + d_actions.numel() * 4
     d2h = sim_d2h + (h_obs.numel() + h_rew.numel()) * 4 + h_reset.numel()
-    e2e = dict(value=world * N * e2e_steps / float(e2e_secs.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
-               d2h_bytes_per_step=int(d2h), steps=e2e_steps, cuda_graph=bool(getattr(env_h, "_graph", None) is not None))
+    out = dict(value=world * N * e2e_steps / float(e2e_secs.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
+               d2h_bytes_per_step=int(d2h), steps=e2e_steps, us_per_step=round(float(e2e_secs.item()) / e2e_steps * 1e6, 1),
+               cuda_graph=bool(getattr(env_h, "_graph", None) is not None))
     del env_h, feeder_h
-
-    # ---- the one collective of the job (learning side): the flat PPO gradient bucket, 20 all-reduces per iteration
-    allreduce = None
-    if world > 1:
-        nparam = 2 * (235 * 512 + 512 + 512 * 256 + 256 + 256 * 128 + 128) + 128 * 12 + 12 + 128 + 1 + 12      # actor + critic + std
-        flat = torch.zeros(nparam, device=dev)
-        for _ in range(5):
-            dist.all_reduce(flat)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(100):
-            dist.all_reduce(flat)
-        b.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b) / 100 * 1e3], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        us = float(t.item())
-        allreduce = dict(what="PPO gradient bucket all-reduce over NCCL (20 per iteration; not on the env-step path)",
-                         bytes=nparam * 4, us=round(us, 2), bus_gbs=round(2 * (world - 1) / world * nparam * 4 / us / 1e3, 1))
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-    # ---- rank 0 extras: per-kernel rooflines, size sweep, CPU baseline
-    roof = kernel_rooflines(envs, [f.synthetic_actions for f in feeders], peak_gbs)
-    del envs[1:], feeders[1:]
     torch.cuda.empty_cache()
-    sweep = {}
-    if not args.no_sweep and world == 1:
-        for n2 in (16384, 65536):
-            if n2 == N:
-                continue
-            envs2, feeders2, _ = make_replicas(n2, dev, 0, args.l2)
-            env2, feeder2 = envs2[0], feeders2[0]
-            s2, _ = time_steps(envs2, [f.synthetic_actions for f in feeders2], 100, 10, flush, lambda: None)
-            r2 = kernel_rooflines(envs2, [f.synthetic_actions for f in feeders2], peak_gbs, reps=50)
-            r2["torque_lstm"]["traffic"] = ncu_traffic(n2, r"torque_kernel<1(, 0)?>")
-            r2["post_physics"]["traffic"] = ncu_traffic(n2, r"post_(scalar_)?kernel", "scan_obs_fast_kernel")
-            sweep[str(n2)] = dict(value=n2 * 100 / s2, ms_per_step=s2 / 100 * 1e3,
-                                  roofline_torque_lstm=r2["torque_lstm"], roofline_post_physics=r2["post_physics"])
-            del env2, feeder2, envs2, feeders2
-            torch.cuda.empty_cache()
-    rollout = rollout_phase(dev)
-    # single-process legs only: a PPO update on rank 0 alone would all-reduce against ranks that are waiting in the barrier
-    training = None if (args.no_train or world > 1) else train_iteration(dev)
-    game = None if (args.no_train or world > 1) else game_phase(dev)
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        # N=1 only: with other ranks spinning in the closing barrier the OpenMP team of the CPU arm is oversubscribed and
-        # collapses (the N=2 run sat here for > 10 minutes)
-        cpu = cpu_arm(N, steps=500, warmup=5)        # ~10 s of CPU work on the box's host cores
-        try:
-            cpu["eager_torch_gpu"] = eager_gpu_arm(N, dev)
-        except Exception as e:                       # a baseline, never a reason to lose the bench line
-            cpu["eager_torch_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
-    dom = dict(roof["torque_lstm"])
-    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, r"torque_kernel<1(, 0)?>"))
-    roof["post_physics"]["traffic"] = ncu_traffic(N, r"post_(scalar_)?kernel", "scan_obs_fast_kernel")
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{TASK}: {N} envs/GPU, 187-point height scan + 4x LSTM actuator-net torques + full reward set "
-                               "+ termination/reset/command resampling + noisy observations (BASELINE.json configs[1])",
-                   "num_envs_per_gpu": N, "resets_per_step": float(env.reset_buf.float().mean()), "l2": l2_note, "cuda_graph": bool(getattr(env, "_graph", None) is not None), "pdl": not args.no_pdl,
-                   "timing": "CUDA events on the launch stream around the K steps; barrier+synchronize both sides",
-                   "parallelism": f"env-sharded x{world}, no data-path collective"},
-        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": dom, "roofline_post_physics": roof["post_physics"], "sweep": sweep, "rollout_phase": rollout, "train_iteration": training, "game_phase": game,
-    }
-    if cpu is not None:
-        line["cpu_baseline"] = cpu
-    if allreduce is not None:
-        line["allreduce"] = allreduce
-    print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    return out
 
 
 def reference_arm(args):
@@ -626,8 +722,9 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{TASK}: {args.num_envs} envs, reference algorithm (torch CPU, oracle port pinned bit-exact "
-                                   "to the reference), same step as the GPU arm"},
+            "config": {"workload": workload(TASK, args.num_envs), "num_envs_per_gpu": args.num_envs,
+                       "implementation": "reference algorithm on the host cores (torch CPU; oracle port pinned bit-exact to the "
+                                         "reference), the same step as the GPU arm"},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

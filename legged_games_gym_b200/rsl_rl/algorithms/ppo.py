@@ -1,9 +1,10 @@
 """PPO with the rsl_rl v1.0.2 API.  act / process_env_step / compute_returns feed the CUDA hot path; update() is plain
 PyTorch autograd -- on a single GPU captured once into a CUDA graph (one replay per mini-batch: gathers, forward, losses,
 backward, gradient clipping, Adam, the adaptive-KL learning-rate rule and the loss accumulators all on the device, no
-host synchronisation inside the loop), eager otherwise.  Multi-GPU (one process per GPU, envs sharded): gradients are flattened into one bucket and
-all-reduced over NCCL once per mini-batch; the KL estimate that drives the adaptive learning rate is all-reduced so
-every rank takes the same schedule."""
+host synchronisation inside the loop), eager otherwise.  Multi-GPU (one process per GPU, envs sharded): the parameters'
+.grad tensors are views of ONE flat bucket, which is all-reduced over NCCL once per mini-batch -- inside the captured graph
+on CUDA (NCCL collectives are capturable), so N > 1 keeps the one-replay-per-mini-batch structure; the KL estimate that
+drives the adaptive learning rate is all-reduced on the device too, so every rank takes the same schedule."""
 import copy
 
 import torch
@@ -91,22 +92,28 @@ class PPO:
             last_values = self.actor_critic.critic(last_critic_obs)
         self.storage.compute_returns(last_values, self.gamma, self.lam)
 
+    def _bucket_grads(self):
+        """Make every parameter's .grad a view of one flat fp32 buffer (autograd accumulates into existing .grad tensors
+        in place): the bucket IS the gradients, no gather / scatter around the all-reduce."""
+        params = list(self.actor_critic.parameters())
+        n = sum(p.numel() for p in params)
+        if self._flat_grad is None or self._flat_grad.numel() != n or self._flat_grad.device != params[0].device:
+            self._flat_grad = torch.zeros(n, device=params[0].device, dtype=torch.float32)
+        off = 0
+        for p in params:
+            k = p.numel()
+            view = self._flat_grad[off:off + k].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
+            off += k
+
     def _allreduce_grads(self):
+        """mean of the shards' gradients: one NCCL all-reduce of the flat bucket (2.29 MB for the 512-256-128 nets)"""
         ws = _world()
         if ws == 1:
             return
-        params = [p for p in self.actor_critic.parameters() if p.grad is not None]
-        n = sum(p.grad.numel() for p in params)
-        if self._flat_grad is None or self._flat_grad.numel() != n:
-            self._flat_grad = torch.empty(n, device=self.device)
-        torch.cat([p.grad.reshape(-1) for p in params], out=self._flat_grad)
         dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
         self._flat_grad.div_(ws)
-        off = 0
-        for p in params:
-            k = p.grad.numel()
-            p.grad.copy_(self._flat_grad[off:off + k].view_as(p.grad))
-            off += k
         self.allreduce_calls += 1
 
     # ------------------------------------------------------------------ graphed update (single process, CUDA)
@@ -122,6 +129,9 @@ class PPO:
                 kl = torch.sum(torch.log(sigma / old_sigma + 1.e-5) +
                                (torch.square(old_sigma) + torch.square(old_mu - mu)) / (2.0 * torch.square(sigma)) - 0.5, axis=-1)
                 kl_mean = torch.mean(kl)
+                if _world() > 1:                      # every rank takes the same learning-rate schedule
+                    dist.all_reduce(kl_mean, op=dist.ReduceOp.SUM)
+                    kl_mean = kl_mean / _world()
                 down = torch.clamp(lr_t / 1.5, min=1e-5)
                 up = torch.clamp(lr_t * 1.5, max=1e-2)
                 new_lr = torch.where(kl_mean > self.desired_kl * 2.0, down,
@@ -147,6 +157,7 @@ class PPO:
                                             take(st["rets"]), take(st["olp"]), take(st["mu"]), take(st["sg"]), g["lr"])
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
+        self._allreduce_grads()
         nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
         self.optimizer.step()
         g["acc"][0] += vl.detach()
@@ -183,8 +194,10 @@ class PPO:
         self.actor_critic.distribution = None
         for p_ in self.actor_critic.parameters():
             p_.grad = None
+        self._bucket_grads()
         # the live weights / optimizer state must not be touched by warm-up and capture: snapshot, run, restore
         snap_p = [p.detach().clone() for p in self.actor_critic.parameters()]
+        calls = self.allreduce_calls                     # warm-up / capture launches do not count as update steps
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -209,6 +222,7 @@ class PPO:
         for grp in self.optimizer.param_groups:
             grp["lr"] = lr_t
         lr_t.fill_(float(self.learning_rate))
+        self.allreduce_calls = calls
         g["graph"] = graph
         self._graph = g
 
@@ -225,6 +239,8 @@ class PPO:
                 g["idx"].copy_(perm[i * g["mb"]:(i + 1) * g["mb"]])
                 g["graph"].replay()
         n = self.num_learning_epochs * self.num_mini_batches
+        if _world() > 1:
+            self.allreduce_calls += n                                       # one bucket all-reduce inside every replay
         acc = (g["acc"] / n).tolist()                                       # the only host synchronisation of the update
         self.learning_rate = float(g["lr"].item())
         self.storage.clear()
@@ -284,9 +300,10 @@ class PPO:
         self.learning_rate = lr
 
     def _update(self):
-        if (self.use_cuda_graph and _world() == 1 and torch.device(self.device).type == "cuda"
-                and self.storage.observations.is_cuda):
+        if (self.use_cuda_graph and torch.device(self.device).type == "cuda" and self.storage.observations.is_cuda
+                and (_world() == 1 or dist.get_backend() == "nccl")):
             return self._update_graphed()
+        self._bucket_grads()
         mean_value_loss = mean_surrogate_loss = 0.0
         ac = self.actor_critic
         gen = self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs)
@@ -318,7 +335,7 @@ class PPO:
             else:
                 value_loss = (rets - value).pow(2).mean()
             loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy.mean()
-            self.optimizer.zero_grad()
+            self.optimizer.zero_grad(set_to_none=False)       # (the .grad tensors are views of the bucket: keep them)
             loss.backward()
             self._allreduce_grads()
             nn.utils.clip_grad_norm_(ac.parameters(), self.max_grad_norm)

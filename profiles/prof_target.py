@@ -14,7 +14,7 @@ ap.add_argument("--num-envs", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--tile", type=int, default=0)
 a = ap.parse_args()
-bench.TILE, bench.USE_GRAPH = a.tile, False
+bench.USE_GRAPH = False
 env, feeder = bench.make_env(a.num_envs, "cuda:0")
 for _ in range(a.steps):
     env.step(feeder.synthetic_actions)

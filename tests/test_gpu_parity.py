@@ -521,7 +521,7 @@ def test_host_sim_state_step_replays_inside_the_graph(mode, monkeypatch):
     cudaMemcpyAsync nodes.  The host state changes between steps, pushes happen every second step, and everything must
     equal an env whose state lives on the device."""
     import bench
-    bench.USE_GRAPH, bench.TILE = True, 0
+    bench.USE_GRAPH = True
     monkeypatch.setenv("LGK_HOST_UNIFIED", "1" if mode == "unified" else "0")
     monkeypatch.setenv("LGK_HOST_ZERO_COPY", "0" if mode == "memcpy" else "1")
     torch.manual_seed(0)                         # initial terrain levels come from torch's generator (LR:762)

@@ -705,9 +705,26 @@ def e2e_leg(N, dev, rank, world, args, barrier):
         dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
     h2d = sim_h2d + d_actions.numel() * 4
     d2h = sim_d2h + (h_obs.numel() + h_rew.numel()) * 4 + h_reset.numel()
+    step_s = float(e2e_secs.item()) / e2e_steps
+    # the link the step is bound by: pinned cudaMemcpyAsync rates of this host, each direction alone (64 MiB, best of 5)
+    big_h, big_d = torch.empty(64 << 20, dtype=torch.uint8).pin_memory(), torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    rates = {}
+    for name, dst, src in (("h2d", big_d, big_h), ("d2h", big_h, big_d)):
+        best = 1e9
+        for _ in range(5):
+            a.record(); dst.copy_(src, non_blocking=True); b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) / 1e3)
+        rates[name] = big_h.numel() / best / 1e9
+    floor_s = h2d / (rates["h2d"] * 1e9) + d2h / (rates["d2h"] * 1e9)      # both directions back to back, nothing else
     out = dict(value=world * N * e2e_steps / float(e2e_secs.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
-               d2h_bytes_per_step=int(d2h), steps=e2e_steps, us_per_step=round(float(e2e_secs.item()) / e2e_steps * 1e6, 1),
-               cuda_graph=bool(getattr(env_h, "_graph", None) is not None))
+               d2h_bytes_per_step=int(d2h), steps=e2e_steps, us_per_step=round(step_s * 1e6, 1),
+               cuda_graph=bool(getattr(env_h, "_graph", None) is not None),
+               pcie=dict(h2d_gbs_peak=round(rates["h2d"], 1), d2h_gbs_peak=round(rates["d2h"], 1),
+                         serial_transfer_floor_us=round(floor_s * 1e6, 1), pcie_frac=round(floor_s / step_s, 3),
+                         note="pcie_frac = time the step's bytes need on this host's link (each direction at its measured "
+                              "pinned-memcpy rate, back to back) / measured step time"))
+    del big_h, big_d
     del env_h, feeder_h
     torch.cuda.empty_cache()
     return out

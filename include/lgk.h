@@ -114,7 +114,9 @@ typedef struct LgkStepParams {
   int32_t actors_per_env;             /* root_states rows per env (1; 2 in low_level_game, LLG:532) */
   int32_t root_actor_offset;          /* row of the robot inside the env's actor group (prey index) */
   int32_t phase_mask;                 /* LGK_PHASE_* */
-  int32_t tile_envs;                  /* reserved (the scalar kernel tiles 32 envs per CTA) */
+  int32_t host_state;                 /* 1: root_states / dof_state / contact_forces live in pinned HOST memory (the kernels reach
+                                       * them over the unified address space): no L2 prefetch of those chunks, every byte crosses
+                                       * PCIe exactly once */
   int32_t push_interval;              /* used with step_counter_dev: push when step % interval == 0 (0 = never) */
   int32_t step;                       /* common_step_counter AFTER the += 1 of LR:115 (RNG counter) */
   uint64_t seed;

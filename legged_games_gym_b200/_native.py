@@ -42,7 +42,7 @@ class LstmWeights(C.Structure):
 class StepParams(C.Structure):
     _fields_ = [
         ("num_envs", i32), ("num_bodies", i32), ("num_obs", i32), ("num_height_points", i32),
-        ("actors_per_env", i32), ("root_actor_offset", i32), ("phase_mask", i32), ("tile_envs", i32),
+        ("actors_per_env", i32), ("root_actor_offset", i32), ("phase_mask", i32), ("host_state", i32),
         ("push_interval", i32), ("step", i32),
         ("seed", u64), ("env_id_offset", i64),
         ("heading_command", i32), ("measure_heights", i32), ("terrain_is_plane", i32), ("do_push", i32),

@@ -166,9 +166,11 @@ post_kernel(const __grid_constant__ LgkStepParams p, const __grid_constant__ Til
   // prefetch carries no data into the SM: whatever that kernel still writes lands in the same L2)
   if (FAST && tid == 0 && (int)blockIdx.x < ntiles) {
     const size_t n0 = (size_t)blockIdx.x * kTile;
-    bulk_prefetch_l2(p.root_states + n0 * 13, kTile * 13 * 4);
-    bulk_prefetch_l2(p.dof_state + n0 * 24, kTile * 24 * 4);
-    bulk_prefetch_l2(p.contact_forces + n0 * NB * 3, kTile * NB * 3 * 4);
+    if (!p.host_state) {
+      bulk_prefetch_l2(p.root_states + n0 * 13, kTile * 13 * 4);
+      bulk_prefetch_l2(p.dof_state + n0 * 24, kTile * 24 * 4);
+      bulk_prefetch_l2(p.contact_forces + n0 * NB * 3, kTile * NB * 3 * 4);
+    }
     bulk_prefetch_l2(p.actions + n0 * 12, kTile * 12 * 4);
     bulk_prefetch_l2(p.last_actions + n0 * 12, kTile * 12 * 4);
     bulk_prefetch_l2(p.last_dof_vel + n0 * 12, kTile * 12 * 4);
@@ -231,9 +233,11 @@ post_kernel(const __grid_constant__ LgkStepParams p, const __grid_constant__ Til
       const int nt = tile + gridDim.x;
       if (nt < ntiles && (nt + 1) * kTile <= N) {
         const size_t n0 = (size_t)nt * kTile;
-        bulk_prefetch_l2(p.root_states + n0 * 13, kTile * 13 * 4);
-        bulk_prefetch_l2(p.dof_state + n0 * 24, kTile * 24 * 4);
-        bulk_prefetch_l2(p.contact_forces + n0 * NB * 3, kTile * NB * 3 * 4);
+        if (!p.host_state) {        // (sim state in pinned host memory: a prefetch would pull the chunk over PCIe twice)
+          bulk_prefetch_l2(p.root_states + n0 * 13, kTile * 13 * 4);
+          bulk_prefetch_l2(p.dof_state + n0 * 24, kTile * 24 * 4);
+          bulk_prefetch_l2(p.contact_forces + n0 * NB * 3, kTile * NB * 3 * 4);
+        }
         bulk_prefetch_l2(p.actions + n0 * 12, kTile * 12 * 4);
         bulk_prefetch_l2(p.torques + n0 * 12, kTile * 12 * 4);
         bulk_prefetch_l2(p.last_actions + n0 * 12, kTile * 12 * 4);

@@ -683,6 +683,7 @@ class LeggedRobot(BaseTask):
             p.obs_head = ptr(self._obs_head)
         dr = cfg.domain_rand
         p.push_interval = int(dr.push_interval) if dr.push_robots else 0
+        p.host_state = int(bool(getattr(self.gym, "state_in_host_memory", False)))
         if mh:
             p.measured_heights = ptr(self.measured_heights)
             if not p.terrain_is_plane:

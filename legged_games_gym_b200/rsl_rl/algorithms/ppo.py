@@ -97,8 +97,8 @@ class PPO:
         in place): the bucket IS the gradients, no gather / scatter around the all-reduce."""
         params = list(self.actor_critic.parameters())
         n = sum(p.numel() for p in params)
-        if self._flat_grad is None or self._flat_grad.numel() != n or self._flat_grad.device != params[0].device:
-            self._flat_grad = torch.zeros(n, device=params[0].device, dtype=torch.float32)
+        if self._flat_grad is None or self._flat_grad.numel() != n + 1 or self._flat_grad.device != params[0].device:
+            self._flat_grad = torch.zeros(n + 1, device=params[0].device, dtype=torch.float32)   # + 1: the KL estimate
         off = 0
         for p in params:
             k = p.numel()
@@ -124,19 +124,12 @@ class PPO:
         lp = ac.distribution.log_prob(acts).sum(dim=-1)
         value = ac.critic(cobs)
         mu, sigma, entropy = ac.distribution.mean, ac.distribution.stddev, ac.entropy
+        kl_mean = None
         if self.desired_kl is not None and self.schedule == "adaptive":
             with torch.no_grad():
                 kl = torch.sum(torch.log(sigma / old_sigma + 1.e-5) +
                                (torch.square(old_sigma) + torch.square(old_mu - mu)) / (2.0 * torch.square(sigma)) - 0.5, axis=-1)
                 kl_mean = torch.mean(kl)
-                if _world() > 1:                      # every rank takes the same learning-rate schedule
-                    dist.all_reduce(kl_mean, op=dist.ReduceOp.SUM)
-                    kl_mean = kl_mean / _world()
-                down = torch.clamp(lr_t / 1.5, min=1e-5)
-                up = torch.clamp(lr_t * 1.5, max=1e-2)
-                new_lr = torch.where(kl_mean > self.desired_kl * 2.0, down,
-                                     torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr_t))
-                lr_t.copy_(new_lr)
         ratio = torch.exp(lp - torch.squeeze(old_lp))
         a = torch.squeeze(adv)
         surrogate_loss = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param)).mean()
@@ -146,18 +139,33 @@ class PPO:
         else:
             value_loss = (rets - value).pow(2).mean()
         loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy.mean()
-        return loss, value_loss, surrogate_loss
+        return loss, value_loss, surrogate_loss, kl_mean
+
+    def _adapt_lr(self, kl_mean, lr_t):
+        """rsl_rl's adaptive-KL rule on the device (lr_t: 0-dim tensor the capturable optimizer reads)"""
+        down = torch.clamp(lr_t / 1.5, min=1e-5)
+        up = torch.clamp(lr_t * 1.5, max=1e-2)
+        new_lr = torch.where(kl_mean > self.desired_kl * 2.0, down,
+                             torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr_t))
+        lr_t.copy_(new_lr)
 
     def _graph_step(self, g):
         """gather the mini-batch named by g['idx'] from the flat rollout tensors, then one optimisation step"""
         st = g["flat"]
         idx = g["idx"]
         take = lambda t: t.index_select(0, idx)
-        loss, vl, sl = self._minibatch_loss(take(st["obs"]), take(st["cobs"]), take(st["acts"]), take(st["vals"]), take(st["adv"]),
-                                            take(st["rets"]), take(st["olp"]), take(st["mu"]), take(st["sg"]), g["lr"])
+        loss, vl, sl, kl = self._minibatch_loss(take(st["obs"]), take(st["cobs"]), take(st["acts"]), take(st["vals"]), take(st["adv"]),
+                                                take(st["rets"]), take(st["olp"]), take(st["mu"]), take(st["sg"]), g["lr"])
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
-        self._allreduce_grads()
+        # ONE collective per mini-batch: the KL estimate rides in the last element of the gradient bucket, so every rank
+        # takes the same learning-rate decision from the same all-reduce that averages the gradients
+        with torch.no_grad():
+            if kl is not None:
+                self._flat_grad[-1] = kl
+            self._allreduce_grads()
+            if kl is not None:
+                self._adapt_lr(self._flat_grad[-1], g["lr"])
         nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
         self.optimizer.step()
         g["acc"][0] += vl.detach()

@@ -1,8 +1,6 @@
 """OnPolicyRunner with the rsl_rl v1.0.2 API (constructor, learn, save, load, get_inference_policy)."""
 import os
-import statistics
 import time
-from collections import deque
 
 import torch
 import torch.distributed as dist
@@ -36,11 +34,16 @@ class OnPolicyRunner:
         critic_obs = pobs if pobs is not None else obs
         obs, critic_obs = obs.to(self.device), critic_obs.to(self.device)
         alg.actor_critic.train()
-        ep_infos, rewbuffer, lenbuffer = [], deque(maxlen=100), deque(maxlen=100)
+        ep_infos = []
         cur_rew = torch.zeros(env.num_envs, dtype=torch.float, device=self.device)
         cur_len = torch.zeros(env.num_envs, dtype=torch.float, device=self.device)
+        # finished-episode statistics live on the device (sum of returns, sum of lengths, count): no host synchronisation
+        # inside the rollout; read (and, multi-GPU, all-reduced) once per iteration
+        ep_stats = torch.zeros(3, dtype=torch.float64, device=self.device)
         tot_iter = self.current_learning_iteration + num_learning_iterations
         act_step = 0
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        track = self.log_dir is not None or world > 1
         for it in range(self.current_learning_iteration, tot_iter):
             start = time.time()
             with torch.inference_mode():
@@ -51,39 +54,35 @@ class OnPolicyRunner:
                     obs, pobs, rewards, dones, infos = env.step(actions)
                     critic_obs = pobs if pobs is not None else obs
                     alg.process_env_step(rewards, dones, infos)
-                    if self.log_dir is not None or (dist.is_available() and dist.is_initialized()):
-                        if "episode" in infos:
+                    if track:
+                        if self.log_dir is not None and "episode" in infos:
                             ep_infos.append(infos["episode"])
                         cur_rew += rewards
                         cur_len += 1
-                        new_ids = (dones > 0).nonzero(as_tuple=False)
-                        rewbuffer.extend(cur_rew[new_ids][:, 0].cpu().numpy().tolist())
-                        lenbuffer.extend(cur_len[new_ids][:, 0].cpu().numpy().tolist())
-                        cur_rew[new_ids] = 0
-                        cur_len[new_ids] = 0
+                        done = (dones > 0).to(cur_rew.dtype)
+                        ep_stats[0] += (cur_rew * done).sum()
+                        ep_stats[1] += (cur_len * done).sum()
+                        ep_stats[2] += done.sum()
+                        cur_rew *= 1.0 - done
+                        cur_len *= 1.0 - done
                 stop = time.time()
                 self.collection_time = stop - start
                 start = stop
                 alg.compute_returns(critic_obs)
             mean_value_loss, mean_surrogate_loss = alg.update()
             self.learn_time = time.time() - start
-            self.tot_timesteps += self.num_steps_per_env * env.num_envs
+            self.tot_timesteps += world * self.num_steps_per_env * env.num_envs
             self.tot_time += self.collection_time + self.learn_time
-            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-            self.tot_timesteps += (world - 1) * self.num_steps_per_env * env.num_envs
-            if world > 1:
-                # episode statistics over ALL shards: (sum of finished-episode returns, lengths, count) all-reduced
-                stats = torch.tensor([sum(rewbuffer), sum(lenbuffer), float(len(rewbuffer))], device=self.device,
-                                     dtype=torch.float64)
-                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-                self.global_episode_stats = dict(mean_reward=(stats[0] / stats[2]).item() if stats[2] > 0 else float("nan"),
-                                                 mean_length=(stats[1] / stats[2]).item() if stats[2] > 0 else float("nan"),
-                                                 episodes=int(stats[2].item()))
+            if track:
+                stats = ep_stats.clone()
+                if world > 1:      # episode statistics over ALL shards
+                    dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+                s_rew, s_len, s_cnt = stats.tolist()
+                self.global_episode_stats = dict(mean_reward=s_rew / s_cnt if s_cnt > 0 else float("nan"),
+                                                 mean_length=s_len / s_cnt if s_cnt > 0 else float("nan"), episodes=int(s_cnt))
             if self.log_dir is not None:
                 fps = int(world * self.num_steps_per_env * env.num_envs / (self.collection_time + self.learn_time))
-                mr = statistics.mean(rewbuffer) if len(rewbuffer) else float("nan")
-                if world > 1:
-                    mr = self.global_episode_stats["mean_reward"]
+                mr = self.global_episode_stats["mean_reward"]
                 print(f"it {it}/{tot_iter} steps/s {fps} collection {self.collection_time:.3f}s learning {self.learn_time:.3f}s "
                       f"value_loss {mean_value_loss:.4f} surrogate {mean_surrogate_loss:.4f} mean_reward {mr:.3f}")
                 if it % self.save_interval == 0:

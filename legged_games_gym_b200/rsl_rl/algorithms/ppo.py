@@ -234,6 +234,10 @@ class PPO:
         g["graph"] = graph
         self._graph = g
 
+    def release_graph(self):
+        """Drop the captured update graph (multi-GPU: it holds NCCL work; release it before destroy_process_group)."""
+        self._graph = None
+
     def _update_graphed(self):
         if self._graph is None:
             self._build_graph()

@@ -43,4 +43,11 @@ def train(args, log_root="default"):
 
 if __name__ == "__main__":
     import sys
-    train(get_args(sys.argv[1:]))
+    runner = train(get_args(sys.argv[1:]))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        runner.alg.release_graph()          # the captured update graph holds NCCL work
+        del runner
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()

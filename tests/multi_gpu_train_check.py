@@ -29,5 +29,12 @@ if rank == 0:
     assert runner.env.env_id_offset == 0 and runner.tot_timesteps == 2 * world * 512 * runner.num_steps_per_env
     print(f"multi-GPU train check ok: world {world}, {runner.alg.allreduce_calls} gradient all-reduces, "
           f"max parameter difference {max(diffs)}, global episode stats {getattr(runner, 'global_episode_stats', None)}")
+# a captured update graph holds NCCL work: release it before the communicator goes away (destroy_process_group waits
+# on it otherwise)
+runner.alg.release_graph()
+del runner
+import gc
+gc.collect()
+torch.cuda.synchronize()
 dist.barrier()
 dist.destroy_process_group()

@@ -19,6 +19,6 @@ obs = torch.randn(a.num_envs, 235, device="cuda:0")
 with torch.inference_mode():
     for i in range(a.calls):
         ac.set_rng(1, i)
-        out = ac.act(obs)
+        out = ac.act_and_evaluate(obs, obs)["actions"]      # PPO.act's call: actor + critic in one launch
 torch.cuda.synchronize()
 print("ok", a.num_envs, float(out.mean()))

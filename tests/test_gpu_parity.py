@@ -419,6 +419,36 @@ def test_reset_idx_override_runs_where_the_reference_calls_it():
     assert n_reset > 20
 
 
+def test_step_is_deterministic_run_to_run():
+    """compute-sanitizer is closed on the GPU pool, so the race evidence for K1 (shared-memory tiles re-used across the
+    persistent loop, generic-proxy writes feeding async-proxy bulk stores, the warp-cooperative reset tail, named barriers)
+    is behavioural: two envs fed the same state must agree bit for bit over steps with resets, pushes and resampling, on
+    the fast path, the ragged-tile path and the two-actor path.  (extras["episode"] sums go through float atomics whose
+    order is free: compared at 1e-6.)"""
+    for task, n in (("anymal_c_rough", 148 * 32 + 96), ("a1", 4003), ("low_level_game", 1501)):
+        ov = {"env.episode_length_s": 0.08, "domain_rand.push_interval_s": 0.04, "commands.resampling_time": 0.06}
+        case = harness.build_case(task, n, seed=13, overrides=ov)
+        runs = []
+        for rep in range(2):
+            env, feeder = product_env(case)
+            st = feeder_state(feeder)
+            snaps = []
+            for step in range(1, 6):
+                acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (n, 12)).astype(np.float32)).to(DEV)
+                env.step(acts)
+                torch.cuda.synchronize()
+                snaps.append(harness.snapshot(env))
+                harness.apply_noise(st, harness.make_noise(case, step, 5))
+            runs.append(snaps)
+        assert sum(int(s["reset_buf"].sum()) for s in runs[0]) > n // 10
+        for step, (a, b) in enumerate(zip(*runs), 1):
+            for k in a:
+                if k.startswith("ex_"):
+                    assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), f"{task} step {step}: {k}"
+                else:
+                    assert torch.equal(a[k], b[k]), f"{task} step {step}: {k} differs between two identical runs"
+
+
 def test_k1_persistent_loop_many_tiles_per_cta():
     """K1's CTAs are persistent: with one resident CTA per SM (tuning knob of the launcher) 20 000 envs are 625 tiles on at
     most 148 CTAs, i.e. up to five tiles per CTA incl. a partial last tile -- shared-memory reuse, mbarrier phases and the

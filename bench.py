@@ -368,8 +368,9 @@ def rollout_phase(dev, n_envs=4096, T=24, reps=20):
     ac = ActorCritic(235, 235, 12, hid, hid).to(dev)
     obs = [torch.randn(n_envs, 235, device=dev) for _ in range(4)]
     with torch.inference_mode():
-        ac.act(obs[0])
+        ac.act_and_evaluate(obs[0], obs[0])      # PPO.act's launch: actor AND critic (LgkPolicyParams.nets = 3)
     p = ac._last_params
+    assert p.nets == 3
     st = torch.cuda.current_stream().cuda_stream
     rew, val = torch.randn(T, n_envs, 1, device=dev), torch.randn(T, n_envs, 1, device=dev)
     dones = (torch.rand(T, n_envs, 1, device=dev) < 0.02).to(torch.uint8)
@@ -669,8 +670,16 @@ def gpu_arm(args):
 
 
 def e2e_leg(N, dev, rank, world, args, barrier):
+    """End to end through the public API with the sim state in pinned HOST memory.  Every step: actions host->device,
+    `LeggedRobot.step` (its kernels pull the sim state over PCIe and push torques / reset rows back), observations /
+    rewards / reset flags device->host.  `value` is the pipelined loop (HostResultMirror: step k's results download on a
+    copy stream while step k+1 runs; the host holds step k's results before it launches step k+3); `serial` is the same
+    loop with a host synchronisation after every step's download (round 1's definition)."""
     import torch
     import torch.distributed as dist
+    from legged_games_gym_b200.sim.result_mirror import HostResultMirror
+    from legged_games_gym_b200.utils.affinity import bind_to_gpu, restore_affinity
+    prev_aff, new_aff = bind_to_gpu(torch.cuda.current_device())     # pinned buffers land on the GPU's NUMA node
     env_h, feeder_h = make_env(N, dev, host_sim=True, env_id_offset=rank * N)
     h_actions = feeder_h.synthetic_actions.cpu().pin_memory()
     h_obs = torch.empty(env_h.obs_buf.shape).pin_memory()
@@ -679,7 +688,7 @@ def e2e_leg(N, dev, rank, world, args, barrier):
     e2e_steps = max(10, min(args.steps, 200))
     d_actions = env_h.action_buffer
 
-    def e2e_step():
+    def serial_step():
         d_actions.copy_(h_actions, non_blocking=True)
         obs, _, rew, reset, _ = env_h.step(d_actions)
         h_obs.copy_(obs, non_blocking=True)
@@ -687,27 +696,48 @@ def e2e_leg(N, dev, rank, world, args, barrier):
         h_reset.copy_(reset, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    LAG = 2                                     # the host runs two steps ahead of the results it consumes
+    mirror = HostResultMirror(env_h, depth=LAG + 1)
+
+    def pipelined(steps):
+        k = -1
+        for _ in range(steps):
+            d_actions.copy_(h_actions, non_blocking=True)
+            env_h.step(d_actions)
+            k = mirror.push()
+            if k >= LAG:
+                mirror.wait(k - LAG)        # step k-2's results are in host memory while steps k-1 and k are in flight
+        for j in range(max(0, k - LAG + 1), k + 1):
+            mirror.wait(j)
+
+    def timed(fn):
+        barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     feeder_h.h2d_bytes = feeder_h.d2h_bytes = 0
-    e2e_step()                                  # the env's first step runs eagerly: count the sim-side bytes of one step
+    serial_step()                               # the env's first step runs eagerly: count the sim-side bytes of one step
     sim_h2d, sim_d2h = feeder_h.h2d_bytes, feeder_h.d2h_bytes
     for _ in range(5):
-        e2e_step()
-    barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    b.record()
-    torch.cuda.synchronize()
-    e2e_secs = torch.tensor([a.elapsed_time(b) / 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
+        serial_step()
+    serial_secs = timed(lambda: [serial_step() for _ in range(e2e_steps)])
+    pipelined(6)
+    pipe_secs = timed(lambda: pipelined(e2e_steps))
     h2d = sim_h2d + d_actions.numel() * 4
     d2h = sim_d2h + (h_obs.numel() + h_rew.numel()) * 4 + h_reset.numel()
-    step_s = float(e2e_secs.item()) / e2e_steps
+    assert mirror.bytes_per_push == (h_obs.numel() + h_rew.numel()) * 4 + h_reset.numel()
+    step_s = pipe_secs / e2e_steps
     # the link the step is bound by: pinned cudaMemcpyAsync rates of this host, each direction alone (64 MiB, best of 5)
     big_h, big_d = torch.empty(64 << 20, dtype=torch.uint8).pin_memory(), torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rates = {}
     for name, dst, src in (("h2d", big_d, big_h), ("d2h", big_h, big_d)):
         best = 1e9
@@ -716,17 +746,29 @@ def e2e_leg(N, dev, rank, world, args, barrier):
             torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b) / 1e3)
         rates[name] = big_h.numel() / best / 1e9
-    floor_s = h2d / (rates["h2d"] * 1e9) + d2h / (rates["d2h"] * 1e9)      # both directions back to back, nothing else
-    out = dict(value=world * N * e2e_steps / float(e2e_secs.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
+    t_h2d, t_d2h = h2d / (rates["h2d"] * 1e9), d2h / (rates["d2h"] * 1e9)
+    floor_serial, floor_duplex = t_h2d + t_d2h, max(t_h2d, t_d2h)
+    out = dict(value=world * N * e2e_steps / pipe_secs, unit=UNIT, h2d_bytes_per_step=int(h2d),
                d2h_bytes_per_step=int(d2h), steps=e2e_steps, us_per_step=round(step_s * 1e6, 1),
                cuda_graph=bool(getattr(env_h, "_graph", None) is not None),
+               mode="pipelined: step k's observations / rewards / reset flags are snapshotted on the device and downloaded on a "
+                    "copy stream while step k+1 runs (HostResultMirror, 3 slots); the host waits for step k-2's results "
+                    "after launching step k; every step's inputs and results cross PCIe inside the timed region",
+               serial=dict(value=world * N * e2e_steps / serial_secs, us_per_step=round(serial_secs / e2e_steps * 1e6, 1),
+                           note="host synchronisation after every step's download (round 1's e2e definition)"),
+               cpu_affinity=dict(bound=bool(new_aff), cores=len(new_aff) if new_aff else len(prev_aff)),
                pcie=dict(h2d_gbs_peak=round(rates["h2d"], 1), d2h_gbs_peak=round(rates["d2h"], 1),
-                         serial_transfer_floor_us=round(floor_s * 1e6, 1), pcie_frac=round(floor_s / step_s, 3),
-                         note="pcie_frac = time the step's bytes need on this host's link (each direction at its measured "
-                              "pinned-memcpy rate, back to back) / measured step time"))
-    del big_h, big_d
+                         serial_transfer_floor_us=round(floor_serial * 1e6, 1),
+                         duplex_transfer_floor_us=round(floor_duplex * 1e6, 1),
+                         pcie_frac=round(floor_duplex / step_s, 3),
+                         pcie_frac_serial=round(floor_serial / (serial_secs / e2e_steps), 3),
+                         note="pcie_frac = time the busier direction's bytes need at this host's measured pinned-memcpy rate "
+                              "(both directions run concurrently in the pipelined loop) / measured step time; "
+                              "pcie_frac_serial = both directions back to back / the serial loop's step time"))
+    del big_h, big_d, mirror
     del env_h, feeder_h
     torch.cuda.empty_cache()
+    restore_affinity(prev_aff)
     return out
 
 

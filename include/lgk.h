@@ -335,10 +335,11 @@ int lgk_rng_dump(uint64_t seed, int32_t step, int64_t env_id_offset, int32_t num
 /* Fused actor + critic MLP forward (ELU), Normal(mean, std).sample(), log_prob.sum(-1)
  * (rsl_rl ActorCritic.act / evaluate / get_actions_log_prob; PPO.act).  Weights are nn.Linear layout
  * [out,in] fp32.  The three hidden layers run on tcgen05 tensor cores (TF32 operands rounded to nearest, FP32
- * accumulation in TMEM, one CTA per 128-env tile and network, activations never leave the SM); the last layer,
+ * accumulation in TMEM, one CTA per 128-env tile and network, activations never leave tensor memory); the last layer,
  * biases, ELU and the distribution epilogue are FP32.  Shapes the tensor-core kernel does not cover (hidden[0] not a
- * multiple of 64 or > 512, hidden[1] > hidden[0]/2, hidden[2] > 128, obs wider than 256, > 16 actions) run an FP32
- * tiled-GEMM path with the same results to 1e-3. */
+ * multiple of 128 or > 512, hidden[1] not a multiple of 64 / > 256, hidden[0]/2 + hidden[1] > 512, hidden[2] not a
+ * multiple of 32 / > 128 / > hidden[0]/2, obs wider than 256, > 16 actions, biases not 16-byte aligned) run an FP32 tiled-GEMM path
+ * with the same results to 1e-3. */
 typedef struct LgkPolicyParams {
   int32_t num_envs, num_obs, num_critic_obs, num_actions;
   int32_t hidden[3];                  /* actor and critic hidden sizes (must match pairwise) */
@@ -372,9 +373,12 @@ int lgk_policy_act(const LgkPolicyParams* p, void* stream);
  * fit).  Process-wide; returns the previous value.  For tests and benchmarks. */
 int lgk_policy_set_variant(int variant);
 /* Profiling hook: when non-NULL, CTA (0,0) of the tcgen05 kernel writes %globaltimer stamps (ns) of its phases into
- * device_buf16[0..9] (setup, obs staged, L1 done, drain 1, L2a done, drain 2, L2b done, drain 3, L3 done, outputs).
+ * device_buf128[0..13] (0 setup, 1 obs staged, 2 first half of layer 1 accumulated, 3-4 its two column groups activated in
+ * place, 5-7 the same for the second half, 8 layer 2 done, 9-10 its groups activated, 11 layer 3 done, 12 last layer summed,
+ * 13 outputs written); slots 16..55 take the issuer's clock64 at the start of each weight tile, 100..103 its cycles spent
+ * waiting for activations / for weight tiles / issuing MMAs / committing.  The buffer must hold 128 entries.
  * flags (profiling experiments only, results are then meaningless): bit 0 skips the weight-tile copies, bit 1 the MMAs. */
-int lgk_policy_debug_timeline(int64_t* device_buf16, int flags);
+int lgk_policy_debug_timeline(int64_t* device_buf128, int flags);
 
 /* ------------------------------------------------------------------ rsl_rl: RolloutStorage.compute_returns */
 /* Reverse GAE scan over [T,N] + global advantage normalisation (unbiased std, +1e-8).

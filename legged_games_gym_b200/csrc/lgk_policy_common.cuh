@@ -54,6 +54,53 @@ __device__ __forceinline__ void policy_finish_row(const LgkPolicyParams& p, int 
   p.actions_log_prob[n] = logp;
 }
 
+// The same distribution step for the four actions 4*blk .. 4*blk+3 of one environment (= the two Box-Muller pairs of Philox
+// block `blk` of the ACT stream): lets four warps share a row's epilogue.  Returns the partial log-prob of these actions.
+// sd3 = [std | 1/std | log(std)] x 16 (precomputed once per CTA): log N(a; mu, sd) = -((a - mu)/sd)^2 / 2 - log sd - log sqrt(2 pi)
+// without a division or a logarithm per action.
+__device__ __forceinline__ float policy_finish_quad(const LgkPolicyParams& p, int n, int blk, const float (&mu)[4],
+                                                    const float* __restrict__ sd3) {
+  const int A = p.num_actions;
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.sample) {
+    const RngKey key = make_key(p.seed, p.step);
+    const U4 r = rng_block(key, (uint32_t)(p.env_id_offset + n), LGK_STREAM_ACT, (uint32_t)blk);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = 1.0f - u32_to_uniform(w[2 * h]), u2 = u32_to_uniform(w[2 * h + 1]);
+      const float th = 6.283185307179586f * u2;
+      const float rad = __fsqrt_rn(-2.0f * __logf(u1));
+      float sn, cs;
+      __sincosf(th, &sn, &cs);
+      z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
+    }
+  }
+  float logp = 0.f;
+  float act[4], sd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int a = 4 * blk + j;
+    sd[j] = sd3[a];
+    act[j] = mu[j] + sd[j] * z[j];
+    if (a < A) {
+      const float t = (act[j] - mu[j]) * sd3[16 + a];
+      logp += -0.5f * (t * t) - sd3[32 + a] - 0.9189385332046727f;     // log(sqrt(2*pi))
+    }
+  }
+  const size_t o = (size_t)n * A + 4 * blk;
+  if ((A & 3) == 0) {      // rows are 16-byte aligned: one vector store per output
+    *reinterpret_cast<float4*>(p.action_mean + o) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    *reinterpret_cast<float4*>(p.actions + o) = make_float4(act[0], act[1], act[2], act[3]);
+    *reinterpret_cast<float4*>(p.action_sigma + o) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * blk + j < A) { p.action_mean[o + j] = mu[j]; p.actions[o + j] = act[j]; p.action_sigma[o + j] = sd[j]; }
+  }
+  return logp;
+}
+
 struct TcPlan;
 bool policy_tc_plan(const LgkPolicyParams* p, TcPlan* pl);
 long long policy_tc_workspace_bytes(const TcPlan& pl);

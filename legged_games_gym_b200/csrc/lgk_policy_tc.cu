@@ -4,24 +4,34 @@
 //   actor / critic = Linear(O,h0) ELU Linear(h0,h1) ELU Linear(h1,h2) ELU Linear(h2,A|1)
 //
 // One CTA owns a tile of 128 environments (= the 128 TMEM lanes) of ONE network and carries it through all four layers
-// without touching global memory in between:
+// without touching global memory in between.  Activations never leave TENSOR MEMORY: an accumulator block is drained
+// tcgen05.ld -> bias -> ELU -> TF32 -> tcgen05.st back into the SAME columns, and the next layer's MMAs take their A
+// operand from there (tcgen05.mma with A in TMEM: lane = row, one 32-bit column per k).  Only layer 1 reads its A
+// operand (the observation tile) from shared memory.
 //
-//   warps 0-15 stage the observation tile into shared memory (TF32, 128-byte swizzled K-major chunks of 32 columns),
-//              later drain accumulators TMEM -> registers (tcgen05.ld 32x32b; warp w reads lane quadrant w%4, the four
-//              warps of a quadrant split the columns), add bias, ELU, round to TF32 and write the next layer's A
-//              operand back into the same chunks; the last drain feeds the h2->A layer on FP32 FFMA, then Normal
-//              sampling (Philox ACT stream) / log-prob / value.
-//   warp 16    streams pre-packed weight tiles (<=128 rows x 32 k, already swizzled + TF32-rounded by
-//              policy_pack_kernel) through a 5-stage 16 KB ring with TMA bulk copies (cp.async.bulk + mbarrier tx).
-//   warp 17    owns TMEM (512 columns) and issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=128, K=8) from one
-//              thread; tcgen05.commit releases ring stages and signals finished accumulations.
+// What the shape of the kernel follows from (profiles/umma_rate_probe.cu, measured on B200): one tcgen05.mma
+// kind::tf32 M=128 K=8 takes 126 cycles for ANY N <= 128, 138 cycles for N = 256 with A in TMEM and 171 cycles for
+// N = 256 with A in shared memory -- so every MMA is issued as wide as the layer allows (N = h0/2, h1, h2); and one
+// cp.async.bulk costs its issuing thread ~270 cycles whatever its size, so weight tiles are as large as the ring allows
+// (<= 256 rows x 32 k = 32 KB: 110 B/cycle/SM from L2, against 60 for 16 KB tiles).
 //
-// Accumulator schedule in TMEM (fp32, one column per output feature), default 512-256-128 nets:
-//   L1 -> cols [0,h0)   drain cols [0,h0/2) -> A   L2a (k < h0/2) -> cols [0,h1)
-//                       drain cols [h0/2,h0) -> A  L2b (k >= h0/2) accumulates into cols [0,h1)
-//   drain [0,h1) -> A   L3 -> cols [h0/2, h0/2+h2)  final drain.
-// The A buffer (128 rows x 256 k x 4 B = 128 KB) is reused by every layer; 128 KB A + 80 KB ring + 14 KB constants
-// fit the 227 KB of one SM.
+//   warps 0-15 stage the observation tile into shared memory (TF32, 128-byte swizzled K-major chunks of 32 columns; each
+//              chunk is released to the tensor pipe as soon as it is complete), later drain accumulator blocks in place
+//              (warp w owns lane quadrant w%4, the four warps of a quadrant split the 32-column blocks); the last drain
+//              feeds the h2->A layer on FP32 FFMA, then Normal sampling (Philox ACT stream) / log-prob / value.
+//   warp 16    streams pre-packed weight tiles (<=256 rows x 32 k, already swizzled + TF32-rounded by
+//              policy_pack_kernel) through a 3-stage 32 KB ring with TMA bulk copies (cp.async.bulk + mbarrier tx).
+//   warp 17    owns TMEM (512 columns) and issues tcgen05.mma.cta_group::1.kind::tf32 from one thread, walking the tile
+//              schedule the host built (TcPlan::sched); tcgen05.commit releases ring stages and signals finished
+//              accumulator blocks.
+//
+// TMEM columns (fp32 accumulators / TF32 activations), H = h0/2, G = H/2; default 512-256-128 nets: H = 256, G = 128:
+//   S = [0,H)  one half of layer 1's columns at a time      ACC2 = [H, H+h1)  layer-2 accumulators      layer 3 -> [0,h2)
+//   tensor pipe: L1a>S | L2a(A=S group 0) L2a(A=S group 1) | L1b>S | L2b(g0) L2b(g1) | L3(A=ACC2 g0) L3(A=ACC2 g1)
+//   epilogue   :        drain S g0, g1 (in place)                   drain S g0, g1     drain ACC2 g0, g1     final layer
+// Layer 2 accumulates one k-group at a time as its inputs appear, so a drain of G columns (not of the whole block) is what
+// the tensor pipe waits for.  The MMAs of one thread execute in issue order, which is what makes the reuse of S safe
+// (L1b overwrites S only after L2a has read it).
 //
 // Numerics: TF32 operands rounded to nearest (cvt.rna), FP32 accumulation in TMEM, biases / ELU / last layer / sampling
 // in FP32: within the north_star's 1e-3 for policy outputs (tests/test_gpu_parity.py).
@@ -35,9 +45,9 @@ namespace lgk {
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                     // fp32 per 128-byte swizzle row
 constexpr int kChunkBytes = kTileM * 128;       // one A chunk: [128 rows][32 k] = 16 KB
-constexpr int kMaxChunks = 8;                   // K <= 256 per accumulation phase
-constexpr int kStageBytes = 16384;              // one weight tile: <= 128 rows x 128 B
-constexpr int kStages = 5;
+constexpr int kMaxChunks = 8;                   // observation width <= 256
+constexpr int kStageBytes = 32768;              // one weight tile: <= 256 rows x 128 B
+constexpr int kStages = 3;
 constexpr int kColSplit = 4;                     // warps per TMEM lane quadrant: they split the accumulator columns
 constexpr int kEpiWarps = 4 * kColSplit, kEpiThreads = 32 * kEpiWarps;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
@@ -46,41 +56,84 @@ constexpr int kMaxH2 = 128;
 constexpr int kMaxOut = 16;
 constexpr int kTmemCols = 512;
 
-// shared-memory carve-up (offsets from a 1024-byte aligned base)
+// shared-memory carve-up (offsets from a 1024-byte aligned base).  Biases are read from global memory (uniform 16-byte
+// loads, L1-resident) and the transposed last layer is loaded into the observation buffer once layer 1 has consumed it, so
+// that the tile + a three-stage ring of 32 KB weight tiles fit.
 constexpr int kOffA = 0;
 constexpr int kOffRing = kOffA + kMaxChunks * kChunkBytes;            // 131072
-constexpr int kOffW4 = kOffRing + kStages * kStageBytes;              // 212992: [h2][16] fp32, transposed last layer
-constexpr int kOffBias = kOffW4 + kMaxH2 * kMaxOut * 4;               // b1[512] b2[256] b3[128] b4[16] std[16]
-constexpr int kBiasFloats = 512 + 256 + 128 + 16 + 16;
-constexpr int kOffBar = kOffBias + kBiasFloats * 4;
-constexpr int kSmemBytes = kOffBar + 128 + 1024;                      // + barriers + alignment slack
+constexpr int kOffSched = kOffRing + kStages * kStageBytes;           // 229376: IssueRec[kTcMaxTiles]
+constexpr int kOffMisc = kOffSched + kTcMaxTiles * 32;                // b4[16] std[16]
+constexpr int kOffBar = kOffMisc + 256;                              // b4[16] | std[16] 1/std[16] log std[16]
+constexpr int kSmemBytes = kOffBar + 256 + 1024;                      // + barriers + alignment slack
+static_assert(kSmemBytes <= 232448, "policy_tc_kernel: shared memory budget");
+// inside the (dead) observation buffer, after layer 1: partial sums of the last layer [4][16][128] fp32 + partial log-probs
+// [4][128], then W4^T [h2][16]
+constexpr int kOffPartial = 0;
+constexpr int kOffW4 = 36864;
 
-static inline int tile_rows(int n) { return n < 128 ? n : 128; }
+// barrier ids of the schedule (TcTile::wait_bar / commit_bar are 1 + id)
+enum { kWaitChunk0 = 0, kWaitAct = 8, kWaitAct2 = 10, kNumWaitBars = 12 };     // obs chunk c | S group g activated | ACC2 group g activated
+enum { kCommitS = 0, kCommitAcc = 1 };
+
+static int build_schedule(TcPlan* pl, int net) {
+  TcTile* out = pl->sched[net];
+  int n = 0;
+  const int H = pl->q, G = H / 2, h1 = pl->h1, h2 = pl->h2, O = pl->o[net], kc1 = pl->kc1[net];
+  auto put = [&](int a, int d_col, int rows, int ksteps, bool ts, bool first, int wait_bar, int wait_par, int commit_bar,
+                 int layer, int n0, int k0) {
+    TcTile t;
+    t.a = (uint16_t)a; t.d_col = (uint16_t)d_col; t.rows = (uint16_t)rows; t.ksteps = (uint8_t)ksteps;
+    t.flags = (uint8_t)((ts ? 1 : 0) | (first ? 2 : 0));
+    t.wait_bar = (uint8_t)wait_bar; t.wait_par = (uint8_t)wait_par; t.commit_bar = (uint8_t)commit_bar;
+    t.layer = (uint8_t)layer; t.n0 = (uint16_t)n0; t.k0 = (uint16_t)k0;
+    out[n++] = t;
+  };
+  auto l1 = [&](int half) {     // layer-1 columns [half*H, (half+1)*H) into S, A = observation chunks in shared memory
+    for (int kc = 0; kc < kc1; ++kc) {
+      const int left = O - kc * kChunkK;
+      const int ks = left >= kChunkK ? 4 : (left + 7) / 8;
+      put(kc, 0, H, ks, false, kc == 0, half == 0 ? 1 + kWaitChunk0 + kc : 0, 0, kc == kc1 - 1 ? 1 + kCommitS : 0, 0,
+          half * H, kc * kChunkK);
+    }
+  };
+  auto l2 = [&](int half) {     // layer-2 partial sums over k in [half*H, (half+1)*H), A = the activated groups of S in TMEM
+    for (int g = 0; g < 2; ++g)
+      for (int kc = 0; kc < G / kChunkK; ++kc)
+        put(g * G + kc * kChunkK, H, h1, 4, true, half == 0 && g == 0 && kc == 0, kc == 0 ? 1 + kWaitAct + g : 0, half,
+            (half == 1 && g == 1 && kc == G / kChunkK - 1) ? 1 + kCommitAcc : 0, 1, 0, half * H + g * G + kc * kChunkK);
+  };
+  l1(0); l2(0); l1(1); l2(1);
+  const int g2 = h1 / 2;        // layer 3: A = the activated groups of ACC2, accumulators at column 0 (S is free)
+  for (int g = 0; g < 2; ++g)
+    for (int kc = 0; kc < g2 / kChunkK; ++kc)
+      put(H + g * g2 + kc * kChunkK, 0, h2, 4, true, g == 0 && kc == 0, kc == 0 ? 1 + kWaitAct2 + g : 0, 0,
+          (g == 1 && kc == g2 / kChunkK - 1) ? 1 + kCommitAcc : 0, 2, 0, g * g2 + kc * kChunkK);
+  return n;
+}
 
 // returns false when the shape does not fit this kernel (the FP32 path in lgk_policy.cu handles it)
 bool policy_tc_plan(const LgkPolicyParams* p, TcPlan* pl) {
   const int h0 = p->hidden[0], h1 = p->hidden[1], h2 = p->hidden[2];
   if (h0 <= 0 || h1 <= 0 || h2 <= 0) return false;
-  if (h0 % 64 != 0 || h0 > 512) return false;
-  const int half = h0 / 2;
-  if (h1 % 32 != 0 || h1 > half) return false;
-  if (h2 % 32 != 0 || h2 > kMaxH2 || half + h2 > kTmemCols) return false;
+  if (h0 % 128 != 0 || h0 > 512) return false;                 // halves of 64..256 columns, drained in groups of 32..128
+  const int H = h0 / 2;
+  if (h1 % 64 != 0 || h1 > 256 || H + h1 > kTmemCols) return false;
+  if (h2 % 32 != 0 || h2 > kMaxH2 || h2 > H) return false;
   if (p->num_actions < 1 || p->num_actions > kMaxOut) return false;
   if (p->num_obs < 1 || p->num_obs > kMaxChunks * kChunkK || p->num_critic_obs < 1 || p->num_critic_obs > kMaxChunks * kChunkK) return false;
-  const int nb1 = tile_rows(half), nb2 = tile_rows(h1), nb3 = tile_rows(h2);
-  if (half % nb1 || h1 % nb2 || h2 % nb3 || nb1 % 16 || nb2 % 16 || nb3 % 16) return false;
+  for (int i = 0; i < 3; ++i)                                   // biases are read with 16-byte loads
+    if ((reinterpret_cast<uintptr_t>(p->actor_b[i]) & 15u) || (reinterpret_cast<uintptr_t>(p->critic_b[i]) & 15u)) return false;
   pl->o[0] = p->num_obs; pl->o[1] = p->num_critic_obs;
-  pl->h0 = h0; pl->h1 = h1; pl->h2 = h2; pl->half = half; pl->nact = p->num_actions;
-  pl->nb1 = nb1; pl->nb2 = nb2; pl->nb3 = nb3;
-  pl->t2 = 2 * (h1 / nb2) * (half / kChunkK);
-  pl->t3 = (h2 / nb3) * (h1 / kChunkK);
+  pl->h0 = h0; pl->h1 = h1; pl->h2 = h2; pl->q = H; pl->nact = p->num_actions;
   long long off = 0;
   for (int net = 0; net < 2; ++net) {
     pl->kc1[net] = (pl->o[net] + kChunkK - 1) / kChunkK;
-    pl->t1[net] = 2 * (half / nb1) * pl->kc1[net];
-    pl->net_bytes[net] = 128LL * ((long long)pl->t1[net] * nb1 + (long long)pl->t2 * nb2 + (long long)pl->t3 * nb3);
+    pl->ntiles[net] = build_schedule(pl, net);
+    long long bytes = 0;
+    for (int t = 0; t < pl->ntiles[net]; ++t) bytes += 128LL * pl->sched[net][t].rows;
+    pl->net_bytes[net] = bytes;
     pl->net_off[net] = off;
-    off += pl->net_bytes[net];
+    off += bytes;
   }
   return true;
 }
@@ -154,36 +207,53 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 
+// A operand from tensor memory (lane = row, 32-bit column per k): D[tmem] (+)= A[tmem] x B[smem]
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ------------------------------------------------------------------ weight packing
-// job j = net*3 + layer.  Tile order == the order the MMA warp consumes tiles:
-//   layer 0 : half (0,1) | n-block | k-chunk              rows nb1, K = O
-//   layer 1 : k-part (0,1) | n-block | k-chunk in part    rows nb2, K = h0
-//   layer 2 : n-block | k-chunk                           rows nb3, K = h1
-// A tile is the shared-memory image itself: row r holds 32 consecutive k as eight 16-byte chunks, logical chunk c at
-// physical chunk c ^ (r & 7) (128-byte swizzle), values rounded to TF32, zero beyond K.
+// One block per tile of the schedule.  A tile is the shared-memory image itself: row r holds 32 consecutive k as eight
+// 16-byte chunks, logical chunk c at physical chunk c ^ (r & 7) (128-byte swizzle), values rounded to TF32, zero beyond K.
 struct PackJobs {
-  const float* w[6];
-  float* dst[6];
-  int n[6], k[6], nb[6], tiles[6], kchunks[6], nblks[6];
+  const float* w[6];        // [net*3 + layer]
+  int k[6];                 // input width of that matrix
+  float* dst[2];            // packed image of each net
+  int ntiles[2];
+  uint32_t off[2][kTcMaxTiles];      // float offset of each tile inside its net's image
+  TcTile sched[2][kTcMaxTiles];
 };
 
 __global__ void __launch_bounds__(256) policy_pack_kernel(const __grid_constant__ PackJobs jobs) {
-  const int j = blockIdx.y, layer = j % 3;
-  const int nb = jobs.nb[j], K = jobs.k[j], kch = jobs.kchunks[j], nblks = jobs.nblks[j];
-  const long long total = (long long)jobs.tiles[j] * nb * kChunkK;
-  const float* __restrict__ W = jobs.w[j];
-  float* __restrict__ dst = jobs.dst[j];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(i % (nb * kChunkK)), t = (int)(i / (nb * kChunkK));
+  const int net = blockIdx.y, t = blockIdx.x;
+  if (t >= jobs.ntiles[net]) return;
+  const TcTile T = jobs.sched[net][t];
+  const float* __restrict__ W = jobs.w[net * 3 + T.layer];
+  const int K = jobs.k[net * 3 + T.layer];
+  float* __restrict__ dst = jobs.dst[net] + jobs.off[net][t];
+  const int total = T.rows * kChunkK;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int row = e >> 5, pc = (e >> 2) & 7, w = e & 3;
     const int lc = pc ^ (row & 7);
-    const int outer = t / (nblks * kch), rem = t % (nblks * kch);     // half (layer 0) / k-part (layer 1) / 0 (layer 2)
-    const int nblk = rem / kch, kc = rem % kch;
-    int n, k;
-    if (layer == 0) { n = outer * (nblks * nb) + nblk * nb + row; k = kc * kChunkK + lc * 4 + w; }
-    else if (layer == 1) { n = nblk * nb + row; k = (outer * kch + kc) * kChunkK + lc * 4 + w; }
-    else { n = nblk * nb + row; k = kc * kChunkK + lc * 4 + w; }
-    dst[i] = (k < K) ? to_tf32(W[(size_t)n * K + k]) : 0.f;
+    const int n = T.n0 + row, k = T.k0 + lc * 4 + w;
+    dst[e] = (k < K) ? to_tf32(W[(size_t)n * K + k]) : 0.f;
   }
 }
 
@@ -197,13 +267,28 @@ struct TcArgs {
   int net0;                   // first network of the grid's y dimension (0 actor, 1 critic): LgkPolicyParams.nets
 };
 
+// What the issuing thread needs for one tile, precomputed at kernel start by the other threads: a single tcgen05.mma issue
+// blocks its thread for ~125 cycles and everything else that thread does between MMAs is time the tensor pipe idles
+// (profiles/umma_rate_probe.cu, issue-loop section), so the loop is two 16-byte loads, the waits, the MMAs and the commits.
+struct __align__(16) IssueRec {
+  uint32_t d_tmem;        // accumulator address
+  uint32_t idesc;
+  uint32_t a_lo;          // TS: TMEM address of the first k; SS: low word of the A descriptor (k-step = +2)
+  uint32_t b_lo;          // low word of the B descriptor of the tile's ring stage (k-step = +2)
+  uint32_t wait_addr;     // 0: none; else shared address of the barrier to wait on before the tile, parity in bit 0 (barriers are 8-byte aligned)
+  uint32_t commit_addr;   // 0: none; else barrier committed after the tile (besides the stage's empty barrier)
+  uint32_t full_addr;     // the stage's full barrier, parity in bit 0
+  uint32_t misc;          // bits 0-2 ksteps | bit 3 TS | bit 4 first MMA overwrites | bits 8.. bytes of the tile / 128 (rows)
+};
+static_assert(sizeof(IssueRec) == 32, "IssueRec is 32 bytes");
+constexpr uint32_t kDescHi = (uint32_t)(((uint64_t)(1024 >> 4) << 32 | (1ull << 46) | (2ull << 61)) >> 32);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
+
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
-}
-__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void sts_f1(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
@@ -220,43 +305,79 @@ __device__ __forceinline__ float elu_fast(float x) {
   return x > 0.f ? x : e - 1.0f;
 }
 
-// drain accumulator column blocks cb = part, part + kColSplit, ... (32 columns each) of `ncols` columns starting at TMEM
-// column col0 into A chunks cb: + bias, ELU, round to TF32, 128-byte swizzled row
-__device__ __forceinline__ void drain_to_a(uint32_t tmem_lane_base, int part, int row, int col0, int ncols,
-                                           uint32_t bias_addr, uint32_t abuf_addr) {
-  for (int cb = part; cb < ncols / 32; cb += kColSplit) {
-    uint32_t v[32];
-    tmem_ld32(tmem_lane_base + (uint32_t)(col0 + cb * 32), v);
-    const uint32_t rowp = abuf_addr + cb * kChunkBytes + row * 128;
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// biases of one 32-column block (global memory, 16-byte aligned): loaded ahead of the wait for the accumulators
+struct Bias32 { float4 b[8]; };
+__device__ __forceinline__ void load_bias32(Bias32& B, const float* __restrict__ bias, bool active) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b = lds_f4(bias_addr + (cb * 32 + 4 * q) * 4);
-      float4 o;
-      o.x = to_tf32(elu_fast(__uint_as_float(v[4 * q + 0]) + b.x));
-      o.y = to_tf32(elu_fast(__uint_as_float(v[4 * q + 1]) + b.y));
-      o.z = to_tf32(elu_fast(__uint_as_float(v[4 * q + 2]) + b.z));
-      o.w = to_tf32(elu_fast(__uint_as_float(v[4 * q + 3]) + b.w));
-      sts_f4(rowp + ((q ^ (row & 7)) << 4), o);
+  for (int q4 = 0; q4 < 8; ++q4) B.b[q4] = active ? ldg_f4(bias + 4 * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// activate the 32 accumulator columns at `taddr` IN PLACE: + bias, ELU, round to TF32, store back to the same columns,
+// where the next layer's MMAs read them as their A operand
+__device__ __forceinline__ void drain_block_in_place(uint32_t taddr, const Bias32& B) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    v[4 * q4 + 0] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 0]) + B.b[q4].x)));
+    v[4 * q4 + 1] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 1]) + B.b[q4].y)));
+    v[4 * q4 + 2] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 2]) + B.b[q4].z)));
+    v[4 * q4 + 3] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 3]) + B.b[q4].w)));
+  }
+  tmem_st32(taddr, v);
+  tmem_st_wait();
+}
+
+// a group of `ncols` (<= 128) columns at TMEM column col0: this warp owns block `part` of its lane quadrant
+__device__ __forceinline__ void drain_group(uint32_t tmem_lane_base, int part, int col0, int ncols, const Bias32& B) {
+  if (part * 32 < ncols) drain_block_in_place(tmem_lane_base + (uint32_t)(col0 + part * 32), B);
+}
+
+// last layer for this thread's 32 hidden columns: acc[o] += elu(h) * W4^T[k][o], NQ float4 groups of outputs
+// last layer for this thread's 32 hidden columns: acc[o] += elu(h) * W4^T[k][o] for 4*NQ outputs, two outputs per packed
+// FFMA2 (acc2[j] = outputs 2j, 2j+1)
+template <int NQ>
+__device__ __forceinline__ void last_layer_block(const uint32_t (&v)[32], const float* __restrict__ b3, uint32_t w4t_addr,
+                                                 f2_t (&acc2)[kMaxOut / 2]) {
+#pragma unroll
+  for (int jj = 0; jj < 32; jj += 4) {
+    const float4 b = ldg_f4(b3 + jj);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float h = elu_fast(__uint_as_float(v[jj + u]) + bb[u]);
+      const f2_t hh = pack2(h, h);
+      const uint32_t wr = w4t_addr + (jj + u) * kMaxOut * 4;
+#pragma unroll
+      for (int g = 0; g < NQ; ++g) {
+        f2_t w01, w23;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w01), "=l"(w23) : "r"(wr + 16 * g));
+        acc2[2 * g] = fma2(hh, w01, acc2[2 * g]);
+        acc2[2 * g + 1] = fma2(hh, w23, acc2[2 * g + 1]);
+      }
     }
   }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);     // 128-byte swizzle atoms need 1024-byte alignment
   const uint32_t s_base = smem_addr(smem);
   const uint32_t abuf = s_base + kOffA, ring = s_base + kOffRing;
-  float* s_w4t = reinterpret_cast<float*>(smem + kOffW4);
-  float* s_b1 = reinterpret_cast<float*>(smem + kOffBias);
-  float* s_b2 = s_b1 + 512;
-  float* s_b3 = s_b2 + 256;
-  float* s_b4 = s_b3 + 128;
+  float* s_w4t = reinterpret_cast<float*>(smem + kOffA + kOffW4);       // valid once layer 1 is done with the tile
+  float* s_b4 = reinterpret_cast<float*>(smem + kOffMisc);
   float* s_std = s_b4 + 16;
-  const uint32_t a_b1 = s_base + kOffBias, a_b2 = a_b1 + 512 * 4, a_b3 = a_b2 + 256 * 4, a_w4t = s_base + kOffW4;
+  const uint32_t a_w4t = abuf + kOffW4, a_partial = abuf + kOffPartial;
+  IssueRec* s_rec = reinterpret_cast<IssueRec*>(smem + kOffSched);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   const uint32_t bar_full = smem_addr(bars), bar_empty = bar_full + 8 * kStages;
-  const uint32_t bar_acc = bar_full + 16 * kStages, bar_a = bar_acc + 8;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  const uint32_t bar_s = bar_empty + 8 * kStages;              // a half of layer 1 accumulated into S
+  const uint32_t bar_acc = bar_s + 8;                          // layer 2 done / layer 3 done
+  const uint32_t bar_wait = bar_acc + 8;                       // [kNumWaitBars] what the issuer waits for: obs chunks, activated groups
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 + kNumWaitBars);
 
   const LgkPolicyParams& p = a.p;
   const TcPlan& pl = a.pl;
@@ -265,7 +386,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   const int m0 = blockIdx.x * kTileM;
   const int N = p.num_envs;
   const int O = pl.o[net], kc1 = pl.kc1[net];
-  const int h0 = pl.h0, h1 = pl.h1, h2 = pl.h2, half = pl.half;
+  const int h1 = pl.h1, h2 = pl.h2, H = pl.q, G = pl.q / 2;
+  const int ntiles = pl.ntiles[net];
   const int nout = net ? 1 : pl.nact;
   const float* const* Wg = net ? p.critic_w : p.actor_w;
   const float* const* Bg = net ? p.critic_b : p.actor_b;
@@ -273,31 +395,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   // ---- one-time setup
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_s, 1);
     mbar_init(bar_acc, 1);
-    mbar_init(bar_a, kEpiThreads);
+    for (int c = 0; c < kMaxChunks; ++c) mbar_init(bar_wait + 8 * (kWaitChunk0 + c), kEpiThreads);
+    for (int g = 0; g < 2; ++g) { mbar_init(bar_wait + 8 * (kWaitAct + g), kEpiThreads); mbar_init(bar_wait + 8 * (kWaitAct2 + g), kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"((uint32_t)kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // constants: biases, transposed last layer [k][16]
-  for (int i = tid; i < h0; i += kTcThreads) s_b1[i] = Bg[0][i];
-  for (int i = tid; i < h1; i += kTcThreads) s_b2[i] = Bg[1][i];
-  for (int i = tid; i < h2; i += kTcThreads) s_b3[i] = Bg[2][i];
-  if (tid < kMaxOut) { s_b4[tid] = tid < nout ? Bg[3][tid] : 0.f; s_std[tid] = (net == 0 && tid < nout) ? p.std[tid] : 1.f; }
-  for (int i = tid; i < h2 * kMaxOut; i += kTcThreads) {
-    const int k = i >> 4, o = i & 15;
-    s_w4t[i] = o < nout ? Wg[3][(size_t)o * h2 + k] : 0.f;
+  if (tid < kMaxOut) {
+    const float sd = (net == 0 && tid < nout) ? p.std[tid] : 1.f;
+    s_b4[tid] = tid < nout ? Bg[3][tid] : 0.f;
+    s_std[tid] = sd; s_std[16 + tid] = 1.0f / sd; s_std[32 + tid] = logf(sd);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  // phase stamps of CTA (0,0): 0 setup done | 1 obs staged | 2 L1 done | 3 drain 1 | 4 L2a done | 5 drain 2 | 6 L2b done |
-  // 7 drain 3 | 8 L3 done | 9 outputs written
+  if (tid < ntiles) {   // tile schedule -> issue records (needs the TMEM base)
+    const TcTile T = pl.sched[net][tid];
+    const int s = tid % kStages;
+    IssueRec r;
+    r.d_tmem = tmem_base + T.d_col;
+    r.idesc = make_idesc(T.rows);
+    r.a_lo = (T.flags & 1) ? tmem_base + T.a : desc_lo(abuf + T.a * kChunkBytes);
+    r.b_lo = desc_lo(ring + s * kStageBytes);
+    r.wait_addr = T.wait_bar ? ((bar_wait + 8 * (T.wait_bar - 1)) | (uint32_t)T.wait_par) : 0u;
+    r.commit_addr = T.commit_bar ? (T.commit_bar - 1 == kCommitS ? bar_s : bar_acc) : 0u;
+    r.full_addr = (bar_full + 8 * s) | (uint32_t)((tid / kStages) & 1);
+    r.misc = (uint32_t)T.ksteps | ((T.flags & 1) ? 8u : 0u) | ((T.flags & 2) ? 16u : 0u) | ((uint32_t)T.rows << 8);
+    s_rec[tid] = r;
+  }
+  __syncthreads();
+  // phase stamps of CTA (0,0): 0 setup done | 1 obs staged | 2 L1a accumulated | 3, 4 its groups activated | 5 L1b accumulated |
+  // 6, 7 its groups activated | 8 layer 2 done | 9, 10 its groups activated | 11 layer 3 done | 12 last layer summed | 13 outputs written
   auto stamp = [&](int slot) {
-    if (a.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0)) {
+    if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0)) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
       a.timeline[slot] = (long long)t;
@@ -311,173 +446,205 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
     const int quad = warp & 3, part = warp >> 2;
     const int row = quad * 32 + lane;                       // TMEM lane == row of the tile
     const uint32_t tmem_lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    {   // observation tile -> A chunks (coalesced 128-byte row segments; lane = k inside the chunk); four rows per pass
-        // so that up to 32 independent loads are in flight per thread
+    {   // observation tile -> A chunks (coalesced 128-byte row segments; lane = k inside the chunk).  A warp owns 8 rows and
+        // issues the loads of four chunks at once (32 in flight per thread), then stores chunk by chunk: a chunk goes to the
+        // tensor pipe as soon as every warp has stored its rows of it.
       const float* __restrict__ X = net ? p.critic_obs : p.obs;
-      constexpr int kRowsPerWarp = kTileM / kEpiWarps, kRowsPerPass = 4;
-      for (int r0 = warp * kRowsPerWarp; r0 < (warp + 1) * kRowsPerWarp; r0 += kRowsPerPass) {
-        float vals[kRowsPerPass][kMaxChunks];
+      constexpr int kRowsPerWarp = kTileM / kEpiWarps, kHalfChunks = kMaxChunks / 2;
+      const int r0 = warp * kRowsPerWarp;
 #pragma unroll
-        for (int i = 0; i < kRowsPerPass; ++i) {
-          const int n = m0 + r0 + i;
-          const float* src = X + (size_t)n * O;
+      for (int hc = 0; hc < 2; ++hc) {          // chunks 0-3, then 4-7: the second half's loads fly under the first MMAs
+        float vals[kHalfChunks][kRowsPerWarp];
 #pragma unroll
-          for (int kc = 0; kc < kMaxChunks; ++kc) {
+        for (int c = 0; c < kHalfChunks; ++c) {
+          const int kc = hc * kHalfChunks + c;
+#pragma unroll
+          for (int i = 0; i < kRowsPerWarp; ++i) {
+            const int n = m0 + r0 + i;
             const int k = kc * kChunkK + lane;
-            vals[i][kc] = (kc < kc1 && n < N && k < O) ? __ldg(src + k) : 0.f;
+            vals[c][i] = (kc < kc1 && n < N && k < O) ? __ldg(X + (size_t)n * O + k) : 0.f;
           }
         }
 #pragma unroll
-        for (int i = 0; i < kRowsPerPass; ++i) {
-          const int r = r0 + i;
-          const uint32_t dstp = abuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
+        for (int c = 0; c < kHalfChunks; ++c) {
+          const int kc = hc * kHalfChunks + c;
+          if (kc < kc1) {
 #pragma unroll
-          for (int kc = 0; kc < kMaxChunks; ++kc)
-            if (kc < kc1) sts_f1(dstp + kc * kChunkBytes, to_tf32(vals[i][kc]));
+            for (int i = 0; i < kRowsPerWarp; ++i) {
+              const int r = r0 + i;
+              sts_f1(abuf + kc * kChunkBytes + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4, to_tf32(vals[c][i]));
+            }
+          }
         }
+        fence_proxy_async();                      // one generic->async proxy fence per half (it waits for the stores above)
+#pragma unroll
+        for (int c = 0; c < kHalfChunks; ++c)
+          if (hc * kHalfChunks + c < kc1) mbar_arrive(bar_wait + 8 * (kWaitChunk0 + hc * kHalfChunks + c));
       }
     }
     stamp(1);
-    fence_proxy_async();
-    mbar_arrive(bar_a);                                     // A ready #0 (layer-1 input)
 
-    mbar_wait(bar_acc, 0);                                  // L1 done (both halves)
-    tc_fence_after();
-    stamp(2);
-    drain_to_a(tmem_lane_base, part, row, 0, half, a_b1, abuf);
-    fence_proxy_async(); tc_fence_before();
-    stamp(3);
-    mbar_arrive(bar_a);                                     // A ready #1 (h1 columns [0, half))
-
-    mbar_wait(bar_acc, 1);                                  // L2a done: A consumed, cols [0,h1) hold partial sums
-    tc_fence_after();
-    stamp(4);
-    drain_to_a(tmem_lane_base, part, row, half, half, a_b1 + half * 4, abuf);
-    fence_proxy_async(); tc_fence_before();
-    stamp(5);
-    mbar_arrive(bar_a);                                     // A ready #2 (h1 columns [half, h0))
-
-    mbar_wait(bar_acc, 0);                                  // L2b done
-    tc_fence_after();
-    stamp(6);
-    drain_to_a(tmem_lane_base, part, row, 0, h1, a_b2, abuf);
-    fence_proxy_async(); tc_fence_before();
-    stamp(7);
-    mbar_arrive(bar_a);                                     // A ready #3 (layer-3 input)
-
-    mbar_wait(bar_acc, 1);                                  // L3 done: the A buffer is free again
+    // ---- layer 1, half by half: activate S in place, group by group, while the tensor pipe multiplies the groups already done
+    Bias32 B0, B1;
+    const bool act1 = part * 32 < G, act2 = part * 32 < h1 / 2;
+    for (int half = 0; half < 2; ++half) {
+      load_bias32(B0, Bg[0] + half * H + part * 32, act1);
+      load_bias32(B1, Bg[0] + half * H + G + part * 32, act1);
+      mbar_wait(bar_s, (uint32_t)half);
+      tc_fence_after();
+      stamp(2 + 3 * half);
+      drain_group(tmem_lane_base, part, 0, G, B0);
+      tc_fence_before();
+      mbar_arrive(bar_wait + 8 * (kWaitAct + 0));
+      stamp(3 + 3 * half);
+      drain_group(tmem_lane_base, part, G, G, B1);
+      tc_fence_before();
+      mbar_arrive(bar_wait + 8 * (kWaitAct + 1));
+      stamp(4 + 3 * half);
+    }
+    // layer 1 is done with the observation tile: its buffer takes the transposed last layer [k][16]
+    for (int i = tid; i < h2 * kMaxOut; i += kEpiThreads) {
+      const int k = i >> 4, o = i & 15;
+      s_w4t[i] = o < nout ? Wg[3][(size_t)o * h2 + k] : 0.f;
+    }
+    // ---- layer 2
+    load_bias32(B0, Bg[1] + part * 32, act2);
+    load_bias32(B1, Bg[1] + h1 / 2 + part * 32, act2);
+    mbar_wait(bar_acc, 0);
     tc_fence_after();
     stamp(8);
+    drain_group(tmem_lane_base, part, H, h1 / 2, B0);
+    tc_fence_before();
+    mbar_arrive(bar_wait + 8 * (kWaitAct2 + 0));
+    stamp(9);
+    drain_group(tmem_lane_base, part, H + h1 / 2, h1 / 2, B1);
+    tc_fence_before();
+    mbar_arrive(bar_wait + 8 * (kWaitAct2 + 1));
+    stamp(10);
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // s_w4t complete
+    mbar_wait(bar_acc, 1);                                  // layer 3 done
+    tc_fence_after();
+    stamp(11);
     // ---- last layer (h2 -> nout) on FP32 FFMA: every part sums its column blocks, parts 1.. hand their partial sums
-    //      to part 0 through the (now idle) A buffer, laid out [part-1][output][row]
-    float acc[kMaxOut];
+    //      to part 0 through the observation buffer, laid out [part-1][output][row]
+    f2_t acc2[kMaxOut / 2];
 #pragma unroll
-    for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.f;
+    for (int o = 0; o < kMaxOut / 2; ++o) acc2[o] = pack2(0.f, 0.f);
     for (int cb = part; cb < h2 / 32; cb += kColSplit) {
       uint32_t v[32];
-      tmem_ld32(tmem_lane_base + (uint32_t)(half + cb * 32), v);
-#pragma unroll
-      for (int jj = 0; jj < 32; jj += 4) {
-        const float4 b = lds_f4(a_b3 + (cb * 32 + jj) * 4);
-        const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float h = elu_fast(__uint_as_float(v[jj + u]) + bb[u]);
-          const uint32_t wr = a_w4t + (cb * 32 + jj + u) * kMaxOut * 4;
-          const float4 w0 = lds_f4(wr), w1 = lds_f4(wr + 16), w2 = lds_f4(wr + 32), w3 = lds_f4(wr + 48);
-          acc[0] = fmaf(h, w0.x, acc[0]); acc[1] = fmaf(h, w0.y, acc[1]); acc[2] = fmaf(h, w0.z, acc[2]); acc[3] = fmaf(h, w0.w, acc[3]);
-          acc[4] = fmaf(h, w1.x, acc[4]); acc[5] = fmaf(h, w1.y, acc[5]); acc[6] = fmaf(h, w1.z, acc[6]); acc[7] = fmaf(h, w1.w, acc[7]);
-          acc[8] = fmaf(h, w2.x, acc[8]); acc[9] = fmaf(h, w2.y, acc[9]); acc[10] = fmaf(h, w2.z, acc[10]); acc[11] = fmaf(h, w2.w, acc[11]);
-          acc[12] = fmaf(h, w3.x, acc[12]); acc[13] = fmaf(h, w3.y, acc[13]); acc[14] = fmaf(h, w3.z, acc[14]); acc[15] = fmaf(h, w3.w, acc[15]);
-        }
-      }
+      tmem_ld32(tmem_lane_base + (uint32_t)(cb * 32), v);
+      const uint32_t wa = a_w4t + cb * 32 * kMaxOut * 4;
+      if (nout <= 4) last_layer_block<1>(v, Bg[2] + cb * 32, wa, acc2);
+      else if (nout <= 12) last_layer_block<3>(v, Bg[2] + cb * 32, wa, acc2);
+      else last_layer_block<4>(v, Bg[2] + cb * 32, wa, acc2);
     }
+    float acc[kMaxOut];
+#pragma unroll
+    for (int o = 0; o < kMaxOut / 2; ++o) unpack2(acc2[o], acc[2 * o], acc[2 * o + 1]);
     tc_fence_before();
-    if (part > 0) {
+    // every part publishes its partial sums [part][output][row]; part b then owns the actions 4b..4b+3 of its rows (one
+    // Philox block, two Box-Muller pairs), part 3 adds the partial log-probs in a fixed order
 #pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) sts_f1(abuf + (((part - 1) * kMaxOut + o) * kTileM + row) * 4, acc[o]);
-    }
+    for (int o = 0; o < kMaxOut; ++o)
+      if (o < nout) sts_f1(a_partial + ((part * kMaxOut + o) * kTileM + row) * 4, acc[o]);
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-    if (part == 0) {
+    stamp(12);
+    const int n = m0 + row;
+    const uint32_t a_logp = a_partial + kColSplit * kMaxOut * kTileM * 4;         // [4][row]
+    if (net == 1) {
+      if (part == 0 && n < N) {
+        float t = s_b4[0];
 #pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) {
-        float t = acc[o] + s_b4[o];
-#pragma unroll
-        for (int q = 0; q < kColSplit - 1; ++q) t += lds_f1(abuf + ((q * kMaxOut + o) * kTileM + row) * 4);
-        acc[o] = t;
+        for (int pp = 0; pp < kColSplit; ++pp) t += lds_f1(a_partial + ((pp * kMaxOut) * kTileM + row) * 4);
+        p.values[n] = t;
       }
-      const int n = m0 + row;
-      if (n < N) {
-        if (net == 1) p.values[n] = acc[0];
-        else policy_finish_row<kMaxOut, true>(p, n, acc, s_std);
+    } else {
+      if (4 * part < nout) {
+        float mu[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = 4 * part + j;
+          float t = s_b4[o];
+#pragma unroll
+          for (int pp = 0; pp < kColSplit; ++pp) t += lds_f1(a_partial + ((pp * kMaxOut + o) * kTileM + row) * 4);
+          mu[j] = t;
+        }
+        const float lp = n < N ? policy_finish_quad(p, n, part, mu, s_std) : 0.f;
+        sts_f1(a_logp + (part * kTileM + row) * 4, lp);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (part == 3 && n < N) {
+        float lp = 0.f;
+#pragma unroll
+        for (int b = 0; b < kColSplit; ++b)
+          if (4 * b < nout) lp += lds_f1(a_logp + (b * kTileM + row) * 4);
+        p.actions_log_prob[n] = lp;
       }
     }
-    stamp(9);
+    stamp(13);
   } else if (warp == kProducerWarp) {
     // ================= weight-tile producer =================
     if (lane == 0) {
       const uint8_t* src = a.packed + pl.net_off[net];
-      const int ntiles[3] = {pl.t1[net], pl.t2, pl.t3};
-      const int bytes[3] = {pl.nb1 * 128, pl.nb2 * 128, pl.nb3 * 128};
-      int i = 0;
-      for (int ph = 0; ph < 3; ++ph) {
-        for (int t = 0; t < ntiles[ph]; ++t, ++i) {
-          const int s = i % kStages;
-          mbar_wait(bar_empty + 8 * s, ((i / kStages) & 1) ^ 1);
-          if (a.dbg_flags & 1) {
-            mbar_arrive(bar_full + 8 * s);
-          } else {
-            mbar_expect_tx(bar_full + 8 * s, (uint32_t)bytes[ph]);
-            bulk_g2s(ring + s * kStageBytes, src, (uint32_t)bytes[ph], bar_full + 8 * s);
-          }
-          src += bytes[ph];
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i % kStages;
+        const uint32_t bytes = (s_rec[i].misc >> 8) * 128u;
+        mbar_wait(bar_empty + 8 * s, ((i / kStages) & 1) ^ 1);
+        if (PROF && (a.dbg_flags & 1)) {
+          mbar_arrive(bar_full + 8 * s);
+        } else {
+          mbar_expect_tx(bar_full + 8 * s, bytes);
+          bulk_g2s(ring + s * kStageBytes, src, bytes, bar_full + 8 * s);
         }
+        src += bytes;
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================= MMA issuer =================
+    // ================= MMA issuer: walks the precomputed issue records =================
     if (lane == 0) {
-      int i = 0;
-      uint32_t a_par = 0;
-      const bool skip_mma = (a.dbg_flags & 2) != 0;
-      // one weight tile = one n-block x one 32-wide k-chunk: `ksteps` MMAs of K = 8
-      auto tile_mma = [&](int a_chunk, uint32_t d_col, int nb, bool first_k, int ksteps) {
-        const int s = i % kStages;
-        mbar_wait(bar_full + 8 * s, (i / kStages) & 1);
+      const bool skip_mma = PROF && (a.dbg_flags & 2) != 0;
+      long long c_bar = 0, c_full = 0, c_issue = 0, c_commit = 0;
+      uint32_t empty = bar_empty;
+      int stage = 0;
+      const uint4* recs = reinterpret_cast<const uint4*>(s_rec);
+      uint4 ra = recs[0], rb = recs[1];
+      for (int i = 0; i < ntiles; ++i) {
+        const uint32_t d = ra.x, idesc = ra.y, a_lo = ra.z, b_lo = ra.w;
+        const uint32_t wait_addr = rb.x, commit_addr = rb.y, full_addr = rb.z, misc = rb.w;
+        if (i + 1 < ntiles) { ra = recs[2 * i + 2]; rb = recs[2 * i + 3]; }      // next tile's record: in flight under this tile's MMAs
+        long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        if (PROF) t0 = clock64();
+        if (wait_addr) { mbar_wait(wait_addr & ~7u, wait_addr & 1u); }
+        if (PROF) t1 = clock64();
+        mbar_wait(full_addr & ~7u, full_addr & 1u);
         tc_fence_after();
-        const uint32_t idesc = make_idesc(nb);
+        if (PROF) t2 = clock64();
         if (!skip_mma) {
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ad = make_smem_desc(abuf + a_chunk * kChunkBytes + ks * 32);
-            const uint64_t bd = make_smem_desc(ring + s * kStageBytes + ks * 32);
-            mma_tf32(tmem_base + d_col, ad, bd, idesc, (first_k && ks == 0) ? 0u : 1u);
+          const int ksteps = (int)(misc & 7u);
+          const uint32_t acc0 = (misc & 16u) ? 0u : 1u;
+          if (misc & 8u) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ksteps) mma_tf32_ts(d, a_lo + ks * 8, desc_from_lo(b_lo + 2 * ks), idesc, ks == 0 ? acc0 : 1u);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ksteps) mma_tf32(d, desc_from_lo(a_lo + 2 * ks), desc_from_lo(b_lo + 2 * ks), idesc, ks == 0 ? acc0 : 1u);
           }
         }
-        tc_commit(bar_empty + 8 * s);                       // stage is free once these MMAs have read it
-        ++i;
-      };
-      // ---- L1: both halves into cols [0, h0)
-      mbar_wait(bar_a, a_par); a_par ^= 1; tc_fence_after();
-      const int last_ks = (O - (kc1 - 1) * kChunkK + 7) / 8;     // K-steps of the (zero-padded) last chunk that hold data
-      for (int hb = 0; hb < 2; ++hb)
-        for (int nb = 0; nb < half / pl.nb1; ++nb)
-          for (int kc = 0; kc < kc1; ++kc)
-            tile_mma(kc, (uint32_t)(hb * half + nb * pl.nb1), pl.nb1, kc == 0, kc == kc1 - 1 ? last_ks : 4);
-      tc_commit(bar_acc);
-      // ---- L2: two k-parts into cols [0, h1)
-      for (int part = 0; part < 2; ++part) {
-        mbar_wait(bar_a, a_par); a_par ^= 1; tc_fence_after();
-        for (int nb = 0; nb < h1 / pl.nb2; ++nb)
-          for (int kc = 0; kc < half / kChunkK; ++kc)
-            tile_mma(kc, (uint32_t)(nb * pl.nb2), pl.nb2, part == 0 && kc == 0, 4);
-        tc_commit(bar_acc);
+        if (PROF) t3 = clock64();
+        tc_commit(empty);                                   // stage is free once these MMAs have read it
+        if (commit_addr) tc_commit(commit_addr);
+        if (++stage == kStages) { stage = 0; empty = bar_empty; } else { empty += 8; }
+        if (PROF) {
+          const long long t4 = clock64();
+          c_bar += t1 - t0; c_full += t2 - t1; c_issue += t3 - t2; c_commit += t4 - t3;
+          if (blockIdx.x == 0 && blockIdx.y == 0) a.timeline[16 + i] = t2;      // cycle stamp of the tile's start
+        }
       }
-      // ---- L3 into cols [half, half + h2)
-      mbar_wait(bar_a, a_par); a_par ^= 1; tc_fence_after();
-      for (int nb = 0; nb < h2 / pl.nb3; ++nb)
-        for (int kc = 0; kc < h1 / kChunkK; ++kc)
-          tile_mma(kc, (uint32_t)(half + nb * pl.nb3), pl.nb3, kc == 0, 4);
-      tc_commit(bar_acc);
+      if (PROF && blockIdx.x == 0 && blockIdx.y == 0) {
+        a.timeline[100] = c_bar; a.timeline[101] = c_full; a.timeline[102] = c_issue; a.timeline[103] = c_commit;
+      }
     }
   }
   __syncthreads();
@@ -514,22 +681,22 @@ int policy_tc_launch(const LgkPolicyParams* p, const TcPlan& pl, cudaStream_t st
   }
   if (!cached) {
     PackJobs jobs;
+    int max_tiles = 0;
     for (int net = 0; net < 2; ++net) {
       const float* const* W = net ? p->critic_w : p->actor_w;
-      float* dst = reinterpret_cast<float*>(base + pl.net_off[net]);
-      const int nbs[3] = {pl.nb1, pl.nb2, pl.nb3};
-      const int tiles[3] = {pl.t1[net], pl.t2, pl.t3};
-      const int ns[3] = {pl.h0, pl.h1, pl.h2}, ks[3] = {pl.o[net], pl.h0, pl.h1};
-      const int kch[3] = {pl.kc1[net], pl.half / kChunkK, pl.h1 / kChunkK};
-      const int nblks[3] = {pl.half / pl.nb1, pl.h1 / pl.nb2, pl.h2 / pl.nb3};
-      for (int l = 0; l < 3; ++l) {
-        const int j = net * 3 + l;
-        jobs.w[j] = W[l]; jobs.dst[j] = dst; jobs.n[j] = ns[l]; jobs.k[j] = ks[l]; jobs.nb[j] = nbs[l];
-        jobs.tiles[j] = tiles[l]; jobs.kchunks[j] = kch[l]; jobs.nblks[j] = nblks[l];
-        dst += (size_t)tiles[l] * nbs[l] * kChunkK;
+      const int ks[3] = {pl.o[net], pl.h0, pl.h1};
+      for (int l = 0; l < 3; ++l) { jobs.w[net * 3 + l] = W[l]; jobs.k[net * 3 + l] = ks[l]; }
+      jobs.dst[net] = reinterpret_cast<float*>(base + pl.net_off[net]);
+      jobs.ntiles[net] = pl.ntiles[net];
+      uint32_t off = 0;
+      for (int t = 0; t < pl.ntiles[net]; ++t) {
+        jobs.sched[net][t] = pl.sched[net][t];
+        jobs.off[net][t] = off;
+        off += (uint32_t)pl.sched[net][t].rows * kChunkK;
       }
+      if (pl.ntiles[net] > max_tiles) max_tiles = pl.ntiles[net];
     }
-    policy_pack_kernel<<<dim3(74, 6), 256, 0, st>>>(jobs);
+    policy_pack_kernel<<<dim3(max_tiles, 2), 256, 0, st>>>(jobs);
     count_launch();
     if (int rc = check_cuda(cudaGetLastError(), "policy_pack_kernel launch")) return rc;
     if (p->weights_version != 0) {
@@ -538,12 +705,14 @@ int policy_tc_launch(const LgkPolicyParams* p, const TcPlan& pl, cudaStream_t st
       g_pack[p->workspace] = want;
     }
   }
-  if (int rc = ensure_func_attr(reinterpret_cast<const void*>(policy_tc_kernel), kSmemBytes, "policy_tc_kernel")) return rc;
+  const bool prof = g_timeline != nullptr;
+  auto kern = prof ? policy_tc_kernel<true> : policy_tc_kernel<false>;
+  if (int rc = ensure_func_attr(reinterpret_cast<const void*>(kern), kSmemBytes, "policy_tc_kernel")) return rc;
   TcArgs args;
   args.p = *p; args.pl = pl; args.packed = base; args.timeline = g_timeline; args.dbg_flags = g_dbg_flags;
   args.net0 = p->nets == 2 ? 1 : 0;
   const int nets = (p->nets == 1 || p->nets == 2) ? 1 : 2;
-  policy_tc_kernel<<<dim3((p->num_envs + kTileM - 1) / kTileM, nets), kTcThreads, kSmemBytes, st>>>(args);
+  kern<<<dim3((p->num_envs + kTileM - 1) / kTileM, nets), kTcThreads, kSmemBytes, st>>>(args);
   count_launch();
   return check_cuda(cudaGetLastError(), "policy_tc_kernel launch");
 }

@@ -587,6 +587,37 @@ def test_host_sim_state_step_replays_inside_the_graph(mode, monkeypatch):
     assert fh.h2d_bytes > 0 and fh.d2h_bytes > 0
 
 
+def test_host_result_mirror_delivers_every_step_in_order():
+    """bench.py's pipelined e2e loop: step k's observations / rewards / reset flags are downloaded on a copy stream while
+    step k+1 runs.  Each wait(k) must return exactly what the env held after step k (the env rewrites its buffers in
+    place, so a mirror that read them late would return step k+1's values)."""
+    import bench
+    from legged_games_gym_b200.sim.result_mirror import HostResultMirror
+    bench.USE_GRAPH = True
+    env, f = bench.make_env(1024, DEV, host_sim=True)
+    mirror = HostResultMirror(env, depth=2)
+    acts = f.synthetic_actions
+    want = []
+    g = torch.Generator().manual_seed(7)
+    for k in range(7):
+        env.step(acts)
+        assert mirror.push() == k
+        want.append((env.obs_buf.clone(), env.rew_buf.clone(), env.reset_buf.clone()))      # stream-ordered after the step
+        f.h_dof[:, 1] += torch.randn(f.h_dof.shape[0], generator=g) * 0.1                  # the host "simulator" moves on
+        if k > 0:
+            got = mirror.wait(k - 1)
+            o, r, z = want[k - 1]
+            assert got["obs_buf"].is_pinned() and not got["obs_buf"].is_cuda
+            assert torch.equal(got["obs_buf"], o.cpu()) and torch.equal(got["rew_buf"], r.cpu()) and torch.equal(got["reset_buf"], z.cpu()), k
+    got = mirror.wait(6)
+    assert torch.equal(got["obs_buf"], want[6][0].cpu())
+    assert not torch.equal(want[5][0], want[6][0])                     # the steps did differ
+    with pytest.raises(IndexError):
+        mirror.wait(3)                                                 # slot long since reused
+    assert mirror.bytes_per_push == env.obs_buf.numel() * 4 + env.rew_buf.numel() * 4 + env.reset_buf.numel()
+    mirror.drain()
+
+
 def feeder_actions(n, step):
     return torch.from_numpy(np.random.default_rng(100 + step).normal(0, 1, (n, 12)).astype(np.float32)).to(DEV)
 

@@ -336,9 +336,9 @@ int lgk_rng_dump(uint64_t seed, int32_t step, int64_t env_id_offset, int32_t num
  * (rsl_rl ActorCritic.act / evaluate / get_actions_log_prob; PPO.act).  Weights are nn.Linear layout
  * [out,in] fp32.  The three hidden layers run on tcgen05 tensor cores (TF32 operands rounded to nearest, FP32
  * accumulation in TMEM, one CTA per 128-env tile and network, activations never leave tensor memory); the last layer,
- * biases, ELU and the distribution epilogue are FP32.  Shapes the tensor-core kernel does not cover (hidden[0] not a
- * multiple of 128 or > 512, hidden[1] not a multiple of 64 / > 256, hidden[0]/2 + hidden[1] > 512, hidden[2] not a
- * multiple of 32 / > 128 / > hidden[0]/2, obs wider than 256, > 16 actions, biases not 16-byte aligned) run an FP32 tiled-GEMM path
+ * biases, ELU and the distribution epilogue are FP32.  The tensor-core kernel covers hidden[0] in {128, 256, 512},
+ * hidden[1] in {64, 128, 256} with hidden[0]/2 + hidden[1] <= 512, hidden[2] a multiple of 32 up to min(128, hidden[0]/2),
+ * observations up to 256 wide, up to 16 actions, 16-byte aligned biases; every other shape runs an FP32 tiled-GEMM path
  * with the same results to 1e-3. */
 typedef struct LgkPolicyParams {
   int32_t num_envs, num_obs, num_critic_obs, num_actions;

@@ -61,8 +61,7 @@ constexpr int kTmemCols = 512;
 // that the tile + a three-stage ring of 32 KB weight tiles fit.
 constexpr int kOffA = 0;
 constexpr int kOffRing = kOffA + kMaxChunks * kChunkBytes;            // 131072
-constexpr int kOffSched = kOffRing + kStages * kStageBytes;           // 229376: IssueRec[kTcMaxTiles]
-constexpr int kOffMisc = kOffSched + kTcMaxTiles * 32;                // b4[16] std[16]
+constexpr int kOffMisc = kOffRing + kStages * kStageBytes;            // 229376
 constexpr int kOffBar = kOffMisc + 256;                              // b4[16] | std[16] 1/std[16] log std[16]
 constexpr int kSmemBytes = kOffBar + 256 + 1024;                      // + barriers + alignment slack
 static_assert(kSmemBytes <= 232448, "policy_tc_kernel: shared memory budget");
@@ -72,13 +71,13 @@ constexpr int kOffPartial = 0;
 constexpr int kOffW4 = 36864;
 
 // barrier ids of the schedule (TcTile::wait_bar / commit_bar are 1 + id)
-enum { kWaitChunk0 = 0, kWaitAct = 8, kWaitAct2 = 10, kNumWaitBars = 12 };     // obs chunk c | S group g activated | ACC2 group g activated
+enum { kWaitChunk0 = 0, kWaitAct = 8, kWaitAct2 = 12, kNumWaitBars = 16 };     // obs chunk c | S group g activated | ACC2 group g activated
 enum { kCommitS = 0, kCommitAcc = 1 };
 
 static int build_schedule(TcPlan* pl, int net) {
   TcTile* out = pl->sched[net];
   int n = 0;
-  const int H = pl->q, G = H / 2, h1 = pl->h1, h2 = pl->h2, O = pl->o[net], kc1 = pl->kc1[net];
+  const int H = pl->q, h1 = pl->h1, h2 = pl->h2, O = pl->o[net], kc1 = pl->kc1[net];
   auto put = [&](int a, int d_col, int rows, int ksteps, bool ts, bool first, int wait_bar, int wait_par, int commit_bar,
                  int layer, int n0, int k0) {
     TcTile t;
@@ -96,18 +95,18 @@ static int build_schedule(TcPlan* pl, int net) {
           half * H, kc * kChunkK);
     }
   };
+  const int ng1 = pl->ng1, G1 = H / ng1, ng2 = pl->ng2, G2 = h1 / ng2;
   auto l2 = [&](int half) {     // layer-2 partial sums over k in [half*H, (half+1)*H), A = the activated groups of S in TMEM
-    for (int g = 0; g < 2; ++g)
-      for (int kc = 0; kc < G / kChunkK; ++kc)
-        put(g * G + kc * kChunkK, H, h1, 4, true, half == 0 && g == 0 && kc == 0, kc == 0 ? 1 + kWaitAct + g : 0, half,
-            (half == 1 && g == 1 && kc == G / kChunkK - 1) ? 1 + kCommitAcc : 0, 1, 0, half * H + g * G + kc * kChunkK);
+    for (int g = 0; g < ng1; ++g)
+      for (int kc = 0; kc < G1 / kChunkK; ++kc)
+        put(g * G1 + kc * kChunkK, H, h1, 4, true, half == 0 && g == 0 && kc == 0, kc == 0 ? 1 + kWaitAct + g : 0, half,
+            (half == 1 && g == ng1 - 1 && kc == G1 / kChunkK - 1) ? 1 + kCommitAcc : 0, 1, 0, half * H + g * G1 + kc * kChunkK);
   };
   l1(0); l2(0); l1(1); l2(1);
-  const int g2 = h1 / 2;        // layer 3: A = the activated groups of ACC2, accumulators at column 0 (S is free)
-  for (int g = 0; g < 2; ++g)
-    for (int kc = 0; kc < g2 / kChunkK; ++kc)
-      put(H + g * g2 + kc * kChunkK, 0, h2, 4, true, g == 0 && kc == 0, kc == 0 ? 1 + kWaitAct2 + g : 0, 0,
-          (g == 1 && kc == g2 / kChunkK - 1) ? 1 + kCommitAcc : 0, 2, 0, g * g2 + kc * kChunkK);
+  for (int g = 0; g < ng2; ++g)   // layer 3: A = the activated groups of ACC2, accumulators at column 0 (S is free)
+    for (int kc = 0; kc < G2 / kChunkK; ++kc)
+      put(H + g * G2 + kc * kChunkK, 0, h2, 4, true, g == 0 && kc == 0, kc == 0 ? 1 + kWaitAct2 + g : 0, 0,
+          (g == ng2 - 1 && kc == G2 / kChunkK - 1) ? 1 + kCommitAcc : 0, 2, 0, g * G2 + kc * kChunkK);
   return n;
 }
 
@@ -115,9 +114,9 @@ static int build_schedule(TcPlan* pl, int net) {
 bool policy_tc_plan(const LgkPolicyParams* p, TcPlan* pl) {
   const int h0 = p->hidden[0], h1 = p->hidden[1], h2 = p->hidden[2];
   if (h0 <= 0 || h1 <= 0 || h2 <= 0) return false;
-  if (h0 % 128 != 0 || h0 > 512) return false;                 // halves of 64..256 columns, drained in groups of 32..128
+  if (h0 != 128 && h0 != 256 && h0 != 512) return false;        // halves of 64 / 128 / 256 columns, drained in groups of 32 or 64
   const int H = h0 / 2;
-  if (h1 % 64 != 0 || h1 > 256 || H + h1 > kTmemCols) return false;
+  if ((h1 != 64 && h1 != 128 && h1 != 256) || H + h1 > kTmemCols) return false;
   if (h2 % 32 != 0 || h2 > kMaxH2 || h2 > H) return false;
   if (p->num_actions < 1 || p->num_actions > kMaxOut) return false;
   if (p->num_obs < 1 || p->num_obs > kMaxChunks * kChunkK || p->num_critic_obs < 1 || p->num_critic_obs > kMaxChunks * kChunkK) return false;
@@ -125,6 +124,7 @@ bool policy_tc_plan(const LgkPolicyParams* p, TcPlan* pl) {
     if ((reinterpret_cast<uintptr_t>(p->actor_b[i]) & 15u) || (reinterpret_cast<uintptr_t>(p->critic_b[i]) & 15u)) return false;
   pl->o[0] = p->num_obs; pl->o[1] = p->num_critic_obs;
   pl->h0 = h0; pl->h1 = h1; pl->h2 = h2; pl->q = H; pl->nact = p->num_actions;
+  pl->ng1 = H / 32 < 4 ? H / 32 : 4; pl->ng2 = h1 / 32 < 4 ? h1 / 32 : 4;      // drain groups: 4 warps x {8, 16} columns each
   long long off = 0;
   for (int net = 0; net < 2; ++net) {
     pl->kc1[net] = (pl->o[net] + kChunkK - 1) / kChunkK;
@@ -227,6 +227,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ weight packing
@@ -267,20 +272,6 @@ struct TcArgs {
   int net0;                   // first network of the grid's y dimension (0 actor, 1 critic): LgkPolicyParams.nets
 };
 
-// What the issuing thread needs for one tile, precomputed at kernel start by the other threads: a single tcgen05.mma issue
-// blocks its thread for ~125 cycles and everything else that thread does between MMAs is time the tensor pipe idles
-// (profiles/umma_rate_probe.cu, issue-loop section), so the loop is two 16-byte loads, the waits, the MMAs and the commits.
-struct __align__(16) IssueRec {
-  uint32_t d_tmem;        // accumulator address
-  uint32_t idesc;
-  uint32_t a_lo;          // TS: TMEM address of the first k; SS: low word of the A descriptor (k-step = +2)
-  uint32_t b_lo;          // low word of the B descriptor of the tile's ring stage (k-step = +2)
-  uint32_t wait_addr;     // 0: none; else shared address of the barrier to wait on before the tile, parity in bit 0 (barriers are 8-byte aligned)
-  uint32_t commit_addr;   // 0: none; else barrier committed after the tile (besides the stage's empty barrier)
-  uint32_t full_addr;     // the stage's full barrier, parity in bit 0
-  uint32_t misc;          // bits 0-2 ksteps | bit 3 TS | bit 4 first MMA overwrites | bits 8.. bytes of the tile / 128 (rows)
-};
-static_assert(sizeof(IssueRec) == 32, "IssueRec is 32 bytes");
 constexpr uint32_t kDescHi = (uint32_t)(((uint64_t)(1024 >> 4) << 32 | (1ull << 46) | (2ull << 61)) >> 32);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
@@ -307,43 +298,81 @@ __device__ __forceinline__ float elu_fast(float x) {
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// biases of one 32-column block (global memory, 16-byte aligned): loaded ahead of the wait for the accumulators
-struct Bias32 { float4 b[8]; };
-__device__ __forceinline__ void load_bias32(Bias32& B, const float* __restrict__ bias, bool active) {
-#pragma unroll
-  for (int q4 = 0; q4 < 8; ++q4) B.b[q4] = active ? ldg_f4(bias + 4 * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+// tcgen05.ld / st of CW (8, 16) consecutive 32-bit columns of this warp's lane quadrant
+template <int CW> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CW]);
+template <int CW> __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[CW]);
+template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <> __device__ __forceinline__ void tmem_st<8>(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <> __device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                 "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 
-// activate the 32 accumulator columns at `taddr` IN PLACE: + bias, ELU, round to TF32, store back to the same columns,
-// where the next layer's MMAs read them as their A operand
-__device__ __forceinline__ void drain_block_in_place(uint32_t taddr, const Bias32& B) {
-  uint32_t v[32];
-  tmem_ld32(taddr, v);
+// biases of this warp's CW columns of a group (global memory, 16-byte aligned): loaded ahead of the accumulators
+template <int CW> struct BiasR { float4 b[CW / 4]; };
+template <int CW> __device__ __forceinline__ void load_bias(BiasR<CW>& B, const float* __restrict__ bias) {
 #pragma unroll
-  for (int q4 = 0; q4 < 8; ++q4) {
-    v[4 * q4 + 0] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 0]) + B.b[q4].x)));
-    v[4 * q4 + 1] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 1]) + B.b[q4].y)));
-    v[4 * q4 + 2] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 2]) + B.b[q4].z)));
-    v[4 * q4 + 3] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 3]) + B.b[q4].w)));
+  for (int q4 = 0; q4 < CW / 4; ++q4) B.b[q4] = ldg_f4(bias + 4 * q4);
+}
+
+// Activate an accumulator block of `ng` groups of 4*CW columns IN PLACE, group by group: + bias, ELU, round to TF32, store
+// back to the same TMEM columns, where the next layer's MMAs read them as their A operand; group g is handed to the issuer
+// (barrier bar0 + 8g) as soon as all sixteen warps have stored their CW columns of it.  `on_first` / `on_last` are the
+// profiling stamps.
+template <int CW, class F0, class F1, class F2>
+__device__ __forceinline__ void drain_groups(uint32_t tmem_lane_base, int part, int col0, int ng, const float* __restrict__ bias,
+                                             uint32_t bar0, uint32_t wait_bar, uint32_t wait_par, F0 on_full, F1 on_first, F2 on_last) {
+  BiasR<CW> B;
+  load_bias<CW>(B, bias + part * CW);
+  mbar_wait(wait_bar, wait_par);
+  tc_fence_after();
+  on_full();
+  for (int g = 0; g < ng; ++g) {
+    const uint32_t taddr = tmem_lane_base + (uint32_t)(col0 + g * 4 * CW + part * CW);
+    uint32_t v[CW];
+    tmem_ld<CW>(taddr, v);
+    BiasR<CW> Bn;
+    if (g + 1 < ng) load_bias<CW>(Bn, bias + (g + 1) * 4 * CW + part * CW);
+#pragma unroll
+    for (int q4 = 0; q4 < CW / 4; ++q4) {
+      v[4 * q4 + 0] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 0]) + B.b[q4].x)));
+      v[4 * q4 + 1] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 1]) + B.b[q4].y)));
+      v[4 * q4 + 2] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 2]) + B.b[q4].z)));
+      v[4 * q4 + 3] = __float_as_uint(to_tf32(elu_fast(__uint_as_float(v[4 * q4 + 3]) + B.b[q4].w)));
+    }
+    tmem_st<CW>(taddr, v);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(bar0 + 8 * g);
+    if (g == 0) on_first();
+    if (g + 1 < ng) B = Bn;
   }
-  tmem_st32(taddr, v);
-  tmem_st_wait();
-}
-
-// a group of `ncols` (<= 128) columns at TMEM column col0: this warp owns block `part` of its lane quadrant
-__device__ __forceinline__ void drain_group(uint32_t tmem_lane_base, int part, int col0, int ncols, const Bias32& B) {
-  if (part * 32 < ncols) drain_block_in_place(tmem_lane_base + (uint32_t)(col0 + part * 32), B);
+  on_last();
 }
 
 // last layer for this thread's 32 hidden columns: acc[o] += elu(h) * W4^T[k][o], NQ float4 groups of outputs
 // last layer for this thread's 32 hidden columns: acc[o] += elu(h) * W4^T[k][o] for 4*NQ outputs, two outputs per packed
 // FFMA2 (acc2[j] = outputs 2j, 2j+1)
 template <int NQ>
-__device__ __forceinline__ void last_layer_block(const uint32_t (&v)[32], const float* __restrict__ b3, uint32_t w4t_addr,
+__device__ __forceinline__ void last_layer_block(const uint32_t (&v)[32], const float4 (&b3)[8], uint32_t w4t_addr,
                                                  f2_t (&acc2)[kMaxOut / 2]) {
 #pragma unroll
   for (int jj = 0; jj < 32; jj += 4) {
-    const float4 b = ldg_f4(b3 + jj);
+    const float4 b = b3[jj / 4];
     const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -371,7 +400,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   float* s_b4 = reinterpret_cast<float*>(smem + kOffMisc);
   float* s_std = s_b4 + 16;
   const uint32_t a_w4t = abuf + kOffW4, a_partial = abuf + kOffPartial;
-  IssueRec* s_rec = reinterpret_cast<IssueRec*>(smem + kOffSched);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   const uint32_t bar_full = smem_addr(bars), bar_empty = bar_full + 8 * kStages;
   const uint32_t bar_s = bar_empty + 8 * kStages;              // a half of layer 1 accumulated into S
@@ -386,25 +414,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   const int m0 = blockIdx.x * kTileM;
   const int N = p.num_envs;
   const int O = pl.o[net], kc1 = pl.kc1[net];
-  const int h1 = pl.h1, h2 = pl.h2, H = pl.q, G = pl.q / 2;
+  const int h1 = pl.h1, h2 = pl.h2, H = pl.q;
   const int ntiles = pl.ntiles[net];
   const int nout = net ? 1 : pl.nact;
   const float* const* Wg = net ? p.critic_w : p.actor_w;
   const float* const* Bg = net ? p.critic_b : p.actor_b;
 
-  // ---- one-time setup
+  // ---- one-time setup.  Programmatic dependent launch: barrier init and the TMEM allocation overlap the tail of the
+  // preceding kernel on the stream (the env step that writes the observations, or the previous act()); nothing in global
+  // memory is read before pdl_wait().
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_s, 1);
     mbar_init(bar_acc, 1);
     for (int c = 0; c < kMaxChunks; ++c) mbar_init(bar_wait + 8 * (kWaitChunk0 + c), kEpiThreads);
-    for (int g = 0; g < 2; ++g) { mbar_init(bar_wait + 8 * (kWaitAct + g), kEpiThreads); mbar_init(bar_wait + 8 * (kWaitAct2 + g), kEpiThreads); }
+    for (int g = 0; g < 4; ++g) { mbar_init(bar_wait + 8 * (kWaitAct + g), kEpiThreads); mbar_init(bar_wait + 8 * (kWaitAct2 + g), kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"((uint32_t)kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();
   if (tid < kMaxOut) {
     const float sd = (net == 0 && tid < nout) ? p.std[tid] : 1.f;
     s_b4[tid] = tid < nout ? Bg[3][tid] : 0.f;
@@ -414,21 +446,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if (tid < ntiles) {   // tile schedule -> issue records (needs the TMEM base)
-    const TcTile T = pl.sched[net][tid];
-    const int s = tid % kStages;
-    IssueRec r;
-    r.d_tmem = tmem_base + T.d_col;
-    r.idesc = make_idesc(T.rows);
-    r.a_lo = (T.flags & 1) ? tmem_base + T.a : desc_lo(abuf + T.a * kChunkBytes);
-    r.b_lo = desc_lo(ring + s * kStageBytes);
-    r.wait_addr = T.wait_bar ? ((bar_wait + 8 * (T.wait_bar - 1)) | (uint32_t)T.wait_par) : 0u;
-    r.commit_addr = T.commit_bar ? (T.commit_bar - 1 == kCommitS ? bar_s : bar_acc) : 0u;
-    r.full_addr = (bar_full + 8 * s) | (uint32_t)((tid / kStages) & 1);
-    r.misc = (uint32_t)T.ksteps | ((T.flags & 1) ? 8u : 0u) | ((T.flags & 2) ? 16u : 0u) | ((uint32_t)T.rows << 8);
-    s_rec[tid] = r;
-  }
-  __syncthreads();
   // phase stamps of CTA (0,0): 0 setup done | 1 obs staged | 2 L1a accumulated | 3, 4 its groups activated | 5 L1b accumulated |
   // 6, 7 its groups activated | 8 layer 2 done | 9, 10 its groups activated | 11 layer 3 done | 12 last layer summed | 13 outputs written
   auto stamp = [&](int slot) {
@@ -485,22 +502,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
     stamp(1);
 
     // ---- layer 1, half by half: activate S in place, group by group, while the tensor pipe multiplies the groups already done
-    Bias32 B0, B1;
-    const bool act1 = part * 32 < G, act2 = part * 32 < h1 / 2;
+    const int ng1 = pl.ng1, ng2 = pl.ng2;
     for (int half = 0; half < 2; ++half) {
-      load_bias32(B0, Bg[0] + half * H + part * 32, act1);
-      load_bias32(B1, Bg[0] + half * H + G + part * 32, act1);
-      mbar_wait(bar_s, (uint32_t)half);
-      tc_fence_after();
-      stamp(2 + 3 * half);
-      drain_group(tmem_lane_base, part, 0, G, B0);
-      tc_fence_before();
-      mbar_arrive(bar_wait + 8 * (kWaitAct + 0));
-      stamp(3 + 3 * half);
-      drain_group(tmem_lane_base, part, G, G, B1);
-      tc_fence_before();
-      mbar_arrive(bar_wait + 8 * (kWaitAct + 1));
-      stamp(4 + 3 * half);
+      const float* bias = Bg[0] + half * H;
+      auto f0 = [&]() { stamp(2 + 3 * half); };
+      auto f1 = [&]() { stamp(3 + 3 * half); };
+      auto f2 = [&]() { stamp(4 + 3 * half); };
+      if (H / ng1 == 64) drain_groups<16>(tmem_lane_base, part, 0, ng1, bias, bar_wait + 8 * kWaitAct, bar_s, (uint32_t)half, f0, f1, f2);
+      else drain_groups<8>(tmem_lane_base, part, 0, ng1, bias, bar_wait + 8 * kWaitAct, bar_s, (uint32_t)half, f0, f1, f2);
     }
     // layer 1 is done with the observation tile: its buffer takes the transposed last layer [k][16]
     for (int i = tid; i < h2 * kMaxOut; i += kEpiThreads) {
@@ -508,20 +517,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
       s_w4t[i] = o < nout ? Wg[3][(size_t)o * h2 + k] : 0.f;
     }
     // ---- layer 2
-    load_bias32(B0, Bg[1] + part * 32, act2);
-    load_bias32(B1, Bg[1] + h1 / 2 + part * 32, act2);
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    stamp(8);
-    drain_group(tmem_lane_base, part, H, h1 / 2, B0);
-    tc_fence_before();
-    mbar_arrive(bar_wait + 8 * (kWaitAct2 + 0));
-    stamp(9);
-    drain_group(tmem_lane_base, part, H + h1 / 2, h1 / 2, B1);
-    tc_fence_before();
-    mbar_arrive(bar_wait + 8 * (kWaitAct2 + 1));
-    stamp(10);
+    {
+      auto f0 = [&]() { stamp(8); };
+      auto f1 = [&]() { stamp(9); };
+      auto f2 = [&]() { stamp(10); };
+      if (h1 / ng2 == 64) drain_groups<16>(tmem_lane_base, part, H, ng2, Bg[1], bar_wait + 8 * kWaitAct2, bar_acc, 0u, f0, f1, f2);
+      else drain_groups<8>(tmem_lane_base, part, H, ng2, Bg[1], bar_wait + 8 * kWaitAct2, bar_acc, 0u, f0, f1, f2);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // s_w4t complete
+    float4 b3r[8];                                          // this warp's block of the layer-3 bias, ahead of the wait
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) b3r[q4] = part * 32 < h2 ? ldg_f4(Bg[2] + part * 32 + 4 * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(bar_acc, 1);                                  // layer 3 done
     tc_fence_after();
     stamp(11);
@@ -534,9 +540,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
       uint32_t v[32];
       tmem_ld32(tmem_lane_base + (uint32_t)(cb * 32), v);
       const uint32_t wa = a_w4t + cb * 32 * kMaxOut * 4;
-      if (nout <= 4) last_layer_block<1>(v, Bg[2] + cb * 32, wa, acc2);
-      else if (nout <= 12) last_layer_block<3>(v, Bg[2] + cb * 32, wa, acc2);
-      else last_layer_block<4>(v, Bg[2] + cb * 32, wa, acc2);
+      if (nout <= 4) last_layer_block<1>(v, b3r, wa, acc2);
+      else if (nout <= 12) last_layer_block<3>(v, b3r, wa, acc2);
+      else last_layer_block<4>(v, b3r, wa, acc2);
     }
     float acc[kMaxOut];
 #pragma unroll
@@ -588,7 +594,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
       const uint8_t* src = a.packed + pl.net_off[net];
       for (int i = 0; i < ntiles; ++i) {
         const int s = i % kStages;
-        const uint32_t bytes = (s_rec[i].misc >> 8) * 128u;
+        const uint32_t bytes = (uint32_t)pl.sched[net][i].rows * 128u;
         mbar_wait(bar_empty + 8 * s, ((i / kStages) & 1) ^ 1);
         if (PROF && (a.dbg_flags & 1)) {
           mbar_arrive(bar_full + 8 * s);
@@ -600,52 +606,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================= MMA issuer: walks the precomputed issue records =================
-    if (lane == 0) {
-      const bool skip_mma = PROF && (a.dbg_flags & 2) != 0;
-      long long c_bar = 0, c_full = 0, c_issue = 0, c_commit = 0;
-      uint32_t empty = bar_empty;
-      int stage = 0;
-      const uint4* recs = reinterpret_cast<const uint4*>(s_rec);
-      uint4 ra = recs[0], rb = recs[1];
-      for (int i = 0; i < ntiles; ++i) {
-        const uint32_t d = ra.x, idesc = ra.y, a_lo = ra.z, b_lo = ra.w;
-        const uint32_t wait_addr = rb.x, commit_addr = rb.y, full_addr = rb.z, misc = rb.w;
-        if (i + 1 < ntiles) { ra = recs[2 * i + 2]; rb = recs[2 * i + 3]; }      // next tile's record: in flight under this tile's MMAs
-        long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-        if (PROF) t0 = clock64();
-        if (wait_addr) { mbar_wait(wait_addr & ~7u, wait_addr & 1u); }
-        if (PROF) t1 = clock64();
-        mbar_wait(full_addr & ~7u, full_addr & 1u);
-        tc_fence_after();
-        if (PROF) t2 = clock64();
+    // ================= MMA issuer =================
+    // The whole warp walks the schedule with warp-uniform control flow and takes every MMA operand from uniform sources
+    // (the tile table in the kernel-parameter constant bank, the TMEM base broadcast once): the descriptors then live in
+    // uniform registers and a tcgen05.mma is a single UTCHMMA.  Operands loaded per thread (LDS) cost an R2UR + ELECT loop
+    // of ~25 instructions around every MMA, which is what bounded the issue rate at ~125 cycles per MMA.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const TcTile* __restrict__ sched = pl.sched[net];
+    const bool skip_mma = PROF && (a.dbg_flags & 2) != 0;
+    const bool prof = PROF && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+    long long c_bar = 0, c_full = 0, c_issue = 0, c_commit = 0;
+    uint32_t stage = 0, phase = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      const TcTile T = sched[i];
+      long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      if (PROF) t0 = clock64();
+      if (T.wait_bar) mbar_wait(bar_wait + 8 * (T.wait_bar - 1), T.wait_par);
+      if (PROF) t1 = clock64();
+      mbar_wait(bar_full + 8 * stage, phase);
+      tc_fence_after();
+      if (PROF) t2 = clock64();
+      const uint32_t d = tmem_u + T.d_col;
+      const uint32_t idesc = make_idesc(T.rows);
+      const uint32_t b_lo = desc_lo(ring + stage * kStageBytes);
+      const uint32_t acc0 = (T.flags & 2) ? 0u : 1u;
+      const int ksteps = T.ksteps;
+      if (elect_one()) {
         if (!skip_mma) {
-          const int ksteps = (int)(misc & 7u);
-          const uint32_t acc0 = (misc & 16u) ? 0u : 1u;
-          if (misc & 8u) {
+          if (T.flags & 1) {
+            const uint32_t a_t = tmem_u + T.a;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              if (ks < ksteps) mma_tf32_ts(d, a_lo + ks * 8, desc_from_lo(b_lo + 2 * ks), idesc, ks == 0 ? acc0 : 1u);
+              if (ks < ksteps) mma_tf32_ts(d, a_t + ks * 8, desc_from_lo(b_lo + 2 * ks), idesc, ks == 0 ? acc0 : 1u);
           } else {
+            const uint32_t a_lo = desc_lo(abuf + T.a * kChunkBytes);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               if (ks < ksteps) mma_tf32(d, desc_from_lo(a_lo + 2 * ks), desc_from_lo(b_lo + 2 * ks), idesc, ks == 0 ? acc0 : 1u);
           }
         }
         if (PROF) t3 = clock64();
-        tc_commit(empty);                                   // stage is free once these MMAs have read it
-        if (commit_addr) tc_commit(commit_addr);
-        if (++stage == kStages) { stage = 0; empty = bar_empty; } else { empty += 8; }
-        if (PROF) {
-          const long long t4 = clock64();
-          c_bar += t1 - t0; c_full += t2 - t1; c_issue += t3 - t2; c_commit += t4 - t3;
-          if (blockIdx.x == 0 && blockIdx.y == 0) a.timeline[16 + i] = t2;      // cycle stamp of the tile's start
-        }
+        tc_commit(bar_empty + 8 * stage);                   // stage is free once these MMAs have read it
+        if (T.commit_bar) tc_commit(T.commit_bar - 1 == kCommitS ? bar_s : bar_acc);
       }
-      if (PROF && blockIdx.x == 0 && blockIdx.y == 0) {
-        a.timeline[100] = c_bar; a.timeline[101] = c_full; a.timeline[102] = c_issue; a.timeline[103] = c_commit;
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      if (prof) {
+        const long long t4 = clock64();
+        c_bar += t1 - t0; c_full += t2 - t1; c_issue += t3 - t2; c_commit += t4 - t3;
+        a.timeline[16 + i] = t2;                            // cycle stamp of the tile's start
       }
     }
+    if (prof) { a.timeline[100] = c_bar; a.timeline[101] = c_full; a.timeline[102] = c_issue; a.timeline[103] = c_commit; }
   }
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -712,7 +724,8 @@ int policy_tc_launch(const LgkPolicyParams* p, const TcPlan& pl, cudaStream_t st
   args.p = *p; args.pl = pl; args.packed = base; args.timeline = g_timeline; args.dbg_flags = g_dbg_flags;
   args.net0 = p->nets == 2 ? 1 : 0;
   const int nets = (p->nets == 1 || p->nets == 2) ? 1 : 2;
-  kern<<<dim3((p->num_envs + kTileM - 1) / kTileM, nets), kTcThreads, kSmemBytes, st>>>(args);
+  cudaError_t le = launch_chained(kern, dim3((p->num_envs + kTileM - 1) / kTileM, nets), dim3(kTcThreads), (size_t)kSmemBytes, st, args);
+  if (int rc = check_cuda(le, "policy_tc_kernel launch")) return rc;
   count_launch();
   return check_cuda(cudaGetLastError(), "policy_tc_kernel launch");
 }

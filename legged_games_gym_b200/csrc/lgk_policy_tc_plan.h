@@ -25,6 +25,7 @@ struct TcPlan {
   int o[2];          // input widths: actor obs, critic obs
   int kc1[2];        // k-chunks of layer 1 per net
   int h0, h1, h2, q, nact;       // q = h0 / 2: layer 1 is computed in two column halves of q (<= 256) columns
+  int ng1, ng2;      // drain groups per layer-1 half / of the layer-2 block (each 4 warps x 8 or 16 columns)
   int ntiles[2];
   long long net_bytes[2];        // packed bytes per net
   long long net_off[2];          // offset of each net's packed image in the workspace

@@ -150,6 +150,61 @@ __global__ void __launch_bounds__(128, 1) group_probe(int n, int groups, int do_
   }
 }
 
+// ---- CTA-pair probe: cta_group::2, M = 256 (128 rows in each CTA's tensor memory), N wide, A from TMEM, each CTA holds half
+// of B's rows in its own shared memory; the leader CTA's thread issues for both, one multicast commit ends the run.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) pair_probe(int n, int groups, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = raw + ((1024u - (smem_addr(raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const uint32_t b_addr = smem_addr(smem) + 16384;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const long long t0 = clock64();
+  if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    uint64_t bd[4];
+    for (int k = 0; k < 4; ++k) bd[k] = make_smem_desc(b_addr + k * 32);
+    for (int g = 0; g < groups; ++g) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+                     ::"r"(tmem), "r"(tmem + 256 + 8 * k), "l"(bd[k]), "r"(idesc), "r"((g | k) ? 1u : 0u) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_addr(&bar)), "h"((uint16_t)3) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    uint32_t ok;
+    do {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(ok) : "r"(smem_addr(&bar)) : "memory");
+    } while (!ok);
+    if (blockIdx.x < 2) out[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
 // ---- weight-stream probe: one producer thread streams `total` bytes from an L2-resident buffer through a ring of `stages`
 // stages of `stage_bytes` (cp.async.bulk + mbarrier tx); one consumer thread frees a stage as soon as it is full.
 // Reports bytes per cycle per SM: what a weight ring of that geometry can deliver at best.
@@ -231,6 +286,17 @@ int main() {
       cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
       printf("%3d  %d  %d  %2d  %8.1f  %8.1f\n", n, cm[cfg], wt[cfg], sp[cfg], (double)h[0] / 128, (double)h[1] / 128);
     }
+  cudaFuncSetAttribute(pair_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  printf("\nCTA pair (cta_group::2, M=256, tf32, A from tmem, groups of 4 MMAs): N  cycles/MMA seen by CTA 0 / CTA 1\n");
+  for (int n : {128, 256}) {
+    for (int w = 0; w < 3; ++w) pair_probe<<<148, 128, 64 * 1024>>>(n, 128, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+    long long h[2];
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("%3d  %8.1f  %8.1f   (%.1f TFLOP/s chip)\n", n, (double)h[0] / 512, (double)h[1] / 512,
+           2.0 * 256 * n * 8 / ((double)h[0] / 512) * 74 * (clk_khz * 1e3) / 1e12);
+  }
   // ---- weight stream
   uint8_t* w;
   const int total = 1152 * 1024;                // one net's packed weights

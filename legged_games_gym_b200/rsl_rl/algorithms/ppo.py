@@ -122,7 +122,7 @@ class PPO:
         ac = self.actor_critic
         ac.update_distribution(obs)
         lp = ac.distribution.log_prob(acts).sum(dim=-1)
-        value = ac.critic(cobs)
+        value = ac.evaluate(cobs)
         mu, sigma, entropy = ac.distribution.mean, ac.distribution.stddev, ac.entropy
         kl_mean = None
         if self.desired_kl is not None and self.schedule == "adaptive":
@@ -154,7 +154,9 @@ class PPO:
         st = g["flat"]
         idx = g["idx"]
         take = lambda t: t.index_select(0, idx)
-        loss, vl, sl, kl = self._minibatch_loss(take(st["obs"]), take(st["cobs"]), take(st["acts"]), take(st["vals"]), take(st["adv"]),
+        obs_mb = take(st["obs"])
+        cobs_mb = obs_mb if st["cobs"] is st["obs"] else take(st["cobs"])      # no privileged observations: one gather
+        loss, vl, sl, kl = self._minibatch_loss(obs_mb, cobs_mb, take(st["acts"]), take(st["vals"]), take(st["adv"]),
                                                 take(st["rets"]), take(st["olp"]), take(st["mu"]), take(st["sg"]), g["lr"])
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
@@ -175,8 +177,20 @@ class PPO:
         st, dev = self.storage, self.device
         B = st.num_envs * st.num_transitions_per_env
         mb = B // self.num_mini_batches
-        obs = st.observations.flatten(0, 1)
-        flat = dict(obs=obs, cobs=st.privileged_observations.flatten(0, 1) if st.privileged_observations is not None else obs,
+        # observation rows padded with zeros to a multiple of 8 floats (refreshed from the storage at every update): see
+        # ActorCritic._forward_padded
+        pads = []
+
+        def padded(t):
+            k, src = t.shape[-1], t.flatten(0, 1)
+            if k % 8 == 0:
+                return src
+            dst = torch.zeros(B, -(-k // 8) * 8, device=dev, dtype=t.dtype)
+            pads.append((dst, src))
+            return dst
+        obs = padded(st.observations)
+        cobs = padded(st.privileged_observations) if st.privileged_observations is not None else obs
+        flat = dict(obs=obs, cobs=cobs,
                     acts=st.actions.flatten(0, 1), vals=st.values.flatten(0, 1), rets=st.returns.flatten(0, 1),
                     olp=st.actions_log_prob.flatten(0, 1), adv=st.advantages.flatten(0, 1), mu=st.mu.flatten(0, 1),
                     sg=st.sigma.flatten(0, 1))
@@ -196,7 +210,9 @@ class PPO:
         for grp in self.optimizer.param_groups:
             grp["lr"] = lr_t
         g = dict(flat=flat, idx=torch.zeros(mb, dtype=torch.long, device=dev), lr=lr_t, mb=mb,
-                 acc=torch.zeros(2, device=dev))
+                 acc=torch.zeros(2, device=dev), pads=pads)
+        for dst, src in pads:
+            dst[:, :src.shape[1]].copy_(src)
         # an autograd graph left over from an eager update (ActorCritic.distribution holds the actor's output) would keep
         # the parameters' AccumulateGrad nodes alive on the stream they were created on: drop it before warm-up / capture
         self.actor_critic.distribution = None
@@ -242,6 +258,8 @@ class PPO:
         if self._graph is None:
             self._build_graph()
         g = self._graph
+        for dst, src in g["pads"]:
+            dst[:, :src.shape[1]].copy_(src)
         g["acc"].zero_()
         g["lr"].fill_(float(self.learning_rate))
         B = g["mb"] * self.num_mini_batches
@@ -322,7 +340,7 @@ class PPO:
         for obs, cobs, acts, tvals, adv, rets, old_lp, old_mu, old_sigma, _, _ in gen:
             ac.update_distribution(obs)
             lp = ac.distribution.log_prob(acts).sum(dim=-1)
-            value = ac.critic(cobs)
+            value = ac.evaluate(cobs)
             mu, sigma, entropy = ac.distribution.mean, ac.distribution.stddev, ac.entropy
             if self.desired_kl is not None and self.schedule == "adaptive":
                 with torch.inference_mode():

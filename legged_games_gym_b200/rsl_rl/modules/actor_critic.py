@@ -6,6 +6,7 @@ import itertools
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 from torch.distributions import Normal
 
 from ... import _native as nat
@@ -22,6 +23,45 @@ def _mlp(n_in, hidden, n_out, act):
         else:
             layers += [nn.Linear(hidden[i], hidden[i + 1]), act()]
     return nn.Sequential(*layers)
+
+
+_ONES = {}
+
+
+def _ones(n, like):
+    key = (n, like.device, like.dtype)
+    t = _ONES.get(key)
+    if t is None:
+        t = _ONES[key] = torch.ones(n, device=like.device, dtype=like.dtype)
+    return t
+
+
+class _Linear(torch.autograd.Function):
+    """F.linear with a backward shaped for PPO's mini-batches of 24 576 rows (profiles/update_profile.py): the bias gradient
+    is a matrix-vector product with a vector of ones (cuBLAS gemv, one pass over dY at memory speed; autograd's generic
+    column reduction took 28 us per layer = 4.5 ms of a 30 ms update) and the weight gradient is split over the batch."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return F.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
+        dx = (dy2 @ w).view_as(x) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            # dW = dY^T X has a tiny output ([512 x 240] at most) and the whole batch as its inner dimension: one GEMM fills
+            # 16 CTAs (cuBLAS does not split K here: 56 us per layer).  Eight batch slices as one bmm fill the machine.
+            m = dy2.shape[0]
+            if m >= 4096 and m % 8 == 0 and dy2.is_contiguous() and x2.is_contiguous():
+                dw = torch.bmm(dy2.view(8, m // 8, -1).transpose(1, 2), x2.view(8, m // 8, -1)).sum(0)
+            else:
+                dw = dy2.t() @ x2
+        db = torch.mv(dy2.t(), _ones(dy2.shape[0], dy2)) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
 
 
 class ActorCritic(nn.Module):
@@ -92,8 +132,25 @@ class ActorCritic(nn.Module):
     def entropy(self):
         return self.distribution.entropy().sum(dim=-1)
 
+    @staticmethod
+    def _forward_padded(seq, x):
+        """seq(x) for an input that may carry zero columns beyond the first layer's width.  PPO's captured update feeds
+        mini-batches whose rows are padded to a multiple of 8 floats (235 -> 240): with a 16-byte aligned leading dimension
+        cuBLAS runs the first layer's forward and weight-gradient GEMMs on its sm_100 tensor-op kernels instead of the
+        unaligned legacy path (4x slower at [24 576 x 235]); the weight is zero-padded to match, so the result is the same sum."""
+        h = x
+        for i, m in enumerate(seq):
+            if isinstance(m, nn.Linear):
+                w = m.weight
+                if i == 0 and h.shape[-1] != w.shape[1]:
+                    w = F.pad(w, (0, h.shape[-1] - w.shape[1]))
+                h = _Linear.apply(h, w, m.bias) if torch.is_grad_enabled() else F.linear(h, w, m.bias)
+            else:
+                h = m(h)
+        return h
+
     def update_distribution(self, observations):
-        mean = self.actor(observations)
+        mean = self._forward_padded(self.actor, observations)
         # validate_args=False: no host-synchronising range checks (rsl_rl disables validation too), CUDA-graph capturable
         self.distribution = Normal(mean, mean * 0. + self.std, validate_args=False)
         self._fused = None
@@ -159,4 +216,4 @@ class ActorCritic(nn.Module):
     def evaluate(self, critic_observations, **kwargs):
         # always evaluated: env observation buffers are persistent and rewritten in place, so a cache keyed by the tensor's
         # address would hand back the values of the PREVIOUS observation
-        return self.critic(critic_observations)
+        return self._forward_padded(self.critic, critic_observations)

@@ -57,14 +57,20 @@ class PPO:
         self.actor_critic.train()
 
     def act(self, obs, critic_obs):
-        out = self.actor_critic.act_and_evaluate(obs, critic_obs)
+        st = self.storage
+        slot = None
+        if st is not None and st.step < st.num_transitions_per_env and obs.is_cuda and st.actions.is_cuda:
+            # the kernel writes the transition straight into its rollout-storage slot (add_transitions then has nothing to copy)
+            s = st.step
+            slot = dict(actions=st.actions[s], mean=st.mu[s], sigma=st.sigma[s], values=st.values[s],
+                        logp=st.actions_log_prob[s].view(-1))
+        out = self.actor_critic.act_and_evaluate(obs, critic_obs, out=slot)
         t = self.transition
         t.actions, t.values, t.actions_log_prob = out["actions"], out["values"], out["logp"]
         t.action_mean, t.action_sigma = out["mean"], out["sigma"]
         # Snapshot NOW: `obs` is usually the env's persistent obs_buf, which env.step() rewrites in place before
         # process_env_step() stores the transition (the reference's env rebinds obs_buf to a fresh tensor every step, so
         # rsl_rl can keep the reference there).  The copy lands in its final place, the rollout storage slot.
-        st = self.storage
         if st is not None and st.step < st.num_transitions_per_env:
             t.observations = st.observations[st.step]
             t.observations.copy_(obs)

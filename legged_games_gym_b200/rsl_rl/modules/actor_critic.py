@@ -86,6 +86,7 @@ class ActorCritic(nn.Module):
         self._seed, self._step, self._env_offset = 0, 0, 0
         self._fused = None            # outputs of the last fused call
         self._ws = None
+        self._params, self._params_dev = None, None      # cached LgkPolicyParams (pointers to the parameters, workspace)
         # generation of the weight VALUES: the packed TF32 image the kernel keeps in the workspace is rebuilt when it moves.
         # torch's per-tensor version counters see eager in-place updates (optimizer.step, load_state_dict, .to()) but NOT the
         # replay of a captured update graph, so whoever changes the parameters out of torch's sight calls weights_changed().
@@ -99,6 +100,7 @@ class ActorCritic(nn.Module):
     def _apply(self, fn, *a, **kw):
         self._weights_gen += 1
         self._ws = None
+        self._params = None
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):
@@ -155,16 +157,31 @@ class ActorCritic(nn.Module):
         self.distribution = Normal(mean, mean * 0. + self.std, validate_args=False)
         self._fused = None
 
-    def _run_fused(self, obs, critic_obs, sample):
-        """critic_obs=None runs the actor alone (act / act_inference): nothing is read through the critic pointer."""
+    def _run_fused(self, obs, critic_obs, sample, out=None):
+        """critic_obs=None runs the actor alone (act / act_inference): nothing is read through the critic pointer.
+        `out` (optional): dict of preallocated contiguous fp32 outputs -- actions / mean / sigma [n, A], values [n, 1],
+        logp [n] -- e.g. views of a rollout-storage slot, so that the kernel writes a transition where it is kept."""
         n = obs.shape[0]
         dev = obs.device
-        p = nat.PolicyParams()
-        p.num_envs, p.num_obs, p.num_critic_obs, p.num_actions = n, self.num_actor_obs, self.num_critic_obs, self.num_actions
-        p.hidden[:] = self.hidden
         obs = obs.contiguous()
         if obs.shape[1] != self.num_actor_obs:
             raise ValueError(f"observations have {obs.shape[1]} columns, the actor takes {self.num_actor_obs}")
+        p = self._params
+        if p is None or p.num_envs != n or self._params_dev != dev:
+            # everything that does not change from call to call is filled once (the module's parameters keep their storage:
+            # optimizer steps and load_state_dict write in place; .to() / _apply drop this cache)
+            p = nat.PolicyParams()
+            p.num_envs, p.num_obs, p.num_critic_obs, p.num_actions = n, self.num_actor_obs, self.num_critic_obs, self.num_actions
+            p.hidden[:] = self.hidden
+            for i, li in enumerate((0, 2, 4, 6)):
+                p.actor_w[i], p.actor_b[i] = self.actor[li].weight.data_ptr(), self.actor[li].bias.data_ptr()
+                p.critic_w[i], p.critic_b[i] = self.critic[li].weight.data_ptr(), self.critic[li].bias.data_ptr()
+            p.std = self.std.data_ptr()
+            need = int(nat.lib.lgk_policy_workspace_bytes(C.byref(p)))
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+            self._params, self._params_dev = p, dev
         p.obs = obs.data_ptr()
         if critic_obs is not None:
             critic_obs = critic_obs.contiguous()
@@ -173,30 +190,26 @@ class ActorCritic(nn.Module):
             p.critic_obs, p.nets = critic_obs.data_ptr(), 3
         else:
             p.critic_obs, p.nets = None, 1
-        for i, li in enumerate((0, 2, 4, 6)):
-            p.actor_w[i], p.actor_b[i] = self.actor[li].weight.data_ptr(), self.actor[li].bias.data_ptr()
-            p.critic_w[i], p.critic_b[i] = self.critic[li].weight.data_ptr(), self.critic[li].bias.data_ptr()
-        p.std = self.std.data_ptr()
         p.seed, p.step, p.env_id_offset, p.sample = self._seed, self._step, self._env_offset, int(sample)
-        out = dict(actions=torch.empty(n, self.num_actions, device=dev), mean=torch.empty(n, self.num_actions, device=dev),
-                   sigma=torch.empty(n, self.num_actions, device=dev), values=torch.empty(n, 1, device=dev),
-                   logp=torch.empty(n, device=dev))
+        if out is None:
+            A = self.num_actions
+            buf = torch.empty(n, 3 * A + 2, device=dev)          # one allocation, five outputs
+            flat = buf.view(-1)
+            out = dict(actions=flat[:n * A].view(n, A), mean=flat[n * A:2 * n * A].view(n, A),
+                       sigma=flat[2 * n * A:3 * n * A].view(n, A), values=flat[3 * n * A:3 * n * A + n].view(n, 1),
+                       logp=flat[3 * n * A + n:])
         p.actions, p.action_mean, p.action_sigma = out["actions"].data_ptr(), out["mean"].data_ptr(), out["sigma"].data_ptr()
         p.values, p.actions_log_prob = out["values"].data_ptr(), out["logp"].data_ptr()
-        need = int(nat.lib.lgk_policy_workspace_bytes(C.byref(p)))
-        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        p.workspace, p.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
         p.weights_version = self._weights_version()
         nat.check(nat.lib.lgk_policy_act(C.byref(p), torch.cuda.current_stream().cuda_stream), "lgk_policy_act")
         self._last_params, self._last_inputs = p, (obs, critic_obs)      # keeps the launch's buffers alive
         self._fused = out
         return out
 
-    def act_and_evaluate(self, observations, critic_observations):
+    def act_and_evaluate(self, observations, critic_observations, out=None):
         """PPO.act in one launch set: actions, values, log-prob, mean, sigma (rollout time, no autograd)."""
         with torch.no_grad():
-            return self._run_fused(observations, critic_observations, sample=True)
+            return self._run_fused(observations, critic_observations, sample=True, out=out)
 
     def act(self, observations, **kwargs):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not torch.is_inference_mode_enabled():

@@ -37,13 +37,13 @@ class RolloutStorage:
             self.observations[s].copy_(t.observations)
         if self.privileged_observations is not None and t.critic_observations.data_ptr() != self.privileged_observations[s].data_ptr():
             self.privileged_observations[s].copy_(t.critic_observations)
-        self.actions[s].copy_(t.actions)
         self.rewards[s].copy_(t.rewards.view(-1, 1))
         self.dones[s].copy_(t.dones.view(-1, 1))
-        self.values[s].copy_(t.values)
-        self.actions_log_prob[s].copy_(t.actions_log_prob.view(-1, 1))
-        self.mu[s].copy_(t.action_mean)
-        self.sigma[s].copy_(t.action_sigma)
+        for dst, src in ((self.actions[s], t.actions), (self.values[s], t.values),
+                         (self.actions_log_prob[s], t.actions_log_prob.view(-1, 1)), (self.mu[s], t.action_mean),
+                         (self.sigma[s], t.action_sigma)):
+            if src.data_ptr() != dst.data_ptr():        # PPO.act lets the policy kernel write the slot directly
+                dst.copy_(src)
         self.step += 1
 
     def clear(self):

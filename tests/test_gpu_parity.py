@@ -686,6 +686,41 @@ def test_policy_act_matches_restated_rsl_rl(n, nobs, hidden, variant):
     nat().lib.lgk_policy_set_variant(0)
 
 
+@pytest.mark.parametrize("n,nobs,ncobs,nact,hidden", [
+    (300, 48, 61, 5, (256, 64, 32)),        # 5 actions: rows not 16-byte aligned (scalar output stores), critic wider than actor
+    (1000, 235, 187, 16, (512, 128, 64)),   # 16 actions: all four warps of a quadrant own an action quad
+    (129, 19, 19, 3, (128, 64, 32))])       # the games' high-level agents: 19 observations, 3 commands
+def test_policy_kernel_action_counts_and_privileged_obs(n, nobs, ncobs, nact, hidden):
+    """The tcgen05 kernel beyond the 12-action / shared-observation case: odd action counts, the 16-action maximum,
+    privileged observations of another width, and its actor-only (act / act_inference) and PPO.act launches agreeing."""
+    from oracle.rsl_oracle import ActorCriticOracle
+    from legged_games_gym_b200.rsl_rl.modules import ActorCritic
+    torch.manual_seed(1)
+    nat().lib.lgk_policy_set_variant(2)
+    orc = ActorCriticOracle(nobs, ncobs, nact, hidden, hidden)
+    with torch.no_grad():
+        orc.std.copy_(torch.linspace(0.3, 1.2, nact))
+    ac = ActorCritic(nobs, ncobs, nact, list(hidden), list(hidden)).to(DEV)
+    ac.load_state_dict(orc.state_dict())
+    obs, cobs = torch.randn(n, nobs) * 2, torch.randn(n, ncobs) * 2
+    seed, step = 23, 9
+    eps = torch.from_numpy(philox.normals(seed, step, np.arange(n), nact))
+    a, v, lp, mu, sg = orc.act(obs, cobs, eps)
+    ac.set_rng(seed, step)
+    tol = dict(rtol=1e-3, atol=1e-3)
+    with torch.inference_mode():
+        out = ac.act_and_evaluate(obs.to(DEV), cobs.to(DEV))
+        got = {k: t.clone() for k, t in out.items()}
+        assert torch.equal(ac.act(obs.to(DEV)), got["actions"])                  # actor-only launch: same draws
+        assert torch.allclose(ac.act_inference(obs.to(DEV)).cpu(), mu, **tol)    # no sampling: the mean
+        assert torch.allclose(ac.evaluate(cobs.to(DEV)).cpu(), v, **tol)         # torch critic on the same weights
+    torch.cuda.synchronize()
+    assert torch.allclose(got["mean"].cpu(), mu, **tol) and torch.allclose(got["actions"].cpu(), a, **tol)
+    assert torch.allclose(got["values"].cpu(), v, **tol) and torch.allclose(got["sigma"].cpu(), sg, **tol)
+    assert torch.allclose(got["logp"].cpu(), lp, **tol)
+    nat().lib.lgk_policy_set_variant(0)
+
+
 def test_pinned_copy_kernels():
     """lgk_copy_from_pinned / lgk_copy_to_pinned / lgk_copy_rows_to_pinned: exact copies over the unified address space,
     argument errors as codes."""

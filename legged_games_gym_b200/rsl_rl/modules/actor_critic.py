@@ -1,6 +1,11 @@
 """ActorCritic with the rsl_rl API and state_dict layout (actor.{0,2,4,6}.*, critic.{0,2,4,6}.*, std).
 Rollout-time calls (no autograd) run the fused lgk_policy_act kernel; calls that need gradients (PPO.update) go through
-the nn.Sequential modules so autograd sees ordinary Linear/ELU ops."""
+the nn.Sequential modules so autograd sees ordinary Linear/ELU ops.
+
+The kernel covers what the reference trains (ELU, three hidden layers, actor and critic of equal widths: LRC:203-208 and
+every task cfg).  rsl_rl's other options -- selu / relu / crelu / lrelu / tanh / sigmoid, any depth, different actor and
+critic widths -- build the same modules and run every call through them (torch on the module's device, torch's sampler):
+same API and state_dict, no fused rollout kernel."""
 import ctypes as C
 import itertools
 
@@ -13,6 +18,16 @@ from ... import _native as nat
 
 
 _INSTANCE_IDS = itertools.count(1)      # process-wide: no two modules ever present the same weights_version
+
+
+def get_activation(act_name):
+    """rsl_rl's activation table (modules/actor_critic.py of rsl_rl v1.0.2)."""
+    table = {"elu": nn.ELU, "selu": nn.SELU, "relu": nn.ReLU, "lrelu": nn.LeakyReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}
+    if act_name == "crelu":
+        raise NotImplementedError("crelu doubles the layer width (rsl_rl maps it to nn.ReLU as well): use relu")
+    if act_name not in table:
+        raise ValueError(f"invalid activation function {act_name!r}")
+    return table[act_name]
 
 
 def _mlp(n_in, hidden, n_out, act):
@@ -72,14 +87,13 @@ class ActorCritic(nn.Module):
         if kwargs:
             print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs)))
         super().__init__()
-        if activation != "elu":
-            raise NotImplementedError("the fused policy kernel implements ELU (the reference's cfg, LRC:208)")
+        act = get_activation(activation)
         self.num_actor_obs, self.num_critic_obs, self.num_actions = num_actor_obs, num_critic_obs, num_actions
         self.hidden = list(actor_hidden_dims)
-        if list(critic_hidden_dims) != self.hidden or len(self.hidden) != 3:
-            raise NotImplementedError("fused kernel needs three hidden layers, identical for actor and critic")
-        self.actor = _mlp(num_actor_obs, self.hidden, num_actions, nn.ELU)
-        self.critic = _mlp(num_critic_obs, self.hidden, 1, nn.ELU)
+        # what lgk_policy_act implements; anything else runs through the torch modules (see the module docstring)
+        self.fusable = activation == "elu" and len(self.hidden) == 3 and list(critic_hidden_dims) == self.hidden
+        self.actor = _mlp(num_actor_obs, self.hidden, num_actions, act)
+        self.critic = _mlp(num_critic_obs, list(critic_hidden_dims), 1, act)
         self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
         self.distribution = None
         Normal.set_default_validate_args = False
@@ -161,6 +175,8 @@ class ActorCritic(nn.Module):
         """critic_obs=None runs the actor alone (act / act_inference): nothing is read through the critic pointer.
         `out` (optional): dict of preallocated contiguous fp32 outputs -- actions / mean / sigma [n, A], values [n, 1],
         logp [n] -- e.g. views of a rollout-storage slot, so that the kernel writes a transition where it is kept."""
+        if not obs.is_cuda:
+            raise RuntimeError("lgk_policy_act runs on CUDA tensors (there is no CPU path for the rollout kernel)")
         n = obs.shape[0]
         dev = obs.device
         obs = obs.contiguous()
@@ -206,13 +222,29 @@ class ActorCritic(nn.Module):
         self._fused = out
         return out
 
+    def _run_modules(self, obs, critic_obs, out=None):
+        """PPO.act for the configurations the kernel does not cover: torch modules, torch's Normal sampler."""
+        self.update_distribution(obs)
+        actions = self.distribution.sample()
+        res = dict(actions=actions, mean=self.distribution.mean, sigma=self.distribution.stddev,
+                   values=self.critic(critic_obs), logp=self.distribution.log_prob(actions).sum(dim=-1))
+        if out is not None:
+            for k, v in res.items():
+                out[k].copy_(v.view_as(out[k]))
+            res = out
+        self._fused = res
+        return res
+
     def act_and_evaluate(self, observations, critic_observations, out=None):
         """PPO.act in one launch set: actions, values, log-prob, mean, sigma (rollout time, no autograd)."""
         with torch.no_grad():
+            if not self.fusable:
+                return self._run_modules(observations, critic_observations, out)
             return self._run_fused(observations, critic_observations, sample=True, out=out)
 
     def act(self, observations, **kwargs):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not torch.is_inference_mode_enabled():
+        if (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not torch.is_inference_mode_enabled()) \
+                or not self.fusable:
             self.update_distribution(observations)
             return self.distribution.sample()
         return self._run_fused(observations, None, sample=True)["actions"]
@@ -224,6 +256,8 @@ class ActorCritic(nn.Module):
 
     def act_inference(self, observations):
         with torch.no_grad():
+            if not self.fusable:
+                return self.actor(observations)
             return self._run_fused(observations, None, sample=False)["mean"]
 
     def evaluate(self, critic_observations, **kwargs):

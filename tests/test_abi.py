@@ -73,3 +73,26 @@ def test_unknown_task_raises_value_error():
         task_registry.make_env("no_such_task", get_args([]))
     with pytest.raises(ValueError, match="Either 'name' or 'train_cfg'"):
         task_registry.make_alg_runner(env=None, name=None, args=get_args([]), train_cfg=None)
+
+
+def test_actor_critic_configurations_outside_the_kernel_use_the_modules():
+    """rsl_rl's ActorCritic options the fused kernel does not implement (other activations, depths, unequal widths) keep
+    the API and the state_dict layout and run through the torch modules; the kernel's own configuration refuses CPU
+    tensors loudly instead of falling back."""
+    import pytest
+    import torch
+    from legged_games_gym_b200.rsl_rl.modules import ActorCritic
+    ac = ActorCritic(10, 12, 3, [32, 16], [64, 32, 16], activation="tanh")
+    assert not ac.fusable and sorted(ac.state_dict())[:2] == ["actor.0.bias", "actor.0.weight"]
+    o, c = torch.randn(5, 10), torch.randn(5, 12)
+    with torch.inference_mode():
+        out = ac.act_and_evaluate(o, c)
+        assert {k: tuple(v.shape) for k, v in out.items()} == dict(actions=(5, 3), mean=(5, 3), sigma=(5, 3), values=(5, 1), logp=(5,))
+        assert torch.equal(ac.act_inference(o), ac.actor(o)) and torch.equal(ac.evaluate(c), ac.critic(c))
+        assert torch.allclose(ac.get_actions_log_prob(out["actions"]), out["logp"])
+    with pytest.raises(ValueError):
+        ActorCritic(10, 10, 3, [32, 16, 8], [32, 16, 8], activation="swish")
+    fused = ActorCritic(10, 10, 3, [128, 64, 32], [128, 64, 32])
+    assert fused.fusable
+    with torch.inference_mode(), pytest.raises(RuntimeError, match="CUDA"):
+        fused.act_inference(torch.randn(4, 10))

@@ -66,6 +66,7 @@ class PPO:
                         logp=st.actions_log_prob[s].view(-1))
         out = self.actor_critic.act_and_evaluate(obs, critic_obs, out=slot)
         t = self.transition
+        t.in_slot = slot is not None
         t.actions, t.values, t.actions_log_prob = out["actions"], out["values"], out["logp"]
         t.action_mean, t.action_sigma = out["mean"], out["sigma"]
         # Snapshot NOW: `obs` is usually the env's persistent obs_buf, which env.step() rewrites in place before
@@ -85,11 +86,24 @@ class PPO:
 
     def process_env_step(self, rewards, dones, infos):
         t = self.transition
-        t.rewards = rewards.clone()
-        t.dones = dones
-        if "time_outs" in infos:          # bootstrap on time-outs
-            t.rewards += self.gamma * torch.squeeze(t.values * infos["time_outs"].unsqueeze(1).to(self.device), 1)
-        self.storage.add_transitions(t)
+        st = self.storage
+        s = st.step
+        if t.in_slot and s < st.num_transitions_per_env:
+            # rollout fast path: PPO.act already placed observations and the policy outputs in slot s; rewards (with the
+            # time-out bootstrap, rsl_rl PPO.process_env_step) and dones go there directly
+            r = st.rewards[s].view(-1)
+            if "time_outs" in infos:
+                torch.addcmul(rewards, t.values.view(-1), infos["time_outs"].to(device=r.device, dtype=r.dtype), value=self.gamma, out=r)
+            else:
+                r.copy_(rewards)
+            st.dones[s].view(-1).copy_(dones)
+            st.step = s + 1
+        else:
+            t.rewards = rewards.clone()
+            t.dones = dones
+            if "time_outs" in infos:          # bootstrap on time-outs
+                t.rewards += self.gamma * torch.squeeze(t.values * infos["time_outs"].unsqueeze(1).to(self.device), 1)
+            st.add_transitions(t)
         t.clear()
         self.actor_critic.reset(dones)
 

@@ -115,6 +115,7 @@ class ActorCritic(nn.Module):
         self._weights_gen += 1
         self._ws = None
         self._params = None
+        self.__dict__.pop("_plist", None)
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):
@@ -123,12 +124,18 @@ class ActorCritic(nn.Module):
 
     def _weights_version(self):
         # instance id (bits 40..62) | generation (bits 20..39) | sum of the tensors' version counters (bits 0..19)
-        tv = sum(int(q._version) for q in self.parameters())
+        plist = self.__dict__.get("_plist")
+        if plist is None:          # nn.Module.parameters() walks the module tree: ~25 us per call at rollout rate
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        tv = 0
+        for q in plist:
+            tv += q._version
         return (self._instance_id << 40) | ((self._weights_gen & 0xFFFFF) << 20) | (tv & 0xFFFFF)
 
     # -- RNG of the sampling epilogue (Philox ACT stream); the runner bumps `step` once per env step
     def set_rng(self, seed, step, env_id_offset=0):
-        self._seed, self._step, self._env_offset = int(seed), int(step), int(env_id_offset)
+        d = self.__dict__
+        d["_seed"], d["_step"], d["_env_offset"] = int(seed), int(step), int(env_id_offset)
 
     def reset(self, dones=None):
         pass
@@ -197,7 +204,7 @@ class ActorCritic(nn.Module):
             if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
-            self._params, self._params_dev = p, dev
+            self.__dict__["_params"], self.__dict__["_params_dev"] = p, dev
         p.obs = obs.data_ptr()
         if critic_obs is not None:
             critic_obs = critic_obs.contiguous()
@@ -218,8 +225,9 @@ class ActorCritic(nn.Module):
         p.values, p.actions_log_prob = out["values"].data_ptr(), out["logp"].data_ptr()
         p.weights_version = self._weights_version()
         nat.check(nat.lib.lgk_policy_act(C.byref(p), torch.cuda.current_stream().cuda_stream), "lgk_policy_act")
-        self._last_params, self._last_inputs = p, (obs, critic_obs)      # keeps the launch's buffers alive
-        self._fused = out
+        d = self.__dict__           # plain attributes: skip nn.Module.__setattr__'s parameter / buffer / module checks
+        d["_last_params"], d["_last_inputs"] = p, (obs, critic_obs)      # keeps the launch's buffers alive
+        d["_fused"] = out
         return out
 
     def _run_modules(self, obs, critic_obs, out=None):

@@ -10,6 +10,7 @@ class RolloutStorage:
             self.observations = self.critic_observations = self.actions = self.rewards = self.dones = None
             self.values = self.actions_log_prob = self.action_mean = self.action_sigma = None
             self.hidden_states = None
+            self.in_slot = False          # PPO.act wrote observations / policy outputs straight into the storage slot
 
         def clear(self):
             self.__init__()

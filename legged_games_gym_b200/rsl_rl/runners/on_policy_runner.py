@@ -35,8 +35,11 @@ class OnPolicyRunner:
         obs, critic_obs = obs.to(self.device), critic_obs.to(self.device)
         alg.actor_critic.train()
         ep_infos = []
-        cur_rew = torch.zeros(env.num_envs, dtype=torch.float, device=self.device)
-        cur_len = torch.zeros(env.num_envs, dtype=torch.float, device=self.device)
+        # running return / length of the episode in progress, per env: rows of one [2, N] tensor so that a step updates and
+        # harvests both with a handful of launches (this bookkeeping is host-bound: every op is a launch per rollout step)
+        cur = torch.zeros(2, env.num_envs, dtype=torch.float, device=self.device)
+        step_inc = torch.zeros(2, env.num_envs, dtype=torch.float, device=self.device)
+        step_inc[1] = 1.0
         # finished-episode statistics live on the device (sum of returns, sum of lengths, count): no host synchronisation
         # inside the rollout; read (and, multi-GPU, all-reduced) once per iteration
         ep_stats = torch.zeros(3, dtype=torch.float64, device=self.device)
@@ -57,14 +60,12 @@ class OnPolicyRunner:
                     if track:
                         if self.log_dir is not None and "episode" in infos:
                             ep_infos.append(infos["episode"])
-                        cur_rew += rewards
-                        cur_len += 1
-                        done = (dones > 0).to(cur_rew.dtype)
-                        ep_stats[0] += (cur_rew * done).sum()
-                        ep_stats[1] += (cur_len * done).sum()
+                        step_inc[0].copy_(rewards)
+                        cur += step_inc                                  # return += reward, length += 1
+                        done = (dones > 0).to(cur.dtype)
+                        ep_stats[:2] += torch.mv(cur, done)              # sums over the episodes that just ended
                         ep_stats[2] += done.sum()
-                        cur_rew *= 1.0 - done
-                        cur_len *= 1.0 - done
+                        cur *= (1.0 - done)
                 stop = time.time()
                 self.collection_time = stop - start
                 start = stop

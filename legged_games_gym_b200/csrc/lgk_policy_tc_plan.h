@@ -3,9 +3,9 @@
 #include <stdint.h>
 namespace lgk {
 
-constexpr int kTcMaxTiles = 40;      // 2 x 8 (layer 1) + 2 x 2 x 4 (layer 2) + 2 x 4 (layer 3) for the 512-256-128 nets
+constexpr int kTcMaxTiles = 48;      // 2 x 8 (layer 1) + 2 x 4 x 2 (layer 2) + 4 x 2 (layer 3) = 40 for the 512-256-128 nets
 
-// One weight tile (<= 128 output rows x 32 k, the unit the producer copies and the issuer multiplies) in the order the
+// One weight tile (<= 256 output rows x 32 k, the unit the producer copies and the issuer multiplies) in the order the
 // tensor pipe consumes it.  The same table drives the packing kernel, the TMA producer and the MMA issuer.
 struct TcTile {
   uint16_t a;          // A operand: shared-memory chunk index of the observation tile (SS) / TMEM column of the first k (TS)

@@ -388,6 +388,12 @@ int lgk_gae(const float* rewards, const float* values, const uint8_t* dones, con
             int32_t T, int32_t N, float gamma, float lam, float* returns, float* advantages,
             double* scratch, void* stream);
 
+/* rsl_rl OnPolicyRunner's episode bookkeeping of one rollout step (cur_reward_sum / cur_episode_length / rewbuffer /
+ * lenbuffer of on_policy_runner.py, the finished episodes reduced to three running sums): cur_return += rewards,
+ * cur_length += 1; envs with dones != 0 add (cur_return, cur_length, 1) to stats3 (double[3], device) and restart at 0. */
+int lgk_episode_stats(const float* rewards, const uint8_t* dones, float* cur_return, float* cur_length,
+                      double* stats3, int32_t n, void* stream);
+
 /* ------------------------------------------------------------------ misc */
 const char* lgk_last_error_string(void);
 int lgk_abi_version(void);

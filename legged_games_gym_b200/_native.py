@@ -134,6 +134,7 @@ def _load():
     lib.lgk_policy_set_variant.argtypes = [C.c_int]
     lib.lgk_policy_debug_timeline.argtypes = [vp, C.c_int]
     lib.lgk_gae.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp]
+    lib.lgk_episode_stats.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.lgk_l2_flush.argtypes = [vp, i64, vp]
     lib.lgk_copy_from_pinned.argtypes = [vp, vp, i64, vp]
     lib.lgk_copy_to_pinned.argtypes = [vp, vp, i64, vp]
@@ -156,7 +157,7 @@ lib = _load()
 
 EXPORTS = ["lgk_set_lstm_weights", "lgk_compute_torques", "lgk_post_physics", "lgk_reset_idx", "lgk_finalize_step",
            "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline", "lgk_set_pdl", "lgk_game_step", "lgk_game_prepare", "lgk_step_debug_timeline",
-           "lgk_gae", "lgk_last_error_string", "lgk_abi_version", "lgk_l2_flush", "lgk_copy_from_pinned", "lgk_copy_to_pinned", "lgk_copy_rows_to_pinned", "lgk_launch_count",
+           "lgk_gae", "lgk_episode_stats", "lgk_last_error_string", "lgk_abi_version", "lgk_l2_flush", "lgk_copy_from_pinned", "lgk_copy_to_pinned", "lgk_copy_rows_to_pinned", "lgk_launch_count",
            "lgk_struct_size"]
 
 

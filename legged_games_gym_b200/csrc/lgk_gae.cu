@@ -72,3 +72,45 @@ extern "C" int lgk_gae(const float* rewards, const float* values, const uint8_t*
   count_launch(2);
   return check_cuda(cudaGetLastError(), "gae kernels launch");
 }
+
+// ------------------------------------------------------------------ rsl_rl OnPolicyRunner: episode bookkeeping of a rollout step
+// cur_return += reward; cur_length += 1; for every env whose episode ended: stats += (cur_return, cur_length, 1) and both
+// running values restart at 0 (rsl_rl on_policy_runner.py: cur_reward_sum / cur_episode_length / rewbuffer / lenbuffer,
+// with the finished episodes reduced to three sums that stay on the device).  One launch instead of six torch ops.
+namespace lgk {
+__global__ void __launch_bounds__(256) episode_stats_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
+                                                            float* __restrict__ cur_return, float* __restrict__ cur_length,
+                                                            double* __restrict__ stats, int n) {
+  __shared__ double s_part[3][8];
+  double ret = 0.0, len = 0.0, cnt = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float r = cur_return[i] + rewards[i], l = cur_length[i] + 1.0f;
+    const bool d = dones[i] != 0;
+    if (d) { ret += (double)r; len += (double)l; cnt += 1.0; }
+    cur_return[i] = d ? 0.f : r;
+    cur_length[i] = d ? 0.f : l;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ret += __shfl_xor_sync(0xffffffffu, ret, o); len += __shfl_xor_sync(0xffffffffu, len, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_part[0][warp] = ret; s_part[1][warp] = len; s_part[2][warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[threadIdx.x][w];
+    if (t != 0.0) atomicAdd(stats + threadIdx.x, t);
+  }
+}
+}  // namespace lgk
+
+extern "C" int lgk_episode_stats(const float* rewards, const uint8_t* dones, float* cur_return, float* cur_length,
+                                 double* stats3, int32_t n, void* stream) {
+  LGK_REQUIRE(rewards && dones && cur_return && cur_length && stats3 && n > 0, "episode_stats: bad arguments");
+  const int blocks = (n + 255) / 256 < 296 ? (n + 255) / 256 : 296;
+  lgk::episode_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rewards, dones, cur_return, cur_length, stats3, n);
+  lgk::count_launch();
+  return lgk::check_cuda(cudaGetLastError(), "episode_stats_kernel launch");
+}
+

@@ -5,6 +5,7 @@ import time
 import torch
 import torch.distributed as dist
 
+from ... import _native as nat
 from ..algorithms import PPO
 from ..modules import ActorCritic
 
@@ -47,6 +48,7 @@ class OnPolicyRunner:
         act_step = 0
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         track = self.log_dir is not None or world > 1
+        native_stats = None       # decided at the first tracked step (CUDA fp32 rewards + 1-byte dones: one kernel)
         for it in range(self.current_learning_iteration, tot_iter):
             start = time.time()
             with torch.inference_mode():
@@ -58,14 +60,22 @@ class OnPolicyRunner:
                     critic_obs = pobs if pobs is not None else obs
                     alg.process_env_step(rewards, dones, infos)
                     if track:
+                        if native_stats is None:
+                            native_stats = bool(rewards.is_cuda and rewards.dtype == torch.float32 and rewards.is_contiguous()
+                                                and dones.element_size() == 1 and dones.is_contiguous() and cur.is_cuda)
                         if self.log_dir is not None and "episode" in infos:
                             ep_infos.append(infos["episode"])
-                        step_inc[0].copy_(rewards)
-                        cur += step_inc                                  # return += reward, length += 1
-                        done = (dones > 0).to(cur.dtype)
-                        ep_stats[:2] += torch.mv(cur, done)              # sums over the episodes that just ended
-                        ep_stats[2] += done.sum()
-                        cur *= (1.0 - done)
+                        if native_stats:
+                            nat.check(nat.lib.lgk_episode_stats(rewards.data_ptr(), dones.data_ptr(), cur[0].data_ptr(),
+                                                                cur[1].data_ptr(), ep_stats.data_ptr(), env.num_envs,
+                                                                torch.cuda.current_stream().cuda_stream), "lgk_episode_stats")
+                        else:
+                            step_inc[0].copy_(rewards)
+                            cur += step_inc                                  # return += reward, length += 1
+                            done = (dones > 0).to(cur.dtype)
+                            ep_stats[:2] += torch.mv(cur, done)              # sums over the episodes that just ended
+                            ep_stats[2] += done.sum()
+                            cur *= (1.0 - done)
                 stop = time.time()
                 self.collection_time = stop - start
                 start = stop

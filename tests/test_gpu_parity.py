@@ -721,6 +721,31 @@ def test_policy_kernel_action_counts_and_privileged_obs(n, nobs, ncobs, nact, hi
     nat().lib.lgk_policy_set_variant(0)
 
 
+def test_episode_stats_kernel_matches_the_runner_bookkeeping():
+    """lgk_episode_stats = rsl_rl OnPolicyRunner's cur_reward_sum / cur_episode_length bookkeeping with the finished
+    episodes reduced to (sum of returns, sum of lengths, count)."""
+    g = torch.Generator().manual_seed(11)
+    n = 5000
+    cur = torch.zeros(2, n, device=DEV)
+    stats = torch.zeros(3, dtype=torch.float64, device=DEV)
+    w_rew, w_len, w_stats = torch.zeros(n), torch.zeros(n), torch.zeros(3, dtype=torch.float64)
+    for step in range(12):
+        rew = torch.randn(n, generator=g)
+        done = torch.rand(n, generator=g) < 0.1
+        r_d, d_d = rew.to(DEV), done.to(DEV)
+        assert nat().lib.lgk_episode_stats(r_d.data_ptr(), d_d.data_ptr(), cur[0].data_ptr(), cur[1].data_ptr(), stats.data_ptr(),
+                                           n, stream()) == 0
+        w_rew += rew
+        w_len += 1
+        w_stats += torch.stack([(w_rew[done]).double().sum(), (w_len[done]).double().sum(), done.double().sum()])
+        w_rew[done] = 0
+        w_len[done] = 0
+    torch.cuda.synchronize()
+    assert torch.equal(cur[0].cpu(), w_rew) and torch.equal(cur[1].cpu(), w_len)
+    assert torch.allclose(stats.cpu(), w_stats, rtol=1e-12, atol=1e-9)
+    assert nat().lib.lgk_episode_stats(None, None, None, None, None, 0, stream()) != 0
+
+
 def test_pinned_copy_kernels():
     """lgk_copy_from_pinned / lgk_copy_to_pinned / lgk_copy_rows_to_pinned: exact copies over the unified address space,
     argument errors as codes."""

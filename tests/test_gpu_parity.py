@@ -689,7 +689,9 @@ def test_policy_act_matches_restated_rsl_rl(n, nobs, hidden, variant):
 @pytest.mark.parametrize("n,nobs,ncobs,nact,hidden", [
     (300, 48, 61, 5, (256, 64, 32)),        # 5 actions: rows not 16-byte aligned (scalar output stores), critic wider than actor
     (1000, 235, 187, 16, (512, 128, 64)),   # 16 actions: all four warps of a quadrant own an action quad
-    (129, 19, 19, 3, (128, 64, 32))])       # the games' high-level agents: 19 observations, 3 commands
+    (129, 19, 19, 3, (128, 64, 32)),        # the games' high-level agents: 19 observations, 3 commands
+    (1, 235, 235, 12, (512, 256, 128)),     # a single environment: 127 empty rows in the tile
+    (255, 256, 8, 12, (256, 256, 128))])    # widest observation (8 full chunks) next to the narrowest, hidden[1] = hidden[0]
 def test_policy_kernel_action_counts_and_privileged_obs(n, nobs, ncobs, nact, hidden):
     """The tcgen05 kernel beyond the 12-action / shared-observation case: odd action counts, the 16-action maximum,
     privileged observations of another width, and its actor-only (act / act_inference) and PPO.act launches agreeing."""

@@ -58,10 +58,10 @@ __device__ __forceinline__ void policy_finish_row(const LgkPolicyParams& p, int 
 // block `blk` of the ACT stream): lets four warps share a row's epilogue.  Returns the partial log-prob of these actions.
 // sd3 = [std | 1/std | log(std)] x 16 (precomputed once per CTA): log N(a; mu, sd) = -((a - mu)/sd)^2 / 2 - log sd - log sqrt(2 pi)
 // without a division or a logarithm per action.
-__device__ __forceinline__ float policy_finish_quad(const LgkPolicyParams& p, int n, int blk, const float (&mu)[4],
-                                                    const float* __restrict__ sd3) {
-  const int A = p.num_actions;
-  float z[4] = {0.f, 0.f, 0.f, 0.f};
+// the four N(0,1) draws of actions 4*blk .. 4*blk+3 (independent of the network's output: the tensor-core kernel draws them
+// while the last MMAs are still running)
+__device__ __forceinline__ void policy_draw_quad(const LgkPolicyParams& p, int n, int blk, float (&z)[4]) {
+  z[0] = z[1] = z[2] = z[3] = 0.f;
   if (p.sample) {
     const RngKey key = make_key(p.seed, p.step);
     const U4 r = rng_block(key, (uint32_t)(p.env_id_offset + n), LGK_STREAM_ACT, (uint32_t)blk);
@@ -76,6 +76,11 @@ __device__ __forceinline__ float policy_finish_quad(const LgkPolicyParams& p, in
       z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
     }
   }
+}
+
+__device__ __forceinline__ float policy_finish_quad(const LgkPolicyParams& p, int n, int blk, const float (&mu)[4],
+                                                    const float* __restrict__ sd3, const float (&z)[4]) {
+  const int A = p.num_actions;
   float logp = 0.f;
   float act[4], sd[4];
 #pragma unroll

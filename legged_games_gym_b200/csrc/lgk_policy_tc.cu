@@ -528,6 +528,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
     float4 b3r[8];                                          // this warp's block of the layer-3 bias, ahead of the wait
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) b3r[q4] = part * 32 < h2 ? ldg_f4(Bg[2] + part * 32 + 4 * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float zq[4] = {0.f, 0.f, 0.f, 0.f};                     // this thread's action quad: the draws do not depend on the network
+    if (net == 0 && 4 * part < nout && m0 + row < N) policy_draw_quad(p, m0 + row, part, zq);
     mbar_wait(bar_acc, 1);                                  // layer 3 done
     tc_fence_after();
     stamp(11);
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
           for (int pp = 0; pp < kColSplit; ++pp) t += lds_f1(a_partial + ((pp * kMaxOut + o) * kTileM + row) * 4);
           mu[j] = t;
         }
-        const float lp = n < N ? policy_finish_quad(p, n, part, mu, s_std) : 0.f;
+        const float lp = n < N ? policy_finish_quad(p, n, part, mu, s_std, zq) : 0.f;
         sts_f1(a_logp + (part * kTileM + row) * 4, lp);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");

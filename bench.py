@@ -63,7 +63,7 @@ def parse():
                     help="rotate: cycle over env replicas whose buffers exceed L2; flush: write 256 MiB between steps")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launch")
-    ap.add_argument("--lstm-variant", type=int, default=0, help="0 auto, 1 thread-per-sequence, 2 role-split")
+    ap.add_argument("--lstm-variant", type=int, default=0, help="0 auto, 1 thread-per-sequence, 2 role-split, 3 thread-per-sequence with packed gate arithmetic")
     return ap.parse_args()
 
 

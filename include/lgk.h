@@ -71,7 +71,8 @@ typedef struct LgkTorqueParams {
   int32_t use_lstm;                   /* ANY:73 cfg.control.use_actuator_network */
   float action_scale;                 /* cfg.control.action_scale */
   float clip_actions;                 /* LR:86-87: actions are clipped to +-clip on load */
-  int32_t lstm_variant;               /* 0 = auto (by batch size), 1 = one thread per sequence, 2 = role-split CTA */
+  int32_t lstm_variant;               /* 0 = auto (by batch size), 1 = one thread per sequence, 2 = role-split CTA,
+                                       * 3 = one thread per sequence with packed-fp32 gate arithmetic (auto's choice up to 12 628 envs) */
   float sim_dt;                       /* LR:390 divides by sim_params.dt ("V" control) */
   float p_gains[LGK_NUM_DOF];         /* LR:566-580 */
   float d_gains[LGK_NUM_DOF];

@@ -36,25 +36,54 @@ constexpr float kTanhClamp = 43.0f;   // = 2*log2(e)*14.9: tanh saturates in fp3
 // one LSTM layer, hidden 8; IN = input width.  torch gate order i, f, g, o (rows 0-7, 8-15, 16-23, 24-31).
 //   c' = sigmoid(f)*c + sigmoid(i)*tanh(g) ; h' = sigmoid(o)*tanh(c')
 // with sigmoid(a)*tanh(b) = (1 - eb) / ((1 + ea)(1 + eb)), ea = e^-a, eb = e^-2b: 5 ex2 + 3 rcp per unit.
-template <int IN>
+template <int IN, bool PACKED = false>
 __device__ __forceinline__ void lstm_layer(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                            const float* __restrict__ bias, const float (&x)[IN], float (&h)[8],
                                            float (&c)[8]) {
   unsigned long long acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = pack2(bias[2 * j], bias[2 * j + 1]);
-#pragma unroll
-  for (int k = 0; k < IN; ++k) {
-    const unsigned long long xx = pack2(x[k], x[k]);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = fma2(pack2(w_ih[k * 32 + 2 * j], w_ih[k * 32 + 2 * j + 1]), xx, acc[j]);
-  }
+  // recurrent part first: in this order ptxas keeps the hoisted LDCU.128 weight loads inside the 63 uniform registers
+  // (8 spill instructions instead of 112 with the input part first; 1176 instead of 1280 instructions per sequence)
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const unsigned long long hh = pack2(h[k], h[k]);
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = fma2(pack2(w_hh[k * 32 + 2 * j], w_hh[k * 32 + 2 * j + 1]), hh, acc[j]);
   }
+#pragma unroll
+  for (int k = 0; k < IN; ++k) {
+    const unsigned long long xx = pack2(x[k], x[k]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = fma2(pack2(w_ih[k * 32 + 2 * j], w_ih[k * 32 + 2 * j + 1]), xx, acc[j]);
+  }
+  if (PACKED) {
+  // gates two hidden units at a time on the packed fp32 pipe (acc[j] already pairs the units 2j', 2j'+1 of one gate type:
+  // rows 0-7 i, 8-15 f, 16-23 g, 24-31 o); only the MUFU ops and the clamps are scalar
+  const f2_t one2 = pack2(1.0f, 1.0f), mone2 = pack2(-1.0f, -1.0f), scale2 = pack2(-2.0f * kLog2e, -2.0f * kLog2e);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float gi0, gi1, gf0, gf1, gg0, gg1, go0, go1;
+    unpack2(acc[q], gi0, gi1); unpack2(acc[4 + q], gf0, gf1); unpack2(acc[8 + q], gg0, gg1); unpack2(acc[12 + q], go0, go1);
+    const f2_t ei = pack2(ex2_approx(gi0), ex2_approx(gi1)), ef = pack2(ex2_approx(gf0), ex2_approx(gf1));
+    const f2_t eo = pack2(ex2_approx(go0), ex2_approx(go1));
+    const f2_t eg = pack2(ex2_approx(fminf(gg0, kTanhClamp)), ex2_approx(fminf(gg1, kTanhClamp)));
+    float d0, d1, f0, f1;
+    unpack2(mul2(add2(ei, one2), add2(eg, one2)), d0, d1);                  // (1 + ei)(1 + eg)
+    unpack2(add2(ef, one2), f0, f1);                                        // 1 + ef
+    const f2_t num = fma2(eg, mone2, one2);                                 // 1 - eg
+    const f2_t cn = fma2(pack2(c[2 * q], c[2 * q + 1]), pack2(rcp_approx(f0), rcp_approx(f1)),
+                         mul2(num, pack2(rcp_approx(d0), rcp_approx(d1))));
+    float t0, t1;
+    unpack2(mul2(cn, scale2), t0, t1);
+    const f2_t ec = pack2(ex2_approx(fminf(t0, kTanhClamp)), ex2_approx(fminf(t1, kTanhClamp)));
+    float e0, e1;
+    unpack2(mul2(add2(eo, one2), add2(ec, one2)), e0, e1);                  // (1 + eo)(1 + ec)
+    const f2_t hn = mul2(fma2(ec, mone2, one2), pack2(rcp_approx(e0), rcp_approx(e1)));
+    unpack2(cn, c[2 * q], c[2 * q + 1]);
+    unpack2(hn, h[2 * q], h[2 * q + 1]);
+  }
+  } else {
   float g[32];
 #pragma unroll
   for (int j = 0; j < 16; ++j) unpack2(acc[j], g[2 * j], g[2 * j + 1]);
@@ -66,6 +95,7 @@ __device__ __forceinline__ void lstm_layer(const float* __restrict__ w_ih, const
     const float ec = ex2_approx(fminf(cn * (-2.0f * kLog2e), kTanhClamp));
     c[u] = cn;
     h[u] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+  }
   }
 }
 
@@ -80,7 +110,10 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 
 // HOSTIO: dof_state may be pinned host memory (uncached loads) and the torques are mirrored into torques_mirror; the
 // device-resident instantiation carries neither (the uncached load alone cost 3 % at 65 536 envs).
-template <bool LSTM, bool HOSTIO = false>
+// one wave of the device-resident LSTM kernel: 8 CTAs of 128 sequences on each of the 148 SMs
+constexpr size_t kLstmWaveSeqs = (size_t)148 * 8 * 128;
+
+template <bool LSTM, bool HOSTIO = false, bool PACKED = false>
 __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_constant__ LgkTorqueParams p) {
   pdl_launch_dependents();
   const int idx = blockIdx.x * 128 + threadIdx.x;
@@ -104,8 +137,17 @@ __global__ void __launch_bounds__(128, LSTM ? 8 : 4) torque_kernel(const __grid_
     float* C = p.sea_cell_state + (size_t)idx * 8;
     float h0[8], c0[8], h1[8], c1[8];
     load8(H, h0); load8(C, c0); load8(H + layer, h1); load8(C + layer, c1);
-    lstm_layer<2>(c_lstm.w_ih0, c_lstm.w_hh0, c_lstm.b0, x, h0, c0);
-    lstm_layer<8>(c_lstm.w_ih1, c_lstm.w_hh1, c_lstm.b1, h0, h1, c1);
+    if (!HOSTIO) {  // the state of the block that takes this CTA's slot one wave later: into L2 now, a DRAM round trip saved then
+      const size_t pf = (size_t)idx + kLstmWaveSeqs;
+      if (pf < (size_t)total) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sea_hidden_state + pf * 8));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sea_cell_state + pf * 8));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sea_hidden_state + layer + pf * 8));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sea_cell_state + layer + pf * 8));
+      }
+    }
+    lstm_layer<2, PACKED>(c_lstm.w_ih0, c_lstm.w_hh0, c_lstm.b0, x, h0, c0);
+    lstm_layer<8, PACKED>(c_lstm.w_ih1, c_lstm.w_hh1, c_lstm.b1, h0, h1, c1);
     float y = c_lstm.lin_b;
 #pragma unroll
     for (int k = 0; k < 8; ++k) y = fmaf(c_lstm.lin_w[k], h1[k], y);
@@ -310,14 +352,19 @@ extern "C" int lgk_compute_torques(const LgkTorqueParams* p, void* stream) {
   }
   if ((reinterpret_cast<uintptr_t>(p->dof_state) & 7u) != 0) return set_error(LGK_ERR_ALIGN, "dof_state must be 8-byte aligned");
   const int blocks = (p->num_envs * kDof + 127) / 128;
-  LGK_REQUIRE(p->lstm_variant >= 0 && p->lstm_variant <= 2, "lstm_variant must be 0, 1 or 2");
+  LGK_REQUIRE(p->lstm_variant >= 0 && p->lstm_variant <= 3, "lstm_variant must be 0..3");
   LGK_REQUIRE(p->host_io || p->torques_mirror == nullptr, "torques_mirror needs host_io = 1");
   LGK_REQUIRE(!(p->host_io && p->use_lstm && p->lstm_variant == 2), "the role-split LSTM kernel has no host_io path");
-  // auto = one thread per sequence: measured faster at 4096, 16384 and 65536 envs (bench.py --lstm-variant 2 to compare)
+  // auto = one thread per sequence (measured faster than the role-split CTA at 4096, 16384 and 65536 envs), with the gate
+  // arithmetic on the packed fp32 pipe while the batch fits one wave (latency-bound: 6.2 against 6.6 us at 4096 envs) and
+  // scalar beyond (throughput-bound: 37.1 against 41.1 us at 65 536 envs); profiles/torque_probe.py compares the variants
   const bool split = p->lstm_variant == 2;
+  const bool packed = p->lstm_variant == 3 || (p->lstm_variant == 0 && (size_t)p->num_envs * kDof <= kLstmWaveSeqs);
   cudaError_t e;
   if (p->use_lstm && split)
     e = launch_chained(torque_lstm_split_kernel, dim3((p->num_envs * kDof + kSeqPerCta - 1) / kSeqPerCta), dim3(128), 0, (cudaStream_t)stream, *p);
+  else if (p->use_lstm && packed && !p->host_io)
+    e = launch_chained(torque_kernel<true, false, true>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p);
   else if (p->use_lstm) e = p->host_io ? launch_chained(torque_kernel<true, true>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p)
                                        : launch_chained(torque_kernel<true, false>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p);
   else e = p->host_io ? launch_chained(torque_kernel<false, true>, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, *p)

@@ -15,7 +15,7 @@ bench.USE_GRAPH = True
 for n in (4096, 16384, 65536):
     envs, feeders, _ = bench.make_replicas(n, dev, 0, "rotate")
     st = torch.cuda.current_stream().cuda_stream
-    for variant in [int(v) for v in os.environ.get("VARIANTS", "1,2").split(",")]:
+    for variant in [int(v) for v in os.environ.get("VARIANTS", "1,3,2").split(",")]:
         fns = []
         for env, f in zip(envs, feeders):
             env._tq_params.actions_in = f.synthetic_actions.data_ptr()

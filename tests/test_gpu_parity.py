@@ -108,9 +108,10 @@ def test_pd_torques_bit_exact(ct):
     assert np.array_equal(got.cpu().numpy(), want.numpy())
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_lstm_torques_and_state(variant):
-    """both actuator-net kernels: 1 = one thread per (env, joint) sequence, 2 = role-split CTA (4 warps x 32 sequences)"""
+    """the actuator-net kernels: 1 = one thread per (env, joint) sequence, 2 = role-split CTA (4 warps x 32 sequences),
+    3 = one thread per sequence with the gate arithmetic on the packed fp32 pipe, 0 = auto (3 at this size)"""
     case = harness.build_case("anymal_c_flat", 323, seed=32)       # 3876 sequences: not a multiple of 32 or 128
     orc = harness.make_oracle(case)
     env, feeder = product_env(case)

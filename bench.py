@@ -595,7 +595,7 @@ def gpu_arm(args):
             if n2 != N:
                 sweep[str(n2)] = size_leg(n2, dev, rank, world, peak_gbs, args.l2, flush, barrier=barrier)
                 if rank == 0:
-                    sweep[str(n2)]["roofline_torque_lstm"]["traffic"] = ncu_traffic(n2, r"torque_kernel<1(, 0)?>")
+                    sweep[str(n2)]["roofline_torque_lstm"]["traffic"] = ncu_traffic(n2, r"torque_kernel<1(, 0)?(, [01])?>")
                     sweep[str(n2)]["roofline_post_physics"]["traffic"] = ncu_traffic(n2, r"post_kernel", "scan_obs")
 
     # ---- one PPO iteration on all ranks, NCCL gradient all-reduce inside (the learning side of configs[4])
@@ -645,7 +645,7 @@ def gpu_arm(args):
             except Exception as e:                       # a baseline, never a reason to lose the bench line
                 cpu["eager_torch_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     dom = dict(roof["torque_lstm"])
-    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, r"torque_kernel<1(, 0)?>"))
+    dom.update(kernel="torque_kernel<LSTM> (4 launches per step)", peak_source=peak_src, traffic=ncu_traffic(N, r"torque_kernel<1(, 0)?(, [01])?>"))
     roof["post_physics"]["traffic"] = ncu_traffic(N, r"post_kernel", "scan_obs")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LGK_ABI_VERSION 5
+#define LGK_ABI_VERSION 6
 #define LGK_NUM_DOF 12          /* every registered task has 12 DOF = 12 actions */
 #define LGK_MAX_FEET 4
 #define LGK_MAX_PEN 16

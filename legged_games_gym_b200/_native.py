@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 5          # include/lgk.h LGK_ABI_VERSION
+ABI_VERSION = 6          # include/lgk.h LGK_ABI_VERSION
 LIB_PATH = os.environ.get("LGK_LIB_PATH") or os.path.join(_HERE, "liblgk.so")      # override: A/B of kernel builds
 
 NUM_DOF, MAX_FEET, MAX_PEN, MAX_TERM, MAX_BODIES = 12, 4, 16, 8, 32

@@ -15,20 +15,23 @@
 // cp.async.bulk costs its issuing thread ~270 cycles whatever its size, so weight tiles are as large as the ring allows
 // (<= 256 rows x 32 k = 32 KB: 110 B/cycle/SM from L2, against 60 for 16 KB tiles).
 //
-//   warps 0-15 stage the observation tile into shared memory (TF32, 128-byte swizzled K-major chunks of 32 columns; each
-//              chunk is released to the tensor pipe as soon as it is complete), later drain accumulator blocks in place
-//              (warp w owns lane quadrant w%4, the four warps of a quadrant split the 32-column blocks); the last drain
-//              feeds the h2->A layer on FP32 FFMA, then Normal sampling (Philox ACT stream) / log-prob / value.
+//   warps 0-15 stage the observation tile into shared memory (TF32, 128-byte swizzled K-major chunks of 32 columns; the
+//              first four chunks are released to the tensor pipe while the last four are still loading), later drain
+//              accumulator blocks in place, group by group (warp w owns lane quadrant w%4, the four warps of a quadrant
+//              split a group's columns); the last drain feeds the h2->A layer on FP32 FFMA2, then Normal sampling (Philox
+//              ACT stream, drawn while layer 3 is still running) / log-prob / value, spread over all sixteen warps.
 //   warp 16    streams pre-packed weight tiles (<=256 rows x 32 k, already swizzled + TF32-rounded by
 //              policy_pack_kernel) through a 3-stage 32 KB ring with TMA bulk copies (cp.async.bulk + mbarrier tx).
-//   warp 17    owns TMEM (512 columns) and issues tcgen05.mma.cta_group::1.kind::tf32 from one thread, walking the tile
-//              schedule the host built (TcPlan::sched); tcgen05.commit releases ring stages and signals finished
-//              accumulator blocks.
+//   warp 17    owns TMEM (512 columns) and walks the tile schedule the host built (TcPlan::sched, read from the kernel-
+//              parameter constant bank) with warp-uniform control flow; one elected lane issues
+//              tcgen05.mma.cta_group::1.kind::tf32 with uniform-register operands (one UTCHMMA per MMA) and the
+//              tcgen05.commit that releases ring stages and signals finished accumulator blocks.
 //
-// TMEM columns (fp32 accumulators / TF32 activations), H = h0/2, G = H/2; default 512-256-128 nets: H = 256, G = 128:
+// TMEM columns (fp32 accumulators / TF32 activations), H = h0/2, drain groups of G columns (up to four per block);
+// default 512-256-128 nets: H = 256, G = 64:
 //   S = [0,H)  one half of layer 1's columns at a time      ACC2 = [H, H+h1)  layer-2 accumulators      layer 3 -> [0,h2)
-//   tensor pipe: L1a>S | L2a(A=S group 0) L2a(A=S group 1) | L1b>S | L2b(g0) L2b(g1) | L3(A=ACC2 g0) L3(A=ACC2 g1)
-//   epilogue   :        drain S g0, g1 (in place)                   drain S g0, g1     drain ACC2 g0, g1     final layer
+//   tensor pipe: L1a>S | L2a(A=S g0) .. L2a(A=S g3) | L1b>S | L2b(g0) .. L2b(g3) | L3(A=ACC2 g0) .. L3(A=ACC2 g3)
+//   epilogue   :        drain S g0 .. g3 (in place)           drain S g0 .. g3     drain ACC2 g0 .. g3           final layer
 // Layer 2 accumulates one k-group at a time as its inputs appear, so a drain of G columns (not of the whole block) is what
 // the tensor pipe waits for.  The MMAs of one thread execute in issue order, which is what makes the reuse of S safe
 // (L1b overwrites S only after L2a has read it).

@@ -149,7 +149,12 @@ STEP_CASES = [("anymal_c_flat", 64, None), ("anymal_c_rough", 256, None), ("anym
                                       "rewards.scales.stand_still": -0.1, "rewards.scales.orientation": -1.0,
                                       "rewards.scales.termination": -5.0, "rewards.scales.feet_contact_forces": -0.01,
                                       "rewards.scales.dof_vel_limits": -0.5, "rewards.scales.torque_limits": -0.01,
-                                      "rewards.scales.dof_pos_limits": -2.0, "rewards.max_contact_force": 1.5})]
+                                      "rewards.scales.dof_pos_limits": -2.0, "rewards.max_contact_force": 1.5}),
+              # configuration switches off the defaults (each pinned oracle == reference in tests/test_oracle_vs_reference.py)
+              ("anymal_c_rough", 160, {"commands.heading_command": False, "env.episode_length_s": 0.1}),
+              ("anymal_c_rough", 96, {"terrain.curriculum": False, "control.decimation": 2}),
+              ("a1", 160, {"domain_rand.push_robots": False, "commands.resampling_time": 0.04}),
+              ("a1", 96, {"terrain.measure_heights": False, "env.num_observations": 48})]
 
 
 @pytest.mark.parametrize("task,n,ov", STEP_CASES)

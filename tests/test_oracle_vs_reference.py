@@ -15,7 +15,14 @@ CASES = [("anymal_c_flat", 64, None), ("anymal_c_rough", 128, None), ("a1", 128,
          ("a1", 64, {"control.control_type": "V"}), ("a1", 64, {"control.control_type": "T"}),
          # low_level_game: two actors per env (prey robot + predator sphere), 18-body contact view, predator re-spawn
          ("low_level_game", 96, None),
-         ("low_level_game", 64, {"domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1})]
+         ("low_level_game", 64, {"domain_rand.push_interval_s": 0.04, "env.episode_length_s": 0.1}),
+         # configuration switches off the defaults: yaw-rate commands instead of heading, fixed terrain levels, no noise and
+         # signed rewards, two decimation sub-steps, rapid command resampling without pushes, a rough-terrain robot without scan
+         ("anymal_c_rough", 64, {"commands.heading_command": False, "env.episode_length_s": 0.1}),
+         ("anymal_c_rough", 64, {"terrain.curriculum": False, "control.decimation": 2}),
+         ("a1", 64, {"noise.add_noise": False, "rewards.only_positive_rewards": False}),
+         ("a1", 64, {"domain_rand.push_robots": False, "commands.resampling_time": 0.04}),
+         ("a1", 64, {"terrain.measure_heights": False, "env.num_observations": 48})]
 
 
 @pytest.mark.parametrize("task,n,ov", CASES)

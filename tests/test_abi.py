@@ -96,3 +96,15 @@ def test_actor_critic_configurations_outside_the_kernel_use_the_modules():
     assert fused.fusable
     with torch.inference_mode(), pytest.raises(RuntimeError, match="CUDA"):
         fused.act_inference(torch.randn(4, 10))
+
+
+def test_affinity_helpers_degrade_quietly_without_a_gpu():
+    """utils/affinity.py: with no NVML answer (this container has no GPU) nothing is bound and the affinity is untouched."""
+    import os
+    from legged_games_gym_b200.utils import affinity
+    before = sorted(os.sched_getaffinity(0))
+    assert affinity.gpu_cpu_affinity(0) == [] or set(affinity.gpu_cpu_affinity(0)) <= set(range(os.cpu_count()))
+    prev, new = affinity.bind_to_gpu(0)
+    assert prev == before
+    affinity.restore_affinity(prev)
+    assert sorted(os.sched_getaffinity(0)) == before

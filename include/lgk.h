@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LGK_ABI_VERSION 6
+#define LGK_ABI_VERSION 7
 #define LGK_NUM_DOF 12          /* every registered task has 12 DOF = 12 actions */
 #define LGK_MAX_FEET 4
 #define LGK_MAX_PEN 16
@@ -215,7 +215,7 @@ typedef struct LgkStepParams {
   /* optional device-resident step counter (number of completed steps).  When non-NULL it overrides `step`
    * (post_physics / finalize(advance=1) use counter+1, reset_idx uses counter) and `do_push` (derived from
    * push_interval), and finalize(advance=1) stores counter+1: a whole env step then has no per-step host-side
-   * parameter and can be replayed as one CUDA graph. */
+   * parameter and can be replayed as one CUDA graph.  lgk_post_physics_finalize needs room for a second int32. */
   int32_t* step_counter_dev;
   /* optional output [N,4]: the root quaternion (xyzw) this step's rotations used, i.e. the pose BEFORE reset_idx.
    * LowLevelGame keeps exactly this copy as `base_quat` until its next step (LLG:123), and the high-level games read
@@ -246,6 +246,15 @@ int lgk_step_debug_timeline(int64_t* device_buf32);
  * of time_out_buf into time_outs_extras; (c) clears the other ping-pong slot of reset_stats. */
 int lgk_finalize_step(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset_count,
                       float* episode_means, uint8_t* time_outs_extras, int32_t advance, void* stream);
+
+/* lgk_post_physics(PRE | POST) followed by lgk_finalize_step(advance = 1), as one call: the whole of LR:106-137 + the
+ * id list / extras of LR:147-191.  Same results as the two calls.  On the rough-terrain path (height field, scan +
+ * observations in one K2 pass, hand-over buffers present) the finalize pass does not end the step's dependent chain as
+ * a kernel of its own but rides in K2's grid as one more CTA; K1 then hands the step number to K2 through word [1]
+ * of the counter, so step_counter_dev, when non-NULL, must point at TWO int32 here ([0] completed steps, [1] scratch).
+ * Every other configuration runs the two calls back to back. */
+int lgk_post_physics_finalize(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset_count,
+                              float* episode_means, uint8_t* time_outs_extras, void* stream);
 
 /* ------------------------------------------------------------------ hierarchical predator / prey games
  * HighLevelGame.step after ll_env.step (legged_gym/envs/a1_game/high_level_game.py:178-239 = HLG) and

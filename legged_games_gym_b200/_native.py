@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 6          # include/lgk.h LGK_ABI_VERSION
+ABI_VERSION = 7          # include/lgk.h LGK_ABI_VERSION
 LIB_PATH = os.environ.get("LGK_LIB_PATH") or os.path.join(_HERE, "liblgk.so")      # override: A/B of kernel builds
 
 NUM_DOF, MAX_FEET, MAX_PEN, MAX_TERM, MAX_BODIES = 12, 4, 16, 8, 32
@@ -126,6 +126,7 @@ def _load():
     lib.lgk_post_physics.argtypes = [C.POINTER(StepParams), vp]
     lib.lgk_reset_idx.argtypes = [C.POINTER(StepParams), vp, i32, vp]
     lib.lgk_finalize_step.argtypes = [C.POINTER(StepParams), vp, vp, vp, vp, i32, vp]
+    lib.lgk_post_physics_finalize.argtypes = [C.POINTER(StepParams), vp, vp, vp, vp, vp]
     lib.lgk_height_min3.argtypes = [vp, vp, i32, i32, vp]
     lib.lgk_height_scan.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, i32, f32, f32, f32, vp, vp, vp, vp]
     lib.lgk_rng_dump.argtypes = [u64, i32, i64, i32, i32, i32, i32, vp, vp]
@@ -155,7 +156,7 @@ def _load():
 
 lib = _load()
 
-EXPORTS = ["lgk_set_lstm_weights", "lgk_compute_torques", "lgk_post_physics", "lgk_reset_idx", "lgk_finalize_step",
+EXPORTS = ["lgk_set_lstm_weights", "lgk_compute_torques", "lgk_post_physics", "lgk_reset_idx", "lgk_finalize_step", "lgk_post_physics_finalize",
            "lgk_height_min3", "lgk_height_scan", "lgk_rng_dump", "lgk_policy_workspace_bytes", "lgk_policy_act", "lgk_policy_set_variant", "lgk_policy_debug_timeline", "lgk_set_pdl", "lgk_game_step", "lgk_game_prepare", "lgk_step_debug_timeline",
            "lgk_gae", "lgk_episode_stats", "lgk_last_error_string", "lgk_abi_version", "lgk_l2_flush", "lgk_copy_from_pinned", "lgk_copy_to_pinned", "lgk_copy_rows_to_pinned", "lgk_launch_count",
            "lgk_struct_size"]

@@ -182,6 +182,9 @@ post_kernel(const __grid_constant__ LgkStepParams p, const __grid_constant__ Til
   const bool do_push = pre && (p.step_counter_dev ? (p.push_interval > 0 && step_eff % p.push_interval == 0) : (p.do_push != 0));
   const RngKey key = make_key(p.seed, step_eff);
   float* stats = p.reset_stats + (size_t)(step_eff & 1) * (K + 2);
+  // lgk_post_physics_finalize: K2 and the finalize CTA riding in its grid take the step from word [1] of the counter (no
+  // kernel that runs concurrently with this one reads it), so that the finalize CTA may advance word [0] while K2 runs
+  if ((p.phase_mask & kPhaseFusedFin) && p.step_counter_dev && blockIdx.x == 0 && tid == 0) p.step_counter_dev[1] = step_eff;
 
   // per-env scalar rows (one 128-byte row segment per tensor and tile; lane = env) travel through registers, loaded one
   // tile AHEAD: the loads of tile i+1 are in flight while tile i is processed
@@ -554,7 +557,7 @@ post_kernel(const __grid_constant__ LgkStepParams p, const __grid_constant__ Til
 
 int launch_k1(const LgkStepParams* p, cudaStream_t st) {
   const TileLayout L = make_layout(p->num_bodies, p->num_feet, p->num_reward_slots);
-  const bool fast = p->phase_mask == (LGK_PHASE_PRE | LGK_PHASE_POST) && p->actors_per_env == 1 && p->num_envs % kTile == 0;
+  const bool fast = (p->phase_mask & ~kPhaseFusedFin) == (LGK_PHASE_PRE | LGK_PHASE_POST) && p->actors_per_env == 1 && p->num_envs % kTile == 0;
   const void* fn = fast ? reinterpret_cast<const void*>(post_kernel<true>) : reinterpret_cast<const void*>(post_kernel<false>);
   // ~31 KB of staged tiles per CTA: ask for the largest shared-memory carve-out so that LGK_K1_MINBLOCKS CTAs are resident per SM
   if (int rc = ensure_func_attr(fn, L.total, "cudaFuncSetAttribute(post_kernel)", true)) return rc;

@@ -64,4 +64,8 @@ __device__ __forceinline__ float noisy_obs(float v, uint32_t word, float scale) 
 // host launchers of the two step kernels (lgk_post_k1.cu / lgk_post_physics.cu)
 int launch_k1(const LgkStepParams* p, cudaStream_t st);
 
+// internal phase_mask bit (never accepted from callers): the launch belongs to lgk_post_physics_finalize, whose finalize
+// CTA rides in K2's grid.  K1 then publishes the step in step_counter_dev[1] for K2 and that CTA.
+constexpr int kPhaseFusedFin = 0x100;
+
 }  // namespace lgk

@@ -3,7 +3,7 @@
 Same constructor, attributes, tensor layouts and method names; every per-env computation of LR:80-230,
 329-508 and 831-969 is executed by liblgk.so (include/lgk.h) through ``_native``:
 
-    step()                -> 4 x lgk_compute_torques  +  lgk_post_physics(PRE|POST)  +  lgk_finalize_step
+    step()                -> 4 x lgk_compute_torques  +  lgk_post_physics_finalize (= lgk_post_physics(PRE|POST) + lgk_finalize_step)
     reset_idx(env_ids)    -> lgk_reset_idx + lgk_finalize_step
     _get_heights()        -> lgk_height_scan
 
@@ -128,8 +128,10 @@ class LeggedRobot(BaseTask):
                 return self._step_eager(self._actions_in)
             g = torch.cuda.CUDAGraph()
             counter = self.common_step_counter
+            l0 = nat.launch_count()
             with torch.cuda.graph(g):
                 self._step_eager(self._actions_in)
+            self._graph_launches = nat.launch_count() - l0     # kernel nodes of the graph (the library counts its launches)
             self.common_step_counter = counter     # capture ran the Python side once without executing kernels
             self._graph = g
         self._graph.replay()
@@ -215,10 +217,18 @@ class LeggedRobot(BaseTask):
                         self.update_command_curriculum(ids)
                 p.phase_mask = nat.PHASE_POST
                 nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics(POST)")
-        else:
+            self._finalize(st, advance=1)
+        elif not getattr(self, "fuse_finalize", True):       # the two calls lgk_post_physics_finalize stands for (tests)
             p.phase_mask = nat.PHASE_PRE | nat.PHASE_POST
             nat.check(nat.lib.lgk_post_physics(C.byref(p), st), "lgk_post_physics")
-        self._finalize(st, advance=1)
+            self._finalize(st, advance=1)
+        else:
+            # the whole step: K1, K2 and the finalize pass in one call (on rough terrain finalize rides in K2's grid)
+            p.phase_mask = nat.PHASE_PRE | nat.PHASE_POST
+            nat.check(nat.lib.lgk_post_physics_finalize(C.byref(p), self.reset_env_ids.data_ptr(), self.reset_count.data_ptr(),
+                                                        self._episode_means.data_ptr(), self._time_outs_extras.data_ptr(), st),
+                      "lgk_post_physics_finalize")
+            self._arm_extras()
         if do_push:
             gym.set_actor_root_state_tensor(self.root_states)
         self._push_resets_to_sim()
@@ -231,6 +241,9 @@ class LeggedRobot(BaseTask):
         nat.check(nat.lib.lgk_finalize_step(C.byref(self._params), self.reset_env_ids.data_ptr(),
                                             self.reset_count.data_ptr(), self._episode_means.data_ptr(),
                                             self._time_outs_extras.data_ptr(), advance, st), "lgk_finalize_step")
+        self._arm_extras()
+
+    def _arm_extras(self):
         # extras are refreshed only when something was reset (LR:157-158, 179-191): the kernel keeps the previous
         # values otherwise.  extras["episode"] is materialised (one clone of the means vector) when it is READ, so a
         # runner that keeps the dicts of several steps gets distinct tensors and a step that nobody logs costs nothing.
@@ -530,7 +543,8 @@ class LeggedRobot(BaseTask):
         self._time_outs_extras = z(N, dt=torch.bool)
         self.reset_env_ids = z(N, dt=torch.int32)
         self.reset_count = z(1, dt=torch.int32)
-        self._step_counter_dev = z(1, dt=torch.int32)      # completed steps, advanced by lgk_finalize_step
+        # [0] completed steps, advanced by the finalize pass; [1] K1 -> K2 hand-over of lgk_post_physics_finalize
+        self._step_counter_dev = z(2, dt=torch.int32)
         self._actions_in = z(N, self.num_actions)          # staging for the graph-replayed step
         self._graph, self._eager_steps = None, 0
 

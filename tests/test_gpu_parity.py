@@ -200,7 +200,7 @@ def test_env_step_cuda_graph(task, n):
         orc.step(acts.clone(), tables)
         env.step(acts.to(DEV))
         torch.cuda.synchronize()
-        assert int(env._step_counter_dev.item()) == step == env.common_step_counter
+        assert int(env._step_counter_dev[0].item()) == step == env.common_step_counter
         assert_snapshots_close(harness.snapshot(env), harness.snapshot(orc), step,
                                atol_scale={"torques": max(1.0, float(orc.torques.abs().max()))},
                                heading_command=bool(env.cfg.commands.heading_command))
@@ -453,6 +453,47 @@ def test_step_is_deterministic_run_to_run():
                     assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), f"{task} step {step}: {k}"
                 else:
                     assert torch.equal(a[k], b[k]), f"{task} step {step}: {k} differs between two identical runs"
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_finalize_equals_the_two_calls(graph):
+    """lgk_post_physics_finalize (the finalize pass riding in K2's grid, step handed over in word [1] of the counter)
+    against lgk_post_physics + lgk_finalize_step on identical envs: state, reset id list and count, extras and the device
+    step counter, bit for bit (extras go through float atomics: 1e-6).  4096 envs take the register-resident flag path,
+    9000 (not a multiple of 16) and 16 384 the generic sweep; 20 000 envs are above the fused form's size limit (both
+    envs then run the two calls: the entry point's fallback)."""
+    for task, n in (("anymal_c_rough", 4096), ("anymal_c_rough", 9000), ("a1", 16384), ("anymal_c_rough", 20000)):
+        ov = {"env.episode_length_s": 0.08, "domain_rand.push_interval_s": 0.04, "commands.resampling_time": 0.06}
+        case = harness.build_case(task, n, seed=21, overrides=ov)
+        runs = []
+        for fuse in (True, False):
+            env, feeder = product_env(case, graph=graph)
+            env.fuse_finalize = fuse
+            st = feeder_state(feeder)
+            snaps = []
+            for step in range(1, 7):
+                acts = torch.from_numpy(np.random.default_rng(step).normal(0, 1, (n, 12)).astype(np.float32)).to(DEV)
+                _, _, _, _, extras = env.step(acts)
+                torch.cuda.synchronize()
+                snap = harness.snapshot(env)
+                cnt = int(env.reset_count.item())
+                snap["reset_count"] = env.reset_count.clone()
+                snap["reset_ids"] = env.reset_env_ids[:cnt].clone()
+                snap["counter"] = env._step_counter_dev[:1].clone()
+                snap["ex_means"] = env._episode_means.clone()
+                snap["time_outs"] = extras["time_outs"].clone()
+                assert torch.equal(snap["reset_ids"].long(), env.reset_buf.nonzero().flatten())
+                snaps.append(snap)
+                harness.apply_noise(st, harness.make_noise(case, step, 5))
+            assert int(env._step_counter_dev[0].item()) == 6
+            runs.append(snaps)
+        assert sum(int(s["reset_count"]) for s in runs[0]) > n // 10
+        for step, (a, b) in enumerate(zip(*runs), 1):
+            for k in a:
+                if k.startswith("ex_"):
+                    assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), f"{task} {n} step {step}: {k}"
+                else:
+                    assert torch.equal(a[k], b[k]), f"{task} {n} step {step}: {k} differs between the fused and the two-call step"
 
 
 def test_k1_persistent_loop_many_tiles_per_cta():

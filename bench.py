@@ -222,7 +222,9 @@ def make_env(num_envs, device, host_sim=False, env_id_offset=0, task=None, overr
     env = cls(cfg=cfg, sim_params=SimParams(dt=cfg.sim.dt, use_gpu_pipeline=True), physics_engine="physx",
               sim_device=device, headless=True, sim_backend=feeder, terrain=_TERRAINS.get(tkey))
     env.env_id_offset = env_id_offset
-    env._graph_launches = 4 + 1 + (1 if cfg.terrain.measure_heights else 0) + 1      # torques + K1 (+ K2) + finalize
+    # fallback only: the env counts the kernel nodes of its step graph itself when it captures (6 on rough terrain up to
+    # 16 384 envs -- the finalize pass rides in K2's grid --, 7 above; 6 on flat terrain: no K2)
+    env._graph_launches = 4 + 1 + (1 if cfg.terrain.measure_heights else 0) + 1
     env._tq_params.lstm_variant = LSTM_VARIANT
     env._params.env_id_offset = env_id_offset
     env.episode_length_buf.copy_(feeder.synthetic_episode_length)
@@ -268,7 +270,7 @@ def time_steps(envs, actions, steps, warmup, flush, dist_barrier):
     dist_barrier()
     launches = nat.launch_count() - l0
     graphed = sum(1 for e in envs if getattr(e, "_graph", None) is not None)
-    if graphed:        # replayed graphs bypass the library's launch counter: 6-7 kernels per replayed step
+    if graphed:        # replayed graphs bypass the library's launch counter: the env counted its graph's kernel nodes at capture
         launches += steps * getattr(envs[0], "_graph_launches", 7)
     return secs, launches
 

@@ -252,7 +252,8 @@ int lgk_finalize_step(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset
  * observations in one K2 pass, hand-over buffers present) the finalize pass does not end the step's dependent chain as
  * a kernel of its own but rides in K2's grid as one more CTA; K1 then hands the step number to K2 through word [1]
  * of the counter, so step_counter_dev, when non-NULL, must point at TWO int32 here ([0] completed steps, [1] scratch).
- * Every other configuration runs the two calls back to back. */
+ * Every other configuration (flat terrain, two actors per env, a plane under a height scan, more than 131 072 envs, the
+ * base_height reward, which needs the scan before K1) runs the two calls back to back. */
 int lgk_post_physics_finalize(const LgkStepParams* p, int32_t* reset_ids, int32_t* reset_count,
                               float* episode_means, uint8_t* time_outs_extras, void* stream);
 

@@ -488,6 +488,7 @@ __device__ __forceinline__ int count_flags16(uint4 v) {
 }
 
 constexpr int kFinRegs = 2;      // 16-byte vectors of flags (and of time-out flags) a thread keeps in registers
+constexpr int kFinBatch = 8;     // vectors per round trip on the longer sweeps
 
 // in_k2: the body runs as CTA 0 of K2's grid (lgk_post_physics_finalize) instead of as a kernel of its own at the end of
 // the chain: the step is then word [1] of the counter (K1 put it there; K2's other CTAs read the same word) and the
@@ -528,10 +529,20 @@ __device__ __noinline__ void finalize_body(const LgkStepParams& p, int32_t* rese
 #pragma unroll
     for (int q = 0; q < kFinRegs; ++q) c += count_flags16(fl[q]);
   } else {
-    for (int i = first; i < last; i += 16) {
-      if (vec && i + 16 <= last) c += count_flags16(*reinterpret_cast<const uint4*>(p.reset_buf + i));
-      else for (int k = i; k < min(i + 16, last); ++k) c += p.reset_buf[k] != 0;
+    // longer ranges: kFinBatch vectors in flight per round trip (one load per iteration would make the sweep a chain of
+    // L2 latencies: the riding CTA then outlasts K2 at 65 536 envs)
+    int i = first;
+    if (vec) {
+      for (; i + 16 * kFinBatch <= last; i += 16 * kFinBatch) {
+        uint4 v[kFinBatch];
+#pragma unroll
+        for (int q = 0; q < kFinBatch; ++q) v[q] = *reinterpret_cast<const uint4*>(p.reset_buf + i + 16 * q);
+#pragma unroll
+        for (int q = 0; q < kFinBatch; ++q) c += count_flags16(v[q]);
+      }
+      for (; i + 16 <= last; i += 16) c += count_flags16(*reinterpret_cast<const uint4*>(p.reset_buf + i));
     }
+    for (; i < last; ++i) c += p.reset_buf[i] != 0;
   }
   int incl = c;
 #pragma unroll
@@ -562,19 +573,26 @@ __device__ __noinline__ void finalize_body(const LgkStepParams& p, int32_t* rese
         }
       }
     } else {
-      for (int i = first; i < last; i += 16) {
-        if (vec && i + 16 <= last) {
-          const uint4 v = *reinterpret_cast<const uint4*>(p.reset_buf + i);
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      auto emit16 = [&](uint4 v, int base) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t m = w[q];
-            while (m) { const int b = __ffs(m) - 1; m &= m - 1; reset_ids[off++] = i + 4 * q + (b >> 3); }
-          }
-        } else {
-          for (int k = i; k < min(i + 16, last); ++k) if (p.reset_buf[k]) reset_ids[off++] = k;
+        for (int r = 0; r < 4; ++r) {
+          uint32_t m = w[r];
+          while (m) { const int b = __ffs(m) - 1; m &= m - 1; reset_ids[off++] = base + 4 * r + (b >> 3); }
         }
+      };
+      int i = first;
+      if (vec) {
+        for (; i + 16 * kFinBatch <= last; i += 16 * kFinBatch) {
+          uint4 v[kFinBatch];
+#pragma unroll
+          for (int q = 0; q < kFinBatch; ++q) v[q] = *reinterpret_cast<const uint4*>(p.reset_buf + i + 16 * q);
+#pragma unroll
+          for (int q = 0; q < kFinBatch; ++q) emit16(v[q], i + 16 * q);
+        }
+        for (; i + 16 <= last; i += 16) emit16(*reinterpret_cast<const uint4*>(p.reset_buf + i), i);
       }
+      for (; i < last; ++i) if (p.reset_buf[i]) reset_ids[off++] = i;
     }
   }
   const int step_eff = p.step_counter_dev ? (ctr + (advance ? 1 : 0)) : p.step;
@@ -592,8 +610,17 @@ __device__ __noinline__ void finalize_body(const LgkStepParams& p, int32_t* rese
         for (int q = 0; q < kFinRegs; ++q)
           if (tid + q * nthr < n16) reinterpret_cast<uint4*>(time_outs_extras)[tid + q * nthr] = tv[q];
       } else {
-        for (int i = tid; i < n16; i += nthr)
-          reinterpret_cast<uint4*>(time_outs_extras)[i] = reinterpret_cast<const uint4*>(p.time_out_buf)[i];
+        const uint4* src = reinterpret_cast<const uint4*>(p.time_out_buf);
+        uint4* dst = reinterpret_cast<uint4*>(time_outs_extras);
+        int i = tid;
+        for (; i + (kFinBatch - 1) * nthr < n16; i += kFinBatch * nthr) {
+          uint4 v[kFinBatch];
+#pragma unroll
+          for (int q = 0; q < kFinBatch; ++q) v[q] = src[i + q * nthr];
+#pragma unroll
+          for (int q = 0; q < kFinBatch; ++q) dst[i + q * nthr] = v[q];
+        }
+        for (; i < n16; i += nthr) dst[i] = src[i];
       }
       for (int i = n16 * 16 + tid; i < N; i += nthr) time_outs_extras[i] = p.time_out_buf[i];
     }
@@ -763,9 +790,10 @@ extern "C" int lgk_post_physics_finalize(const LgkStepParams* p, int32_t* reset_
   LGK_REQUIRE(p->phase_mask == (LGK_PHASE_PRE | LGK_PHASE_POST), "lgk_post_physics_finalize runs the whole step (PRE | POST)");
   const bool scan_first = p->measure_heights && p->reward_active[LGK_R_BASE_HEIGHT] != 0;
   static const int no_fuse = getenv("LGK_NO_FUSED_FINALIZE") ? 1 : 0;      // A/B aid
-  // the riding CTA has K2's 128 threads: beyond 128 flags per thread its serial sweep outlasts K2 itself (measured at
-  // 65 536 envs: 249 against 245 us per step; at 4096 / 16 384 envs the fused form saves 3.4 / 3.8 us of 45.5 / 81.2)
-  const bool small = p->num_envs <= 128 * kK2Threads;
+  // the riding CTA has K2's 128 threads: up to 1024 flags per thread (three sweeps of eight 16-byte vectors per round
+  // trip); beyond that the stand-alone 1024-thread kernel.  At 4096 / 16 384 envs the fused form saves 3.4 / 3.8 us of 45.5 / 81.2
+  static const int limit = getenv("LGK_FUSED_FINALIZE_MAX") ? atoi(getenv("LGK_FUSED_FINALIZE_MAX")) : 1024 * kK2Threads;   // A/B aid
+  const bool small = p->num_envs <= limit;
   if (no_fuse || !small || scan_first || !k2_hot(p, kScan | kObs) || p->num_height_points > 256 || p->num_reward_slots + 2 > kK2Threads) {
     if (int rc = lgk_post_physics(p, stream)) return rc;                   // no K2 after K1, or not the specialised one
     return lgk_finalize_step(p, reset_ids, reset_count, episode_means, time_outs_extras, 1, stream);

@@ -460,8 +460,8 @@ def test_fused_finalize_equals_the_two_calls(graph):
     """lgk_post_physics_finalize (the finalize pass riding in K2's grid, step handed over in word [1] of the counter)
     against lgk_post_physics + lgk_finalize_step on identical envs: state, reset id list and count, extras and the device
     step counter, bit for bit (extras go through float atomics: 1e-6).  4096 envs take the register-resident flag path,
-    9000 (not a multiple of 16) and 16 384 the generic sweep; 20 000 envs are above the fused form's size limit (both
-    envs then run the two calls: the entry point's fallback, which flat tasks -- no K2 -- always take)."""
+    9000 (not a multiple of 16), 16 384 and 20 000 the longer sweeps (single vectors / one batch of eight / a batch plus
+    singles per thread); flat tasks -- no K2 -- take the entry point's fallback to the two calls on both envs."""
     for task, n in (("anymal_c_rough", 4096), ("anymal_c_rough", 9000), ("a1", 16384), ("anymal_c_rough", 20000),
                     ("anymal_c_flat", 2100), ("cassie", 77)):
         ov = {"env.episode_length_s": 0.08, "domain_rand.push_interval_s": 0.04, "commands.resampling_time": 0.06}

@@ -39,6 +39,10 @@ def test_argument_errors_are_codes_not_crashes():
     assert rc == 1 and b"num_envs" in nat.lib.lgk_last_error_string()
     t = nat.TorqueParams()
     assert nat.lib.lgk_compute_torques(ctypes.byref(t), None) == 1
+    # the one-call form of the step validates like the two calls it stands for
+    assert nat.lib.lgk_post_physics_finalize(ctypes.byref(p), None, None, None, None, None) == 1
+    assert b"num_envs" in nat.lib.lgk_last_error_string()
+    assert nat.lib.lgk_post_physics_finalize(None, None, None, None, None, None) == 1
 
 
 def test_reward_order_is_alphabetical():
